@@ -1,0 +1,214 @@
+# -*- coding: utf-8 -*-
+"""OPOM (Output Prediction Oriented Model) builder -- host side, NumPy FP64.
+
+Stands in for the un-vendored third-party package ``opom`` the reference imports
+(``/root/reference/example_distillation.py:11``: ``from opom import OPOM,
+TransferFunction``; README.md:1-3 installs it unpinned from
+github.com/mllima/OPOM).  Its source is NOT under /root/reference, so this is a
+restatement of the published model form (Odloak 2004; Rodrigues & Odloak 2003;
+Santoro & Odloak 2012 for the dead-time states), shaped to expose exactly the
+attributes the reference controller reads (``sihmpc/ihmpccontroller.py:17-34,
+101-104,333-334``): ``Ts, theta_max, nx, nu, ny, nd, nz, A, B, C, D, Psi, F``.
+
+Model form.  For every channel (output i, input j) the step response is
+``S_ij(t) = d0 + sum_a dd_a * exp(r_a t) + di * t`` (t measured after the dead
+time theta_ij).  State ``x = [xs (ny) | xd (nd) | xi (ny) | z (nu*theta_max)]``
+with ``z_l(k) = du(k-l)`` (l = 1..theta_max, most recent first -- the ordering
+the reference's own scratch vectors pin: ``teste.py:80-101`` has x[8:10] equal
+to the previous move).  One step:
+
+    xs+ = xs + Ts*xi + sum_l Bs_l z_l      Bs_l[i,j] = (d0_ij + Ts*di_ij)  if theta_ij == l
+    xd+ = F xd       + sum_l Bd_l z_l      Bd_l[(i,j,a), j] = dd_ija * F_ija if theta_ij == l
+    xi+ = xi         + sum_l Bi_l z_l      Bi_l[i,j] = di_ij              if theta_ij == l
+    z_1+ = du,  z_{l+1}+ = z_l             (z_0 := du, the move being applied)
+    y   = xs + Psi xd                       (C = [I, Psi, 0, 0], D = 0)
+
+``F = diag(exp(r*Ts))`` ordered output-major: index ``(i*nu + j)*na + a``.
+"""
+from __future__ import annotations
+
+import numpy as np
+from scipy import signal
+
+__all__ = ["TransferFunction", "OPOM"]
+
+
+class TransferFunction(signal.TransferFunction):
+    """Continuous-time SISO transfer function with a pure dead time.
+
+    Call form of the reference: ``TransferFunction(num, den, delay=1)``
+    (``example_distillation.py:16-30``).
+    """
+
+    def __new__(cls, num, den, delay=0.0):
+        return signal.TransferFunction.__new__(cls, num, den)
+
+    def __init__(self, num, den, delay=0.0):
+        signal.TransferFunction.__init__(self, num, den)
+        self.delay = float(delay)
+
+    def step_coefficients(self, pole_tol=1e-9):
+        """Partial fractions of G(s)/s -> (d0, [(dd_a, r_a)...], di).
+
+        Supported pole sets: distinct real stable poles plus at most one pole at
+        the origin (integrating channel).  Anything else raises
+        NotImplementedError (SURVEY.md section 8(f) item 2 -- not needed by the
+        named configurations).
+        """
+        num = np.atleast_1d(np.asarray(self.num, dtype=float))
+        den = np.atleast_1d(np.asarray(self.den, dtype=float))
+        # G(s)/s
+        r, p, k = signal.residue(num, np.polymul(den, [1.0, 0.0]))
+        if len(np.atleast_1d(k)) and np.any(np.abs(k) > 0):
+            raise NotImplementedError("improper transfer function (direct term in G(s)/s)")
+        if np.any(np.abs(np.imag(p)) > pole_tol):
+            raise NotImplementedError("complex poles are not supported by this OPOM builder")
+        p = np.real(p)
+        r = np.real(r)
+        zero = np.abs(p) <= pole_tol
+        nzero = int(np.sum(zero))
+        if nzero > 2:
+            raise NotImplementedError("more than one integrator per channel")
+        stable = p[~zero]
+        if np.any(stable >= 0):
+            raise NotImplementedError("unstable pole in channel")
+        if len(stable) > 1 and np.min(np.abs(np.subtract.outer(stable, stable))
+                                       + np.eye(len(stable)) * 1e9) <= pole_tol:
+            raise NotImplementedError("repeated poles are not supported")
+        # scipy.signal.residue orders repeated roots by ascending power: r/(s-p), r/(s-p)^2
+        rz = r[zero]
+        d0 = float(rz[0]) if nzero >= 1 else 0.0
+        di = float(rz[1]) if nzero == 2 else 0.0
+        modes = [(float(rr), float(pp)) for rr, pp in zip(r[~zero], stable)]
+        return d0, modes, di
+
+
+class OPOM(object):
+    """OPOM state-space realisation of a matrix ``H`` of TransferFunction objects.
+
+    ``OPOM(h, Ts)`` with ``h = [[h11, h12], [h21, h22]]``
+    (``example_distillation.py:33-38``).
+    """
+
+    def __init__(self, H, Ts):
+        Hm = np.array(H, dtype=object)
+        if Hm.ndim == 0:
+            Hm = Hm.reshape(1, 1)
+        if Hm.ndim == 1:
+            Hm = Hm.reshape(1, -1)
+        self.H = Hm
+        self.ny, self.nu = Hm.shape
+        self.Ts = Ts
+        ny, nu = self.ny, self.nu
+
+        coeffs = [[Hm[i, j].step_coefficients() for j in range(nu)] for i in range(ny)]
+        self.na = max(1, max(len(coeffs[i][j][1]) for i in range(ny) for j in range(nu)))
+        na = self.na
+        self.nd = ny * nu * na
+
+        theta = np.zeros((ny, nu), dtype=int)
+        for i in range(ny):
+            for j in range(nu):
+                th = Hm[i, j].delay / Ts
+                if abs(th - round(th)) > 1e-9:
+                    raise NotImplementedError("dead time must be an integer multiple of Ts")
+                theta[i, j] = int(round(th))
+        self.theta = theta
+        self.theta_max = int(theta.max())
+        self.nz = self.theta_max * nu
+        self.nx = 2 * ny + self.nd + self.nz
+
+        # coefficient tables
+        self.D0 = np.zeros((ny, nu))
+        self.Di = np.zeros((ny, nu))
+        self.Dd = np.zeros(self.nd)          # diagonal of the Dd matrix
+        self.R = np.zeros(self.nd)           # poles
+        fdiag = np.zeros(self.nd)            # padded (non-existent) modes get F = 0
+        for i in range(ny):
+            for j in range(nu):
+                d0, modes, di = coeffs[i][j]
+                self.D0[i, j] = d0
+                self.Di[i, j] = di
+                for a, (dd, r) in enumerate(modes):
+                    idx = (i * nu + j) * na + a
+                    self.Dd[idx] = dd
+                    self.R[idx] = r
+                    fdiag[idx] = np.exp(r * Ts)
+        self.F = np.diag(fdiag)
+        self.Psi = np.zeros((ny, self.nd))
+        for i in range(ny):
+            self.Psi[i, i * nu * na:(i + 1) * nu * na] = 1.0
+        self.N = np.zeros((self.nd, nu))
+        for i in range(ny):
+            for j in range(nu):
+                for a in range(na):
+                    self.N[(i * nu + j) * na + a, j] = 1.0
+
+        self.A, self.B, self.C, self.D = self._state_space()
+        self.X = np.zeros(self.nx)
+
+    # ---- structured blocks (also used by the batched plant update on the device)
+    def input_blocks(self, l):
+        """(Bs_l, Bd_l, Bi_l): how a move that is ``l`` samples old enters xs, xd, xi."""
+        ny, nu, na, Ts = self.ny, self.nu, self.na, self.Ts
+        mask = (self.theta == l)
+        Bs = np.where(mask, self.D0 + Ts * self.Di, 0.0)
+        Bi = np.where(mask, self.Di, 0.0)
+        Bd = np.zeros((self.nd, nu))
+        f = np.diag(self.F)
+        for i in range(ny):
+            for j in range(nu):
+                if mask[i, j]:
+                    for a in range(na):
+                        idx = (i * nu + j) * na + a
+                        Bd[idx, j] = self.Dd[idx] * f[idx]
+        return Bs, Bd, Bi
+
+    def _state_space(self):
+        ny, nu, nd, nz, nx, Ts = self.ny, self.nu, self.nd, self.nz, self.nx, self.Ts
+        s0, d0, i0, z0 = 0, ny, ny + nd, 2 * ny + nd
+        A = np.zeros((nx, nx))
+        B = np.zeros((nx, nu))
+        A[s0:s0 + ny, s0:s0 + ny] = np.eye(ny)
+        A[s0:s0 + ny, i0:i0 + ny] = Ts * np.eye(ny)
+        A[d0:d0 + nd, d0:d0 + nd] = self.F
+        A[i0:i0 + ny, i0:i0 + ny] = np.eye(ny)
+        for l in range(0, self.theta_max + 1):
+            Bs, Bd, Bi = self.input_blocks(l)
+            if l == 0:
+                B[s0:s0 + ny, :] = Bs
+                B[d0:d0 + nd, :] = Bd
+                B[i0:i0 + ny, :] = Bi
+            else:
+                c = z0 + (l - 1) * nu
+                A[s0:s0 + ny, c:c + nu] = Bs
+                A[d0:d0 + nd, c:c + nu] = Bd
+                A[i0:i0 + ny, c:c + nu] = Bi
+        if nz:
+            B[z0:z0 + nu, :] = np.eye(nu)
+            for l in range(1, self.theta_max):
+                A[z0 + l * nu:z0 + (l + 1) * nu, z0 + (l - 1) * nu:z0 + l * nu] = np.eye(nu)
+        C = np.zeros((ny, nx))
+        C[:, s0:s0 + ny] = np.eye(ny)
+        C[:, d0:d0 + nd] = self.Psi
+        D = np.zeros((ny, nu))
+        return A, B, C, D
+
+    # ---- convenience simulation (host only)
+    def output(self, du):
+        """Advance the internal state by one move ``du`` and return y."""
+        du = np.asarray(du, dtype=float).reshape(self.nu)
+        self.X = self.A @ self.X + self.B @ du
+        return self.C @ self.X + self.D @ du
+
+    def step_response(self, n, j=0):
+        """Unit step in input j held for n samples -> (n+1, ny) outputs, y[0] at t=0."""
+        x = np.zeros(self.nx)
+        out = [self.C @ x]
+        for k in range(n):
+            du = np.zeros(self.nu)
+            if k == 0:
+                du[j] = 1.0
+            x = self.A @ x + self.B @ du
+            out.append(self.C @ x + self.D @ du)
+        return np.array(out)
