@@ -537,10 +537,10 @@ def closed_loop(ctrl, x0, u0, ysp_of_k, n_steps, plant=None, disturbance=None, r
         sol = ctrl.mpc(x0=x, ySP=ysp, w0=w0, u0=u, pesos=pesos)
         du = ctrl.du.reshape(-1)
         x = A_p @ x + B_p @ du
-        y = C @ x + D @ du
-        u = u + du
         if disturbance is not None and k == disturbance[0]:
             x[:ctrl.ny] += np.asarray(disturbance[1], dtype=float)
+        y = C @ x + D @ du
+        u = u + du
         w0 = ctrl.warmStart(sol, ysp)
         pesos, _ = ctrl.satWeights2(x, u, w0, ysp)
         if record:

@@ -1,0 +1,440 @@
+// capi.cu -- C ABI of libsihmpc_b200.so (declared in include/sihmpc_b200.h).
+// Host side only: plan upload (with the transposed copies the kernels want), launch
+// configuration, staging for the host-buffer entry point.  No torch, no Python.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <stdlib.h>
+#include <vector>
+#include <string>
+
+#include "../../include/sihmpc_b200.h"
+#include "devplan.h"
+#include "step_kernel.cuh"
+#include "dist_kernel.cuh"
+
+namespace {
+
+thread_local std::string g_err = "";
+
+int fail(int code, const char *fmt, const char *detail = "") {
+    char buf[512];
+    snprintf(buf, sizeof buf, fmt, detail);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t e__ = (expr);                                                            \
+        if (e__ != cudaSuccess) {                                                            \
+            char b__[512];                                                                   \
+            snprintf(b__, sizeof b__, "%s failed: %s", #expr, cudaGetErrorString(e__));      \
+            g_err = b__;                                                                     \
+            return SIHMPC_E_CUDA;                                                            \
+        }                                                                                    \
+    } while (0)
+
+}  // namespace
+
+struct sihmpc_plan {
+    DevPlan d;
+    int device;
+    int sm_count;
+    int nvr;                 // rows per lane of the general kernel
+    int wpb;                 // warps per block
+    int blocks_per_sm;
+    size_t smem_bytes;
+    int max_grid;
+    int fast_path;           // 1: register-tiled kernel for this shape (dist_kernel.cuh)
+    int fast_blocks_per_sm;
+    std::vector<void *> allocs;
+    // host copies needed by the host-buffer entry point
+    int nw;
+};
+
+namespace {
+
+template <typename T>
+int upload(sihmpc_plan *p, const T *host, size_t n, const T **dev) {
+    *dev = nullptr;
+    if (n == 0) {  // keep a valid pointer so kernels can index conditionally
+        n = 1;
+        void *q = nullptr;
+        CUDA_TRY(cudaMalloc(&q, sizeof(T)));
+        CUDA_TRY(cudaMemset(q, 0, sizeof(T)));
+        p->allocs.push_back(q);
+        *dev = static_cast<const T *>(q);
+        return 0;
+    }
+    if (!host) return fail(SIHMPC_E_INVALID, "plan descriptor has a NULL block%s");
+    void *q = nullptr;
+    CUDA_TRY(cudaMalloc(&q, n * sizeof(T)));
+    p->allocs.push_back(q);
+    CUDA_TRY(cudaMemcpy(q, host, n * sizeof(T), cudaMemcpyHostToDevice));
+    *dev = static_cast<const T *>(q);
+    return 0;
+}
+
+int upload_T(sihmpc_plan *p, const double *host, int rows, int cols, const double **dev) {
+    std::vector<double> t((size_t)rows * cols);
+    if ((size_t)rows * cols && !host) return fail(SIHMPC_E_INVALID, "plan descriptor has a NULL block%s");
+    for (int r = 0; r < rows; ++r)
+        for (int c = 0; c < cols; ++c) t[(size_t)c * rows + r] = host[(size_t)r * cols + c];
+    return upload(p, t.data(), t.size(), dev);
+}
+
+bool any_finite(const double *v, int n) {
+    for (int i = 0; i < n; ++i)
+        if (v[i] > -1e300 && v[i] < 1e300) return true;
+    return false;
+}
+
+template <int NVR>
+int configure(sihmpc_plan *p) {
+    auto kern = sih::ihmpc_step_kernel<NVR>;
+    const WarpLayout lay = make_layout(p->d);
+    const size_t per_warp = (size_t)lay.total * sizeof(double);
+    const size_t limit = 227 * 1024;
+    int wpb = 8;
+    while (wpb > 1 && per_warp * wpb > limit) --wpb;
+    if (per_warp * wpb > limit) return fail(SIHMPC_E_INVALID, "controller too large for shared memory%s");
+    // prefer several small CTAs per SM over one large one
+    while (wpb > 2 && per_warp * wpb > limit / 2) wpb >>= 1;
+    p->wpb = wpb;
+    p->smem_bytes = per_warp * wpb;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));
+    int occ = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpb * 32, p->smem_bytes));
+    if (occ < 1) return fail(SIHMPC_E_INVALID, "step kernel cannot be resident (registers/shared memory)%s");
+    p->blocks_per_sm = occ;
+    p->max_grid = occ * p->sm_count;
+    return 0;
+}
+
+template <int NVR>
+int launch_step(sihmpc_plan *p, const sihmpc_io &io, long long batch, int n_steps, double *scratch,
+                cudaStream_t st) {
+    long long need = (batch + p->wpb - 1) / p->wpb;
+    int grid = (int)(need < p->max_grid ? need : p->max_grid);
+    if (grid < 1) grid = 1;
+    const int max_outer = 8 * (2 * p->d.nv + p->d.ncd) + 16;
+    sih::ihmpc_step_kernel<NVR><<<grid, p->wpb * 32, p->smem_bytes, st>>>(p->d, io, batch, n_steps,
+                                                                           scratch, max_outer);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int check_io(const sihmpc_plan *p, const sihmpc_io *io, int n_steps) {
+    if (!io->x || !io->u || !io->pesos) return fail(SIHMPC_E_INVALID, "io.x, io.u and io.pesos are required%s");
+    if (!io->ysp && !(io->ysp_seq && io->seg_start && io->n_seg > 0))
+        return fail(SIHMPC_E_INVALID, "io.ysp or io.ysp_seq/seg_start is required%s");
+    if (n_steps < 1) return fail(SIHMPC_E_INVALID, "n_steps must be >= 1%s");
+    if (n_steps > 1 && !(io->flags & SIHMPC_F_ADVANCE))
+        return fail(SIHMPC_E_INVALID, "n_steps > 1 needs SIHMPC_F_ADVANCE%s");
+    if (p->d.n_vin > 0 && (io->flags & SIHMPC_F_UPDATE_VIN) && !io->vinant && n_steps == 1)
+        return fail(SIHMPC_E_INVALID, "SIHMPC_F_UPDATE_VIN needs io.vinant%s");
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sihmpc_abi_version(void) { return SIHMPC_ABI_VERSION; }
+
+const char *sihmpc_last_error(void) { return g_err.c_str(); }
+
+int sihmpc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int sihmpc_plan_destroy(sihmpc_plan *plan) {
+    if (!plan) return 0;
+    for (void *q : plan->allocs) cudaFree(q);
+    delete plan;
+    return 0;
+}
+
+int sihmpc_plan_create(const sihmpc_plan_desc *d, sihmpc_plan **out) {
+    if (!d || !out) return fail(SIHMPC_E_INVALID, "NULL argument%s");
+    *out = nullptr;
+    if (d->abi_version != SIHMPC_ABI_VERSION) return fail(SIHMPC_E_INVALID, "ABI version mismatch%s");
+    if (d->nx < 1 || d->nu < 1 || d->ny < 1 || d->N < 1 || d->m < 1 || d->R < 1 || d->nd < 0 ||
+        d->mh < 0 || d->ncd < 0 || d->n_vin < 0 || d->pl_nnz < 1)
+        return fail(SIHMPC_E_INVALID, "bad dimension in plan descriptor%s");
+    const int nv = d->N * d->nu;
+    if (nv > 64) return fail(SIHMPC_E_INVALID, "N*nu > 64 is not supported by the step kernel%s");
+    if (d->R != d->N * d->ny + 2 * d->ny + d->nd) return fail(SIHMPC_E_INVALID, "R must be N*ny+2*ny+nd%s");
+    int ndev = sihmpc_device_count();
+    if (ndev < 1) return fail(SIHMPC_E_CUDA, "no CUDA device: this library has no CPU fallback%s");
+
+    sihmpc_plan *p = new sihmpc_plan();
+    int rc = 0;
+    auto bail = [&](int code) { sihmpc_plan_destroy(p); return code; };
+    if (cudaGetDevice(&p->device) != cudaSuccess) return bail(fail(SIHMPC_E_CUDA, "cudaGetDevice failed%s"));
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, p->device) != cudaSuccess)
+        return bail(fail(SIHMPC_E_CUDA, "cudaGetDeviceProperties failed%s"));
+    p->sm_count = prop.multiProcessorCount;
+
+    DevPlan &P = p->d;
+    memset(&P, 0, sizeof P);
+    P.nx = d->nx; P.nu = d->nu; P.ny = d->ny; P.nd = d->nd; P.N = d->N; P.nv = nv; P.m = d->m;
+    P.mh = d->mh; P.R = d->R; P.ncd = d->ncd; P.n_vin = d->n_vin; P.pl_nnz = d->pl_nnz;
+    P.Ny = d->N * d->ny; P.o_sy = P.Ny; P.o_si = P.Ny + d->ny; P.o_t = P.Ny + 2 * d->ny;
+    P.ld = nv | 1; P.Ts = d->Ts;
+    p->nw = nv + 2 * d->ny;
+    P.has_box = any_finite(d->dulb, d->nu) || any_finite(d->duub, d->nu);
+    P.has_cum = any_finite(d->ulb, d->nu) || any_finite(d->uub, d->nu);
+    P.eval_term = 0;
+    for (int r = P.o_t; r < d->R && d->Wrow; ++r)
+        for (int i = 0; i < d->m; ++i)
+            if (d->Wrow[(size_t)r * d->m + i] != 0.0) P.eval_term = 1;
+
+    const int R = d->R, nx = d->nx, ny = d->ny, nu = d->nu, m = d->m, Ny = P.Ny, ncd = d->ncd;
+#define UP(call) do { rc = (call); if (rc) return bail(rc); } while (0)
+    UP(upload(p, d->E, (size_t)R * nv, &P.E));
+    UP(upload_T(p, d->E, R, nv, &P.ET));
+    UP(upload_T(p, d->Px, R, nx, &P.PxT));
+    UP(upload_T(p, d->Py, R, ny, &P.PyT));
+    UP(upload(p, d->e0, (size_t)R, &P.e0));
+    UP(upload(p, d->Wrow, (size_t)R * m, &P.Wrow));
+    UP(upload_T(p, d->Wrow, R, m, &P.WrowT));
+    UP(upload(p, d->w0row, (size_t)R, &P.w0row));
+    UP(upload(p, d->Wdu, (size_t)nv * m, &P.Wdu));
+    UP(upload_T(p, d->Wdu, nv, m, &P.WduT));
+    UP(upload(p, d->HJ, (size_t)d->mh * nv * nv, &P.HJ));
+    UP(upload(p, d->hj_index, (size_t)d->mh, &P.hj_index));
+    UP(upload(p, d->Ht, (size_t)nv * nv, &P.Ht));
+    UP(upload_T(p, d->Myx, Ny, nx, &P.MyxT));
+    UP(upload_T(p, d->Myu, Ny, nv, &P.MyuT));
+    UP(upload_T(p, d->Mi1x, ny, nx, &P.Mi1xT));
+    UP(upload_T(p, d->Mi1u, ny, nv, &P.Mi1uT));
+    UP(upload(p, d->tau, (size_t)d->N, &P.tau));
+    UP(upload(p, d->gamma, (size_t)m, &P.gamma));
+    UP(upload(p, d->dulb, (size_t)nu, &P.dulb));
+    UP(upload(p, d->duub, (size_t)nu, &P.duub));
+    UP(upload(p, d->ulb, (size_t)nu, &P.ulb));
+    UP(upload(p, d->uub, (size_t)nu, &P.uub));
+    UP(upload(p, d->Gc, (size_t)ncd * nv, &P.Gc));
+    if (ncd) {
+        UP(upload_T(p, d->Gc, ncd, nv, &P.GcT));
+        UP(upload_T(p, d->Gcx, ncd, nx, &P.GcxT));
+        UP(upload_T(p, d->Gcy, ncd, ny, &P.GcyT));
+    } else {
+        UP(upload<double>(p, nullptr, 0, &P.GcT));
+        UP(upload<double>(p, nullptr, 0, &P.GcxT));
+        UP(upload<double>(p, nullptr, 0, &P.GcyT));
+    }
+    UP(upload(p, d->gc0, (size_t)ncd, &P.gc0));
+    UP(upload(p, d->Lc, (size_t)ncd, &P.Lc));
+    UP(upload(p, d->Uc, (size_t)ncd, &P.Uc));
+    UP(upload(p, d->gc_q, (size_t)ncd, &P.gc_q));
+    UP(upload(p, d->gc_vin, (size_t)ncd, &P.gc_vin));
+    UP(upload(p, d->vin_row, (size_t)d->n_vin, &P.vin_row));
+    UP(upload(p, d->vin_q, (size_t)d->n_vin, &P.vin_q));
+    UP(upload(p, d->pl_rowptr, (size_t)nx + 1, &P.pl_rowptr));
+    UP(upload(p, d->pl_col, (size_t)d->pl_nnz, &P.pl_col));
+    UP(upload(p, d->pl_val, (size_t)d->pl_nnz, &P.pl_val));
+    UP(upload_T(p, d->C, ny, nx, &P.CT));
+    UP(upload_T(p, d->D, ny, nu, &P.DT));
+    if (d->Phi && d->Gam) {
+        UP(upload_T(p, d->Phi, d->N * nx, nx, &P.PhiT));
+        UP(upload_T(p, d->Gam, d->N * nx, nv, &P.GamT));
+    }
+#undef UP
+
+    p->nvr = (nv + 31) / 32;
+    rc = (p->nvr == 1) ? configure<1>(p) : configure<2>(p);
+    if (rc) return bail(rc);
+    p->fast_path = 0;
+    p->fast_blocks_per_sm = 0;
+    rc = sih::dist_configure(p->d, &p->fast_path, &p->fast_blocks_per_sm);
+    if (rc) return bail(fail(SIHMPC_E_CUDA, "fast-path configuration failed%s"));
+    *out = p;
+    return 0;
+}
+
+size_t sihmpc_workspace_bytes(const sihmpc_plan *plan, int64_t batch) {
+    (void)batch;
+    if (!plan) return 0;
+    return (size_t)plan->max_grid * plan->wpb * scratch_doubles_per_warp(plan->d.nv) * sizeof(double) + 256;
+}
+
+int sihmpc_step(sihmpc_plan *plan, const sihmpc_io *io, int64_t batch, int32_t n_steps,
+                void *workspace, size_t workspace_bytes, void *stream) {
+    if (!plan || !io) return fail(SIHMPC_E_INVALID, "NULL argument%s");
+    if (batch < 0) return fail(SIHMPC_E_INVALID, "negative batch%s");
+    if (batch == 0) return 0;
+    int rc = check_io(plan, io, n_steps);
+    if (rc) return rc;
+    if (!workspace || workspace_bytes < sihmpc_workspace_bytes(plan, batch))
+        return fail(SIHMPC_E_WORKSPACE, "workspace smaller than sihmpc_workspace_bytes()%s");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    double *scratch = reinterpret_cast<double *>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    if (plan->fast_path && sih::dist_supported(plan->d, *io)) {
+        cudaError_t e = sih::dist_launch(plan->d, *io, batch, n_steps, plan->sm_count,
+                                         plan->fast_blocks_per_sm, st);
+        if (e != cudaSuccess) return fail(SIHMPC_E_CUDA, "fast-path launch failed: %s", cudaGetErrorString(e));
+        return 0;
+    }
+    return (plan->nvr == 1) ? launch_step<1>(plan, *io, batch, n_steps, scratch, st)
+                            : launch_step<2>(plan, *io, batch, n_steps, scratch, st);
+}
+
+// ---- host-buffer variant -----------------------------------------------------------------
+static size_t staging_layout(const sihmpc_plan *p, int64_t batch, size_t off[12]) {
+    const DevPlan &P = p->d;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~(size_t)255; return r; };
+    off[0] = take((size_t)batch * P.nx * 8);                       // x
+    off[1] = take((size_t)batch * P.nu * 8);                       // u
+    off[2] = take((size_t)batch * P.m * 8);                        // pesos
+    off[3] = take((size_t)batch * (P.n_vin > 0 ? P.n_vin : 1) * 8);// vinant
+    off[4] = take((size_t)batch * P.ny * 8);                       // ysp
+    off[5] = take((size_t)batch * P.nu * 8);                       // du
+    off[6] = take((size_t)batch * 8);                              // J
+    off[7] = take((size_t)batch * p->nw * 8);                      // w_opt
+    off[8] = take((size_t)batch * 4);                              // status
+    off[9] = take((size_t)batch * 4);                              // n_active
+    return o;
+}
+
+size_t sihmpc_host_staging_bytes(const sihmpc_plan *plan, int64_t batch) {
+    if (!plan) return 0;
+    size_t off[12];
+    return sihmpc_workspace_bytes(plan, batch) + staging_layout(plan, batch, off) + 512;
+}
+
+int sihmpc_step_host(sihmpc_plan *plan, const sihmpc_io *h, int64_t batch, void *workspace,
+                     size_t workspace_bytes, void *stream) {
+    if (!plan || !h) return fail(SIHMPC_E_INVALID, "NULL argument%s");
+    if (batch <= 0) return batch == 0 ? 0 : fail(SIHMPC_E_INVALID, "negative batch%s");
+    if (!h->x || !h->u || !h->pesos || !h->ysp) return fail(SIHMPC_E_INVALID, "host io needs x,u,pesos,ysp%s");
+    if (!workspace || workspace_bytes < sihmpc_host_staging_bytes(plan, batch))
+        return fail(SIHMPC_E_WORKSPACE, "workspace smaller than sihmpc_host_staging_bytes()%s");
+    const DevPlan &P = plan->d;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    size_t off[12];
+    staging_layout(plan, batch, off);
+    const size_t wsb = sihmpc_workspace_bytes(plan, batch);
+    char *base = reinterpret_cast<char *>((((uintptr_t)workspace + wsb) + 255) & ~(uintptr_t)255);
+    sihmpc_io d = *h;
+    d.x = reinterpret_cast<double *>(base + off[0]);
+    d.u = reinterpret_cast<double *>(base + off[1]);
+    d.pesos = reinterpret_cast<double *>(base + off[2]);
+    d.vinant = (P.n_vin > 0 && h->vinant) ? reinterpret_cast<double *>(base + off[3]) : nullptr;
+    d.ysp = reinterpret_cast<double *>(base + off[4]);
+    d.du = reinterpret_cast<double *>(base + off[5]);
+    d.J = reinterpret_cast<double *>(base + off[6]);
+    d.w_opt = h->w_opt ? reinterpret_cast<double *>(base + off[7]) : nullptr;
+    d.status = reinterpret_cast<int32_t *>(base + off[8]);
+    d.n_active = reinterpret_cast<int32_t *>(base + off[9]);
+    d.ysp_seq = nullptr; d.seg_start = nullptr; d.n_seg = 0;
+    d.dist_step = nullptr; d.dist = nullptr; d.plant_val = nullptr;
+    d.stats = nullptr; d.traj_du = nullptr; d.traj_J = nullptr; d.traj_y = nullptr;
+    CUDA_TRY(cudaMemcpyAsync(d.x, h->x, (size_t)batch * P.nx * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d.u, h->u, (size_t)batch * P.nu * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d.pesos, h->pesos, (size_t)batch * P.m * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(const_cast<double *>(d.ysp), h->ysp, (size_t)batch * P.ny * 8, cudaMemcpyHostToDevice, st));
+    if (d.vinant)
+        CUDA_TRY(cudaMemcpyAsync(d.vinant, h->vinant, (size_t)batch * P.n_vin * 8, cudaMemcpyHostToDevice, st));
+    int rc = sihmpc_step(plan, &d, batch, 1, workspace, wsb, stream);
+    if (rc) return rc;
+    if (h->du) CUDA_TRY(cudaMemcpyAsync(h->du, d.du, (size_t)batch * P.nu * 8, cudaMemcpyDeviceToHost, st));
+    if (h->J) CUDA_TRY(cudaMemcpyAsync(h->J, d.J, (size_t)batch * 8, cudaMemcpyDeviceToHost, st));
+    if (h->w_opt) CUDA_TRY(cudaMemcpyAsync(h->w_opt, d.w_opt, (size_t)batch * plan->nw * 8, cudaMemcpyDeviceToHost, st));
+    if (h->status) CUDA_TRY(cudaMemcpyAsync(h->status, d.status, (size_t)batch * 4, cudaMemcpyDeviceToHost, st));
+    if (h->n_active) CUDA_TRY(cudaMemcpyAsync(h->n_active, d.n_active, (size_t)batch * 4, cudaMemcpyDeviceToHost, st));
+    if (d.vinant && (h->flags & SIHMPC_F_UPDATE_VIN))
+        CUDA_TRY(cudaMemcpyAsync(h->vinant, d.vinant, (size_t)batch * P.n_vin * 8, cudaMemcpyDeviceToHost, st));
+    if (h->flags & SIHMPC_F_ADVANCE) {
+        CUDA_TRY(cudaMemcpyAsync(h->x, d.x, (size_t)batch * P.nx * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(h->u, d.u, (size_t)batch * P.nu * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(h->pesos, d.pesos, (size_t)batch * P.m * 8, cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int sihmpc_predict(sihmpc_plan *plan, const double *x, const double *u, const double *dU,
+                   int64_t batch, double *x_pred, double *y_pred, double *u_pred, void *stream) {
+    if (!plan || !x || !u || !dU) return fail(SIHMPC_E_INVALID, "NULL argument%s");
+    if (batch <= 0) return batch == 0 ? 0 : fail(SIHMPC_E_INVALID, "negative batch%s");
+    if (x_pred && !plan->d.PhiT) return fail(SIHMPC_E_INVALID, "plan was created without Phi/Gam%s");
+    const int threads = 128;
+    long long blocks = (batch * 32 + threads - 1) / threads;
+    if (blocks > plan->sm_count * 16) blocks = plan->sm_count * 16;
+    sih::predict_kernel<<<(int)blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+        plan->d, x, u, dU, batch, x_pred, y_pred, u_pred);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int sihmpc_subobjectives(sihmpc_plan *plan, const double *x, const double *w, const double *ysp,
+                         int64_t batch, double *V, void *stream) {
+    if (!plan || !x || !w || !ysp || !V) return fail(SIHMPC_E_INVALID, "NULL argument%s");
+    if (batch <= 0) return batch == 0 ? 0 : fail(SIHMPC_E_INVALID, "negative batch%s");
+    const DevPlan &P = plan->d;
+    const int wpb = 4;
+    const size_t per = (size_t)(P.nx + P.nv + P.ny + 2 * P.ny + P.R + P.nv + P.m + 8) * 8;
+    const size_t smem = per * wpb;
+    if (smem > 200 * 1024) return fail(SIHMPC_E_INVALID, "controller too large%s");
+    CUDA_TRY(cudaFuncSetAttribute(sih::subobjectives_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long blocks = (batch + wpb - 1) / wpb;
+    if (blocks > plan->sm_count * 8) blocks = plan->sm_count * 8;
+    sih::subobjectives_kernel<<<(int)blocks, wpb * 32, smem, static_cast<cudaStream_t>(stream)>>>(
+        plan->d, x, w, ysp, batch, V);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int sihmpc_stats_reduce(const double *stats, int64_t batch, int32_t nstat, double *out, void *stream) {
+    if (!stats || !out || nstat < 1) return fail(SIHMPC_E_INVALID, "NULL argument%s");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    std::vector<double> init((size_t)3 * nstat, 0.0);
+    for (int c = 0; c < nstat; ++c) init[(size_t)2 * nstat + c] = -1e308;
+    CUDA_TRY(cudaMemcpyAsync(out, init.data(), init.size() * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));   // init[] is a stack-lifetime host buffer
+    if (batch <= 0) return 0;
+    long long bx = (batch + 255) / 256;
+    if (bx > 256) bx = 256;
+    dim3 grid((unsigned)bx, (unsigned)nstat);
+    sih::stats_reduce_kernel<<<grid, 256, 0, st>>>(stats, batch, nstat, out);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int sihmpc_fp64_peak(double *flops_per_s) {
+    if (!flops_per_s) return fail(SIHMPC_E_INVALID, "NULL argument%s");
+    if (sihmpc_device_count() < 1) return fail(SIHMPC_E_CUDA, "no CUDA device%s");
+    cudaDeviceProp prop;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    double *out = nullptr;
+    CUDA_TRY(cudaMalloc(&out, 8));
+    const int threads = 256, blocks = prop.multiProcessorCount * 8, iters = 1 << 16;
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CUDA_TRY(cudaEventRecord(e0));
+        sih::fp64_probe_kernel<<<blocks, threads>>>(out, iters);
+        CUDA_TRY(cudaEventRecord(e1));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        const double fl = 2.0 * 8.0 * (double)iters * threads * blocks / (ms * 1e-3);
+        if (rep > 0 && fl > best) best = fl;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+    *flops_per_s = best;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,796 @@
+// step_kernel.cuh -- general IHMPC step kernel: ONE WARP PER SCENARIO, FP64, any plant shape.
+//
+// One control step for scenario s =
+//   K1  assemble   e = Px x + Py ysp + e0, omega = Wrow pesos + w0row, f = 2 E^T(omega o e),
+//                  H = Ht + sum pesos_i HJ_i + 2 diag(omega_du)        (lower triangle, in smem)
+//   K2  solve      in-shared-memory Cholesky H = L L^T (lanes over rows, pivots broadcast with
+//                  warp shuffles), dU = -H^{-1} f, then a Goldfarb-Idnani dual active-set loop
+//                  on the inequality rows (range-space form: Y = L^{-1} N_A, S = Y Y^T)
+//   K3  advance    J and slacks from the residual r = E dU + e; ViNant; plant x+ = [A|B][x;du]
+//                  (CSR, optionally per-scenario values); shifted plan; sub-objective values at
+//                  the new state; satisficing weight update
+// looped n_steps times with the scenario state resident in shared memory.
+//
+// Reference semantics being replaced (paths under /root/reference):
+//   sihmpc/ihmpccontroller.py:567-604 (mpc), :374-477 (problem), :534-564 (warmStart),
+//   :619-636 (satWeights2), :607-617 (satWeights), :93-113 (dynF);
+//   example_distillation.py:81-113 (loop order).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include "devplan.h"
+
+#define SIH_FULL 0xffffffffu
+#define SIH_INF (__longlong_as_double(0x7ff0000000000000LL))
+
+namespace sih {
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(SIH_FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(SIH_FULL, v, o));
+    return v;
+}
+
+// In-place Cholesky of the lower triangle of M (n x n, leading dimension ld) held in shared or
+// global memory.  Crout form: lane owns rows i = lane + 32 t.  dinv[k] = 1 / L_kk.
+// Returns a non-zero flag if a pivot was not positive.
+template <int NVR>
+__device__ int warp_cholesky(double *M, int ld, int n, double *dinv, int lane) {
+    int bad = 0;
+#pragma unroll
+    for (int t = 0; t < NVR; ++t) {
+        for (int kk = 0; kk < 32; ++kk) {
+            const int k = t * 32 + kk;
+            if (k >= n) break;
+            double s[NVR];
+            const double *Mk = M + (size_t)k * ld;
+#pragma unroll
+            for (int tt = t; tt < NVR; ++tt) {
+                const int i = lane + 32 * tt;
+                s[tt] = 0.0;
+                if (i >= k && i < n) {
+                    const double *Mi = M + (size_t)i * ld;
+                    double a0 = Mi[k], a1 = 0.0;
+                    int j = 0;
+                    for (; j + 1 < k; j += 2) {
+                        a0 = fma(-Mi[j], Mk[j], a0);
+                        a1 = fma(-Mi[j + 1], Mk[j + 1], a1);
+                    }
+                    if (j < k) a0 = fma(-Mi[j], Mk[j], a0);
+                    s[tt] = a0 + a1;
+                }
+            }
+            double d = __shfl_sync(SIH_FULL, s[t], kk);
+            if (!(d > 0.0)) { bad = 1; d = 1e-300; }
+            const double inv = rsqrt(d);
+#pragma unroll
+            for (int tt = t; tt < NVR; ++tt) {
+                const int i = lane + 32 * tt;
+                if (i >= k && i < n) M[(size_t)i * ld + k] = s[tt] * inv;   // i == k: d*inv = sqrt(d)
+            }
+            if (lane == 0) dinv[k] = inv;
+            __syncwarp();
+        }
+    }
+    return bad;
+}
+
+// acc[t] holds b_i for row i = lane + 32 t.  Solves L y = b (forward) in registers.
+template <int NVR>
+__device__ void warp_trsv_lower(const double *L, int ld, const double *dinv, int n,
+                                double (&acc)[NVR], int lane) {
+#pragma unroll
+    for (int t = 0; t < NVR; ++t) {
+        for (int jj = 0; jj < 32; ++jj) {
+            const int j = t * 32 + jj;
+            if (j >= n) break;
+            const double bj = __shfl_sync(SIH_FULL, acc[t], jj) * dinv[j];
+            if (lane == jj) acc[t] = bj;
+#pragma unroll
+            for (int tt = t; tt < NVR; ++tt) {
+                const int i = lane + 32 * tt;
+                if (i > j && i < n) acc[tt] = fma(-L[(size_t)i * ld + j], bj, acc[tt]);
+            }
+        }
+    }
+}
+
+// Solves L^T z = y (backward) in registers.
+template <int NVR>
+__device__ void warp_trsv_lower_T(const double *L, int ld, const double *dinv, int n,
+                                  double (&acc)[NVR], int lane) {
+#pragma unroll
+    for (int t = NVR - 1; t >= 0; --t) {
+        for (int jj = 31; jj >= 0; --jj) {
+            const int j = t * 32 + jj;
+            if (j >= n) continue;
+            const double zj = __shfl_sync(SIH_FULL, acc[t], jj) * dinv[j];
+            if (lane == jj) acc[t] = zj;
+#pragma unroll
+            for (int tt = 0; tt <= t; ++tt) {
+                const int i = lane + 32 * tt;
+                if (i < j) acc[tt] = fma(-L[(size_t)j * ld + i], zj, acc[tt]);
+            }
+        }
+    }
+}
+
+template <int NVR>
+__device__ __forceinline__ void load_acc(double (&acc)[NVR], const double *v, int n, int lane, double scale) {
+#pragma unroll
+    for (int t = 0; t < NVR; ++t) {
+        const int i = lane + 32 * t;
+        acc[t] = (i < n) ? scale * v[i] : 0.0;
+    }
+}
+template <int NVR>
+__device__ __forceinline__ void store_acc(const double (&acc)[NVR], double *v, int n, int lane) {
+#pragma unroll
+    for (int t = 0; t < NVR; ++t) {
+        const int i = lane + 32 * t;
+        if (i < n) v[i] = acc[t];
+    }
+}
+
+// ---- inequality rows ---------------------------------------------------------------------
+// global row index: [0,nv) move box, [nv,2nv) cumulative input box, [2nv,2nv+ncd) dense rows.
+// code = 2*row + side (0: lower bound active, normal +g; 1: upper bound active, normal -g).
+struct RowScan { double rel; double abs; int code; };
+
+__device__ __forceinline__ void scan_check(double val, double lo, double hi, int row, RowScan &b) {
+    if (lo > -SIH_INF) {
+        const double a = lo - val, r = a / (1.0 + fabs(lo));
+        if (a > b.abs) b.abs = a;
+        if (r > b.rel) { b.rel = r; b.code = 2 * row; }
+    }
+    if (hi < SIH_INF) {
+        const double a = val - hi, r = a / (1.0 + fabs(hi));
+        if (a > b.abs) b.abs = a;
+        if (r > b.rel) { b.rel = r; b.code = 2 * row + 1; }
+    }
+}
+
+__device__ RowScan scan_rows(const DevPlan &P, const double *v, const double *uu,
+                             const double *glo, const double *ghi, int lane) {
+    RowScan b; b.rel = 0.0; b.abs = 0.0; b.code = -1;
+    const int nv = P.nv, nu = P.nu;
+    if (P.has_box) {
+        for (int i = lane; i < nv; i += 32) {
+            const int j = i % nu;
+            scan_check(v[i], P.dulb[j], P.duub[j], i, b);
+        }
+    }
+    if (P.has_cum) {
+        for (int i = lane; i < nv; i += 32) {
+            const int j = i % nu;
+            double val = 0.0;
+            for (int c = j; c <= i; c += nu) val += v[c];
+            scan_check(val, P.ulb[j] - uu[j], P.uub[j] - uu[j], nv + i, b);
+        }
+    }
+    for (int r = lane; r < P.ncd; r += 32) {
+        double val = 0.0;
+        for (int c = 0; c < nv; ++c) val = fma(P.GcT[(size_t)c * P.ncd + r], v[c], val);
+        scan_check(val, glo[r], ghi[r], 2 * nv + r, b);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double orl = __shfl_xor_sync(SIH_FULL, b.rel, o);
+        const double oab = __shfl_xor_sync(SIH_FULL, b.abs, o);
+        const int oc = __shfl_xor_sync(SIH_FULL, b.code, o);
+        if (orl > b.rel || (orl == b.rel && oc > b.code)) { b.rel = orl; b.code = oc; }
+        b.abs = fmax(b.abs, oab);
+    }
+    return b;
+}
+
+// writes the signed normal of `code` into nrm[] and returns the right-hand side b (n.v >= b)
+__device__ double load_normal(const DevPlan &P, int code, const double *uu, const double *glo,
+                              const double *ghi, double *nrm, int lane) {
+    const int nv = P.nv, nu = P.nu;
+    const int row = code >> 1, side = code & 1;
+    const double sgn = side ? -1.0 : 1.0;
+    double lo, hi;
+    if (row < nv) {
+        const int j = row % nu;
+        lo = P.dulb[j]; hi = P.duub[j];
+        for (int i = lane; i < nv; i += 32) nrm[i] = (i == row) ? sgn : 0.0;
+    } else if (row < 2 * nv) {
+        const int rr = row - nv, j = rr % nu;
+        lo = P.ulb[j] - uu[j]; hi = P.uub[j] - uu[j];
+        for (int i = lane; i < nv; i += 32) nrm[i] = ((i % nu) == j && i <= rr) ? sgn : 0.0;
+    } else {
+        const int r = row - 2 * nv;
+        lo = glo[r]; hi = ghi[r];
+        for (int i = lane; i < nv; i += 32) nrm[i] = sgn * P.Gc[(size_t)r * nv + i];
+    }
+    __syncwarp();
+    return side ? -hi : lo;
+}
+
+// sub-objective values V_i (i < m) at explicit slacks: yrow(k,i) = Y(k,i) - ysp_i - syN_i - tau_k siN_i
+// (ihmpccontroller.py:174,224,247,200).  Inputs in smem: xs (nx), dv (nv), ysp, sy = [syN ; siN].
+// Scratch: sq (R), sqdu (nv).  Output vn (m).
+__device__ void eval_subobjectives(const DevPlan &P, const double *xs, const double *dv,
+                                   const double *ysp, const double *sy, double *sq, double *sqdu,
+                                   double *vn, int lane) {
+    const int Ny = P.Ny, ny = P.ny, nx = P.nx, nv = P.nv, m = P.m;
+    for (int r = lane; r < Ny; r += 32) {
+        double a0 = 0.0, a1 = 0.0;
+        int j = 0;
+        for (; j + 1 < nx; j += 2) {
+            a0 = fma(P.MyxT[(size_t)j * Ny + r], xs[j], a0);
+            a1 = fma(P.MyxT[(size_t)(j + 1) * Ny + r], xs[j + 1], a1);
+        }
+        if (j < nx) a0 = fma(P.MyxT[(size_t)j * Ny + r], xs[j], a0);
+        int c = 0;
+        for (; c + 1 < nv; c += 2) {
+            a0 = fma(P.MyuT[(size_t)c * Ny + r], dv[c], a0);
+            a1 = fma(P.MyuT[(size_t)(c + 1) * Ny + r], dv[c + 1], a1);
+        }
+        if (c < nv) a0 = fma(P.MyuT[(size_t)c * Ny + r], dv[c], a0);
+        const int i = r % ny, k = r / ny;
+        const double rr = (a0 + a1) - ysp[i] - sy[i] - P.tau[k] * sy[ny + i];
+        sq[r] = rr * rr;
+    }
+    for (int i = lane; i < ny; i += 32) {
+        sq[P.o_sy + i] = sy[i] * sy[i];
+        sq[P.o_si + i] = sy[ny + i] * sy[ny + i];
+    }
+    for (int j = lane; j < nv; j += 32) sqdu[j] = dv[j] * dv[j];
+    int nr = Ny + 2 * ny;
+    if (P.eval_term) {   // terminal rows Lbar^T xd(N): no slack dependence (ihmpccontroller.py:340)
+        const int R = P.R;
+        for (int r = P.o_t + lane; r < R; r += 32) {
+            double a = P.e0[r];
+            for (int j = 0; j < nx; ++j) a = fma(P.PxT[(size_t)j * R + r], xs[j], a);
+            for (int c = 0; c < nv; ++c) a = fma(P.ET[(size_t)c * R + r], dv[c], a);
+            sq[r] = a * a;
+        }
+        nr = R;
+    }
+    __syncwarp();
+    for (int i = lane; i < m; i += 32) {
+        double a = 0.0;
+        for (int r = 0; r < nr; ++r) a = fma(P.Wrow[(size_t)r * m + i], sq[r], a);
+        for (int j = 0; j < nv; ++j) a = fma(P.Wdu[(size_t)j * m + i], sqdu[j], a);
+        vn[i] = a;
+    }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------
+template <int NVR>
+__global__ void __launch_bounds__(256, (NVR == 1 ? 2 : 1))
+ihmpc_step_kernel(const DevPlan P, const sihmpc_io io, const long long batch, const int n_steps,
+                  double *__restrict__ scratch, const int max_outer) {
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const long long gw = (long long)blockIdx.x * wpb + wib;
+    const long long nwarps = (long long)gridDim.x * wpb;
+    const WarpLayout lay = make_layout(P);
+    double *W = smem + (size_t)wib * lay.total;
+    double *Ls = W + lay.L, *dinv = W + lay.dinv, *xin = W + lay.xin, *xnew = W + lay.xnew;
+    double *uu = W + lay.uu, *ysp = W + lay.ysp, *pes = W + lay.pes, *vin = W + lay.vin;
+    double *e = W + lay.e, *om = W + lay.om, *omdu = W + lay.omdu, *f = W + lay.f, *v = W + lay.v;
+    double *nrm = W + lay.nrm, *ybuf = W + lay.ybuf, *dbuf = W + lay.dbuf, *rbuf = W + lay.rbuf;
+    double *cbuf = W + lay.cbuf, *sy = W + lay.sy, *yout = W + lay.yout;
+    double *glo = W + lay.glo, *ghi = W + lay.ghi, *vn = W + lay.vn, *st = W + lay.st;
+
+    const int nx = P.nx, nu = P.nu, ny = P.ny, nv = P.nv, m = P.m, R = P.R, ld = P.ld;
+    const int lds = nv | 1;
+    double *scr = scratch + (size_t)gw * scratch_doubles_per_warp(nv);
+    double *Ya = scr;                               // [nv][nv]
+    double *Sa = Ya + (size_t)nv * nv;              // [nv][lds]
+    double *Rf = Sa + (size_t)nv * lds;             // [nv][lds]
+    double *lam = Rf + (size_t)nv * lds;            // [nv]
+    double *rdinv = lam + nv;                       // [nv]
+    int *act = reinterpret_cast<int *>(rdinv + nv); // [nv]
+    const int nstat = ny + SIHMPC_NSTATS_EXTRA;
+    const bool advance = (io.flags & SIHMPC_F_ADVANCE) != 0;
+
+    for (long long s = gw; s < batch; s += nwarps) {
+        // ---------------- load scenario state
+        for (int i = lane; i < nx; i += 32) xin[i] = io.x[s * nx + i];
+        for (int i = lane; i < nu; i += 32) uu[i] = io.u[s * nu + i];
+        for (int i = lane; i < m; i += 32) pes[i] = io.pesos[s * m + i];
+        for (int i = lane; i < P.n_vin; i += 32) vin[i] = io.vinant ? io.vinant[s * P.n_vin + i] : SIH_INF;
+        for (int i = lane; i < nstat; i += 32) st[i] = io.stats ? io.stats[s * nstat + i] : 0.0;
+        __syncwarp();
+
+        double Jval = 0.0;
+        int status = 0, q = 0, iters_total = 0;
+        double viol_abs = 0.0;
+
+        for (int step = 0; step < n_steps; ++step) {
+            const int kabs = io.k0 + step;
+            // ---------------- set-point of this step
+            if (io.ysp_seq) {
+                int seg = 0;
+                for (int g = 1; g < io.n_seg; ++g)
+                    if (io.seg_start[s * io.n_seg + g] <= kabs) seg = g;
+                for (int i = lane; i < ny; i += 32) ysp[i] = io.ysp_seq[(s * io.n_seg + seg) * ny + i];
+            } else {
+                for (int i = lane; i < ny; i += 32) ysp[i] = io.ysp[s * ny + i];
+            }
+            __syncwarp();
+
+            // ---------------- K1: residual offsets, row weights
+            for (int r = lane; r < R; r += 32) {
+                double a0 = P.e0[r], a1 = 0.0;
+                int j = 0;
+                for (; j + 1 < nx; j += 2) {
+                    a0 = fma(P.PxT[(size_t)j * R + r], xin[j], a0);
+                    a1 = fma(P.PxT[(size_t)(j + 1) * R + r], xin[j + 1], a1);
+                }
+                if (j < nx) a0 = fma(P.PxT[(size_t)j * R + r], xin[j], a0);
+                for (int c = 0; c < ny; ++c) a0 = fma(P.PyT[(size_t)c * R + r], ysp[c], a0);
+                double o = P.w0row[r];
+                for (int i = 0; i < m; ++i) o = fma(P.WrowT[(size_t)i * R + r], pes[i], o);
+                e[r] = a0 + a1;
+                om[r] = o;
+            }
+            for (int j = lane; j < nv; j += 32) {
+                double o = 0.0;
+                for (int i = 0; i < m; ++i) o = fma(P.WduT[(size_t)i * nv + j], pes[i], o);
+                omdu[j] = o;
+            }
+            // dense-row bounds of this step
+            for (int r = lane; r < P.ncd; r += 32) {
+                double off = P.gc0[r];
+                for (int j = 0; j < nx; ++j) off = fma(P.GcxT[(size_t)j * P.ncd + r], xin[j], off);
+                for (int c = 0; c < ny; ++c) off = fma(P.GcyT[(size_t)c * P.ncd + r], ysp[c], off);
+                double lo = P.Lc[r], hi = P.Uc[r];
+                const int slot = P.gc_vin[r];
+                if (slot >= 0) {
+                    const double vv = vin[slot];
+                    const double bnd = (vv < SIH_INF) ? sqrt(fmax(vv, 0.0) / P.gc_q[r]) : SIH_INF;
+                    lo = -bnd; hi = bnd;
+                }
+                glo[r] = lo - off; ghi[r] = hi - off;
+            }
+            __syncwarp();
+            // gradient f = 2 E^T (omega o e)
+            for (int c = lane; c < nv; c += 32) {
+                double a0 = 0.0, a1 = 0.0;
+                int r = 0;
+                for (; r + 1 < R; r += 2) {
+                    a0 = fma(P.E[(size_t)r * nv + c], om[r] * e[r], a0);
+                    a1 = fma(P.E[(size_t)(r + 1) * nv + c], om[r + 1] * e[r + 1], a1);
+                }
+                if (r < R) a0 = fma(P.E[(size_t)r * nv + c], om[r] * e[r], a0);
+                f[c] = 2.0 * (a0 + a1);
+            }
+            // Hessian, lower triangle
+            {
+                int i = 0, j = lane;
+                while (j >= nv) { j -= nv; ++i; }
+                const int nn = nv * nv;
+                for (int idx = lane; idx < nn; idx += 32) {
+                    if (j <= i) {
+                        double h = P.Ht[idx];
+                        for (int a = 0; a < P.mh; ++a)
+                            h = fma(pes[P.hj_index[a]], P.HJ[(size_t)a * nn + idx], h);
+                        if (i == j) h += 2.0 * omdu[i];
+                        Ls[i * ld + j] = h;
+                    }
+                    j += 32;
+                    while (j >= nv) { j -= nv; ++i; }
+                }
+            }
+            __syncwarp();
+
+            // ---------------- K2: factor and solve
+            if (warp_cholesky<NVR>(Ls, ld, nv, dinv, lane)) status |= SIHMPC_ST_NOTPD;
+            double acc[NVR];
+            load_acc<NVR>(acc, f, nv, lane, -1.0);
+            warp_trsv_lower<NVR>(Ls, ld, dinv, nv, acc, lane);
+            warp_trsv_lower_T<NVR>(Ls, ld, dinv, nv, acc, lane);
+            store_acc<NVR>(acc, v, nv, lane);
+            __syncwarp();
+
+            // dual active set (Goldfarb-Idnani, range-space form)
+            q = 0;
+            int outer = 0;
+            RowScan sc;
+            const bool any_rows = P.has_box || P.has_cum || P.ncd > 0;
+            sc.rel = 0.0; sc.abs = 0.0; sc.code = -1;
+            while (any_rows) {
+                sc = scan_rows(P, v, uu, glo, ghi, lane);
+                if (sc.rel <= 1e-10 || sc.code < 0) break;
+                if (outer++ >= max_outer) { status |= SIHMPC_ST_MAXITER; break; }
+                const int code = sc.code;
+                const double bp = load_normal(P, code, uu, glo, ghi, nrm, lane);
+                double lam_p = 0.0;
+                bool infeasible = false;
+                for (int inner = 0; inner <= nv + 1; ++inner) {
+                    ++iters_total;
+                    // y = L^{-1} n_p
+                    load_acc<NVR>(acc, nrm, nv, lane, 1.0);
+                    warp_trsv_lower<NVR>(Ls, ld, dinv, nv, acc, lane);
+                    store_acc<NVR>(acc, ybuf, nv, lane);
+                    double yy = 0.0;
+#pragma unroll
+                    for (int t = 0; t < NVR; ++t) yy = fma(acc[t], acc[t], yy);
+                    yy = warp_sum(yy);
+                    __syncwarp();
+                    double zn = yy;
+                    if (q > 0) {
+                        // c = Y y ;  S r = c  (Cholesky of S refreshed) ; d = y - Y^T r ; one refinement
+                        for (int a = lane; a < q; a += 32) {
+                            double c = 0.0;
+                            for (int i = 0; i < nv; ++i) c = fma(Ya[(size_t)a * nv + i], ybuf[i], c);
+                            cbuf[a] = c;
+                        }
+                        for (int idx = lane; idx < q * q; idx += 32) {
+                            const int a = idx / q, b = idx % q;
+                            if (b <= a) Rf[(size_t)a * lds + b] = Sa[(size_t)a * lds + b];
+                        }
+                        __syncwarp();
+                        warp_cholesky<NVR>(Rf, lds, q, rdinv, lane);
+                        double ra[NVR];
+                        load_acc<NVR>(ra, cbuf, q, lane, 1.0);
+                        warp_trsv_lower<NVR>(Rf, lds, rdinv, q, ra, lane);
+                        warp_trsv_lower_T<NVR>(Rf, lds, rdinv, q, ra, lane);
+                        store_acc<NVR>(ra, rbuf, q, lane);
+                        __syncwarp();
+                        for (int i = lane; i < nv; i += 32) {
+                            double d = ybuf[i];
+                            for (int a = 0; a < q; ++a) d = fma(-Ya[(size_t)a * nv + i], rbuf[a], d);
+                            dbuf[i] = d;
+                        }
+                        __syncwarp();
+                        // refinement: delta = S^{-1} Y d
+                        double rc[NVR];
+#pragma unroll
+                        for (int t = 0; t < NVR; ++t) {
+                            const int a = lane + 32 * t;
+                            double c = 0.0;
+                            if (a < q)
+                                for (int i = 0; i < nv; ++i) c = fma(Ya[(size_t)a * nv + i], dbuf[i], c);
+                            rc[t] = c;
+                        }
+                        warp_trsv_lower<NVR>(Rf, lds, rdinv, q, rc, lane);
+                        warp_trsv_lower_T<NVR>(Rf, lds, rdinv, q, rc, lane);
+                        __syncwarp();
+#pragma unroll
+                        for (int t = 0; t < NVR; ++t) {
+                            const int a = lane + 32 * t;
+                            if (a < q) { rbuf[a] += rc[t]; }
+                        }
+                        // cbuf keeps Y y of the un-refined pass: reuse it as the new S column later
+                        // stash delta in Rf's spare column area is not needed: recompute d
+                        __syncwarp();
+                        double dd = 0.0;
+                        for (int i = lane; i < nv; i += 32) {
+                            double d = ybuf[i];
+                            for (int a = 0; a < q; ++a) d = fma(-Ya[(size_t)a * nv + i], rbuf[a], d);
+                            dbuf[i] = d;
+                            dd = fma(d, d, dd);
+                        }
+                        zn = warp_sum(dd);
+                        __syncwarp();
+                    } else {
+                        for (int i = lane; i < nv; i += 32) dbuf[i] = ybuf[i];
+                        __syncwarp();
+                    }
+                    // dual step limit
+                    double t1 = SIH_INF;
+                    int kdrop = -1;
+                    for (int a = lane; a < q; a += 32) {
+                        const double ra_ = rbuf[a];
+                        if (ra_ > 1e-14) {
+                            const double ta = lam[a] / ra_;
+                            if (ta < t1) { t1 = ta; kdrop = a; }
+                        }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const double ot = __shfl_xor_sync(SIH_FULL, t1, o);
+                        const int ok = __shfl_xor_sync(SIH_FULL, kdrop, o);
+                        if (ot < t1 || (ot == t1 && ok >= 0 && (kdrop < 0 || ok < kdrop))) { t1 = ot; kdrop = ok; }
+                    }
+                    const bool dependent = (zn <= 1e-14 * yy);
+                    double t;
+                    bool full = false;
+                    if (dependent) {
+                        if (!(t1 < SIH_INF)) { infeasible = true; break; }
+                        t = t1;
+                    } else {
+                        // z = L^{-T} d ; primal step length
+                        load_acc<NVR>(acc, dbuf, nv, lane, 1.0);
+                        warp_trsv_lower_T<NVR>(Ls, ld, dinv, nv, acc, lane);
+                        double nvdot = 0.0;
+                        for (int i = lane; i < nv; i += 32) nvdot = fma(nrm[i], v[i], nvdot);
+                        nvdot = warp_sum(nvdot);
+                        const double t2 = (bp - nvdot) / zn;
+                        full = (t2 <= t1);
+                        t = full ? t2 : t1;
+#pragma unroll
+                        for (int tt = 0; tt < NVR; ++tt) {
+                            const int i = lane + 32 * tt;
+                            if (i < nv) v[i] = fma(t, acc[tt], v[i]);
+                        }
+                    }
+                    for (int a = lane; a < q; a += 32) lam[a] = fma(-t, rbuf[a], lam[a]);
+                    lam_p += t;
+                    __syncwarp();
+                    if (full) {
+                        // add p: Y[q] = y, S[q][.] = Y y, S[q][q] = y.y
+                        for (int i = lane; i < nv; i += 32) Ya[(size_t)q * nv + i] = ybuf[i];
+                        for (int a = lane; a < q; a += 32) {
+                            Sa[(size_t)q * lds + a] = cbuf[a];
+                            Sa[(size_t)a * lds + q] = cbuf[a];
+                        }
+                        if (lane == 0) { Sa[(size_t)q * lds + q] = yy; lam[q] = lam_p; act[q] = code; }
+                        ++q;
+                        __syncwarp();
+                        break;
+                    }
+                    // drop kdrop: move the last active row into its place
+                    const int last = q - 1;
+                    if (kdrop != last) {
+                        for (int i = lane; i < nv; i += 32) Ya[(size_t)kdrop * nv + i] = Ya[(size_t)last * nv + i];
+                        __syncwarp();
+                        for (int a = lane; a < q; a += 32) {
+                            const double sv = (a == kdrop) ? Sa[(size_t)last * lds + last] : Sa[(size_t)last * lds + a];
+                            // column/row `last` replaces column/row `kdrop`
+                            if (a != last) { Sa[(size_t)kdrop * lds + a] = sv; Sa[(size_t)a * lds + kdrop] = sv; }
+                        }
+                        if (lane == 0) { lam[kdrop] = lam[last]; act[kdrop] = act[last]; }
+                    }
+                    --q;
+                    __syncwarp();
+                }
+                if (infeasible) { status |= SIHMPC_ST_INFEASIBLE; break; }
+            }
+            viol_abs = sc.abs;
+
+            // ---------------- K3: residual, cost, slacks
+            double Jacc = 0.0;
+            for (int r = lane; r < R; r += 32) {
+                double a0 = e[r], a1 = 0.0;
+                int c = 0;
+                for (; c + 1 < nv; c += 2) {
+                    a0 = fma(P.ET[(size_t)c * R + r], v[c], a0);
+                    a1 = fma(P.ET[(size_t)(c + 1) * R + r], v[c + 1], a1);
+                }
+                if (c < nv) a0 = fma(P.ET[(size_t)c * R + r], v[c], a0);
+                const double rr = a0 + a1;
+                e[r] = rr;
+                Jacc = fma(om[r], rr * rr, Jacc);
+            }
+            for (int j = lane; j < nv; j += 32) Jacc = fma(omdu[j], v[j] * v[j], Jacc);
+            Jval = warp_sum(Jacc);
+            __syncwarp();
+
+            // siN_next = xi(N+1) with a zero move appended; syN kept (ihmpccontroller.py:543-560)
+            for (int i = lane; i < ny; i += 32) {
+                double a = 0.0;
+                for (int j = 0; j < nx; ++j) a = fma(P.Mi1xT[(size_t)j * ny + i], xin[j], a);
+                for (int c = 0; c < nv; ++c) a = fma(P.Mi1uT[(size_t)c * ny + i], v[c], a);
+                sy[i] = e[P.o_sy + i];
+                sy[ny + i] = a;
+            }
+            __syncwarp();
+            if (io.flags & SIHMPC_F_UPDATE_VIN)
+                for (int sl = lane; sl < P.n_vin; sl += 32) {
+                    const double sn = sy[ny + (P.vin_row[sl] - P.o_si)];
+                    vin[sl] = P.vin_q[sl] * sn * sn;
+                }
+
+            const bool last_step = (step == n_steps - 1);
+            if (last_step) {
+                // results of the step, before any in-place advance
+                if (io.du) for (int j = lane; j < nu; j += 32) io.du[s * nu + j] = v[j];
+                if (io.w_opt) {
+                    const int nw = nv + 2 * ny;
+                    for (int i = lane; i < nv; i += 32) io.w_opt[s * nw + i] = v[i];
+                    for (int i = lane; i < ny; i += 32) {
+                        io.w_opt[s * nw + nv + i] = e[P.o_sy + i];
+                        io.w_opt[s * nw + nv + ny + i] = e[P.o_si + i];
+                    }
+                }
+                if (lane == 0) {
+                    if (io.J) io.J[s] = Jval;
+                    if (io.status) io.status[s] = status;
+                    if (io.n_active) io.n_active[s] = q;
+                }
+            }
+            if (io.traj_du) for (int j = lane; j < nu; j += 32) io.traj_du[((long long)step * batch + s) * nu + j] = v[j];
+            if (io.traj_J && lane == 0) io.traj_J[(long long)step * batch + s] = Jval;
+
+            if (advance) {
+                // plant: x+ = [A|B][x;du]  (ihmpccontroller.py:106), u+ = u + du (:108)
+                for (int j = lane; j < nu; j += 32) xin[nx + j] = v[j];
+                __syncwarp();
+                const double *pv = io.plant_val ? io.plant_val + (size_t)s * P.pl_nnz : P.pl_val;
+                for (int i = lane; i < nx; i += 32) {
+                    double a = 0.0;
+                    const int p1 = P.pl_rowptr[i + 1];
+                    for (int p = P.pl_rowptr[i]; p < p1; ++p) a = fma(pv[p], xin[P.pl_col[p]], a);
+                    xnew[i] = a;
+                }
+                for (int j = lane; j < nu; j += 32) uu[j] += v[j];
+                __syncwarp();
+                if (io.dist_step && io.dist_step[s] == kabs)
+                    for (int i = lane; i < ny; i += 32) xnew[i] += io.dist[s * ny + i];
+                __syncwarp();
+                // measured output y = C x+ + D du (:107)
+                for (int i = lane; i < ny; i += 32) {
+                    double a = 0.0;
+                    for (int j = 0; j < nx; ++j) a = fma(P.CT[(size_t)j * ny + i], xnew[j], a);
+                    for (int j = 0; j < nu; ++j) a = fma(P.DT[(size_t)j * ny + i], v[j], a);
+                    yout[i] = a;
+                    const double err = a - ysp[i];
+                    st[i] += err * err;
+                    if (io.traj_y) io.traj_y[((long long)step * batch + s) * ny + i] = a;
+                }
+                {
+                    double d2 = 0.0;
+                    for (int j = lane; j < nu; j += 32) d2 = fma(v[j], v[j], d2);
+                    d2 = warp_sum(d2);
+                    if (lane == 0) {
+                        st[ny] += d2;
+                        st[ny + 1] = fmax(st[ny + 1], viol_abs);
+                        st[ny + 2] = Jval;
+                        st[ny + 3] = (double)(((int)st[ny + 3]) | status);
+                        st[ny + 4] += (double)iters_total;
+                    }
+                    iters_total = 0;
+                }
+                for (int i = lane; i < nx; i += 32) xin[i] = xnew[i];
+                // shifted plan (ihmpccontroller.py:538-541) into f
+                for (int i = lane; i < nv; i += 32) f[i] = (i + nu < nv) ? v[i + nu] : 0.0;
+                __syncwarp();
+                if (io.flags & (SIHMPC_F_WEIGHTS_SAT2 | SIHMPC_F_WEIGHTS_SAT1)) {
+                    eval_subobjectives(P, xin, f, ysp, sy, om, omdu, vn, lane);
+                    if (io.flags & SIHMPC_F_WEIGHTS_SAT2) {
+                        double smax = -SIH_INF;
+                        for (int i = lane; i < m; i += 32) smax = fmax(smax, vn[i] / P.gamma[i]);
+                        smax = warp_max(smax);
+                        for (int i = lane; i < m; i += 32) {
+                            const double g0 = P.gamma[i];
+                            const double g1 = fmax(g0, g0 * smax + 1e-6);
+                            const double nw_ = 1.0 / (g1 - vn[i]);
+                            pes[i] = io.alfa * pes[i] + (1.0 - io.alfa) * nw_;
+                        }
+                    } else {
+                        for (int i = lane; i < m; i += 32) {
+                            const double g0 = P.gamma[i];
+                            const double vc = fmin(fmax(vn[i], 0.0), 0.99 * g0);
+                            pes[i] = 1.0 / (g0 - vc);
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }  // steps
+
+        // ---------------- write back
+        if (advance) {
+            for (int i = lane; i < nx; i += 32) io.x[s * nx + i] = xin[i];
+            for (int i = lane; i < nu; i += 32) io.u[s * nu + i] = uu[i];
+            for (int i = lane; i < m; i += 32) io.pesos[s * m + i] = pes[i];
+            if (io.stats) for (int i = lane; i < nstat; i += 32) io.stats[s * nstat + i] = st[i];
+        }
+        if ((io.flags & SIHMPC_F_UPDATE_VIN) && io.vinant)
+            for (int i = lane; i < P.n_vin; i += 32) io.vinant[s * P.n_vin + i] = vin[i];
+        __syncwarp();
+    }
+}
+
+// ---- auxiliary kernels ---------------------------------------------------------------------
+// pred Function (ihmpccontroller.py:466-472): warp per scenario.
+__global__ void predict_kernel(const DevPlan P, const double *__restrict__ x, const double *__restrict__ u,
+                               const double *__restrict__ dU, long long batch, double *x_pred,
+                               double *y_pred, double *u_pred) {
+    const int lane = threadIdx.x & 31;
+    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int nx = P.nx, nv = P.nv, nu = P.nu, Nx = P.N * P.nx, Ny = P.Ny;
+    for (long long s = gw; s < batch; s += nwarps) {
+        const double *xs = x + s * nx, *dv = dU + s * nv;
+        if (x_pred)
+            for (int r = lane; r < Nx; r += 32) {
+                double a = 0.0;
+                for (int j = 0; j < nx; ++j) a = fma(P.PhiT[(size_t)j * Nx + r], xs[j], a);
+                for (int c = 0; c < nv; ++c) a = fma(P.GamT[(size_t)c * Nx + r], dv[c], a);
+                x_pred[s * Nx + r] = a;
+            }
+        if (y_pred)
+            for (int r = lane; r < Ny; r += 32) {
+                double a = 0.0;
+                for (int j = 0; j < nx; ++j) a = fma(P.MyxT[(size_t)j * Ny + r], xs[j], a);
+                for (int c = 0; c < nv; ++c) a = fma(P.MyuT[(size_t)c * Ny + r], dv[c], a);
+                y_pred[s * Ny + r] = a;
+            }
+        if (u_pred)
+            for (int i = lane; i < nv; i += 32) {
+                const int j = i % nu;
+                double a = u[s * nu + j];
+                for (int c = j; c <= i; c += nu) a += dv[c];
+                u_pred[s * nv + i] = a;
+            }
+    }
+}
+
+// fObj.F for every weighted sub-objective at explicit w = [dU ; syN ; siN]
+__global__ void subobjectives_kernel(const DevPlan P, const double *__restrict__ x,
+                                     const double *__restrict__ w, const double *__restrict__ ysp,
+                                     long long batch, double *V) {
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const long long gw = (long long)blockIdx.x * wpb + wib, nwarps = (long long)gridDim.x * wpb;
+    const int nx = P.nx, nv = P.nv, ny = P.ny, m = P.m, nw = nv + 2 * ny;
+    const int per = nx + nv + ny + 2 * ny + P.R + nv + m + 8;
+    double *B = smem + (size_t)wib * per;
+    double *xs = B, *dv = xs + nx, *yv = dv + nv, *sy = yv + ny, *sq = sy + 2 * ny, *sqdu = sq + P.R,
+           *vn = sqdu + nv;
+    for (long long s = gw; s < batch; s += nwarps) {
+        for (int i = lane; i < nx; i += 32) xs[i] = x[s * nx + i];
+        for (int i = lane; i < nv; i += 32) dv[i] = w[s * nw + i];
+        for (int i = lane; i < 2 * ny; i += 32) sy[i] = w[s * nw + nv + i];
+        for (int i = lane; i < ny; i += 32) yv[i] = ysp[s * ny + i];
+        __syncwarp();
+        eval_subobjectives(P, xs, dv, yv, sy, sq, sqdu, vn, lane);
+        for (int i = lane; i < m; i += 32) V[s * m + i] = vn[i];
+        __syncwarp();
+    }
+}
+
+// block-level reduction of the stats block: out[0][c] += sum, out[1][c] += sum sq, out[2][c] = max
+__global__ void stats_reduce_kernel(const double *__restrict__ stats, long long batch, int nstat,
+                                    double *out) {
+    const int c = blockIdx.y;
+    double s1 = 0.0, s2 = 0.0, mx = -SIH_INF;
+    for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < batch;
+         b += (long long)gridDim.x * blockDim.x) {
+        const double v = stats[b * nstat + c];
+        s1 += v; s2 = fma(v, v, s2); mx = fmax(mx, v);
+    }
+    s1 = warp_sum(s1); s2 = warp_sum(s2); mx = warp_max(mx);
+    __shared__ double sh[3][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) { sh[0][w] = s1; sh[1][w] = s2; sh[2][w] = mx; }
+    __syncthreads();
+    if (w == 0) {
+        const int nw = blockDim.x >> 5;
+        s1 = lane < nw ? sh[0][lane] : 0.0;
+        s2 = lane < nw ? sh[1][lane] : 0.0;
+        mx = lane < nw ? sh[2][lane] : -SIH_INF;
+        s1 = warp_sum(s1); s2 = warp_sum(s2); mx = warp_max(mx);
+        if (lane == 0) {
+            atomicAdd(&out[0 * nstat + c], s1);
+            atomicAdd(&out[1 * nstat + c], s2);
+            // max through the ordered-integer trick (values may be negative)
+            unsigned long long *addr = reinterpret_cast<unsigned long long *>(&out[2 * nstat + c]);
+            unsigned long long old = *addr, assumed;
+            do {
+                assumed = old;
+                if (__longlong_as_double((long long)assumed) >= mx) break;
+                old = atomicCAS(addr, assumed, (unsigned long long)__double_as_longlong(mx));
+            } while (assumed != old);
+        }
+    }
+}
+
+// FP64 FMA throughput probe: 8 independent chains per thread
+__global__ void fp64_probe_kernel(double *out, int iters) {
+    double a0 = 1.0 + threadIdx.x * 1e-9, a1 = a0 + 1e-3, a2 = a0 + 2e-3, a3 = a0 + 3e-3;
+    double a4 = a0 + 4e-3, a5 = a0 + 5e-3, a6 = a0 + 6e-3, a7 = a0 + 7e-3;
+    const double b = 0.999999, c = 1e-7;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    const double r = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (r == 12345.678) out[0] = r;
+}
+
+}  // namespace sih

@@ -1,0 +1,215 @@
+"""GPU parity tests (run on the B200 box): CUDA step through the C ABI vs the NumPy oracle.
+
+Tolerances are the ones BASELINE.json states: control moves and cost within 1e-6 relative,
+constraint violation <= 1e-8.
+"""
+import numpy as np
+import pytest
+
+from tests.util import RTOL, VIOL, oracle_closed_loop, schedule_fn
+from oracle.ihmpc_oracle import OracleIHMPC
+from sihmpc_b200 import scenarios as sc
+from sihmpc_b200.ihmpccontroller import IHMPCController
+
+pytestmark = pytest.mark.gpu
+
+BOUND_SETS = {
+    "example": dict(ulb=[0, 0]),
+    "free": dict(ulb=[-np.inf, -np.inf]),
+    "tight": dict(ulb=[1.9, 1.6], uub=[2.0, 1.8], dulb=[-0.02, -0.02], duub=[0.02, 0.02]),
+    "du_only": dict(dulb=[-0.01, -0.03], duub=[0.015, 0.02]),
+}
+
+
+def _random_states(rng, B):
+    x = np.zeros((B, 22)); x[:, 0] = 96.0; x[:, 1] = 0.5
+    x += rng.normal(size=(B, 22)) * 0.05
+    x[:, 6:8] = 0.0                                   # non-integrating plant: xi stays 0
+    u = np.tile([1.95, 1.71], (B, 1)) + rng.normal(size=(B, 2)) * 0.02
+    ysp = np.tile([96.0, 1.0], (B, 1)) + rng.normal(size=(B, 2)) * 0.4
+    pesos = np.array([0.1, 0.4, 4.4, 4.4]) * (1 + rng.random((B, 4)))
+    return x, u, ysp, pesos
+
+
+@pytest.mark.parametrize("bname", list(BOUND_SETS))
+def test_single_step_parity_distillation(bname):
+    bounds = BOUND_SETS[bname]
+    sys_ = sc.distillation_system()
+    c = sc.declare_distillation(IHMPCController, sys_, **bounds)
+    orc = sc.declare_distillation(OracleIHMPC, sys_, **bounds)
+    B = 48
+    rng = np.random.default_rng(123)
+    x, u, ysp, pesos = _random_states(rng, B)
+    eng = c.engine(B)
+    eng.set_state(x, u, pesos)
+    eng.solve(ysp)
+    du = eng.du.cpu().numpy(); J = eng.J.cpu().numpy(); w = eng.w_opt.cpu().numpy()
+    st = eng.status.cpu().numpy(); na = eng.n_active.cpu().numpy()
+    assert (st == 0).all()
+    n_act_or = []
+    for b in range(B):
+        sol = orc.mpc(x[b], ysp[b], [], u[b], pesos[b], ViN_ant=[np.inf, np.inf])
+        n_act_or.append(sol["info"]["n_active"])
+        scale = max(np.max(np.abs(sol["w_opt"][:20])), 1e-6)
+        assert np.max(np.abs(w[b, :20] - sol["w_opt"][:20])) <= RTOL * scale, (b, bname)
+        assert np.max(np.abs(w[b, 20:] - sol["w_opt"][20:])) <= RTOL * max(1.0, np.max(np.abs(sol["w_opt"][20:])))
+        assert abs(J[b] - sol["J"]) <= RTOL * max(abs(sol["J"]), 1e-9), (b, bname, J[b], sol["J"])
+        assert np.allclose(du[b], sol["du_opt"][:, 0], rtol=0, atol=RTOL * scale)
+        # feasibility of the GPU answer on the reference's own rows
+        kk = orc.kkt_report({"w_opt": w[b], "lam_rows": sol["lam_rows"]}, x[b], ysp[b], u[b], pesos[b],
+                            [np.inf, np.inf])
+        assert kk["violation"] <= VIOL
+    if bname in ("tight", "du_only"):
+        # duplicated normals (move box vs cumulative input box on the first move) make the active
+        # SET non-unique; the optimum is unique, so only require that rows are indeed active
+        assert max(n_act_or) > 0 and (na > 0).mean() > 0.9
+
+
+def test_survey_self_check_value():
+    """J* = 0.30935531, dU_0 = (-0.0143766510, -0.0668630750)."""
+    c = sc.declare_distillation(IHMPCController)
+    x = np.append([96, 0.5], np.zeros(20))
+    sol = c.mpc(x0=x, ySP=[96, 1], w0=[], u0=[1.95, 1.71], pesos=[])
+    assert abs(float(sol["J"]) - 0.30935531) < 1e-8
+    assert np.allclose(c.du.reshape(-1), [-0.0143766510, -0.0668630750], atol=1e-9)
+    w = sol["w_opt"].full().reshape(-1)
+    assert np.allclose(w[20:22], [0.0213581761, -0.154677657], atol=1e-9)
+    assert np.all(w[[15, 17, 18, 19]] == 0.0) or np.max(np.abs(w[[15, 17, 18, 19]])) < 1e-15
+
+
+def test_closed_loop_parity_config3():
+    """Config 3 scenarios (set-point steps + disturbance): GPU closed loop vs oracle loop."""
+    sys_ = sc.distillation_system()
+    c = sc.declare_distillation(IHMPCController, sys_)
+    B, T = 4096, 200
+    scen = sc.distillation_scenarios(B)
+    eng = c.engine(B)
+    eng.set_state(scen["x0"], scen["u0"])
+    eng.set_schedule(scen["ysp_seq"], scen["seg_start"])
+    eng.set_disturbance(scen["dist_step"], scen["dist"])
+    tr = eng.run(T, record=True)
+    du = tr["du"].cpu().numpy(); J = tr["J"].cpu().numpy(); y = tr["y"].cpu().numpy()
+    assert (eng.stats[:, 2 + 3].cpu().numpy() == 0).all()          # status OR
+    for idx in [0, 1, 777, 4095]:
+        ref = oracle_closed_loop(sc.declare_distillation, sys_, scen, idx, T)
+        scale = np.max(np.abs(ref["du"]))
+        assert np.max(np.abs(du[:, idx] - ref["du"])) <= RTOL * scale, idx
+        assert np.max(np.abs(J[:, idx] - ref["J"]) / np.maximum(np.abs(ref["J"]), 1e-6)) <= 10 * RTOL, idx
+        assert np.max(np.abs(y[:, idx] - ref["y"])) <= RTOL * 100.0
+    # size-independent properties over the whole batch: outputs end on the last set-point
+    yend = y[-1]
+    assert np.max(np.abs(yend - scen["ysp_seq"][:, 2] )) < 0.05
+    x = eng.x.cpu().numpy()
+    assert np.isfinite(x).all()
+
+
+def test_steps_per_launch_invariance():
+    """One 50-step launch and fifty 1-step launches must give bit-identical trajectories."""
+    c = sc.declare_distillation(IHMPCController)
+    B, T = 256, 50
+    scen = sc.distillation_scenarios(B)
+    outs = []
+    for spl in (T, 1, 7):
+        eng = c.engine(B)
+        eng.set_state(scen["x0"], scen["u0"])
+        eng.set_schedule(scen["ysp_seq"], scen["seg_start"])
+        eng.set_disturbance(scen["dist_step"], scen["dist"])
+        tr = eng.run(T, steps_per_launch=spl, record=True)
+        outs.append((tr["du"].cpu().numpy(), eng.x.cpu().numpy(), eng.stats.cpu().numpy()))
+    for o in outs[1:]:
+        assert np.array_equal(o[0], outs[0][0])
+        assert np.array_equal(o[1], outs[0][1])
+        assert np.allclose(o[2], outs[0][2], rtol=1e-13, atol=0)
+
+
+def test_closed_loop_constrained_parity():
+    """Tight input/move boxes keep several rows active for many steps."""
+    sys_ = sc.distillation_system()
+    bounds = BOUND_SETS["tight"]
+    c = sc.declare_distillation(IHMPCController, sys_, **bounds)
+    B, T = 64, 120
+    scen = sc.distillation_scenarios(B)
+    eng = c.engine(B)
+    eng.set_state(scen["x0"], scen["u0"])
+    eng.set_schedule(scen["ysp_seq"], scen["seg_start"])
+    eng.set_disturbance(scen["dist_step"], scen["dist"])
+    tr = eng.run(T, record=True)
+    du = tr["du"].cpu().numpy()
+    st = eng.stats.cpu().numpy()
+    assert (st[:, 5] == 0).all()
+    assert st[:, 3].max() <= VIOL                                   # max violation seen
+    assert st[:, 6].max() > 0                                       # active-set iterations happened
+    for idx in [0, 5, 63]:
+        ref = oracle_closed_loop(sc.declare_distillation, sys_, scen, idx, T, bounds=bounds)
+        assert ref["n_active"].max() > 0
+        assert np.max(np.abs(du[:, idx] - ref["du"])) <= RTOL * np.max(np.abs(ref["du"])), idx
+
+
+def test_mismatch_closed_loop_parity():
+    """Config 5: per-scenario plant (gain/time-constant mismatch), nominal controller."""
+    sys_ = sc.distillation_system()
+    c = sc.declare_distillation(IHMPCController, sys_)
+    B, T = 128, 200
+    scen = sc.mismatch_scenarios(B)
+    eng = c.engine(B)
+    eng.set_state(scen["x0"], scen["u0"])
+    eng.set_schedule(scen["ysp_seq"], scen["seg_start"])
+    eng.set_plant_values(scen["plant_val"])
+    tr = eng.run(T, record=True)
+    du = tr["du"].cpu().numpy(); y = tr["y"].cpu().numpy()
+    for idx in [0, 17, 127]:
+        plant = sc.plant_matrices_from_values(sys_, scen["plant_val"][idx])
+        ref = oracle_closed_loop(sc.declare_distillation, sys_, scen, idx, T, plant=plant)
+        assert np.max(np.abs(du[:, idx] - ref["du"])) <= RTOL * np.max(np.abs(ref["du"])), idx
+        assert np.max(np.abs(y[:, idx] - ref["y"])) <= RTOL * 100.0
+
+
+def test_mimo10_parity():
+    """Config 4 shape (10x10, N=5, nv=50, nx=160): single steps and a short closed loop."""
+    sys_ = sc.mimo10_system()
+    c = sc.declare_mimo10(IHMPCController, sys_)
+    B, T = 64, 40
+    scen = sc.mimo10_scenarios(B, sys_)
+    scen["dist_step"][:] = np.minimum(scen["dist_step"], 25)
+    eng = c.engine(B)
+    eng.set_state(scen["x0"], scen["u0"])
+    eng.set_schedule(scen["ysp_seq"], scen["seg_start"])
+    eng.set_disturbance(scen["dist_step"], scen["dist"])
+    tr = eng.run(T, record=True)
+    du = tr["du"].cpu().numpy(); J = tr["J"].cpu().numpy()
+    assert (eng.stats[:, sys_.ny + 3].cpu().numpy() == 0).all()
+    for idx in [0, 63]:
+        ref = oracle_closed_loop(sc.declare_mimo10, sys_, scen, idx, T)
+        assert np.max(np.abs(du[:, idx] - ref["du"])) <= RTOL * np.max(np.abs(ref["du"])), idx
+        assert np.max(np.abs(J[:, idx] - ref["J"]) / np.maximum(np.abs(ref["J"]), 1e-6)) <= 10 * RTOL
+
+
+def test_dropin_example_loop_matches_oracle():
+    """The reference's own driver loop (example_distillation.py:65-113) on the drop-in class."""
+    sys_ = sc.distillation_system()
+    c = sc.declare_distillation(IHMPCController, sys_)
+    orc = sc.declare_distillation(OracleIHMPC, sys_)
+    u = [1.95, 1.71]; x = np.append([96, 0.5], np.zeros(sys_.nx - 2)); ysp = [96, 0.5]
+    uo, xo = np.array(u), x.copy()
+    w0 = []; pesos = []; w0o = []; pesoso = []
+    for k in range(30):
+        if k > 10:
+            ysp = [96, 1]
+        sol = c.mpc(x0=x, ySP=ysp, w0=w0, u0=u, pesos=pesos)
+        du = c.du
+        res = c.dynF(x0=x, u0=u, du0=du)
+        x = res['xkp1'].full(); u = res['ukp1'].full()
+        w0 = c.warmStart(sol, ysp)
+        pesos, _ = c.satWeights2(x, u, w0, ysp)
+        solo = orc.mpc(x0=xo, ySP=ysp, w0=w0o, u0=uo, pesos=pesoso)
+        r = orc.dynF(xo, uo, orc.du)
+        xo, uo = r['xkp1'], r['ukp1']
+        w0o = orc.warmStart(solo, ysp)
+        pesoso, _ = orc.satWeights2(xo, uo, w0o, ysp)
+        assert np.allclose(np.asarray(du).reshape(-1), orc.du.reshape(-1), rtol=0, atol=1e-9), k
+        assert abs(float(sol['J']) - solo['J']) <= 1e-6 * max(abs(solo['J']), 1e-6)
+        assert np.allclose(pesos, pesoso, rtol=1e-7)
+        assert np.allclose(sol['x_pred'].full().reshape(-1), solo['x_pred'], atol=1e-8)
+        assert np.allclose(sol['g'].full().reshape(-1), solo['g'], atol=1e-7)
+    assert len(c.j_hist) == 30 and len(c.V[0].v_hist) == 30
+    assert np.allclose([V.v_hist[-1] for V in c.V], [V.v_hist[-1] for V in orc.V], atol=1e-9)

@@ -1,0 +1,126 @@
+"""CPU tests of the oracle itself: structural fixtures of the reference tree, KKT certificates,
+an independent scipy cross-check on the UN-reduced problem, and the committed golden vectors."""
+import os
+
+import numpy as np
+import pytest
+from scipy.optimize import minimize
+
+from oracle.ihmpc_oracle import OracleIHMPC, solve_qp_exact, closed_loop
+from sihmpc_b200 import scenarios as sc
+from tests.util import oracle_closed_loop
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TIGHT = dict(ulb=[1.9, 1.6], uub=[2.0, 1.8], dulb=[-0.02, -0.02], duub=[0.02, 0.02])
+
+
+@pytest.fixture(scope="module")
+def sys_():
+    return sc.distillation_system()
+
+
+def test_structural_facts_of_reference_scratch_vectors(sys_):
+    """/root/reference/teste.py:66-105 pins nx = 22, nw = 24, state order [xs|xd|xi|z] with
+    z_1 = du(k-1) first, and zero moves at dU indices 15,17,18,19."""
+    c = sc.declare_distillation(OracleIHMPC, sys_)
+    assert sys_.nx == 22 and c.nw == 24 and sys_.nd == 4 and sys_.nz == 14 and sys_.theta_max == 7
+    x = np.append([96, 0.5], np.zeros(20))
+    sol = c.mpc(x, [96, 1], [], [1.95, 1.71], [])
+    w = sol["w_opt"]
+    assert np.all(np.abs(w[[15, 17, 18, 19]]) < 1e-14)
+    assert np.all(np.abs(np.delete(w[:20], [15, 17, 18, 19])) > 1e-5)
+    # z_1 = previous move: after one plant step x[8:10] equals the applied du
+    x1 = c.dynF(x, [1.95, 1.71], c.du)["xkp1"]
+    assert np.allclose(x1[8:10], c.du.reshape(-1))
+    assert len(sol["g"]) == 255                                     # SURVEY.md section 8 size table
+    assert [V.name for V in c.V] == ['Vy_[0]', 'VsyN_[0]', 'VyC_[0]', 'Vy_[1]', 'VsyN_[1]', 'VyC_[1]',
+                                     'Vdu_[0]', 'Vdu_[1]', 'VsiN_[0]', 'VsiN_[1]', 'Vt']
+    assert np.allclose(np.diag(c.Qt), [0.1, 0.4])
+
+
+def test_survey_self_check_value(sys_):
+    c = sc.declare_distillation(OracleIHMPC, sys_)
+    x = np.append([96, 0.5], np.zeros(20))
+    sol = c.mpc(x, [96, 1], [], [1.95, 1.71], [])
+    assert abs(sol["J"] - 0.30935531) < 1e-8
+    assert np.allclose(sol["du_opt"][:, 0], [-0.0143766510, -0.0668630750], atol=1e-9)
+    assert np.allclose(sol["w_opt"][20:22], [0.0213581761, -0.154677657], atol=1e-9)
+    assert sol["info"]["n_active"] == 0
+
+
+@pytest.mark.parametrize("bounds", [dict(ulb=[0, 0]), TIGHT, dict(dulb=[-0.01, -0.03], duub=[0.015, 0.02])])
+def test_kkt_certificate_and_slsqp_crosscheck(sys_, bounds):
+    c = sc.declare_distillation(OracleIHMPC, sys_, **bounds)
+    rng = np.random.default_rng(5)
+    for t in range(4):
+        x = np.append([96, 0.5], np.zeros(20)) + rng.normal(size=22) * 0.05
+        x[6:8] = 0
+        u = np.array([1.95, 1.71]); ysp = np.array([96, 1.0]) + rng.normal(size=2) * 0.3
+        pesos = np.array([0.1, 0.4, 4.4, 4.4]) * (1 + rng.random(4))
+        vin = [np.inf, np.inf]
+        sol = c.mpc(x, ysp, [], u, pesos, ViN_ant=vin)
+        kk = c.kkt_report(sol, x, ysp, u, pesos, vin)
+        assert kk["stationarity"] < 1e-10 and kk["violation"] < 1e-10 and kk["complementarity"] < 1e-10
+        # independent solver on the un-reduced (w, g) problem of ctl.py:374-456
+        H, f, c0, G, lo, hi = c._problem(x, u, ysp, pesos, vin)
+        cons = []
+        for i in range(G.shape[0]):
+            if np.isfinite(lo[i]) and lo[i] == hi[i]:
+                cons.append({"type": "eq", "fun": lambda w, i=i: G[i] @ w - lo[i], "jac": lambda w, i=i: G[i]})
+            else:
+                if np.isfinite(lo[i]):
+                    cons.append({"type": "ineq", "fun": lambda w, i=i: G[i] @ w - lo[i], "jac": lambda w, i=i: G[i]})
+                if np.isfinite(hi[i]):
+                    cons.append({"type": "ineq", "fun": lambda w, i=i: hi[i] - G[i] @ w, "jac": lambda w, i=i: -G[i]})
+        r = minimize(lambda w: 0.5 * w @ H @ w + f @ w + c0, np.zeros(24), jac=lambda w: H @ w + f,
+                     constraints=cons, method="SLSQP", options=dict(ftol=1e-15, maxiter=500))
+        gv = G @ r.x
+        feas = max(0.0, np.max(lo - gv), np.max(gv - hi))
+        if r.success:
+            assert abs(r.fun - sol["J_quad"]) < 1e-8 * max(1.0, abs(sol["J_quad"]))
+            assert np.max(np.abs(r.x - sol["w_opt"])) < 2e-5
+        else:
+            # SLSQP stalls on heavily degenerate active sets; its (feasible) point can then only be
+            # worse than the certified optimum
+            assert feas < 1e-8 and r.fun >= sol["J_quad"] - 1e-9
+        assert abs(sol["J"] - sol["J_quad"]) < 1e-10 * max(1.0, abs(sol["J"]))
+
+
+def test_solver_handles_dependent_and_infeasible_rows():
+    H = np.eye(3); f = np.array([-1.0, -1.0, -1.0])
+    G = np.array([[1.0, 0, 0], [1.0, 0, 0], [1.0, 1.0, 0]])     # duplicated normal
+    w, lam, info = solve_qp_exact(H, f, G, np.array([-np.inf] * 3), np.array([0.5, 0.5, 0.8]))
+    assert np.allclose(w, [0.4, 0.4, 1.0])
+    with pytest.raises(RuntimeError):
+        solve_qp_exact(H, f, np.array([[1.0, 0, 0], [1.0, 0, 0]]), np.array([1.0, -np.inf]), np.array([np.inf, 0.0]))
+
+
+def test_contraction_row_integrating_plant():
+    """An integrating channel exercises siN, ViN_ant and the (k+1-N) Ts siN term (ctl.py:174,265-269)."""
+    from sihmpc_b200.opom import OPOM, TransferFunction
+    h = [[TransferFunction([1.0], [5.0, 1.0, 0.0], delay=1)]]
+    s = OPOM(h, 1.0)
+    c = OracleIHMPC(s, 6, dulb=[-0.5], duub=[0.5])
+    c.subObjComposed(y=[0], Q=1, sat=6.0)
+    c.subObj(du=[0], Q=1, sat=1.0)
+    c.subObj(siN=[0], Q=1, addJ=False)
+    c.set_terminal_objective()
+    out = closed_loop(c, np.zeros(s.nx), [0.0], lambda k: [1.0], 60)
+    assert abs(out["y"][-1, 0] - 1.0) < 1e-3
+    assert np.all(np.diff(np.abs(out["w_opt"][:, -1])) <= 1e-9)   # |siN| is non-increasing
+
+
+def test_golden_vectors_reproduce(sys_):
+    g = np.load(os.path.join(GOLD, "example_distillation_oracle.npz"))
+    from tests.golden.make_golden import example_loop
+    r = example_loop(OracleIHMPC, sys_, n_steps=40)
+    assert np.allclose(r["du"], g["du"][:40], rtol=0, atol=1e-12)
+    assert np.allclose(r["J"], g["J"][:40], rtol=1e-10, atol=1e-14)
+    assert np.allclose(g["y"][-1], [95.5, 1.0], atol=1e-3)          # example converges to its set-point
+    g3 = np.load(os.path.join(GOLD, "config3_oracle.npz"))
+    scen = sc.distillation_scenarios(4)
+    a = oracle_closed_loop(sc.declare_distillation, sys_, scen, 2, 60)
+    assert np.allclose(a["du"], g3["du_2"][:60], rtol=0, atol=1e-12)
+    b = oracle_closed_loop(sc.declare_distillation, sys_, scen, 1, 40, bounds=TIGHT)
+    assert np.allclose(b["du"], g3["tight_du_1"][:40], rtol=0, atol=1e-12)
+    assert g3["tight_nact_1"].max() > 0

@@ -1,0 +1,121 @@
+"""CPU tests of the host logic: OPOM builder, plan compiler, scenario generators, drop-in surface."""
+import numpy as np
+import pytest
+
+from oracle.ihmpc_oracle import OracleIHMPC, solve_qp_exact
+from sihmpc_b200 import scenarios as sc
+from sihmpc_b200.ihmpccontroller import IHMPCController, DM
+from sihmpc_b200.opom import OPOM, TransferFunction
+from sihmpc_b200.plan import assemble_qp
+
+
+def test_opom_matches_analytic_step_responses():
+    wb = sc.WOOD_BERRY
+    s = sc.distillation_system()
+    t = np.arange(61)
+    for j in range(2):
+        y = s.step_response(60, j)
+        for i in range(2):
+            K, tau, th = wb["K"][i][j], wb["tau"][i][j], wb["theta"][i][j]
+            ana = np.where(t >= th, K * (1 - np.exp(-(t - th) / tau)), 0.0)
+            assert np.max(np.abs(y[:, i] - ana)) < 1e-12
+    g = TransferFunction([2.0], [3.0, 1, 0], delay=2)              # integrating channel
+    s2 = OPOM([[g]], 0.5)
+    y = s2.step_response(30, 0)[:, 0]
+    tt = np.maximum(np.arange(31) * 0.5 - 2, 0)
+    assert np.max(np.abs(y - 2 * (tt - 3 * (1 - np.exp(-tt / 3))))) < 1e-12
+    g2 = TransferFunction([1.0], np.polymul([2.0, 1], [5.0, 1]), delay=0)   # two real poles
+    s3 = OPOM([[g2]], 1.0)
+    y = s3.step_response(40, 0)[:, 0]
+    tt = np.arange(41.0)
+    ana = 1 - (5 * np.exp(-tt / 5) - 2 * np.exp(-tt / 2)) / 3
+    assert np.max(np.abs(y - ana)) < 1e-12
+
+
+def test_constructor_asserts_like_reference():
+    s = sc.distillation_system()
+    with pytest.raises(AssertionError):
+        IHMPCController(s, 7)                                      # N must exceed theta_max (ctl.py:22)
+    with pytest.raises(AssertionError):
+        IHMPCController(object(), 10)                              # ctl.py:15
+    c = IHMPCController(s, 10, ulb=[0, 0])
+    assert (c.nx, c.nu, c.ny, c.nxs, c.nxd, c.nxi, c.nxz) == (22, 2, 2, 2, 4, 2, 14)
+    assert c.du.shape == (2, 1)
+
+
+@pytest.mark.parametrize("bounds", [dict(ulb=[0, 0]),
+                                    dict(ulb=[1.9, 1.6], uub=[2.0, 1.8], dulb=[-0.02, -0.02], duub=[0.02, 0.02]),
+                                    dict(xlb=np.r_[95.7, -np.inf * np.ones(21)], xub=np.r_[96.3, np.inf * np.ones(21)],
+                                         sylb=[-0.3, -0.3], syub=[0.3, 0.3])])
+def test_plan_reproduces_oracle_problem(bounds):
+    s = sc.distillation_system()
+    c = sc.declare_distillation(IHMPCController, s, **bounds)
+    orc = sc.declare_distillation(OracleIHMPC, s, **bounds)
+    plan = c.compile()
+    assert [V.name for V in c.V] == [V.name for V in orc.V]
+    assert np.allclose(c.Q_bar, orc.Q_bar) and np.allclose(c.init_pesos(), orc.init_pesos())
+    rng = np.random.default_rng(0)
+    for t in range(6):
+        x = np.append([96, 0.5], np.zeros(20)) + rng.normal(size=22) * 0.05
+        x[6:8] = 0
+        u = np.array([1.95, 1.71]); ysp = np.array([96, 1.0]) + rng.normal(size=2) * 0.3
+        pesos = np.array([0.1, 0.4, 4.4, 4.4]) * (1 + rng.random(4))
+        sol = orc.mpc(x, ysp, [], u, pesos, ViN_ant=[np.inf, np.inf])
+        H, f, c0, G, lo, hi, *_ = assemble_qp(plan, x, u, ysp, pesos, [np.inf, np.inf])
+        v, lam, info = solve_qp_exact(H, f, G, lo, hi)
+        J = c0 + f @ v + 0.5 * v @ H @ v
+        assert np.max(np.abs(v - sol["w_opt"][:20])) < 1e-10
+        assert abs(J - sol["J"]) < 1e-10 * max(1.0, abs(sol["J"]))
+        assert info["n_active"] == sol["info"]["n_active"]
+
+
+def test_plan_mimo10_shapes_and_parity():
+    s = sc.mimo10_system()
+    assert (s.nx, s.nd, s.theta_max) == (160, 100, 4)
+    c = sc.declare_mimo10(IHMPCController, s)
+    orc = sc.declare_mimo10(OracleIHMPC, s)
+    plan = c.compile()
+    assert (plan.nv, plan.m, plan.mh, plan.R) == (50, 20, 10, 170)
+    rng = np.random.default_rng(1)
+    x = rng.normal(size=160) * 0.1; x[110:120] = 0
+    u = rng.normal(size=10) * 0.1; ysp = rng.normal(size=10)
+    pesos = plan.peso0 * (1 + rng.random(20))
+    sol = orc.mpc(x, ysp, [], u, pesos, ViN_ant=[np.inf] * 10)
+    H, f, c0, G, lo, hi, *_ = assemble_qp(plan, x, u, ysp, pesos, [np.inf] * 10)
+    v, lam, info = solve_qp_exact(H, f, G, lo, hi)
+    assert np.max(np.abs(v - sol["w_opt"][:50])) < 1e-9
+
+
+def test_scenario_generators_are_subset_stable():
+    a = sc.distillation_scenarios(10, first=4090)
+    b = sc.distillation_scenarios(5000)
+    assert np.array_equal(a["ysp_seq"], b["ysp_seq"][4090:4100])
+    assert np.array_equal(a["dist_step"], b["dist_step"][4090:4100])
+    ms = sc.mismatch_scenarios(4, first=10000)
+    nom = sc.distillation_system()
+    for k in range(4):
+        sysp = sc.fopdt_system(ms["K"][k], ms["tau"][k], sc.WOOD_BERRY["theta"])
+        A, B = sc.plant_matrices_from_values(nom, ms["plant_val"][k])
+        assert np.max(np.abs(A - sysp.A)) < 1e-12 and np.max(np.abs(B - sysp.B)) < 1e-12
+
+
+def test_dm_behaves_like_casadi_dm():
+    a = DM(np.arange(6.0))
+    assert a.shape == (6, 1) and a[2:4].shape == (2, 1) and a[-2:].full().ravel().tolist() == [4.0, 5.0]
+    m = DM(np.arange(6.0).reshape(2, 3))
+    assert m[:, 0].shape == (2, 1) and m[:, 0].full().ravel().tolist() == [0.0, 3.0]
+    assert float(DM(3.5)) == 3.5
+    with pytest.raises(TypeError):
+        float(a)
+
+
+def test_unsupported_declarations_fail_loudly():
+    s = sc.distillation_system()
+    c = IHMPCController(s, 10, rslb=[-0.1, -0.1], rsub=[0.1, 0.1])
+    c.subObjComposed(y=[0], Q=1, sat=10.0)
+    c.subObj(du=[0], Q=1, sat=1.0); c.subObj(du=[1], Q=1, sat=1.0)
+    with pytest.raises(NotImplementedError):
+        c.compile()
+    c2 = IHMPCController(s, 10)
+    with pytest.raises(NotImplementedError):
+        c2.subObj(siN=[0, 1], Q=np.eye(2), addJ=False)
