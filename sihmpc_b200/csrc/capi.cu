@@ -46,8 +46,8 @@ struct sihmpc_plan {
     int blocks_per_sm;
     size_t smem_bytes;
     int max_grid;
-    int fast_path;           // 1: register-tiled kernel for this shape (dist_kernel.cuh)
-    int fast_blocks_per_sm;
+    sih::QuadPlan quad;      // register-tiled fast path for this shape (dist_kernel.cuh), shape<0: none
+    int use_fast;            // 0 disables the fast path (SIHMPC_NO_FAST=1 in the environment; for A/B tests)
     std::vector<void *> allocs;
     // host copies needed by the host-buffer entry point
     int nw;
@@ -114,13 +114,14 @@ int configure(sihmpc_plan *p) {
 
 template <int NVR>
 int launch_step(sihmpc_plan *p, const sihmpc_io &io, long long batch, int n_steps, double *scratch,
-                cudaStream_t st) {
+                cudaStream_t st, const int *start_step = nullptr, const int *n_handover = nullptr) {
     long long need = (batch + p->wpb - 1) / p->wpb;
     int grid = (int)(need < p->max_grid ? need : p->max_grid);
     if (grid < 1) grid = 1;
     const int max_outer = 8 * (2 * p->d.nv + p->d.ncd) + 16;
     sih::ihmpc_step_kernel<NVR><<<grid, p->wpb * 32, p->smem_bytes, st>>>(p->d, io, batch, n_steps,
-                                                                           scratch, max_outer);
+                                                                           scratch, max_outer, start_step,
+                                                                           n_handover);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -154,6 +155,7 @@ int sihmpc_device_count(void) {
 int sihmpc_plan_destroy(sihmpc_plan *plan) {
     if (!plan) return 0;
     for (void *q : plan->allocs) cudaFree(q);
+    sih::quad_destroy(&plan->quad);
     delete plan;
     return 0;
 }
@@ -172,6 +174,7 @@ int sihmpc_plan_create(const sihmpc_plan_desc *d, sihmpc_plan **out) {
     if (ndev < 1) return fail(SIHMPC_E_CUDA, "no CUDA device: this library has no CPU fallback%s");
 
     sihmpc_plan *p = new sihmpc_plan();
+    p->quad.shape = -1;
     int rc = 0;
     auto bail = [&](int code) { sihmpc_plan_destroy(p); return code; };
     if (cudaGetDevice(&p->device) != cudaSuccess) return bail(fail(SIHMPC_E_CUDA, "cudaGetDevice failed%s"));
@@ -250,10 +253,12 @@ int sihmpc_plan_create(const sihmpc_plan_desc *d, sihmpc_plan **out) {
     p->nvr = (nv + 31) / 32;
     rc = (p->nvr == 1) ? configure<1>(p) : configure<2>(p);
     if (rc) return bail(rc);
-    p->fast_path = 0;
-    p->fast_blocks_per_sm = 0;
-    rc = sih::dist_configure(p->d, &p->fast_path, &p->fast_blocks_per_sm);
-    if (rc) return bail(fail(SIHMPC_E_CUDA, "fast-path configuration failed%s"));
+    {
+        cudaError_t qe = sih::quad_configure(d, p->d, &p->quad);
+        if (qe != cudaSuccess) return bail(fail(SIHMPC_E_CUDA, "fast-path configuration failed: %s", cudaGetErrorString(qe)));
+        const char *nf = getenv("SIHMPC_NO_FAST");
+        p->use_fast = !(nf && nf[0] == '1');
+    }
     *out = p;
     return 0;
 }
@@ -275,14 +280,30 @@ int sihmpc_step(sihmpc_plan *plan, const sihmpc_io *io, int64_t batch, int32_t n
         return fail(SIHMPC_E_WORKSPACE, "workspace smaller than sihmpc_workspace_bytes()%s");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     double *scratch = reinterpret_cast<double *>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-    if (plan->fast_path && sih::dist_supported(plan->d, *io)) {
-        cudaError_t e = sih::dist_launch(plan->d, *io, batch, n_steps, plan->sm_count,
-                                         plan->fast_blocks_per_sm, st);
+    const int *start_step = nullptr, *n_handover = nullptr;
+    if (plan->use_fast && sih::quad_supported(plan->quad, *io)) {
+        cudaError_t e = sih::quad_ensure_capacity(&plan->quad, batch);
+        if (e == cudaSuccess) e = cudaMemsetAsync(plan->quad.start_step, 0x7f, (size_t)batch * sizeof(int), st);
+        if (e == cudaSuccess) e = sih::quad_launch(plan->quad, plan->d, *io, batch, n_steps, plan->sm_count, st);
         if (e != cudaSuccess) return fail(SIHMPC_E_CUDA, "fast-path launch failed: %s", cudaGetErrorString(e));
-        return 0;
+        if (getenv("SIHMPC_DEBUG_HANDOVER")) {                      // debug only: synchronises
+            cudaStreamSynchronize(st);
+            std::vector<int> ss((size_t)batch);
+            int cnt = 0;
+            cudaMemcpy(ss.data(), plan->quad.start_step, (size_t)batch * 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(&cnt, plan->quad.n_handover, 4, cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[sihmpc] handover count %d:", cnt);
+            int shown = 0;
+            for (long long b = 0; b < batch && shown < 24; ++b)
+                if (ss[b] < n_steps) { fprintf(stderr, " %lld@%d", b, ss[b]); ++shown; }
+            fprintf(stderr, "\n");
+        }
+        if (!(plan->d.has_box || plan->d.has_cum)) return 0;      // nothing can be handed over
+        start_step = plan->quad.start_step;
+        n_handover = plan->quad.n_handover;
     }
-    return (plan->nvr == 1) ? launch_step<1>(plan, *io, batch, n_steps, scratch, st)
-                            : launch_step<2>(plan, *io, batch, n_steps, scratch, st);
+    return (plan->nvr == 1) ? launch_step<1>(plan, *io, batch, n_steps, scratch, st, start_step, n_handover)
+                            : launch_step<2>(plan, *io, batch, n_steps, scratch, st, start_step, n_handover);
 }
 
 // ---- host-buffer variant -----------------------------------------------------------------

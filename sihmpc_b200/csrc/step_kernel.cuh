@@ -268,7 +268,10 @@ __device__ void eval_subobjectives(const DevPlan &P, const double *xs, const dou
 template <int NVR>
 __global__ void __launch_bounds__(256, (NVR == 1 ? 2 : 1))
 ihmpc_step_kernel(const DevPlan P, const sihmpc_io io, const long long batch, const int n_steps,
-                  double *__restrict__ scratch, const int max_outer) {
+                  double *__restrict__ scratch, const int max_outer,
+                  const int *__restrict__ start_step, const int *__restrict__ n_handover) {
+    // second pass after the quad fast path: only scenarios it handed over (start_step < n_steps)
+    if (n_handover && *n_handover == 0) return;
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const long long gw = (long long)blockIdx.x * wpb + wib;
@@ -295,6 +298,8 @@ ihmpc_step_kernel(const DevPlan P, const sihmpc_io io, const long long batch, co
     const bool advance = (io.flags & SIHMPC_F_ADVANCE) != 0;
 
     for (long long s = gw; s < batch; s += nwarps) {
+        const int step0 = start_step ? start_step[s] : 0;
+        if (step0 >= n_steps) continue;
         // ---------------- load scenario state
         for (int i = lane; i < nx; i += 32) xin[i] = io.x[s * nx + i];
         for (int i = lane; i < nu; i += 32) uu[i] = io.u[s * nu + i];
@@ -307,7 +312,7 @@ ihmpc_step_kernel(const DevPlan P, const sihmpc_io io, const long long batch, co
         int status = 0, q = 0, iters_total = 0;
         double viol_abs = 0.0;
 
-        for (int step = 0; step < n_steps; ++step) {
+        for (int step = step0; step < n_steps; ++step) {
             const int kabs = io.k0 + step;
             // ---------------- set-point of this step
             if (io.ysp_seq) {

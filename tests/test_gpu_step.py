@@ -213,3 +213,43 @@ def test_dropin_example_loop_matches_oracle():
         assert np.allclose(sol['g'].full().reshape(-1), solo['g'], atol=1e-7)
     assert len(c.j_hist) == 30 and len(c.V[0].v_hist) == 30
     assert np.allclose([V.v_hist[-1] for V in c.V], [V.v_hist[-1] for V in orc.V], atol=1e-9)
+
+
+def test_fast_path_handover_many_rounds(monkeypatch):
+    """Quad fast path with a tiny grid (many scenarios per quad, one after the other) on a bound
+    set that makes a good share of the scenarios hand over to the exact active-set kernel mid-loop:
+    must equal the general kernel run alone, and the oracle.  Regression test for a barrier placed
+    inside a divergent branch (a handed-over quad left its warp one barrier out of phase)."""
+    sys_ = sc.distillation_system()
+    bounds = dict(ulb=[1.80, 1.62], uub=[2.02, 1.78])
+    B, T = 1024, 150
+    scen = sc.distillation_scenarios(B)
+
+    def run(no_fast, grid):
+        monkeypatch.setenv("SIHMPC_NO_FAST", "1" if no_fast else "0")
+        if grid:
+            monkeypatch.setenv("SIHMPC_QUAD_GRID", str(grid))
+        else:
+            monkeypatch.delenv("SIHMPC_QUAD_GRID", raising=False)
+        c = sc.declare_distillation(IHMPCController, sys_, **bounds)
+        eng = c.engine(B)
+        eng.set_state(scen["x0"], scen["u0"])
+        eng.set_schedule(scen["ysp_seq"], scen["seg_start"])
+        eng.set_disturbance(scen["dist_step"], scen["dist"])
+        tr = eng.run(T, steps_per_launch=50, record=True)
+        return tr["du"].cpu().numpy(), eng.x.cpu().numpy(), eng.stats.cpu().numpy()
+
+    du_f, x_f, st_f = run(False, 3)
+    du_g, x_g, st_g = run(True, 0)
+    monkeypatch.delenv("SIHMPC_QUAD_GRID", raising=False)
+    monkeypatch.delenv("SIHMPC_NO_FAST", raising=False)
+    assert (st_f[:, 5] == 0).all() and (st_g[:, 5] == 0).all()
+    n_constrained = int((st_g[:, 6] > 0).sum())
+    assert 0.05 * B < n_constrained < 0.95 * B          # both paths are exercised
+    assert np.max(np.abs(du_f - du_g)) <= 1e-9 * np.max(np.abs(du_g))
+    assert np.max(np.abs(x_f - x_g)) <= 1e-9 * 100.0
+    assert np.allclose(st_f[:, :5], st_g[:, :5], rtol=1e-9, atol=1e-12)
+    idx = int(np.argmax(st_g[:, 6]))
+    ref = oracle_closed_loop(sc.declare_distillation, sys_, scen, idx, T, bounds=bounds)
+    assert ref["n_active"].max() > 0
+    assert np.max(np.abs(du_f[:, idx] - ref["du"])) <= RTOL * np.max(np.abs(ref["du"]))
