@@ -560,7 +560,7 @@ struct QuadPlan {
 using DistillationDims = QuadDims<22, 2, 2, 4, 10, 4>;
 constexpr int QUAD_WARPS = 4;
 #ifndef SIH_QUAD_MINB
-#define SIH_QUAD_MINB 3
+#define SIH_QUAD_MINB 2
 #endif
 constexpr int QUAD_MINB = SIH_QUAD_MINB;
 
