@@ -212,7 +212,8 @@ def main():
     ap.add_argument("--steps-per-launch", type=int, default=0, help="control steps fused in one launch (0 = all)")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-per-core", type=int, default=6)
+    ap.add_argument("--cpu-per-core", type=int, default=48,
+                    help="scenarios per host core in the CPU arm (48 x 200 steps ~ 10 s per core)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -363,9 +364,9 @@ def main():
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_arm(args.workload, args.cpu_per_core, 40, 2)
+        r = cpu_arm(args.workload, args.cpu_per_core, 200, 0)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-               "sample": "%d scenarios x 40 steps of the same workload, NumPy oracle, one process per core (%.1f s)"
+               "sample": "%d scenarios x 200 closed-loop steps of the same workload, NumPy oracle, one process per core (%.1f s)"
                          % (r["cores"] * args.cpu_per_core, r["seconds"]),
                "p50_step_latency_us": r["p50_us"]}
 

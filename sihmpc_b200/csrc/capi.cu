@@ -12,6 +12,7 @@
 #include "devplan.h"
 #include "step_kernel.cuh"
 #include "dist_kernel.cuh"
+#include "mma_kernel.cuh"
 
 namespace {
 
@@ -46,8 +47,9 @@ struct sihmpc_plan {
     int blocks_per_sm;
     size_t smem_bytes;
     int max_grid;
-    sih::QuadPlan quad;      // register-tiled fast path for this shape (dist_kernel.cuh), shape<0: none
-    int use_fast;            // 0 disables the fast path (SIHMPC_NO_FAST=1 in the environment; for A/B tests)
+    sih::QuadPlan quad;      // register-tiled fast path v2 (dist_kernel.cuh), shape<0: none
+    sih::MmaPlan mma;        // register-tiled + FP64 tensor-core fast path v3 (mma_kernel.cuh), shape<0: none
+    int use_fast;            // 0: general kernel only, 1: quad, 2: mma (default; SIHMPC_NO_FAST=1 / SIHMPC_FAST=quad for A/B)
     std::vector<void *> allocs;
     // host copies needed by the host-buffer entry point
     int nw;
@@ -156,6 +158,7 @@ int sihmpc_plan_destroy(sihmpc_plan *plan) {
     if (!plan) return 0;
     for (void *q : plan->allocs) cudaFree(q);
     sih::quad_destroy(&plan->quad);
+    sih::mma_destroy(&plan->mma);
     delete plan;
     return 0;
 }
@@ -175,6 +178,7 @@ int sihmpc_plan_create(const sihmpc_plan_desc *d, sihmpc_plan **out) {
 
     sihmpc_plan *p = new sihmpc_plan();
     p->quad.shape = -1;
+    p->mma.shape = -1;
     int rc = 0;
     auto bail = [&](int code) { sihmpc_plan_destroy(p); return code; };
     if (cudaGetDevice(&p->device) != cudaSuccess) return bail(fail(SIHMPC_E_CUDA, "cudaGetDevice failed%s"));
@@ -256,8 +260,13 @@ int sihmpc_plan_create(const sihmpc_plan_desc *d, sihmpc_plan **out) {
     {
         cudaError_t qe = sih::quad_configure(d, p->d, &p->quad);
         if (qe != cudaSuccess) return bail(fail(SIHMPC_E_CUDA, "fast-path configuration failed: %s", cudaGetErrorString(qe)));
+        qe = sih::mma_configure(d, p->d, &p->mma);
+        if (qe != cudaSuccess) return bail(fail(SIHMPC_E_CUDA, "tensor fast-path configuration failed: %s", cudaGetErrorString(qe)));
         const char *nf = getenv("SIHMPC_NO_FAST");
-        p->use_fast = !(nf && nf[0] == '1');
+        const char *ff = getenv("SIHMPC_FAST");
+        p->use_fast = 2;
+        if (ff && !strcmp(ff, "quad")) p->use_fast = 1;
+        if (nf && nf[0] == '1') p->use_fast = 0;
     }
     *out = p;
     return 0;
@@ -281,23 +290,19 @@ int sihmpc_step(sihmpc_plan *plan, const sihmpc_io *io, int64_t batch, int32_t n
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     double *scratch = reinterpret_cast<double *>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     const int *start_step = nullptr, *n_handover = nullptr;
-    if (plan->use_fast && sih::quad_supported(plan->quad, *io)) {
+    if (plan->use_fast == 2 && plan->mma.shape >= 0) {
+        cudaError_t e = sih::mma_ensure_capacity(&plan->mma, batch);
+        if (e == cudaSuccess) e = cudaMemsetAsync(plan->mma.start_step, 0x7f, (size_t)batch * sizeof(int), st);
+        if (e == cudaSuccess) e = sih::mma_launch(plan->mma, plan->d, *io, batch, n_steps, plan->sm_count, st);
+        if (e != cudaSuccess) return fail(SIHMPC_E_CUDA, "tensor fast-path launch failed: %s", cudaGetErrorString(e));
+        if (!(plan->d.has_box || plan->d.has_cum)) return 0;      // nothing can be handed over
+        start_step = plan->mma.start_step;
+        n_handover = plan->mma.n_handover;
+    } else if (plan->use_fast && sih::quad_supported(plan->quad, *io)) {
         cudaError_t e = sih::quad_ensure_capacity(&plan->quad, batch);
         if (e == cudaSuccess) e = cudaMemsetAsync(plan->quad.start_step, 0x7f, (size_t)batch * sizeof(int), st);
         if (e == cudaSuccess) e = sih::quad_launch(plan->quad, plan->d, *io, batch, n_steps, plan->sm_count, st);
         if (e != cudaSuccess) return fail(SIHMPC_E_CUDA, "fast-path launch failed: %s", cudaGetErrorString(e));
-        if (getenv("SIHMPC_DEBUG_HANDOVER")) {                      // debug only: synchronises
-            cudaStreamSynchronize(st);
-            std::vector<int> ss((size_t)batch);
-            int cnt = 0;
-            cudaMemcpy(ss.data(), plan->quad.start_step, (size_t)batch * 4, cudaMemcpyDeviceToHost);
-            cudaMemcpy(&cnt, plan->quad.n_handover, 4, cudaMemcpyDeviceToHost);
-            fprintf(stderr, "[sihmpc] handover count %d:", cnt);
-            int shown = 0;
-            for (long long b = 0; b < batch && shown < 24; ++b)
-                if (ss[b] < n_steps) { fprintf(stderr, " %lld@%d", b, ss[b]); ++shown; }
-            fprintf(stderr, "\n");
-        }
         if (!(plan->d.has_box || plan->d.has_cum)) return 0;      // nothing can be handed over
         start_step = plan->quad.start_step;
         n_handover = plan->quad.n_handover;

@@ -1,0 +1,723 @@
+// mma_kernel.cuh -- fast path v3: quad layout + FP64 TENSOR-CORE products (DMMA.8x8x4).
+//
+// Same decomposition as dist_kernel.cuh (four lanes per scenario, eight scenarios per warp, the
+// Cholesky factor register resident and rows cyclic over the quad), but every product with a
+// SHARED controller matrix runs on the FP64 tensor pipe:
+//
+//      out^T[scenario][row] += vec^T[scenario][k] * M^T[k][row]        mma.sync.m8n8k4.f64
+//
+//   A fragment (8x4)  : lane (q,g) holds element g of k-tile t of scenario q's vector -- exactly
+//                       the quad distribution, so per-scenario vectors are used where they live;
+//   B fragment (4x8)  : lane (q,g) holds M[row 8T+q][k-tile t, element g] -- one LDS.64 per lane
+//                       per MMA from the constant block staged once per CTA (256 contiguous bytes
+//                       per warp: conflict free);
+//   C/D fragment (8x8): lane (q,g) receives rows 8T+2g and 8T+2g+1 of scenario q.
+// An output fragment pair (T,h) is used directly as k-tile 2T+h of the next product: the constant
+// tiles are permuted on the host so that chained products need no data movement at all, and the
+// QP variables are eliminated in the permuted order the gradient product delivers them in
+// (slot s = 2T+h, lane g <-> variable 8T+2g+h), so the factorisation consumes the fragments as is.
+//
+// Per step and per warp (8 scenarios) this is ~160 DMMA + ~160 LDS.64 instead of ~2000 DFMA +
+// ~1300 LDS.128 for the same products (profiles/r01_v2_quad_kernel_ncu_summary.md: the v2 kernel
+// was bound by shared-memory delivery).  bench_micro/dmma_micro.cu: DMMA reaches 37 TFLOP/s at one
+// warp per SM sub-partition.
+//
+// Reference semantics replaced: the same as step_kernel.cuh.
+#pragma once
+#include <cuda_runtime.h>
+#include <vector>
+#include <functional>
+#include <string.h>
+#include <stdlib.h>
+#include "devplan.h"
+#include "dist_kernel.cuh"
+
+namespace sih {
+
+struct MmaConst {            // offsets in doubles into the packed block
+    int be, bw, w0c, bf, br, bh, bomdu, by, byp, bvn, tau, gamma, bounds, vinq, ell_val, total_d;
+    int ell_col, ell_csr, hj_idx, vin_row, total_i;
+    int ell_w;
+};
+
+template <int NX_, int NU_, int NY_, int ND_, int N_, int M_>
+struct MmaDims {
+    static constexpr int NX = NX_, NU = NU_, NY = NY_, ND = ND_, N = N_, M = M_;
+    static constexpr int NV = N * NU;
+    static constexpr int NYP = N * NY;
+    static constexpr int R = NYP + 2 * NY + ND;
+    static constexpr int RE = R + NY;
+    static constexpr int SV = NV / 4;                  // factorisation slots (NV % 4 == 0 required)
+    static constexpr int TX = (NX + 7) / 8;            // C-layout tiles of x
+    static constexpr int TR = (RE + 7) / 8;            // tiles of the residual stack
+    static constexpr int TV = (NV + 7) / 8;            // tiles of the gradient / dU
+    static constexpr int TY = (NYP + 7) / 8;           // tiles of Y_pred
+    static constexpr int TQ = (NYP + 2 * NY + 7) / 8;  // tiles of the squared-residual stack
+    static constexpr int TC = (NY + 7) / 8;            // tiles of the measured output
+    static constexpr int TM = (M + 7) / 8;             // tiles of the sub-objective values
+    static constexpr int KX = 2 * TX;                  // k-tiles of x
+    static constexpr int KA = (NY + 1 + 3) / 4;        // k-tiles of [ysp ; 1]
+    static constexpr int KP = (M + 3) / 4;             // k-tiles of pesos
+    static constexpr int KH = 1;                       // k-tile [1 ; pesos of <= 3 dense Hessian blocks]
+    static constexpr int KD = (NU + 3) / 4;            // k-tiles of du
+    static constexpr int HPAIRS = SV * (SV + 1);
+    static constexpr int BX = 8 * TX, BV = NV;
+    static constexpr int BRAW = BX + NU + (NU & 1) + BV;
+    static constexpr int BS = BRAW + ((2 - BRAW % 4 + 4) % 4);
+    static constexpr int WARP_DOUBLES = 8 * BS;
+    static_assert(NV % 4 == 0, "N*nu must be a multiple of 4 for the MMA fast path");
+    static_assert(M <= 8 && NY <= 4 && NU <= 4, "shape outside the MMA fast path");
+    // variable held by (slot s, lane g) of the factorisation
+    __host__ __device__ static constexpr int var_of(int s, int g) {
+        return (NV % 8 == 4 && s == SV - 1) ? (NV - 4 + g) : (8 * (s / 2) + 2 * g + (s % 2));
+    }
+};
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, const double a, const double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// c[T][.] += sum_t a[t] (x) B[T][t]     B tile element of this lane: cq[(T*KT + t)*32 + lane]
+template <int NT, int KT>
+__device__ __forceinline__ void mma_block(const double *__restrict__ cq, const double (&a)[KT],
+                                          double (&c)[NT][2], const int lane) {
+#pragma unroll
+    for (int t = 0; t < KT; ++t)
+#pragma unroll
+        for (int T = 0; T < NT; ++T) dmma884(c[T][0], c[T][1], a[t], cq[(T * KT + t) * 32 + lane]);
+}
+
+// host: B tiles of  out(T,n) = sum M[orow(T,n)][icol(t,k)] * in(t,k)   (negative index = padding)
+inline void mma_pack(std::vector<double> &buf, int off, int NT, int KT,
+                     const std::function<int(int, int)> &orow, const std::function<int(int, int)> &icol,
+                     const std::function<double(int, int)> &M) {
+    for (int T = 0; T < NT; ++T)
+        for (int t = 0; t < KT; ++t)
+            for (int lane = 0; lane < 32; ++lane) {
+                const int n = lane >> 2, k = lane & 3;
+                const int r = orow(T, n), c = icol(t, k);
+                buf[off + ((size_t)T * KT + t) * 32 + lane] = (r >= 0 && c >= 0) ? M(r, c) : 0.0;
+            }
+}
+
+template <typename D, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qbuf, const sihmpc_io io,
+                const long long batch, const int n_steps, int *__restrict__ start_step,
+                int *__restrict__ n_handover) {
+    constexpr int NX = D::NX, NU = D::NU, NY = D::NY, M = D::M, NV = D::NV, NYP = D::NYP, R = D::R;
+    constexpr int SV = D::SV, TX = D::TX, TR = D::TR, TV = D::TV, TY = D::TY, TQ = D::TQ, TC = D::TC, TM = D::TM;
+    constexpr int KX = D::KX, KA = D::KA, KP = D::KP, KH = D::KH, KD = D::KD;
+    constexpr int BS = D::BS;
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int g = lane & 3, q = lane >> 2;
+    double *cst = smem;
+    for (int i = threadIdx.x; i < Q.total_d; i += blockDim.x) cst[i] = qbuf[i];
+    int *cint = reinterpret_cast<int *>(cst + Q.total_d);
+    {
+        const int *src = reinterpret_cast<const int *>(qbuf + Q.total_d);
+        for (int i = threadIdx.x; i < Q.total_i; i += blockDim.x) cint[i] = src[i];
+    }
+    __syncthreads();
+    double *wbase = cst + Q.total_d + (((Q.total_i + 3) >> 2) << 1) + (size_t)wib * D::WARP_DOUBLES;
+    double *bx = wbase + q * BS;              // replicated [x (8*TX) ; du (NU)] of this scenario
+    double *bv = bx + D::BX + NU + (NU & 1);  // replicated dU (logical order)
+
+    const long long gq = ((long long)blockIdx.x * WARPS + wib) * 8 + q;
+    const long long nq = (long long)gridDim.x * WARPS * 8;
+    const long long rounds = (batch + nq - 1) / nq;
+    const int nstat = NY + SIHMPC_NSTATS_EXTRA;
+    const bool advance = (io.flags & SIHMPC_F_ADVANCE) != 0;
+    const int W = Q.ell_w;
+    const int mh = P.mh;
+
+    for (long long rd = 0; rd < rounds; ++rd) {
+        const long long s = gq + rd * nq;
+        const bool valid = s < batch;
+        const long long sc = valid ? s : 0;
+        bool alive = valid;
+        // ---- state: x in C-layout registers (rows 8T+2g+h), replicated copy in smem for the plant
+        double xr[TX][2];
+#pragma unroll
+        for (int T = 0; T < TX; ++T)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int r = 8 * T + 2 * g + h;
+                xr[T][h] = (r < NX) ? io.x[sc * NX + r] : 0.0;
+            }
+        double uu[NU], pes[M], ise[2];
+        double st_du2 = 0.0, st_viol = 0.0, st_J = 0.0;
+        int st_or = 0;
+#pragma unroll
+        for (int j = 0; j < NU; ++j) uu[j] = io.u[sc * NU + j];
+#pragma unroll
+        for (int i = 0; i < M; ++i) pes[i] = io.pesos[sc * M + i];
+        ise[0] = ise[1] = 0.0;
+        if (io.stats) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) ise[h] = (2 * g + h < NY) ? io.stats[sc * nstat + 2 * g + h] : 0.0;
+            st_du2 = io.stats[sc * nstat + NY]; st_viol = io.stats[sc * nstat + NY + 1];
+            st_J = io.stats[sc * nstat + NY + 2]; st_or = (int)io.stats[sc * nstat + NY + 3];
+        }
+
+        for (int step = 0; step < n_steps; ++step) {
+            const int kabs = io.k0 + step;
+            double ysp[NY];
+            if (io.ysp_seq) {
+                int seg = 0;
+                for (int a = 1; a < io.n_seg; ++a)
+                    if (io.seg_start[sc * io.n_seg + a] <= kabs) seg = a;
+#pragma unroll
+                for (int i = 0; i < NY; ++i) ysp[i] = io.ysp_seq[(sc * io.n_seg + seg) * NY + i];
+            } else {
+#pragma unroll
+                for (int i = 0; i < NY; ++i) ysp[i] = io.ysp[sc * NY + i];
+            }
+            // A-operand views of the small replicated vectors: element g of [ysp;1], [pesos;1], [1;pw]
+            double aux[KA], apes[KP], ahp[KH];
+#pragma unroll
+            for (int t = 0; t < KA; ++t) {
+                const int e = 4 * t + g;
+                aux[t] = (e < NY) ? sel<NY>(ysp, e) : (e == NY ? 1.0 : 0.0);
+            }
+#pragma unroll
+            for (int t = 0; t < KP; ++t) {
+                const int e = 4 * t + g;
+                apes[t] = (e < M) ? sel<M>(pes, e) : 0.0;
+            }
+#pragma unroll
+            for (int t = 0; t < KH; ++t) {
+                const int e = 4 * t + g;                       // 0 -> 1.0 ; 1+a -> pesos[hj_index[a]]
+                const int a = (e >= 1 && e - 1 < M) ? e - 1 : 0;
+                ahp[t] = (e == 0) ? 1.0 : ((e - 1 < mh) ? sel<M>(pes, cint[Q.hj_idx + a]) : 0.0);
+            }
+            // ---------------- K1: e = Px x + Py ysp + e0 ; omega = Wrow pesos + w0row
+            double er[TR][2], om[TR][2];
+#pragma unroll
+            for (int T = 0; T < TR; ++T) {
+                er[T][0] = er[T][1] = 0.0;
+                const double2 w0 = reinterpret_cast<const double2 *>(cst + Q.w0c)[T * 4 + g];
+                om[T][0] = w0.x; om[T][1] = w0.y;
+            }
+            {
+                double ax[KX + KA];
+#pragma unroll
+                for (int T = 0; T < TX; ++T) { ax[2 * T] = xr[T][0]; ax[2 * T + 1] = xr[T][1]; }
+#pragma unroll
+                for (int t = 0; t < KA; ++t) ax[KX + t] = aux[t];
+                mma_block<TR, KX + KA>(cst + Q.be, ax, er, lane);
+            }
+            mma_block<TR, KP>(cst + Q.bw, apes, om, lane);
+            // ---------------- gradient: fr = -(2 E^T (omega o e)), delivered in factorisation slots
+            double fr[SV];
+            {
+                double at[2 * TR];
+#pragma unroll
+                for (int T = 0; T < TR; ++T) { at[2 * T] = om[T][0] * er[T][0]; at[2 * T + 1] = om[T][1] * er[T][1]; }
+                double fc[TV][2];
+#pragma unroll
+                for (int T = 0; T < TV; ++T) fc[T][0] = fc[T][1] = 0.0;
+                mma_block<TV, 2 * TR>(cst + Q.bf, at, fc, lane);
+#pragma unroll
+                for (int sl = 0; sl < SV; ++sl)
+                    fr[sl] = -((NV % 8 == 4 && sl == SV - 1) ? fc[TV - 1][0] : fc[sl / 2][sl % 2]);
+            }
+            // ---------------- Hessian rows: H = Ht + sum pw_a HJ_a (tensor pipe), + 2 omega_du on the diagonal
+            double L[SV][NV];
+            {
+                double omdu[TV][2];
+#pragma unroll
+                for (int T = 0; T < TV; ++T) omdu[T][0] = omdu[T][1] = 0.0;
+                mma_block<TV, KP>(cst + Q.bomdu, apes, omdu, lane);
+                int pp = 0;
+#pragma unroll
+                for (int t = 0; t < SV; ++t) {
+                    const double o = 2.0 * ((NV % 8 == 4 && t == SV - 1) ? omdu[TV - 1][0] : omdu[t / 2][t % 2]);
+                    const double dlo = (g & 1) ? 0.0 : o, dhi = (g & 1) ? o : 0.0;
+#pragma unroll
+                    for (int jp = 0; jp < (4 * t + 4) / 2; ++jp) {
+                        double h[1][2];
+                        h[0][0] = h[0][1] = 0.0;
+                        mma_block<1, KH>(cst + Q.bh + (size_t)pp * KH * 32, ahp, h, lane);
+                        if (jp == 2 * t || jp == 2 * t + 1) {
+                            const bool mine = (jp - 2 * t) == (g >> 1);
+                            h[0][0] += mine ? dlo : 0.0;
+                            h[0][1] += mine ? dhi : 0.0;
+                        }
+                        L[t][2 * jp] = h[0][0];
+                        L[t][2 * jp + 1] = h[0][1];
+                        ++pp;
+                    }
+                }
+            }
+            // ---------------- K2: factorisation + substitutions (registers, quad shuffles)
+            int notpd = 0;
+            chol_columns<D, 0>(L, fr, g, notpd);
+            back_rows<D, D::NV - 1>(L, fr, g);
+            // replicated dU (logical order) for the bound check, the outputs and the plant
+#pragma unroll
+            for (int sl = 0; sl < SV; ++sl) bv[D::var_of(sl, g)] = fr[sl];
+            __syncwarp();
+            // ---------------- feasibility of the unconstrained optimum
+            double viol = 0.0, viol_abs = 0.0;
+            if (P.has_box) {
+#pragma unroll
+                for (int sl = 0; sl < SV; ++sl) {
+                    const int j = D::var_of(sl, g) % NU;
+                    const double lo = cst[Q.bounds + j], hi = cst[Q.bounds + NU + j];
+                    if (lo > -SIH_INF) { const double a = lo - fr[sl]; viol_abs = fmax(viol_abs, a); viol = fmax(viol, a / (1.0 + fabs(lo))); }
+                    if (hi < SIH_INF) { const double a = fr[sl] - hi; viol_abs = fmax(viol_abs, a); viol = fmax(viol, a / (1.0 + fabs(hi))); }
+                }
+            }
+            if (P.has_cum) {
+                for (int j = g; j < NU; j += 4) {
+                    const double uj = sel<NU>(uu, j);
+                    const double lo = cst[Q.bounds + 2 * NU + j] - uj, hi = cst[Q.bounds + 3 * NU + j] - uj;
+                    double cs = 0.0, cmin = SIH_INF, cmax = -SIH_INF;
+#pragma unroll
+                    for (int k = 0; k < D::N; ++k) { cs += bv[k * NU + j]; cmin = fmin(cmin, cs); cmax = fmax(cmax, cs); }
+                    if (lo > -SIH_INF) { const double a = lo - cmin; viol_abs = fmax(viol_abs, a); viol = fmax(viol, a / (1.0 + fabs(lo))); }
+                    if (hi < SIH_INF) { const double a = cmax - hi; viol_abs = fmax(viol_abs, a); viol = fmax(viol, a / (1.0 + fabs(hi))); }
+                }
+            }
+            viol = quad_max(viol);
+            viol_abs = quad_max(viol_abs);
+            if (alive && (viol > 1e-10 || notpd)) {
+                alive = false;             // hand over to the general kernel from this step on
+                if (g == 0) { start_step[s] = step; atomicAdd(n_handover, 1); }
+#pragma unroll
+                for (int T = 0; T < TX; ++T)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) { const int r = 8 * T + 2 * g + h; if (r < NX) io.x[s * NX + r] = xr[T][h]; }
+                if (g == 0) {
+#pragma unroll
+                    for (int j = 0; j < NU; ++j) io.u[s * NU + j] = uu[j];
+#pragma unroll
+                    for (int i = 0; i < M; ++i) io.pesos[s * M + i] = pes[i];
+                }
+                if (io.stats) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) if (2 * g + h < NY) io.stats[s * nstat + 2 * g + h] = ise[h];
+                    if (g == 0) {
+                        io.stats[s * nstat + NY] = st_du2; io.stats[s * nstat + NY + 1] = st_viol;
+                        io.stats[s * nstat + NY + 2] = st_J; io.stats[s * nstat + NY + 3] = (double)st_or;
+                    }
+                }
+            }
+            // ---------------- K3: r = e + E dU, cost, slacks
+            double syv[3 * NY];
+            double Jval;
+            {
+                mma_block<TR, SV>(cst + Q.br, fr, er, lane);        // er now holds r (rows >= R: xi(N+1))
+                double ja = 0.0;
+#pragma unroll
+                for (int T = 0; T < TR; ++T) { ja = fma(om[T][0], er[T][0] * er[T][0], ja); ja = fma(om[T][1], er[T][1] * er[T][1], ja); }
+                double omdu[TV][2];
+#pragma unroll
+                for (int T = 0; T < TV; ++T) omdu[T][0] = omdu[T][1] = 0.0;
+                mma_block<TV, KP>(cst + Q.bomdu, apes, omdu, lane);
+#pragma unroll
+                for (int sl = 0; sl < SV; ++sl) {
+                    const double o = (NV % 8 == 4 && sl == SV - 1) ? omdu[TV - 1][0] : omdu[sl / 2][sl % 2];
+                    ja = fma(o, fr[sl] * fr[sl], ja);
+                }
+                Jval = quad_sum(ja);
+#pragma unroll
+                for (int i = 0; i < NY; ++i) {
+                    syv[i] = quad_bcast(er[(NYP + i) / 8][(NYP + i) % 2], ((NYP + i) % 8) / 2);
+                    syv[NY + i] = quad_bcast(er[(NYP + NY + i) / 8][(NYP + NY + i) % 2], ((NYP + NY + i) % 8) / 2);
+                    syv[2 * NY + i] = quad_bcast(er[(R + i) / 8][(R + i) % 2], ((R + i) % 8) / 2);
+                }
+            }
+            const bool last_step = (step == n_steps - 1);
+            if (alive) {
+                if (last_step) {
+                    if (io.du) for (int j = g; j < NU; j += 4) io.du[s * NU + j] = bv[j];
+                    if (io.w_opt) {
+                        constexpr int nw = NV + 2 * NY;
+#pragma unroll
+                        for (int sl = 0; sl < SV; ++sl) io.w_opt[s * nw + D::var_of(sl, g)] = fr[sl];
+                        if (g == 0) {
+#pragma unroll
+                            for (int i = 0; i < 2 * NY; ++i) io.w_opt[s * nw + NV + i] = syv[i];
+                        }
+                    }
+                    if (g == 0) {
+                        if (io.J) io.J[s] = Jval;
+                        if (io.status) io.status[s] = 0;
+                        if (io.n_active) io.n_active[s] = 0;
+                    }
+                }
+                if (io.traj_du) for (int j = g; j < NU; j += 4) io.traj_du[((long long)step * batch + s) * NU + j] = bv[j];
+                if (io.traj_J && g == 0) io.traj_J[(long long)step * batch + s] = Jval;
+                if ((io.flags & SIHMPC_F_UPDATE_VIN) && io.vinant && (last_step || !advance)) {
+                    for (int sl = g; sl < P.n_vin; sl += 4) {
+                        const double sn = sel<3 * NY>(syv, 2 * NY + cint[Q.vin_row + sl]);
+                        io.vinant[s * P.n_vin + sl] = cst[Q.vinq + sl] * sn * sn;
+                    }
+                }
+            }
+            if (!advance) continue;
+            // ---------------- advance: plant x+ = [A|B][x;du] (ELL, optional per-scenario values)
+#pragma unroll
+            for (int T = 0; T < TX; ++T) { bx[8 * T + 2 * g] = xr[T][0]; bx[8 * T + 2 * g + 1] = xr[T][1]; }
+            for (int j = g; j < NU; j += 4) bx[D::BX + j] = bv[j];
+            __syncwarp();
+            {
+                const double *pv = io.plant_val ? io.plant_val + (size_t)sc * P.pl_nnz : nullptr;
+#pragma unroll
+                for (int T = 0; T < TX; ++T)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        double a = 0.0;
+                        for (int w = 0; w < W; ++w) {
+                            const int e = ((T * 2 + h) * W + w) * 4 + g;
+                            const int ci = cint[Q.ell_csr + e];
+                            const double val = (pv && ci >= 0) ? pv[ci] : cst[Q.ell_val + e];
+                            a = fma(val, bx[cint[Q.ell_col + e]], a);
+                        }
+                        xr[T][h] = a;
+                    }
+            }
+            double du2 = 0.0;
+            double adu[KD];
+#pragma unroll
+            for (int j = 0; j < NU; ++j) { const double d = bv[j]; uu[j] += d; du2 = fma(d, d, du2); }
+#pragma unroll
+            for (int t = 0; t < KD; ++t) { const int e = 4 * t + g; adu[t] = (e < NU) ? bv[e < NU ? e : 0] : 0.0; }
+            if (io.dist_step && io.dist_step[sc] == kabs) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) if (2 * g + h < NY) xr[0][h] += io.dist[sc * NY + 2 * g + h];
+            }
+            __syncwarp();          // all reads of bx/bv of this step are done
+            // measured output y = C x+ + D du, closed-loop statistics
+            {
+                double ax[KX + KD];
+#pragma unroll
+                for (int T = 0; T < TX; ++T) { ax[2 * T] = xr[T][0]; ax[2 * T + 1] = xr[T][1]; }
+#pragma unroll
+                for (int t = 0; t < KD; ++t) ax[KX + t] = adu[t];
+                double yo[TC][2];
+#pragma unroll
+                for (int T = 0; T < TC; ++T) yo[T][0] = yo[T][1] = 0.0;
+                mma_block<TC, KX + KD>(cst + Q.by, ax, yo, lane);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int i = 2 * g + h;
+                    if (i < NY) {
+                        const double err = yo[0][h] - sel<NY>(ysp, i);
+                        ise[h] = fma(err, err, ise[h]);
+                        if (alive && io.traj_y) io.traj_y[((long long)step * batch + s) * NY + i] = yo[0][h];
+                    }
+                }
+                st_du2 += du2; st_viol = fmax(st_viol, viol_abs); st_J = Jval;
+            }
+            // ---------------- sub-objective values at the new state, weight update
+            if (io.flags & (SIHMPC_F_WEIGHTS_SAT2 | SIHMPC_F_WEIGHTS_SAT1)) {
+                double yp[TY][2];
+#pragma unroll
+                for (int T = 0; T < TY; ++T) yp[T][0] = yp[T][1] = 0.0;
+                {
+                    double ax[KX + SV];
+#pragma unroll
+                    for (int T = 0; T < TX; ++T) { ax[2 * T] = xr[T][0]; ax[2 * T + 1] = xr[T][1]; }
+#pragma unroll
+                    for (int sl = 0; sl < SV; ++sl) ax[KX + sl] = fr[sl];     // shift folded into the constants
+                    mma_block<TY, KX + SV>(cst + Q.byp, ax, yp, lane);
+                }
+                double asq[2 * TQ + SV];
+#pragma unroll
+                for (int T = 0; T < TQ; ++T)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int r = 8 * T + 2 * g + h;
+                        double v;
+                        if (r < NYP) {
+                            const int i = r % NY;
+                            v = (T < TY ? yp[T < TY ? T : 0][h] : 0.0) - sel<NY>(ysp, i) - sel<3 * NY>(syv, i)
+                                - cst[Q.tau + ((T < TY ? T : 0) * 4 + g) * 2 + h] * sel<3 * NY>(syv, 2 * NY + i);
+                        } else if (r < NYP + NY) v = sel<3 * NY>(syv, r - NYP);
+                        else if (r < NYP + 2 * NY) v = sel<3 * NY>(syv, 2 * NY + (r - NYP - NY));
+                        else v = 0.0;
+                        asq[2 * T + h] = v * v;
+                    }
+#pragma unroll
+                for (int sl = 0; sl < SV; ++sl) asq[2 * TQ + sl] = fr[sl] * fr[sl];
+                double vc[TM][2];
+#pragma unroll
+                for (int T = 0; T < TM; ++T) vc[T][0] = vc[T][1] = 0.0;
+                mma_block<TM, 2 * TQ + SV>(cst + Q.bvn, asq, vc, lane);
+                double vn[M];
+#pragma unroll
+                for (int i = 0; i < M; ++i) vn[i] = quad_bcast(vc[i / 8][i % 2], (i % 8) / 2);
+                if (io.flags & SIHMPC_F_WEIGHTS_SAT2) {
+                    double smax = -SIH_INF;
+#pragma unroll
+                    for (int i = 0; i < M; ++i) smax = fmax(smax, vn[i] / cst[Q.gamma + i]);
+#pragma unroll
+                    for (int i = 0; i < M; ++i) {
+                        const double g0 = cst[Q.gamma + i];
+                        const double g1 = fmax(g0, g0 * smax + 1e-6);
+                        pes[i] = io.alfa * pes[i] + (1.0 - io.alfa) * (1.0 / (g1 - vn[i]));
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < M; ++i) {
+                        const double g0 = cst[Q.gamma + i];
+                        pes[i] = 1.0 / (g0 - fmin(fmax(vn[i], 0.0), 0.99 * g0));
+                    }
+                }
+            }
+        }  // steps
+
+        __syncwarp();
+        if (alive && advance) {
+#pragma unroll
+            for (int T = 0; T < TX; ++T)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) { const int r = 8 * T + 2 * g + h; if (r < NX) io.x[s * NX + r] = xr[T][h]; }
+            if (g == 0) {
+#pragma unroll
+                for (int j = 0; j < NU; ++j) io.u[s * NU + j] = uu[j];
+#pragma unroll
+                for (int i = 0; i < M; ++i) io.pesos[s * M + i] = pes[i];
+            }
+            if (io.stats) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) if (2 * g + h < NY) io.stats[s * nstat + 2 * g + h] = ise[h];
+                if (g == 0) {
+                    io.stats[s * nstat + NY] = st_du2; io.stats[s * nstat + NY + 1] = st_viol;
+                    io.stats[s * nstat + NY + 2] = st_J; io.stats[s * nstat + NY + 3] = (double)st_or;
+                }
+            }
+        }
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+struct MmaPlan {
+    int shape;
+    MmaConst qc;
+    double *qbuf;
+    int *start_step;
+    int *n_handover;
+    long long capacity;
+    int blocks_per_sm;
+    size_t smem_bytes;
+};
+
+using DistillationMma = MmaDims<22, 2, 2, 4, 10, 4>;
+constexpr int MMA_WARPS = 4;
+#ifndef SIH_MMA_MINB
+#define SIH_MMA_MINB 2
+#endif
+constexpr int MMA_MINB = SIH_MMA_MINB;
+
+inline int mma_match_shape(const DevPlan &P) {
+    if (P.nx == 22 && P.nu == 2 && P.ny == 2 && P.nd == 4 && P.N == 10 && P.m == 4 && P.ncd == 0 && P.mh <= 3) return 0;
+    return -1;
+}
+
+template <typename D>
+inline void mma_build_constants(const sihmpc_plan_desc *d, MmaConst &qc, std::vector<double> &buf,
+                                std::vector<int> &ibuf) {
+    constexpr int NX = D::NX, NU = D::NU, NY = D::NY, M = D::M, NV = D::NV, R = D::R, RE = D::RE, NYP = D::NYP;
+    constexpr int SV = D::SV;
+    int o = 0;
+    auto take = [&](int n) { int r = o; o += (n + 1) & ~1; return r; };
+    qc.be = take(D::TR * (D::KX + D::KA) * 32);
+    qc.bw = take(D::TR * D::KP * 32);
+    qc.w0c = take(D::TR * 8);
+    qc.bf = take(D::TV * 2 * D::TR * 32);
+    qc.br = take(D::TR * SV * 32);
+    qc.bh = take(D::HPAIRS * D::KH * 32);
+    qc.bomdu = take(D::TV * D::KP * 32);
+    qc.by = take(D::TC * (D::KX + D::KD) * 32);
+    qc.byp = take(D::TY * (D::KX + SV) * 32);
+    qc.bvn = take(D::TM * (2 * D::TQ + SV) * 32);
+    qc.tau = take(D::TY * 8);
+    qc.gamma = take(M);
+    qc.bounds = take(4 * NU);
+    qc.vinq = take(d->n_vin > 0 ? d->n_vin : 1);
+    int W = 1;
+    for (int i = 0; i < NX; ++i) { int n = d->pl_rowptr[i + 1] - d->pl_rowptr[i]; if (n > W) W = n; }
+    qc.ell_w = W;
+    qc.ell_val = take(D::TX * 2 * W * 4);
+    qc.total_d = o;
+    buf.assign(o, 0.0);
+
+    // index maps
+    auto crow = [](int lim) { return [lim](int T, int n) { int r = 8 * T + n; return r < lim ? r : -1; }; };
+    auto ccol = [](int lim) { return [lim](int t, int k) { int r = 8 * (t / 2) + 2 * k + (t % 2); return r < lim ? r : -1; }; };
+    auto vcol = [](int t, int k) { return (t < SV) ? D::var_of(t, k) : -1; };              // dU in factorisation slots
+    auto vrow = [](int T, int n) {                                                            // gradient tiles -> slots
+        if (NV % 8 == 4 && T == D::TV - 1) return (n % 2 == 0) ? (NV - 4 + n / 2) : -1;
+        int r = 8 * T + n; return r < NV ? r : -1;
+    };
+    // e = [Px | Py | e0] [x ; ysp ; 1], rows R.. = xi(N+1) map (Mi1x)
+    mma_pack(buf, qc.be, D::TR, D::KX + D::KA, crow(RE),
+             [&](int t, int k) { if (t < D::KX) { int c = 8 * (t / 2) + 2 * k + (t % 2); return c < NX ? c : -1; }
+                                 int e = 4 * (t - D::KX) + k; return e <= NY ? NX + e : -1; },
+             [&](int r, int c) {
+                 if (c < NX) return r < R ? d->Px[(size_t)r * NX + c] : d->Mi1x[(size_t)(r - R) * NX + c];
+                 if (c < NX + NY) return r < R ? d->Py[(size_t)r * NY + (c - NX)] : 0.0;
+                 return r < R ? d->e0[r] : 0.0; });
+    // omega = [Wrow | w0row] [pesos ; 1]
+    mma_pack(buf, qc.bw, D::TR, D::KP, crow(R),
+             [&](int t, int k) { int e = 4 * t + k; return e < M ? e : -1; },
+             [&](int r, int c) { return d->Wrow[(size_t)r * M + c]; });
+    for (int T = 0; T < D::TR; ++T)
+        for (int g = 0; g < 4; ++g)
+            for (int h = 0; h < 2; ++h) { int r = 8 * T + 2 * g + h; if (r < R) buf[qc.w0c + (T * 4 + g) * 2 + h] = d->w0row[r]; }
+    // f = 2 E^T t : out = variables (slot order), in = residual rows (C-layout)
+    mma_pack(buf, qc.bf, D::TV, 2 * D::TR, vrow, ccol(R),
+             [&](int v, int r) { return 2.0 * d->E[(size_t)r * NV + v]; });
+    // r += E_ext dU
+    mma_pack(buf, qc.br, D::TR, SV, crow(RE), vcol,
+             [&](int r, int v) { return r < R ? d->E[(size_t)r * NV + v] : d->Mi1u[(size_t)(r - R) * NV + v]; });
+    // omega_du = Wdu pesos  (delivered in factorisation slots)
+    mma_pack(buf, qc.bomdu, D::TV, D::KP, vrow,
+             [&](int t, int k) { int e = 4 * t + k; return e < M ? e : -1; },
+             [&](int v, int c) { return d->Wdu[(size_t)v * M + c]; });
+    // Hessian pairs: tile pp row n=2g'+h <-> L[t][2jp+h] of lane g' ; in = [1 ; pw_a]
+    {
+        int pp = 0;
+        for (int t = 0; t < SV; ++t)
+            for (int jp = 0; jp < (4 * t + 4) / 2; ++jp, ++pp) {
+                mma_pack(buf, qc.bh + pp * D::KH * 32, 1, D::KH,
+                         [&](int, int n) { return n; },
+                         [&](int tt, int k) { int e = 4 * tt + k; return e <= d->mh ? e : -1; },
+                         [&](int n, int e) {
+                             const int gq = n / 2, h = n % 2;
+                             const int prow = 4 * t + gq, pcol = 2 * jp + h;      // positions in elimination order
+                             if (pcol > prow) return 0.0;
+                             const int vi = D::var_of(prow / 4, prow % 4), vj = D::var_of(pcol / 4, pcol % 4);
+                             return e == 0 ? d->Ht[(size_t)vi * NV + vj] : d->HJ[((size_t)(e - 1) * NV + vi) * NV + vj]; });
+            }
+    }
+    // y = [C | D] [x+ ; du]
+    mma_pack(buf, qc.by, D::TC, D::KX + D::KD, crow(NY),
+             [&](int t, int k) { if (t < D::KX) { int c = 8 * (t / 2) + 2 * k + (t % 2); return c < NX ? c : -1; }
+                                 int e = 4 * (t - D::KX) + k; return e < NU ? NX + e : -1; },
+             [&](int r, int c) { return c < NX ? d->C[(size_t)r * NX + c] : d->D[(size_t)r * NU + (c - NX)]; });
+    // Y' = Myx x+ + Myu shift(dU): column v of the shifted map is Myu[:, v - NU]
+    mma_pack(buf, qc.byp, D::TY, D::KX + SV, crow(NYP),
+             [&](int t, int k) { if (t < D::KX) { int c = 8 * (t / 2) + 2 * k + (t % 2); return c < NX ? c : -1; }
+                                 return NX + D::var_of(t - D::KX, k); },
+             [&](int r, int c) { if (c < NX) return d->Myx[(size_t)r * NX + c];
+                                 int v = c - NX; return v >= NU ? d->Myu[(size_t)r * NV + (v - NU)] : 0.0; });
+    // V_i = sum_r Wrow[r][i] sq_r + sum_v Wdu[v-NU][i] dU_v^2
+    mma_pack(buf, qc.bvn, D::TM, 2 * D::TQ + SV, crow(M),
+             [&](int t, int k) { if (t < 2 * D::TQ) { int r = 8 * (t / 2) + 2 * k + (t % 2); return r < NYP + 2 * NY ? r : -1; }
+                                 return 1000 + D::var_of(t - 2 * D::TQ, k); },
+             [&](int i, int c) { if (c < 1000) return d->Wrow[(size_t)c * M + i];
+                                 int v = c - 1000; return v >= NU ? d->Wdu[(size_t)(v - NU) * M + i] : 0.0; });
+    for (int T = 0; T < D::TY; ++T)
+        for (int g = 0; g < 4; ++g)
+            for (int h = 0; h < 2; ++h) { int r = 8 * T + 2 * g + h; if (r < NYP) buf[qc.tau + (T * 4 + g) * 2 + h] = d->tau[r / NY]; }
+    for (int i = 0; i < M; ++i) buf[qc.gamma + i] = d->gamma[i];
+    for (int j = 0; j < NU; ++j) {
+        buf[qc.bounds + j] = d->dulb[j]; buf[qc.bounds + NU + j] = d->duub[j];
+        buf[qc.bounds + 2 * NU + j] = d->ulb[j]; buf[qc.bounds + 3 * NU + j] = d->uub[j];
+    }
+    for (int sIdx = 0; sIdx < d->n_vin; ++sIdx) buf[qc.vinq + sIdx] = d->vin_q[sIdx];
+    int io_ = 0;
+    auto takei = [&](int n) { int r = io_; io_ += n; return r; };
+    qc.ell_col = takei(D::TX * 2 * W * 4);
+    qc.ell_csr = takei(D::TX * 2 * W * 4);
+    qc.hj_idx = takei(M);
+    qc.vin_row = takei(d->n_vin > 0 ? d->n_vin : 1);
+    qc.total_i = io_;
+    ibuf.assign(io_, 0);
+    for (int T = 0; T < D::TX; ++T)
+        for (int h = 0; h < 2; ++h)
+            for (int g = 0; g < 4; ++g) {
+                const int i = 8 * T + 2 * g + h;
+                for (int w = 0; w < W; ++w) {
+                    const int e = ((T * 2 + h) * W + w) * 4 + g;
+                    ibuf[qc.ell_csr + e] = -1; ibuf[qc.ell_col + e] = 0;
+                    if (i < NX) {
+                        const int p = d->pl_rowptr[i] + w;
+                        if (p < d->pl_rowptr[i + 1]) {
+                            const int c = d->pl_col[p];
+                            ibuf[qc.ell_csr + e] = p;
+                            ibuf[qc.ell_col + e] = (c < NX) ? c : D::BX + (c - NX);     // du sits after x in the buffer
+                            buf[qc.ell_val + e] = d->pl_val[p];
+                        }
+                    }
+                }
+            }
+    for (int a = 0; a < d->mh; ++a) ibuf[qc.hj_idx + a] = d->hj_index[a];
+    for (int sIdx = 0; sIdx < d->n_vin; ++sIdx) ibuf[qc.vin_row + sIdx] = d->vin_row[sIdx] - (NYP + NY);
+}
+
+template <typename D>
+inline size_t mma_smem_bytes(const MmaConst &qc) {
+    return ((size_t)qc.total_d + (((qc.total_i + 3) >> 2) << 1) + (size_t)MMA_WARPS * D::WARP_DOUBLES) * sizeof(double);
+}
+
+inline cudaError_t mma_configure(const sihmpc_plan_desc *d, const DevPlan &P, MmaPlan *qp) {
+    memset(qp, 0, sizeof *qp);
+    qp->shape = mma_match_shape(P);
+    if (qp->shape < 0) return cudaSuccess;
+    using D = DistillationMma;
+    std::vector<double> buf; std::vector<int> ibuf;
+    mma_build_constants<D>(d, qp->qc, buf, ibuf);
+    const size_t nd = buf.size(), ni = ibuf.size();
+    std::vector<double> all(nd + ((ni + 1) >> 1), 0.0);
+    memcpy(all.data(), buf.data(), nd * sizeof(double));
+    memcpy(all.data() + nd, ibuf.data(), ni * sizeof(int));
+    cudaError_t e = cudaMalloc(&qp->qbuf, all.size() * sizeof(double));
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpy(qp->qbuf, all.data(), all.size() * sizeof(double), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return e;
+    e = cudaMalloc(&qp->n_handover, sizeof(int));
+    if (e != cudaSuccess) return e;
+    qp->smem_bytes = mma_smem_bytes<D>(qp->qc);
+    if (qp->smem_bytes > 227 * 1024) { qp->shape = -1; return cudaSuccess; }
+    auto kern = mma_step_kernel<D, MMA_WARPS, MMA_MINB>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qp->smem_bytes);
+    if (e != cudaSuccess) return e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, MMA_WARPS * 32, qp->smem_bytes);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) { qp->shape = -1; return cudaSuccess; }
+    qp->blocks_per_sm = occ;
+    return cudaSuccess;
+}
+
+inline cudaError_t mma_ensure_capacity(MmaPlan *qp, long long batch) {
+    if (qp->capacity >= batch) return cudaSuccess;
+    if (qp->start_step) cudaFree(qp->start_step);
+    qp->start_step = nullptr; qp->capacity = 0;
+    cudaError_t e = cudaMalloc(&qp->start_step, (size_t)batch * sizeof(int));
+    if (e == cudaSuccess) qp->capacity = batch;
+    return e;
+}
+
+inline cudaError_t mma_launch(const MmaPlan &qp, const DevPlan &P, const sihmpc_io &io, long long batch,
+                              int n_steps, int sm_count, cudaStream_t st) {
+    using D = DistillationMma;
+    const long long per_block = MMA_WARPS * 8;
+    long long need = (batch + per_block - 1) / per_block;
+    const long long cap = (long long)sm_count * qp.blocks_per_sm;
+    int grid = (int)(need < cap ? need : cap);
+    if (const char *gv = getenv("SIHMPC_QUAD_GRID")) { int gg = atoi(gv); if (gg > 0 && gg < grid) grid = gg; }
+    cudaError_t e = cudaMemsetAsync(qp.n_handover, 0, sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    mma_step_kernel<D, MMA_WARPS, MMA_MINB><<<grid, MMA_WARPS * 32, qp.smem_bytes, st>>>(
+        P, qp.qc, qp.qbuf, io, batch, n_steps, qp.start_step, qp.n_handover);
+    return cudaGetLastError();
+}
+
+inline void mma_destroy(MmaPlan *qp) {
+    if (qp->qbuf) cudaFree(qp->qbuf);
+    if (qp->start_step) cudaFree(qp->start_step);
+    if (qp->n_handover) cudaFree(qp->n_handover);
+    memset(qp, 0, sizeof *qp);
+    qp->shape = -1;
+}
+
+}  // namespace sih
