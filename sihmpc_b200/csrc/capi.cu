@@ -51,6 +51,11 @@ struct sihmpc_plan {
     sih::MmaPlan mma;        // register-tiled + FP64 tensor-core fast path v3 (mma_kernel.cuh), shape<0: none
     int use_fast;            // 0: general kernel only, 1: quad, 2: mma (default; SIHMPC_NO_FAST=1 / SIHMPC_FAST=quad for A/B)
     std::vector<void *> allocs;
+    // host-buffer entry point: copy streams + events for the chunked pipeline, pinned pack buffer
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    std::vector<cudaEvent_t> events;
+    void *h_stage = nullptr;
+    size_t h_stage_bytes = 0;
     // host copies needed by the host-buffer entry point
     int nw;
 };
@@ -159,6 +164,10 @@ int sihmpc_plan_destroy(sihmpc_plan *plan) {
     for (void *q : plan->allocs) cudaFree(q);
     sih::quad_destroy(&plan->quad);
     sih::mma_destroy(&plan->mma);
+    for (cudaEvent_t e : plan->events) cudaEventDestroy(e);
+    if (plan->s_h2d) cudaStreamDestroy(plan->s_h2d);
+    if (plan->s_d2h) cudaStreamDestroy(plan->s_d2h);
+    if (plan->h_stage) cudaFreeHost(plan->h_stage);
     delete plan;
     return 0;
 }
@@ -292,7 +301,7 @@ int sihmpc_step(sihmpc_plan *plan, const sihmpc_io *io, int64_t batch, int32_t n
     const int *start_step = nullptr, *n_handover = nullptr;
     if (plan->use_fast == 2 && plan->mma.shape >= 0) {
         cudaError_t e = sih::mma_ensure_capacity(&plan->mma, batch);
-        if (e == cudaSuccess) e = cudaMemsetAsync(plan->mma.start_step, 0x7f, (size_t)batch * sizeof(int), st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(plan->mma.n_handover, 0x7f, (size_t)(batch + 1) * sizeof(int), st);
         if (e == cudaSuccess) e = sih::mma_launch(plan->mma, plan->d, *io, batch, n_steps, plan->sm_count, st);
         if (e != cudaSuccess) return fail(SIHMPC_E_CUDA, "tensor fast-path launch failed: %s", cudaGetErrorString(e));
         if (!(plan->d.has_box || plan->d.has_cum)) return 0;      // nothing can be handed over
@@ -300,7 +309,7 @@ int sihmpc_step(sihmpc_plan *plan, const sihmpc_io *io, int64_t batch, int32_t n
         n_handover = plan->mma.n_handover;
     } else if (plan->use_fast && sih::quad_supported(plan->quad, *io)) {
         cudaError_t e = sih::quad_ensure_capacity(&plan->quad, batch);
-        if (e == cudaSuccess) e = cudaMemsetAsync(plan->quad.start_step, 0x7f, (size_t)batch * sizeof(int), st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(plan->quad.n_handover, 0x7f, (size_t)(batch + 1) * sizeof(int), st);
         if (e == cudaSuccess) e = sih::quad_launch(plan->quad, plan->d, *io, batch, n_steps, plan->sm_count, st);
         if (e != cudaSuccess) return fail(SIHMPC_E_CUDA, "fast-path launch failed: %s", cudaGetErrorString(e));
         if (!(plan->d.has_box || plan->d.has_cum)) return 0;      // nothing can be handed over
@@ -335,6 +344,18 @@ size_t sihmpc_host_staging_bytes(const sihmpc_plan *plan, int64_t batch) {
     return sihmpc_workspace_bytes(plan, batch) + staging_layout(plan, batch, off) + 512;
 }
 
+// Chunk c of the batch: element offsets of every per-scenario array.
+static sihmpc_io slice_io(const sihmpc_io &d, const DevPlan &P, int nw, long long lo) {
+    sihmpc_io r = d;
+    r.x = d.x + lo * P.nx; r.u = d.u + lo * P.nu; r.pesos = d.pesos + lo * P.m;
+    if (d.vinant) r.vinant = d.vinant + lo * P.n_vin;
+    r.ysp = d.ysp + lo * P.ny;
+    r.du = d.du + lo * P.nu; r.J = d.J + lo;
+    if (d.w_opt) r.w_opt = d.w_opt + lo * nw;
+    r.status = d.status + lo; r.n_active = d.n_active + lo;
+    return r;
+}
+
 int sihmpc_step_host(sihmpc_plan *plan, const sihmpc_io *h, int64_t batch, void *workspace,
                      size_t workspace_bytes, void *stream) {
     if (!plan || !h) return fail(SIHMPC_E_INVALID, "NULL argument%s");
@@ -345,14 +366,16 @@ int sihmpc_step_host(sihmpc_plan *plan, const sihmpc_io *h, int64_t batch, void 
     const DevPlan &P = plan->d;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     size_t off[12];
-    staging_layout(plan, batch, off);
+    const size_t stage_bytes = staging_layout(plan, batch, off);
     const size_t wsb = sihmpc_workspace_bytes(plan, batch);
     char *base = reinterpret_cast<char *>((((uintptr_t)workspace + wsb) + 255) & ~(uintptr_t)255);
+    const bool want_vin = (P.n_vin > 0 && h->vinant);
+    const bool adv = (h->flags & SIHMPC_F_ADVANCE) != 0;
     sihmpc_io d = *h;
     d.x = reinterpret_cast<double *>(base + off[0]);
     d.u = reinterpret_cast<double *>(base + off[1]);
     d.pesos = reinterpret_cast<double *>(base + off[2]);
-    d.vinant = (P.n_vin > 0 && h->vinant) ? reinterpret_cast<double *>(base + off[3]) : nullptr;
+    d.vinant = want_vin ? reinterpret_cast<double *>(base + off[3]) : nullptr;
     d.ysp = reinterpret_cast<double *>(base + off[4]);
     d.du = reinterpret_cast<double *>(base + off[5]);
     d.J = reinterpret_cast<double *>(base + off[6]);
@@ -362,26 +385,83 @@ int sihmpc_step_host(sihmpc_plan *plan, const sihmpc_io *h, int64_t batch, void 
     d.ysp_seq = nullptr; d.seg_start = nullptr; d.n_seg = 0;
     d.dist_step = nullptr; d.dist = nullptr; d.plant_val = nullptr;
     d.stats = nullptr; d.traj_du = nullptr; d.traj_J = nullptr; d.traj_y = nullptr;
-    CUDA_TRY(cudaMemcpyAsync(d.x, h->x, (size_t)batch * P.nx * 8, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(d.u, h->u, (size_t)batch * P.nu * 8, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(d.pesos, h->pesos, (size_t)batch * P.m * 8, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(const_cast<double *>(d.ysp), h->ysp, (size_t)batch * P.ny * 8, cudaMemcpyHostToDevice, st));
-    if (d.vinant)
-        CUDA_TRY(cudaMemcpyAsync(d.vinant, h->vinant, (size_t)batch * P.n_vin * 8, cudaMemcpyHostToDevice, st));
-    int rc = sihmpc_step(plan, &d, batch, 1, workspace, wsb, stream);
-    if (rc) return rc;
-    if (h->du) CUDA_TRY(cudaMemcpyAsync(h->du, d.du, (size_t)batch * P.nu * 8, cudaMemcpyDeviceToHost, st));
-    if (h->J) CUDA_TRY(cudaMemcpyAsync(h->J, d.J, (size_t)batch * 8, cudaMemcpyDeviceToHost, st));
-    if (h->w_opt) CUDA_TRY(cudaMemcpyAsync(h->w_opt, d.w_opt, (size_t)batch * plan->nw * 8, cudaMemcpyDeviceToHost, st));
-    if (h->status) CUDA_TRY(cudaMemcpyAsync(h->status, d.status, (size_t)batch * 4, cudaMemcpyDeviceToHost, st));
-    if (h->n_active) CUDA_TRY(cudaMemcpyAsync(h->n_active, d.n_active, (size_t)batch * 4, cudaMemcpyDeviceToHost, st));
-    if (d.vinant && (h->flags & SIHMPC_F_UPDATE_VIN))
-        CUDA_TRY(cudaMemcpyAsync(h->vinant, d.vinant, (size_t)batch * P.n_vin * 8, cudaMemcpyDeviceToHost, st));
-    if (h->flags & SIHMPC_F_ADVANCE) {
-        CUDA_TRY(cudaMemcpyAsync(h->x, d.x, (size_t)batch * P.nx * 8, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(h->u, d.u, (size_t)batch * P.nu * 8, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(h->pesos, d.pesos, (size_t)batch * P.m * 8, cudaMemcpyDeviceToHost, st));
+    const size_t bx = (size_t)P.nx * 8, bu = (size_t)P.nu * 8, bp = (size_t)P.m * 8, bv = (size_t)P.n_vin * 8,
+                 by = (size_t)P.ny * 8, bw = (size_t)plan->nw * 8;
+
+    if (batch <= 512) {
+        // ---- small batch (latency path): pack on the host, ONE upload, ONE download
+        if (plan->h_stage_bytes < stage_bytes) {
+            if (plan->h_stage) cudaFreeHost(plan->h_stage);
+            plan->h_stage = nullptr; plan->h_stage_bytes = 0;
+            CUDA_TRY(cudaHostAlloc(&plan->h_stage, stage_bytes, cudaHostAllocDefault));
+            plan->h_stage_bytes = stage_bytes;
+        }
+        char *hs = static_cast<char *>(plan->h_stage);
+        memcpy(hs + off[0], h->x, batch * bx); memcpy(hs + off[1], h->u, batch * bu);
+        memcpy(hs + off[2], h->pesos, batch * bp); memcpy(hs + off[4], h->ysp, batch * by);
+        if (want_vin) memcpy(hs + off[3], h->vinant, batch * bv);
+        CUDA_TRY(cudaMemcpyAsync(base, hs, off[5], cudaMemcpyHostToDevice, st));
+        int rc = sihmpc_step(plan, &d, batch, 1, workspace, wsb, stream);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(hs, base, stage_bytes, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (h->du) memcpy(h->du, hs + off[5], batch * bu);
+        if (h->J) memcpy(h->J, hs + off[6], batch * 8);
+        if (h->w_opt) memcpy(h->w_opt, hs + off[7], batch * bw);
+        if (h->status) memcpy(h->status, hs + off[8], batch * 4);
+        if (h->n_active) memcpy(h->n_active, hs + off[9], batch * 4);
+        if (want_vin && (h->flags & SIHMPC_F_UPDATE_VIN)) memcpy(h->vinant, hs + off[3], batch * bv);
+        if (adv) { memcpy(h->x, hs + off[0], batch * bx); memcpy(h->u, hs + off[1], batch * bu); memcpy(h->pesos, hs + off[2], batch * bp); }
+        return 0;
     }
+
+    // ---- large batch (throughput path): chunks pipelined over an upload stream, the caller's
+    // stream (all kernels, in order: they share the plan's hand-over buffers) and a download stream
+    const int nchunk = batch >= 32768 ? 8 : (batch >= 4096 ? 4 : 2);
+    if (!plan->s_h2d) CUDA_TRY(cudaStreamCreateWithFlags(&plan->s_h2d, cudaStreamNonBlocking));
+    if (!plan->s_d2h) CUDA_TRY(cudaStreamCreateWithFlags(&plan->s_d2h, cudaStreamNonBlocking));
+    while ((int)plan->events.size() < 2 * nchunk + 2) {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        plan->events.push_back(e);
+    }
+    cudaEvent_t ev_start = plan->events[2 * nchunk], ev_done = plan->events[2 * nchunk + 1];
+    CUDA_TRY(cudaEventRecord(ev_start, st));                 // uploads start after prior work of the caller's stream
+    CUDA_TRY(cudaStreamWaitEvent(plan->s_h2d, ev_start, 0));
+    CUDA_TRY(cudaStreamWaitEvent(plan->s_d2h, ev_start, 0));
+    const long long per = (batch + nchunk - 1) / nchunk;
+    for (int c = 0; c < nchunk; ++c) {
+        const long long lo = (long long)c * per, hi = (lo + per < batch) ? lo + per : batch;
+        if (lo >= hi) break;
+        const size_t n = (size_t)(hi - lo);
+        cudaStream_t su = plan->s_h2d, sd = plan->s_d2h;
+        CUDA_TRY(cudaMemcpyAsync(d.x + lo * P.nx, h->x + lo * P.nx, n * bx, cudaMemcpyHostToDevice, su));
+        CUDA_TRY(cudaMemcpyAsync(d.u + lo * P.nu, h->u + lo * P.nu, n * bu, cudaMemcpyHostToDevice, su));
+        CUDA_TRY(cudaMemcpyAsync(d.pesos + lo * P.m, h->pesos + lo * P.m, n * bp, cudaMemcpyHostToDevice, su));
+        CUDA_TRY(cudaMemcpyAsync(const_cast<double *>(d.ysp) + lo * P.ny, h->ysp + lo * P.ny, n * by, cudaMemcpyHostToDevice, su));
+        if (want_vin) CUDA_TRY(cudaMemcpyAsync(d.vinant + lo * P.n_vin, h->vinant + lo * P.n_vin, n * bv, cudaMemcpyHostToDevice, su));
+        CUDA_TRY(cudaEventRecord(plan->events[2 * c], su));
+        CUDA_TRY(cudaStreamWaitEvent(st, plan->events[2 * c], 0));
+        sihmpc_io dc = slice_io(d, P, plan->nw, lo);
+        int rc = sihmpc_step(plan, &dc, (int64_t)n, 1, workspace, wsb, stream);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(plan->events[2 * c + 1], st));
+        CUDA_TRY(cudaStreamWaitEvent(sd, plan->events[2 * c + 1], 0));
+        if (h->du) CUDA_TRY(cudaMemcpyAsync(h->du + lo * P.nu, d.du + lo * P.nu, n * bu, cudaMemcpyDeviceToHost, sd));
+        if (h->J) CUDA_TRY(cudaMemcpyAsync(h->J + lo, d.J + lo, n * 8, cudaMemcpyDeviceToHost, sd));
+        if (h->w_opt) CUDA_TRY(cudaMemcpyAsync(h->w_opt + lo * plan->nw, d.w_opt + lo * plan->nw, n * bw, cudaMemcpyDeviceToHost, sd));
+        if (h->status) CUDA_TRY(cudaMemcpyAsync(h->status + lo, d.status + lo, n * 4, cudaMemcpyDeviceToHost, sd));
+        if (h->n_active) CUDA_TRY(cudaMemcpyAsync(h->n_active + lo, d.n_active + lo, n * 4, cudaMemcpyDeviceToHost, sd));
+        if (want_vin && (h->flags & SIHMPC_F_UPDATE_VIN))
+            CUDA_TRY(cudaMemcpyAsync(h->vinant + lo * P.n_vin, d.vinant + lo * P.n_vin, n * bv, cudaMemcpyDeviceToHost, sd));
+        if (adv) {
+            CUDA_TRY(cudaMemcpyAsync(h->x + lo * P.nx, d.x + lo * P.nx, n * bx, cudaMemcpyDeviceToHost, sd));
+            CUDA_TRY(cudaMemcpyAsync(h->u + lo * P.nu, d.u + lo * P.nu, n * bu, cudaMemcpyDeviceToHost, sd));
+            CUDA_TRY(cudaMemcpyAsync(h->pesos + lo * P.m, d.pesos + lo * P.m, n * bp, cudaMemcpyDeviceToHost, sd));
+        }
+    }
+    CUDA_TRY(cudaEventRecord(ev_done, plan->s_d2h));
+    CUDA_TRY(cudaStreamWaitEvent(st, ev_done, 0));
     CUDA_TRY(cudaStreamSynchronize(st));
     return 0;
 }

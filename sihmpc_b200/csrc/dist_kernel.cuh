@@ -112,6 +112,21 @@ template <int K> __device__ __forceinline__ double sel(const double (&a)[K], int
     return v;
 }
 
+// 1/sqrt(d) for a positive normal d: MUFU.RSQ64H seed (about 2^-22) + two Newton steps
+// (error ~2^-43 then rounding level).  The library rsqrt() carries a longer dependent chain plus
+// special-case branches; the factorisation's critical path is one of these per column.
+__device__ __forceinline__ double fast_rsqrt(const double d) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    double t = d * y;
+    double e = fma(-t, y, 1.0);
+    y = fma(0.5 * y, e, y);
+    t = d * y;
+    e = fma(-t, y, 1.0);
+    y = fma(0.5 * y, e, y);
+    return y;
+}
+
 // column K of the right-looking factorisation (rows cyclic over the quad), forward substitution fused
 template <typename D, int K>
 __device__ __forceinline__ void chol_columns(double (&L)[D::SV][D::NV], double (&fr)[D::SV], const int g, int &notpd) {
@@ -121,7 +136,7 @@ __device__ __forceinline__ void chol_columns(double (&L)[D::SV][D::NV], double (
         double d = quad_bcast(L[tk][K], gk);
         const double fk = quad_bcast(fr[tk], gk);
         if (!(d > 0.0)) { notpd = 1; d = 1e-300; }
-        const double inv = rsqrt(d);
+        const double inv = fast_rsqrt(d);
         const double yk = fk * inv;
         double lik[SV];
 #pragma unroll
@@ -716,8 +731,6 @@ inline cudaError_t quad_configure(const sihmpc_plan_desc *d, const DevPlan &P, Q
     if (e != cudaSuccess) return e;
     e = cudaMemcpy(qp->qbuf, all.data(), all.size() * sizeof(double), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return e;
-    e = cudaMalloc(&qp->n_handover, sizeof(int));
-    if (e != cudaSuccess) return e;
     qp->smem_bytes = quad_smem_bytes<D>(qp->qc);
     auto kern = quad_step_kernel<D, QUAD_WARPS, QUAD_MINB>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qp->smem_bytes);
@@ -732,10 +745,10 @@ inline cudaError_t quad_configure(const sihmpc_plan_desc *d, const DevPlan &P, Q
 
 inline cudaError_t quad_ensure_capacity(QuadPlan *qp, long long batch) {
     if (qp->capacity >= batch) return cudaSuccess;
-    if (qp->start_step) cudaFree(qp->start_step);
-    qp->start_step = nullptr; qp->capacity = 0;
-    cudaError_t e = cudaMalloc(&qp->start_step, (size_t)batch * sizeof(int));
-    if (e == cudaSuccess) qp->capacity = batch;
+    if (qp->n_handover) cudaFree(qp->n_handover);      // one buffer: [counter | start_step[batch]]
+    qp->n_handover = nullptr; qp->start_step = nullptr; qp->capacity = 0;
+    cudaError_t e = cudaMalloc(&qp->n_handover, (size_t)(batch + 1) * sizeof(int));
+    if (e == cudaSuccess) { qp->start_step = qp->n_handover + 1; qp->capacity = batch; }
     return e;
 }
 
@@ -750,8 +763,6 @@ inline cudaError_t quad_launch(const QuadPlan &qp, const DevPlan &P, const sihmp
     int grid = (int)(need < cap ? need : cap);
     if (const char *gv = getenv("SIHMPC_QUAD_GRID")) { int gg = atoi(gv); if (gg > 0 && gg < grid) grid = gg; }  // debug: force many rounds
     // start_step[] = n_steps (nothing to hand over), counter = 0
-    cudaError_t e = cudaMemsetAsync(qp.n_handover, 0, sizeof(int), st);
-    if (e != cudaSuccess) return e;
     quad_step_kernel<D, QUAD_WARPS, QUAD_MINB><<<grid, QUAD_WARPS * 32, qp.smem_bytes, st>>>(
         P, qp.qc, qp.qbuf, io, batch, n_steps, qp.start_step, qp.n_handover);
     return cudaGetLastError();
@@ -759,7 +770,6 @@ inline cudaError_t quad_launch(const QuadPlan &qp, const DevPlan &P, const sihmp
 
 inline void quad_destroy(QuadPlan *qp) {
     if (qp->qbuf) cudaFree(qp->qbuf);
-    if (qp->start_step) cudaFree(qp->start_step);
     if (qp->n_handover) cudaFree(qp->n_handover);
     memset(qp, 0, sizeof *qp);
     qp->shape = -1;

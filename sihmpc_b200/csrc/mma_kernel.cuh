@@ -64,7 +64,9 @@ struct MmaDims {
     static constexpr int BX = 8 * TX, BV = NV;
     static constexpr int BRAW = BX + NU + (NU & 1) + BV;
     static constexpr int BS = BRAW + ((2 - BRAW % 4 + 4) % 4);
-    static constexpr int WARP_DOUBLES = 8 * BS;
+    static constexpr int WELL = 4;                     // ELL width of the plant map (rows with more non-zeros: no fast path)
+    static constexpr int PV = TX * 2 * WELL * 4;       // staged plant values per scenario
+    static constexpr int WARP_DOUBLES = 8 * BS + 8 * PV;
     static_assert(NV % 4 == 0, "N*nu must be a multiple of 4 for the MMA fast path");
     static_assert(M <= 8 && NY <= 4 && NU <= 4, "shape outside the MMA fast path");
     // variable held by (slot s, lane g) of the factorisation
@@ -82,6 +84,16 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, const double a, 
 template <int NT, int KT>
 __device__ __forceinline__ void mma_block(const double *__restrict__ cq, const double (&a)[KT],
                                           double (&c)[NT][2], const int lane) {
+    if (NT == 1 && KT >= 4) {           // one output tile: two interleaved chains instead of one long one
+        double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+        for (int t = 0; t < KT; ++t) {
+            if (t & 1) dmma884(d0, d1, a[t], cq[t * 32 + lane]);
+            else dmma884(c[0][0], c[0][1], a[t], cq[t * 32 + lane]);
+        }
+        c[0][0] += d0; c[0][1] += d1;
+        return;
+    }
 #pragma unroll
     for (int t = 0; t < KT; ++t)
 #pragma unroll
@@ -124,13 +136,13 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
     double *wbase = cst + Q.total_d + (((Q.total_i + 3) >> 2) << 1) + (size_t)wib * D::WARP_DOUBLES;
     double *bx = wbase + q * BS;              // replicated [x (8*TX) ; du (NU)] of this scenario
     double *bv = bx + D::BX + NU + (NU & 1);  // replicated dU (logical order)
+    double *pval = wbase + 8 * BS + q * D::PV;   // this scenario's plant values in ELL order
 
     const long long gq = ((long long)blockIdx.x * WARPS + wib) * 8 + q;
     const long long nq = (long long)gridDim.x * WARPS * 8;
     const long long rounds = (batch + nq - 1) / nq;
     const int nstat = NY + SIHMPC_NSTATS_EXTRA;
     const bool advance = (io.flags & SIHMPC_F_ADVANCE) != 0;
-    const int W = Q.ell_w;
     const int mh = P.mh;
 
     for (long long rd = 0; rd < rounds; ++rd) {
@@ -138,6 +150,26 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
         const bool valid = s < batch;
         const long long sc = valid ? s : 0;
         bool alive = valid;
+        // ---- plant values of this scenario (nominal or per-scenario), staged once per round
+        __syncwarp();
+        {
+            const double *pv = io.plant_val ? io.plant_val + (size_t)sc * P.pl_nnz : nullptr;
+            for (int e = g; e < D::PV; e += 4) {
+                const int ci = cint[Q.ell_csr + e];
+                pval[e] = (pv && ci >= 0) ? pv[ci] : cst[Q.ell_val + e];
+            }
+        }
+        // ---- set-point schedule and disturbance step in registers (no global loads per step)
+        int seg = 0, next_start = 0x7fffffff, dstep = -1;
+        if (io.ysp_seq) {
+            for (int a = 1; a < io.n_seg; ++a)
+                if (io.seg_start[sc * io.n_seg + a] <= io.k0) seg = a;
+            if (seg + 1 < io.n_seg) next_start = io.seg_start[sc * io.n_seg + seg + 1];
+        }
+        if (io.dist_step) dstep = io.dist_step[sc];
+        double ysp[NY];
+#pragma unroll
+        for (int i = 0; i < NY; ++i) ysp[i] = io.ysp_seq ? io.ysp_seq[(sc * io.n_seg + seg) * NY + i] : io.ysp[sc * NY + i];
         // ---- state: x in C-layout registers (rows 8T+2g+h), replicated copy in smem for the plant
         double xr[TX][2];
 #pragma unroll
@@ -164,16 +196,11 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
 
         for (int step = 0; step < n_steps; ++step) {
             const int kabs = io.k0 + step;
-            double ysp[NY];
-            if (io.ysp_seq) {
-                int seg = 0;
-                for (int a = 1; a < io.n_seg; ++a)
-                    if (io.seg_start[sc * io.n_seg + a] <= kabs) seg = a;
+            if (kabs >= next_start) {                    // rare: the schedule switches segment
+                while (seg + 1 < io.n_seg && io.seg_start[sc * io.n_seg + seg + 1] <= kabs) ++seg;
+                next_start = (seg + 1 < io.n_seg) ? io.seg_start[sc * io.n_seg + seg + 1] : 0x7fffffff;
 #pragma unroll
                 for (int i = 0; i < NY; ++i) ysp[i] = io.ysp_seq[(sc * io.n_seg + seg) * NY + i];
-            } else {
-#pragma unroll
-                for (int i = 0; i < NY; ++i) ysp[i] = io.ysp[sc * NY + i];
             }
             // A-operand views of the small replicated vectors: element g of [ysp;1], [pesos;1], [1;pw]
             double aux[KA], apes[KP], ahp[KH];
@@ -366,19 +393,20 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
             for (int j = g; j < NU; j += 4) bx[D::BX + j] = bv[j];
             __syncwarp();
             {
-                const double *pv = io.plant_val ? io.plant_val + (size_t)sc * P.pl_nnz : nullptr;
+                const int *ecol = cint + Q.ell_col + g;
+                const double *eval = pval + g;
 #pragma unroll
                 for (int T = 0; T < TX; ++T)
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        double a = 0.0;
-                        for (int w = 0; w < W; ++w) {
-                            const int e = ((T * 2 + h) * W + w) * 4 + g;
-                            const int ci = cint[Q.ell_csr + e];
-                            const double val = (pv && ci >= 0) ? pv[ci] : cst[Q.ell_val + e];
-                            a = fma(val, bx[cint[Q.ell_col + e]], a);
+                        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                        for (int w = 0; w < D::WELL; w += 2) {
+                            const int e = ((T * 2 + h) * D::WELL + w) * 4;
+                            a0 = fma(eval[e], bx[ecol[e]], a0);
+                            a1 = fma(eval[e + 4], bx[ecol[e + 4]], a1);
                         }
-                        xr[T][h] = a;
+                        xr[T][h] = a0 + a1;
                     }
             }
             double du2 = 0.0;
@@ -387,7 +415,7 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
             for (int j = 0; j < NU; ++j) { const double d = bv[j]; uu[j] += d; du2 = fma(d, d, du2); }
 #pragma unroll
             for (int t = 0; t < KD; ++t) { const int e = 4 * t + g; adu[t] = (e < NU) ? bv[e < NU ? e : 0] : 0.0; }
-            if (io.dist_step && io.dist_step[sc] == kabs) {
+            if (kabs == dstep) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) if (2 * g + h < NY) xr[0][h] += io.dist[sc * NY + 2 * g + h];
             }
@@ -515,7 +543,9 @@ constexpr int MMA_WARPS = 4;
 #endif
 constexpr int MMA_MINB = SIH_MMA_MINB;
 
-inline int mma_match_shape(const DevPlan &P) {
+inline int mma_match_shape(const DevPlan &P, const sihmpc_plan_desc *d) {
+    for (int i = 0; i < P.nx; ++i)
+        if (d->pl_rowptr[i + 1] - d->pl_rowptr[i] > 4) return -1;      // ELL width of the fast path
     if (P.nx == 22 && P.nu == 2 && P.ny == 2 && P.nd == 4 && P.N == 10 && P.m == 4 && P.ncd == 0 && P.mh <= 3) return 0;
     return -1;
 }
@@ -541,8 +571,7 @@ inline void mma_build_constants(const sihmpc_plan_desc *d, MmaConst &qc, std::ve
     qc.gamma = take(M);
     qc.bounds = take(4 * NU);
     qc.vinq = take(d->n_vin > 0 ? d->n_vin : 1);
-    int W = 1;
-    for (int i = 0; i < NX; ++i) { int n = d->pl_rowptr[i + 1] - d->pl_rowptr[i]; if (n > W) W = n; }
+    const int W = D::WELL;
     qc.ell_w = W;
     qc.ell_val = take(D::TX * 2 * W * 4);
     qc.total_d = o;
@@ -660,7 +689,7 @@ inline size_t mma_smem_bytes(const MmaConst &qc) {
 
 inline cudaError_t mma_configure(const sihmpc_plan_desc *d, const DevPlan &P, MmaPlan *qp) {
     memset(qp, 0, sizeof *qp);
-    qp->shape = mma_match_shape(P);
+    qp->shape = mma_match_shape(P, d);
     if (qp->shape < 0) return cudaSuccess;
     using D = DistillationMma;
     std::vector<double> buf; std::vector<int> ibuf;
@@ -672,8 +701,6 @@ inline cudaError_t mma_configure(const sihmpc_plan_desc *d, const DevPlan &P, Mm
     cudaError_t e = cudaMalloc(&qp->qbuf, all.size() * sizeof(double));
     if (e != cudaSuccess) return e;
     e = cudaMemcpy(qp->qbuf, all.data(), all.size() * sizeof(double), cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) return e;
-    e = cudaMalloc(&qp->n_handover, sizeof(int));
     if (e != cudaSuccess) return e;
     qp->smem_bytes = mma_smem_bytes<D>(qp->qc);
     if (qp->smem_bytes > 227 * 1024) { qp->shape = -1; return cudaSuccess; }
@@ -690,10 +717,10 @@ inline cudaError_t mma_configure(const sihmpc_plan_desc *d, const DevPlan &P, Mm
 
 inline cudaError_t mma_ensure_capacity(MmaPlan *qp, long long batch) {
     if (qp->capacity >= batch) return cudaSuccess;
-    if (qp->start_step) cudaFree(qp->start_step);
-    qp->start_step = nullptr; qp->capacity = 0;
-    cudaError_t e = cudaMalloc(&qp->start_step, (size_t)batch * sizeof(int));
-    if (e == cudaSuccess) qp->capacity = batch;
+    if (qp->n_handover) cudaFree(qp->n_handover);      // one buffer: [counter | start_step[batch]]
+    qp->n_handover = nullptr; qp->start_step = nullptr; qp->capacity = 0;
+    cudaError_t e = cudaMalloc(&qp->n_handover, (size_t)(batch + 1) * sizeof(int));
+    if (e == cudaSuccess) { qp->start_step = qp->n_handover + 1; qp->capacity = batch; }
     return e;
 }
 
@@ -705,8 +732,6 @@ inline cudaError_t mma_launch(const MmaPlan &qp, const DevPlan &P, const sihmpc_
     const long long cap = (long long)sm_count * qp.blocks_per_sm;
     int grid = (int)(need < cap ? need : cap);
     if (const char *gv = getenv("SIHMPC_QUAD_GRID")) { int gg = atoi(gv); if (gg > 0 && gg < grid) grid = gg; }
-    cudaError_t e = cudaMemsetAsync(qp.n_handover, 0, sizeof(int), st);
-    if (e != cudaSuccess) return e;
     mma_step_kernel<D, MMA_WARPS, MMA_MINB><<<grid, MMA_WARPS * 32, qp.smem_bytes, st>>>(
         P, qp.qc, qp.qbuf, io, batch, n_steps, qp.start_step, qp.n_handover);
     return cudaGetLastError();
@@ -714,7 +739,6 @@ inline cudaError_t mma_launch(const MmaPlan &qp, const DevPlan &P, const sihmpc_
 
 inline void mma_destroy(MmaPlan *qp) {
     if (qp->qbuf) cudaFree(qp->qbuf);
-    if (qp->start_step) cudaFree(qp->start_step);
     if (qp->n_handover) cudaFree(qp->n_handover);
     memset(qp, 0, sizeof *qp);
     qp->shape = -1;

@@ -219,19 +219,20 @@ class HostStepper:
         p = self.plan
         return self.batch * 8 * (p.nx + p.nu + p.m + p.ny + (p.n_vin if p.n_vin else 0))
 
-    def d2h_bytes(self, advance=False):
+    def d2h_bytes(self, advance=False, want_w_opt=True):
         p = self.plan
-        b = self.batch * (8 * (p.nu + 1 + p.nv + 2 * p.ny) + 8) + self.batch * 8 * p.n_vin
+        b = self.batch * (8 * (p.nu + 1 + ((p.nv + 2 * p.ny) if want_w_opt else 0)) + 8) + self.batch * 8 * p.n_vin
         if advance:
             b += self.batch * 8 * (p.nx + p.nu + p.m)
         return b
 
-    def step(self, flags=_capi.F_UPDATE_VIN, alfa=0.0):
+    def step(self, flags=_capi.F_UPDATE_VIN, alfa=0.0, want_w_opt=True):
         io = _capi.IO()
         io.x, io.u, io.pesos = self.x.data_ptr(), self.u.data_ptr(), self.pesos.data_ptr()
         io.vinant = self.vinant.data_ptr() if self.plan.n_vin > 0 else None
         io.ysp = self.ysp.data_ptr()
-        io.du, io.J, io.w_opt = self.du.data_ptr(), self.J.data_ptr(), self.w_opt.data_ptr()
+        io.du, io.J = self.du.data_ptr(), self.J.data_ptr()
+        io.w_opt = self.w_opt.data_ptr() if want_w_opt else None
         io.status, io.n_active = self.status.data_ptr(), self.n_active.data_ptr()
         io.flags = flags
         io.alfa = alfa
