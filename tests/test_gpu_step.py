@@ -253,3 +253,157 @@ def test_fast_path_handover_many_rounds(monkeypatch):
     ref = oracle_closed_loop(sc.declare_distillation, sys_, scen, idx, T, bounds=bounds)
     assert ref["n_active"].max() > 0
     assert np.max(np.abs(du_f[:, idx] - ref["du"])) <= RTOL * np.max(np.abs(ref["du"]))
+
+
+def _siso_integrating():
+    from sihmpc_b200.opom import OPOM, TransferFunction
+    return OPOM([[TransferFunction([1.0], [5.0, 1.0, 0.0], delay=1)]], 1.0)
+
+
+def _declare_siso(cls, s, **bounds):
+    c = cls(s, 6, **(bounds or dict(dulb=[-0.5], duub=[0.5])))
+    c.subObjComposed(y=[0], Q=1, sat=6.0)
+    c.subObj(du=[0], Q=1, sat=1.0)
+    c.subObj(siN=[0], Q=1, addJ=False)
+    c.set_terminal_objective()
+    return c
+
+
+def test_integrating_plant_contraction_rows():
+    """Integrating channel: siN != 0, the (k+1-N) Ts siN term and the contraction row
+    q siN^2 <= ViN_ant (ihmpccontroller.py:174,265-269,581-584) -- dense rows of the general kernel."""
+    s = _siso_integrating()
+    c = _declare_siso(IHMPCController, s)
+    plan = c.compile()
+    assert plan.ncd == 1 and plan.n_vin == 1
+    B, T = 40, 60
+    rng = np.random.default_rng(3)
+    ysp = 1.0 + 0.5 * rng.uniform(-1, 1, size=(B, 1))
+    eng = c.engine(B)
+    eng.set_state(np.zeros((B, s.nx)), np.zeros((B, 1)))
+    eng.set_schedule(ysp[:, None, :], np.zeros((B, 1), dtype=np.int32))
+    tr = eng.run(T, steps_per_launch=7, record=True)
+    du = tr["du"].cpu().numpy(); y = tr["y"].cpu().numpy()
+    assert (eng.stats[:, 1 + 3].cpu().numpy() == 0).all()
+    for idx in (0, 17, 39):
+        orc = _declare_siso(OracleIHMPC, s)
+        from oracle.ihmpc_oracle import closed_loop
+        ref = closed_loop(orc, np.zeros(s.nx), [0.0], lambda k: ysp[idx], T)
+        assert np.max(np.abs(du[:, idx, 0] - ref["du"][:, 0])) <= RTOL * np.max(np.abs(ref["du"])), idx
+        assert np.max(np.abs(y[:, idx, 0] - ref["y"][:, 0])) <= RTOL * max(1.0, np.max(np.abs(ref["y"])))
+        assert abs(ref["y"][-1, 0] - ysp[idx, 0]) < 5e-3
+    vin = eng.vinant.cpu().numpy()
+    assert np.isfinite(vin).all() and (vin >= 0).all()
+
+
+def test_dense_rows_state_and_slack_boxes():
+    """Finite xlb/xub (N*nx rows, ihmpccontroller.py:414-418) and slack boxes (:405-412)."""
+    sys_ = sc.distillation_system()
+    bounds = dict(ulb=[0, 0], xlb=np.r_[95.7, -np.inf * np.ones(21)], xub=np.r_[96.25, np.inf * np.ones(21)],
+                  sylb=[-0.3, -0.3], syub=[0.3, 0.3])
+    c = sc.declare_distillation(IHMPCController, sys_, **bounds)
+    orc = sc.declare_distillation(OracleIHMPC, sys_, **bounds)
+    assert c.compile().ncd == 9 + 2      # the k=0 row of x[0] has a zero normal (dead time >= 1): dropped
+    B = 32
+    rng = np.random.default_rng(11)
+    x, u, ysp, pesos = _random_states(rng, B)
+    ysp[:, 0] = 96.0 + rng.uniform(-0.45, 0.45, size=B)
+    ysp[B - 1, 0] = 96.7          # |syN| <= 0.3 and xs(N) <= 96.25 cannot both hold: infeasible rows
+    eng = c.engine(B)
+    eng.set_state(x, u, pesos)
+    eng.solve(ysp)
+    w = eng.w_opt.cpu().numpy(); J = eng.J.cpu().numpy(); na = eng.n_active.cpu().numpy()
+    st = eng.status.cpu().numpy()
+    assert (st[:B - 1] == 0).all() and (st[B - 1] & 2)            # SIHMPC_ST_INFEASIBLE, like the oracle
+    with pytest.raises(RuntimeError):
+        orc.mpc(x[B - 1], ysp[B - 1], [], u[B - 1], pesos[B - 1], ViN_ant=[np.inf, np.inf])
+    nact = 0
+    for b in range(B - 1):
+        sol = orc.mpc(x[b], ysp[b], [], u[b], pesos[b], ViN_ant=[np.inf, np.inf])
+        nact += sol["info"]["n_active"] > 0
+        scale = max(np.max(np.abs(sol["w_opt"][:20])), 1e-6)
+        assert np.max(np.abs(w[b, :20] - sol["w_opt"][:20])) <= RTOL * scale, b
+        assert abs(J[b] - sol["J"]) <= RTOL * max(abs(sol["J"]), 1e-9)
+    assert nact > B // 4 and (na > 0).sum() > B // 4
+
+
+@pytest.mark.parametrize("weights,alfa", [("sat1", 0.0), ("fixed", 0.0), ("sat2", 0.5)])
+def test_weight_rules(weights, alfa):
+    """satWeights (ihmpccontroller.py:607-617), fixed weights and the alfa blend of satWeights2 (:634)."""
+    sys_ = sc.distillation_system()
+    c = sc.declare_distillation(IHMPCController, sys_)
+    B, T = 24, 40
+    scen = sc.distillation_scenarios(B)
+    eng = c.engine(B, weights=weights, alfa=alfa)
+    eng.set_state(scen["x0"], scen["u0"])
+    eng.set_schedule(scen["ysp_seq"], scen["seg_start"])
+    tr = eng.run(T, record=True)
+    du = tr["du"].cpu().numpy()
+    idx = 5
+    orc = sc.declare_distillation(OracleIHMPC, sys_)
+    f = schedule_fn(scen["ysp_seq"][idx], scen["seg_start"][idx])
+    x = scen["x0"][idx].copy(); u = scen["u0"][idx].copy(); pesos = orc.init_pesos(); w0 = []
+    for k in range(T):
+        ysp = np.asarray(f(k), float)
+        sol = orc.mpc(x, ysp, w0, u, pesos)
+        d = orc.du.reshape(-1)
+        assert np.max(np.abs(du[k, idx] - d)) <= RTOL * max(np.max(np.abs(d)), 1e-4), (k, weights)
+        r = orc.dynF(x, u, d); x, u = r["xkp1"], r["ukp1"]
+        w0 = orc.warmStart(sol, ysp)
+        if weights == "sat1":
+            pesos = orc.satWeights(x, u, w0, ysp)
+        elif weights == "sat2":
+            orc.pesos = np.asarray(pesos, float)
+            pesos, _ = orc.satWeights2(x, u, w0, ysp, alfa=alfa)
+
+
+@pytest.mark.parametrize("B", [1, 7, 33, 1000])
+def test_odd_batch_sizes_fast_path_equals_general(B, monkeypatch):
+    sys_ = sc.distillation_system()
+    scen = sc.distillation_scenarios(B)
+    outs = []
+    for no_fast in ("0", "1"):
+        monkeypatch.setenv("SIHMPC_NO_FAST", no_fast)
+        c = sc.declare_distillation(IHMPCController, sys_)
+        eng = c.engine(B)
+        eng.set_state(scen["x0"], scen["u0"])
+        eng.set_schedule(scen["ysp_seq"], scen["seg_start"])
+        eng.set_disturbance(scen["dist_step"], scen["dist"])
+        tr = eng.run(30, steps_per_launch=11, record=True)
+        outs.append((tr["du"].cpu().numpy(), tr["J"].cpu().numpy(), eng.x.cpu().numpy(), eng.w_opt.cpu().numpy()))
+    monkeypatch.delenv("SIHMPC_NO_FAST", raising=False)
+    for a, b in zip(outs[0], outs[1]):
+        assert np.max(np.abs(a - b)) <= 1e-9 * max(1.0, np.max(np.abs(b)))
+
+
+def test_host_buffer_entry_point_matches_device_engine():
+    """sihmpc_step_host (small packed path and chunked pipeline) == sihmpc_step on device buffers."""
+    import torch
+    from sihmpc_b200 import _capi
+    from sihmpc_b200.engine import HostStepper
+    sys_ = sc.distillation_system()
+    c = sc.declare_distillation(IHMPCController, sys_)
+    plan = c.compile()
+    fl = _capi.F_ADVANCE | _capi.F_UPDATE_VIN | _capi.F_WEIGHTS_SAT2
+    for B in (3, 5000):
+        scen = sc.distillation_scenarios(B)
+        ysp = np.ascontiguousarray(scen["ysp_seq"][:, 1, :])
+        eng = c.engine(B)
+        eng.set_state(scen["x0"], scen["u0"])
+        eng.ysp.copy_(torch.as_tensor(ysp))
+        hs = HostStepper(plan, B)
+        hs.x.copy_(torch.as_tensor(scen["x0"])); hs.u.copy_(torch.as_tensor(scen["u0"])); hs.ysp.copy_(torch.as_tensor(ysp))
+        for k in range(4):
+            hs.step(flags=fl)
+            io = eng._io(fl, use_schedule=False)
+            import ctypes as C
+            ws, nb = eng.dp.workspace(B)
+            st = torch.cuda.current_stream(eng.device).cuda_stream
+            _capi.check(eng.dp.lib.sihmpc_step(eng.dp.handle, C.byref(io), B, 1, C.c_void_p(ws.data_ptr()), nb,
+                                               C.c_void_p(st)), "sihmpc_step")
+            torch.cuda.synchronize()
+            assert np.array_equal(hs.du.numpy(), eng.du.cpu().numpy())
+            assert np.array_equal(hs.x.numpy(), eng.x.cpu().numpy())
+            assert np.array_equal(hs.pesos.numpy(), eng.pesos.cpu().numpy())
+            assert np.array_equal(hs.J.numpy(), eng.J.cpu().numpy())
+            assert np.array_equal(hs.w_opt.numpy(), eng.w_opt.cpu().numpy())
