@@ -182,6 +182,18 @@ int sihmpc_predict(sihmpc_plan *plan, const double *x, const double *u, const do
 int sihmpc_subobjectives(sihmpc_plan *plan, const double *x, const double *w, const double *ysp,
                          int64_t batch, double *V, void *stream);
 
+/* replaces: IHMPCController.mpc of the LOG-BARRIER variant (sihmpc/ihmpccontroller_log.py:552-563 and the
+ * NLP of :349-461): minimise Vt + ss^2 - sum_i log(ss*gamma_i - V_i) over (dU, ss) by damped Newton.
+ * The plan is compiled from the log controller's declarations (its weighted list VJ defines V_i and
+ * gamma_i; `pesos` are not used).  DEVICE pointers: x [batch][nx], u [batch][nu], ysp [batch][ny],
+ * w0 [batch][nv+2ny+1] warm start or NULL, w_opt [batch][nv+2ny+1] = [dU ; syN ; siN ; ss], J [batch],
+ * status [batch] (SIHMPC_ST_* bits; bit 8 = an explicit inequality of the reference NLP -- ss >= 1,
+ * ss*gamma_i - V_i >= 0.01, input/move boxes -- is active at the minimiser: not supported yet),
+ * iters [batch] Newton iterations.  NULL outputs are skipped.                                      */
+#define SIHMPC_ST_ACTIVE_UNSUPPORTED 8
+int sihmpc_log_step(sihmpc_plan *plan, const double *x, const double *u, const double *ysp, const double *w0,
+                    int64_t batch, double *w_opt, double *J, int32_t *status, int32_t *iters, void *stream);
+
 /* On-device reduction of the per-scenario statistics block to aggregate moments
  * out[3][nstat] = {sum, sum of squares, max} (feeds one NCCL all-reduce). */
 int sihmpc_stats_reduce(const double *stats, int64_t batch, int32_t nstat, double *out,

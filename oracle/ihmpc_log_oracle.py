@@ -1,0 +1,217 @@
+# -*- coding: utf-8 -*-
+"""CPU ORACLE (test infrastructure, NOT product code) -- NumPy FP64 restatement of the
+log-barrier satisficing IHMPC step, /root/reference/sihmpc/ihmpccontroller_log.py.
+
+PARITY UNPINNED (same reasons as oracle/ihmpc_oracle.py: casadi/opom absent, no reference tests).
+
+Problem handed to IPOPT by the reference (log.py:349-461):
+    w = [dU ; syN ; siN ; ss]                                  (log.py:375-392, ss in [1, inf))
+    J = Vt + ss^2 - sum_{i in VJ} log(ss*gamma_i - V_i)        (log.py:71-92,196,219,241,262,292)
+    g = [X_pred ; U_pred ; xi(N)-siN ; xs(N)-ysp-syN ; V_l for all l ; ss*gamma_i - V_i >= 0.01]
+                                                               (log.py:394-440)
+This oracle eliminates the terminal equalities like the weighted one, runs a damped Newton method
+on (dU, ss) for the smooth convex objective and then CHECKS that every explicit inequality
+(ss >= 1, ss*gamma_i - V_i >= 0.01, input/move boxes) is strictly inactive at the minimiser --
+which is the case for the reference's own example (stationary ss = sqrt(m/2)).
+If one is active it raises NotImplementedError instead of returning an approximate point.
+The sub-objective forms, prediction recursion and V ordering come from OracleIHMPC.
+"""
+from __future__ import annotations
+
+import numpy as np
+from scipy.linalg import solve_discrete_lyapunov
+
+from oracle.ihmpc_oracle import OracleIHMPC, QuadForm, INF
+
+
+class OracleIHMPCLog(OracleIHMPC):
+    def __init__(self, sys, N, **kwargs):                        # log.py:11-92
+        super().__init__(sys, N, **kwargs)
+        self.Qt = np.asarray(kwargs.get('Qt', np.eye(sys.ny)), dtype=float)      # log.py:55
+        self.nw = self.N * self.nu + 2 * self.ny + 1              # + ss (log.py:390)
+        self._terminal()
+        self.Vss = QuadForm(np.zeros((1, self.nxi_)), np.zeros(1), 'Vss')
+        self.V = [self.Vt, self.Vss]                              # log.py:83
+        self.VJ = []
+
+    def _terminal(self):                                          # log.py:304-317
+        F, Psi = self.sys.F, self.sys.Psi
+        Q_lyap = F.T @ Psi.T @ self.Qt @ Psi @ F
+        Q_bar = solve_discrete_lyapunov(F, Q_lyap, method='bilinear')           # log.py:314 (F, not F.T)
+        self.Q_bar = Q_bar
+        XdN = self.X_pred[-1][self.nxs:self.nxs + self.nxd]
+        self.Vt = QuadForm(XdN, 0.5 * (Q_bar + Q_bar.T), 'Vt')
+        self.Vt.varType = 'terminal'
+
+    def set_terminal_objective(self):                             # not part of the log surface
+        raise AttributeError("the log controller builds its terminal cost in __init__ (log.py:71-75)")
+
+    def init_Qt(self):                                            # log.py:94-101
+        Qt = []
+        for V in self.VJ:
+            if V.varType == 'y':
+                qd = np.asarray(V.Q, dtype=float)
+                qd = qd.reshape(-1) if qd.ndim == 1 else np.diag(qd)
+                Qt = np.append(Qt, (1.0 / V.gamma) * qd)
+        self.Qt = np.diag(Qt)
+        # the reference only overwrites V[0].V here, not J nor V[0].F (log.py:100-101):
+        # the optimisation problem keeps the terminal cost built in __init__.
+
+    # ---- evaluation: var = [dU ; syN ; siN ; ss]
+    def F(self, V, x, u, w, ysp):
+        w = np.asarray(w, dtype=float).reshape(-1)
+        if V is self.Vss:
+            return float(w[-1] ** 2)
+        return V.value(self._xi(w[:-1], x, u, ysp))
+
+    def _xi(self, w, x, u, ysp):
+        w = np.asarray(w, dtype=float).reshape(-1)
+        if w.size == self.nw:
+            w = w[:-1]
+        saved, self.nw = self.nw, self.nw - 1
+        try:
+            return super()._xi(w, x, u, ysp)
+        finally:
+            self.nw = saved
+
+    def mpc(self, x0, ySP, w0, u0, lam_w0=None, lam_g0=None, ViN_ant=None):      # log.py:552-563
+        if ViN_ant is None:
+            ViN_ant = self.ViNant
+        elif len(ViN_ant) == 0:                                   # casadi: empty argument = zeros
+            ViN_ant = [0.0] * len(self.ViNant)
+        x0 = np.asarray(x0, float).reshape(-1); u0 = np.asarray(u0, float).reshape(-1)
+        ySP = np.asarray(ySP, float).reshape(-1)
+        nv, ny, N, nu = self.N * self.nu, self.ny, self.N, self.nu
+        nwq = nv + 2 * ny
+        # affine maps in dU after eliminating syN = xs(N)-ysp-rs, siN = xi(N)-ri
+        saved, self.nw = self.nw, nwq
+        try:
+            xi0 = OracleIHMPC._xi(self, np.zeros(nwq), x0, u0, ySP)
+        finally:
+            self.nw = saved
+        XN = self.X_pred[-1]
+        XsN = XN[0:self.nxs]; XiN = XN[self.nxs + self.nxd:self.nxs + self.nxd + self.nxi]
+        # w(dU) = T dU + t0
+        T = np.zeros((nwq, nv)); t0 = np.zeros(nwq)
+        T[:nv] = np.eye(nv)
+        T[nv:nv + ny] = XsN[:, :nv]; t0[nv:nv + ny] = XsN @ xi0 - ySP - self.rslb
+        T[nv + ny:] = XiN[:, :nv]; t0[nv + ny:] = XiN @ xi0 - self.rilb
+        for lo, hi in ((self.rslb, self.rsub), (self.rilb, self.riub)):
+            if not np.array_equal(lo, hi):
+                raise NotImplementedError("terminal residual ranges")
+        # contraction rows with ViN_ant = 0 force siN = 0: must hold identically (non-integrating plant)
+        for V in self.V:
+            if V.ViN_slot is not None and np.isfinite(ViN_ant[V.ViN_slot]):
+                k = nv + ny + V.index[0]
+                bound = np.sqrt(max(ViN_ant[V.ViN_slot], 0.0) / float(V.W[0, 0]))
+                if np.linalg.norm(T[k]) > 1e-13 or abs(t0[k]) > bound + 1e-12:
+                    raise NotImplementedError("active siN contraction row in the log variant")
+
+        def quad(V):
+            Rw = V.R[:, :nwq] @ T
+            r0 = V.R[:, :nwq] @ t0 + V.R @ xi0
+            return Rw, r0, V.W
+        terms = [quad(V) for V in self.VJ]
+        gam = np.array([V.gamma for V in self.VJ], dtype=float)
+        Rt, rt0, Wt = quad(self.Vt)
+        m = len(terms)
+
+        def evaluate(v):
+            dU, ss = v[:nv], v[nv]
+            rt = Rt @ dU + rt0
+            Vt = rt @ Wt @ rt
+            Vi = np.empty(m); gi = np.zeros((m, nv + 1)); Hi = []
+            for i, (Rw, r0, W) in enumerate(terms):
+                r = Rw @ dU + r0
+                Vi[i] = r @ W @ r
+                gi[i, :nv] = 2 * Rw.T @ W @ r
+                Hi.append(2 * Rw.T @ W @ Rw)
+            d = ss * gam - Vi
+            return Vt, Vi, d, gi, Hi, rt
+
+        def phi(v):
+            Vt, Vi, d, *_ = evaluate(v)
+            if np.any(d <= 0):
+                return INF
+            return Vt + v[nv] ** 2 - np.sum(np.log(d))
+
+        # start: warm start if given, else zeros with ss large enough
+        w0 = np.asarray(w0, float).reshape(-1)
+        v = np.zeros(nv + 1)
+        if w0.size == nwq + 1:
+            v[:nv] = w0[:nv]; v[nv] = w0[-1]
+        Vt, Vi, d, *_ = evaluate(v)
+        v[nv] = max(v[nv], 1.0, 1.1 * float(np.max(Vi / gam)) + 0.1)
+        iters = 0
+        for iters in range(1, 200):
+            Vt, Vi, d, gi, Hi, rt = evaluate(v)
+            g = np.zeros(nv + 1); H = np.zeros((nv + 1, nv + 1))
+            g[:nv] = 2 * Rt.T @ Wt @ rt
+            H[:nv, :nv] = 2 * Rt.T @ Wt @ Rt
+            g[nv] = 2 * v[nv]; H[nv, nv] = 2.0
+            for i in range(m):
+                a = gi[i].copy(); a[nv] = -gam[i]               # grad of V_i - ss*gamma_i  (= -grad d_i)
+                g += a / d[i]
+                H[:nv, :nv] += Hi[i] / d[i]
+                H += np.outer(a, a) / d[i] ** 2
+            p = -np.linalg.solve(H, g)
+            dec = -g @ p
+            if dec <= 1e-18 * (1.0 + abs(phi(v))):
+                break
+            t = 1.0
+            f0 = phi(v)
+            while phi(v + t * p) > f0 - 1e-4 * t * dec and t > 1e-12:
+                t *= 0.5
+            if t <= 1e-12:
+                break                                          # rounding level reached
+            v = v + t * p
+        Vt, Vi, d, gi, Hi, rt = evaluate(v)
+        dU, ss = v[:nv], v[nv]
+        # explicit inequalities must be strictly inactive
+        u_pred = np.asarray(u0)[None, :] + np.cumsum(dU.reshape(N, nu), axis=0)
+        margin = [ss - 1.0, float(np.min(d - 0.01)),
+                  float(np.min(u_pred - self.ulb)), float(np.min(self.uub - u_pred)),
+                  float(np.min(dU.reshape(N, nu) - self.dulb)), float(np.min(self.duub - dU.reshape(N, nu)))]
+        if min(margin) <= 1e-9:
+            raise NotImplementedError("an explicit inequality is active at the log-variant optimum: %r" % (margin,))
+        w = np.concatenate([T @ dU + t0, [ss]])
+        xi = self._xi(w, x0, u0, ySP)
+        J = float(Vt + ss ** 2 - np.sum(np.log(d)))
+        sol = {
+            'J': J, 'du_opt': dU.reshape(N, nu).T.copy(), 'w_opt': w,
+            'x_pred': np.concatenate([Xk @ xi for Xk in self.X_pred]),
+            'y_pred': np.concatenate([Yk @ xi for Yk in self.Y_pred]),
+            'u_pred': np.concatenate([Uk @ xi for Uk in self.U_pred]),
+            'lam_w': np.zeros(w.size), 'lam_g': np.zeros(0),
+            'info': {'iters': iters, 'margins': margin, 'V': Vi, 'd': d, 'Vt': float(Vt)},
+        }
+        warm = self.warmStart(sol, ySP)
+        for i, V in enumerate(self.F_ViN):
+            self.ViNant[i] = self.F(V, [0] * self.nx, [0] * self.nu, warm, [0] * self.ny)
+        return sol
+
+    def warmStart(self, sol, ysp):                                # log.py:518-549
+        w0 = np.asarray(sol['w_opt']).reshape(-1)
+        ny, nu, nx = self.ny, self.nu, self.nx
+        dustart = np.concatenate([w0[:-2 * ny - 1][nu:], np.zeros(nu)])
+        xN = np.asarray(sol['x_pred']).reshape(-1)[-nx:]
+        Xknext = self.sys.A @ xN
+        siNnext = Xknext[self.nxs + self.nxd:self.nxs + self.nxd + self.nxi]
+        syNnext = w0[-2 * ny - 1:-ny - 1]
+        return np.concatenate([dustart, syNnext, siNnext, [1.0]])       # log.py:548
+
+    def satWeights(self, x, u, w0, ysp):                          # log.py:566-574
+        return np.array([1.0 / (V.gamma - self.F(V, x, u, w0, ysp)) for V in self.VJ])
+
+
+def declare_distillation_log(cls, sys):
+    """example_distillation_log.py:43-61 (init_Qt is referenced without being called there)."""
+    N = 10
+    c = cls(sys, N, ulb=[0, 0])
+    c.subObjComposed(y=[0], Q=1, sat=N * 0.5 ** 2)
+    c.subObjComposed(y=[1], Q=1, sat=N * 2.0 ** 2)
+    c.subObj(du=[0], Q=1, sat=N * 0.3 ** 2)
+    c.subObj(du=[1], Q=1, sat=N * 0.3 ** 2)
+    c.subObj(siN=[0], Q=1, addJ=False)
+    c.subObj(siN=[1], Q=1, addJ=False)
+    return c

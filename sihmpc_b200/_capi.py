@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, "libsihmpc_b200.so")
 
 ABI_VERSION = 1
 F_ADVANCE, F_UPDATE_VIN, F_WEIGHTS_SAT2, F_WEIGHTS_SAT1 = 1, 2, 4, 8
-ST_MAXITER, ST_INFEASIBLE, ST_NOTPD = 1, 2, 4
+ST_MAXITER, ST_INFEASIBLE, ST_NOTPD, ST_ACTIVE_UNSUPPORTED = 1, 2, 4, 8
 NSTATS_EXTRA = 5
 
 _dp = C.POINTER(C.c_double)
@@ -56,7 +56,7 @@ EXPORTS = [
     "sihmpc_abi_version", "sihmpc_last_error", "sihmpc_device_count", "sihmpc_plan_create",
     "sihmpc_plan_destroy", "sihmpc_workspace_bytes", "sihmpc_step", "sihmpc_step_host",
     "sihmpc_host_staging_bytes", "sihmpc_predict", "sihmpc_subobjectives", "sihmpc_stats_reduce",
-    "sihmpc_fp64_peak",
+    "sihmpc_fp64_peak", "sihmpc_log_step",
 ]
 
 _lib = None
@@ -100,6 +100,8 @@ def load():
     lib.sihmpc_subobjectives.restype = C.c_int
     lib.sihmpc_stats_reduce.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
     lib.sihmpc_stats_reduce.restype = C.c_int
+    lib.sihmpc_log_step.argtypes = [C.c_void_p] + [C.c_void_p] * 4 + [C.c_int64] + [C.c_void_p] * 5
+    lib.sihmpc_log_step.restype = C.c_int
     lib.sihmpc_fp64_peak.argtypes = [C.POINTER(C.c_double)]
     lib.sihmpc_fp64_peak.restype = C.c_int
     if lib.sihmpc_abi_version() != ABI_VERSION:

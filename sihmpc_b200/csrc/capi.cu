@@ -13,6 +13,7 @@
 #include "step_kernel.cuh"
 #include "dist_kernel.cuh"
 #include "mma_kernel.cuh"
+#include "log_kernel.cuh"
 
 namespace {
 
@@ -510,6 +511,30 @@ int sihmpc_stats_reduce(const double *stats, int64_t batch, int32_t nstat, doubl
     if (bx > 256) bx = 256;
     dim3 grid((unsigned)bx, (unsigned)nstat);
     sih::stats_reduce_kernel<<<grid, 256, 0, st>>>(stats, batch, nstat, out);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int sihmpc_log_step(sihmpc_plan *plan, const double *x, const double *u, const double *ysp, const double *w0,
+                    int64_t batch, double *w_opt, double *J, int32_t *status, int32_t *iters, void *stream) {
+    if (!plan || !x || !u || !ysp || !w_opt) return fail(SIHMPC_E_INVALID, "NULL argument%s");
+    if (batch <= 0) return batch == 0 ? 0 : fail(SIHMPC_E_INVALID, "negative batch%s");
+    if (plan->d.ncd > 0) return fail(SIHMPC_E_INVALID, "log variant: dense inequality rows are not supported%s");
+    const sih::LogLayout lay = sih::make_log_layout(plan->d);
+    int wpb = 4;
+    while (wpb > 1 && (size_t)lay.total * 8 * wpb > 200 * 1024) --wpb;
+    const size_t smem = (size_t)lay.total * 8 * wpb;
+    if (smem > 220 * 1024) return fail(SIHMPC_E_INVALID, "controller too large for the log kernel%s");
+    long long blocks = (batch + wpb - 1) / wpb;
+    if (blocks > plan->sm_count * 4) blocks = plan->sm_count * 4;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (plan->d.nv + 1 <= 32) {
+        CUDA_TRY(cudaFuncSetAttribute(sih::ihmpc_log_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sih::ihmpc_log_kernel<1><<<(int)blocks, wpb * 32, smem, st>>>(plan->d, x, u, ysp, w0, batch, w_opt, J, status, iters, 100);
+    } else {
+        CUDA_TRY(cudaFuncSetAttribute(sih::ihmpc_log_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sih::ihmpc_log_kernel<2><<<(int)blocks, wpb * 32, smem, st>>>(plan->d, x, u, ysp, w0, batch, w_opt, J, status, iters, 100);
+    }
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

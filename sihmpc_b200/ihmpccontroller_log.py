@@ -1,0 +1,186 @@
+# -*- coding: utf-8 -*-
+"""Drop-in mirror of the reference's LOG-BARRIER satisficing IHMPC controller surface,
+/root/reference/sihmpc/ihmpccontroller_log.py (class IHMPCController, log.py:10), so that the loop of
+/root/reference/example_distillation_log.py:63-135 runs against it.  `mpc()` runs the damped Newton
+kernel of libsihmpc_b200.so (sihmpc_log_step); there is no CPU fallback.
+
+Differences from the weighted class, all taken from the reference:
+  * decision vector w = [dU ; syN ; siN ; ss] with ss >= 1 (log.py:375-392);
+  * J = Vt + ss^2 - sum_i log(ss*gamma_i - V_i)  (log.py:71-92,196,219,241,262,292); V = [Vt, Vss, ...];
+  * `Qt` constructor kwarg, default eye(ny) (log.py:55); `init_Qt()` only recomputes self.Qt -- the
+    reference overwrites V[0].V but neither J nor V[0].F (log.py:94-101), and its own example references
+    `c.init_Qt` without calling it (example_distillation_log.py:61);
+  * mpc(x0, ySP, w0, u0, lam_w0, lam_g0, ViN_ant=None) (log.py:552); `ViN_ant=[]` means zeros (casadi
+    call semantics), i.e. siN = 0;
+  * warmStart appends ss = 1 (log.py:548); satWeights returns the theoretical weights 1/(gamma - V)
+    (log.py:566-574).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+from scipy.linalg import solve_discrete_lyapunov
+
+from .ihmpccontroller import IHMPCController as _Weighted, DM, _vec
+from .plan import SubObjective, compile_plan
+
+__all__ = ["IHMPCController", "DM"]
+
+
+class IHMPCController(_Weighted):
+
+    def __init__(self, sys, N, **kwargs):                      # log.py:11-92
+        super().__init__(sys, N, **kwargs)
+        self.Qt = np.asarray(kwargs.get('Qt', np.eye(sys.ny)), dtype=float)       # log.py:55
+        self.Q_bar = self._terminal_weight()
+        z = np.zeros
+        self.Vt = self.fObj(self, SubObjective('Vt', z(self.ny), z(self.ny), z(self.ny), z(self.nu), terminal=True), None, 'Vt')
+        self.Vss = self.fObj(self, SubObjective('Vss', z(self.ny), z(self.ny), z(self.ny), z(self.nu)), None, 'Vss')
+        self.Vt.weight = 1
+        self.Vss.weight = 1
+        self.V = [self.Vt, self.Vss]                           # log.py:83
+        self.VJ = []
+        self.status = 0
+        self.newton_iters = 0
+
+    def _terminal_weight(self):                                # log.py:304-317 (F, bilinear)
+        F, Psi = np.asarray(self.sys.F, float), np.asarray(self.sys.Psi, float)
+        Q_lyap = F.T @ Psi.T @ self.Qt @ Psi @ F
+        return solve_discrete_lyapunov(F, Q_lyap, method='bilinear')
+
+    def init_Qt(self):                                         # log.py:94-101
+        Qt = []
+        for V in self.VJ:
+            if V.varType == 'y':
+                _, qd = self._qdiag({'Q': V.Q})
+                Qt = np.append(Qt, (1 / V.gamma) * qd)
+        self.Qt = np.diag(Qt)
+        # log.py:100-101 only replaces the *expression* V[0].V; the NLP objective J and V[0].F keep the
+        # terminal cost built in __init__, so the compiled plan does not change either.
+
+    def set_terminal_objective(self):
+        raise AttributeError("the log controller has no set_terminal_objective (terminal cost is built in __init__)")
+
+    def init_pesos(self):
+        raise AttributeError("the log controller has no weights (ihmpccontroller_log.py)")
+
+    def satWeights2(self, *a, **k):
+        raise AttributeError("the log controller has no satWeights2 (ihmpccontroller_log.py)")
+
+    def _new(self, kind, inds, Q, qd, kwargs, prefix):
+        V = super()._new(kind, inds, Q, qd, kwargs, prefix)
+        V.weight = 1                                           # log.py:133
+        return V
+
+    def subObjComposed(self, **kwargs):
+        V = super().subObjComposed(**kwargs)
+        if V is not None:
+            V.weight = 1
+        return V
+
+    # ---- evaluation: var = [dU ; syN ; siN ; ss]
+    def _eval_all(self, x, w, ysp):
+        w = np.asarray(w, dtype=float).reshape(-1)
+        nwq = self.N * self.nu + 2 * self.ny
+        ss = w[nwq] if w.size == nwq + 1 else 0.0
+        vals = super()._eval_all(x, w[:nwq], ysp)
+        vals[self.V.index(self.Vss)] = ss * ss                 # log.py:76-80
+        return vals
+
+    def compile(self):
+        if not self._dirty and self._plan is not None:
+            return self._plan
+        for lo, hi, nm in ((self.rslb, self.rsub, 'rs'), (self.rilb, self.riub, 'ri')):
+            if not np.array_equal(np.asarray(lo, float), np.asarray(hi, float)):
+                raise NotImplementedError("terminal residual ranges (%slb != %sub) are not supported yet" % (nm, nm))
+        if not self.VJ:
+            raise ValueError("no log sub-objective declared")
+        self._plan = compile_plan(self.sys, self.N, [V.coeff for V in self.VJ], self._bounds(),
+                                  Q_bar=self.Q_bar, vin=self._vin,
+                                  rs=np.asarray(self.rslb, float), ri=np.asarray(self.rilb, float))
+        self._eval_plan = None
+        self._stepper = None
+        self._eval_dp = None
+        self._dirty = False
+        return self._plan
+
+    def engine(self, batch, **kw):
+        raise NotImplementedError("batched closed loops exist for the weighted controller only")
+
+    # ---- step (log.py:552-563)
+    def mpc(self, x0, ySP, w0, u0, lam_w0, lam_g0, ViN_ant=None):
+        import torch
+        from . import _capi
+        hs = self._get_stepper()
+        dp = hs.dp
+        nx, nu, ny, N = self.nx, self.nu, self.ny, self.N
+        nv = N * nu
+        nw = nv + 2 * ny + 1
+        if ViN_ant is None:                                    # log.py:554-555
+            ViN_ant = self.ViNant
+        vin = _vec(ViN_ant, len(self.ViNant), "ViN_ant") if len(self.ViNant) else np.zeros(0)
+        if self._plan.ncd > 0 and np.any(np.isfinite(vin)):
+            raise NotImplementedError("siN contraction rows of an integrating plant in the log variant")
+        x = _vec(x0, nx, "x0"); u = _vec(u0, nu, "u0"); ysp = _vec(ySP, ny, "ySP")
+        w0a = np.asarray(w0, dtype=np.float64).reshape(-1)
+        dev = dp.device
+        t = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).reshape(1, -1).to(dev)
+        xd, ud, yd = t(x), t(u), t(ysp)
+        w0d = t(w0a) if w0a.size == nw else None
+        wo = torch.zeros(1, nw, dtype=torch.float64, device=dev)
+        Jd = torch.zeros(1, dtype=torch.float64, device=dev)
+        sd = torch.zeros(1, dtype=torch.int32, device=dev)
+        itd = torch.zeros(1, dtype=torch.int32, device=dev)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            _capi.check(dp.lib.sihmpc_log_step(
+                dp.handle, C.c_void_p(xd.data_ptr()), C.c_void_p(ud.data_ptr()), C.c_void_p(yd.data_ptr()),
+                C.c_void_p(w0d.data_ptr()) if w0d is not None else None, 1, C.c_void_p(wo.data_ptr()),
+                C.c_void_p(Jd.data_ptr()), C.c_void_p(sd.data_ptr()), C.c_void_p(itd.data_ptr()), C.c_void_p(st)),
+                "sihmpc_log_step")
+        w = wo.cpu().numpy().reshape(-1)
+        J = float(Jd.cpu().numpy()[0])
+        self.status = int(sd.cpu().numpy()[0])
+        self.newton_iters = int(itd.cpu().numpy()[0])
+        if self.status & _capi.ST_ACTIVE_UNSUPPORTED:
+            raise NotImplementedError("an explicit inequality of the log NLP (ss >= 1, ss*gamma_i - V_i >= 0.01, "
+                                      "input/move boxes) is active at the minimiser: not supported yet")
+        x_pred, y_pred, u_pred = self._predict(x, u, w[:nv])
+        vals = self._eval_all(x, w, ysp)
+        XN = x_pred[-nx:]
+        res1 = XN[self.nxs + self.nxd:self.nxs + self.nxd + self.nxi] - w[nv + ny:nv + 2 * ny]
+        res2 = XN[:self.nxs] - ysp - w[nv:nv + ny]
+        sat = np.array([w[-1] * V.gamma - vals[self.V.index(V)] for V in self.VJ])
+        gvec = np.concatenate([x_pred, u_pred, res1, res2, vals, sat])           # log.py:394-440
+        sol = {
+            'J': DM(J), 'du_opt': DM(w[:nv].reshape(N, nu).T), 'w_opt': DM(w),
+            'lam_w': DM(np.zeros(w.size)), 'lam_g': DM(np.zeros(gvec.size)), 'g': DM(gvec),
+            'x_pred': DM(x_pred), 'y_pred': DM(y_pred), 'u_pred': DM(u_pred),
+        }
+        if len(self.ViNant):                                   # log.py:558-561
+            warm = self.warmStart(sol, ysp)
+            allv = self._eval_all(np.zeros(nx), warm, np.zeros(ny))
+            k = 0
+            for V in self.V:
+                if V.coeff.vin_slot >= 0:
+                    self.ViNant[V.coeff.vin_slot] = float(allv[self.V.index(V)])
+                    k += 1
+        self.du = sol['du_opt'][:, 0].full()
+        self.j_value = J
+        return sol
+
+    def warmStart(self, sol, ysp):                             # log.py:518-549
+        w0 = np.asarray(sol['w_opt']).reshape(-1)
+        ny, nu, nx = self.ny, self.nu, self.nx
+        dustart = np.concatenate([w0[:-2 * ny - 1][nu:], np.zeros(nu)])
+        xN = np.asarray(sol['x_pred']).reshape(-1)[-nx:]
+        res = self.dynF(x0=xN, u0=np.zeros(nu), du0=np.zeros(nu))
+        Xknext = res['xkp1'].full().reshape(-1)
+        siNnext = Xknext[self.nxs + self.nxd:self.nxs + self.nxd + self.nxi]
+        syNnext = w0[-2 * ny - 1:-ny - 1]
+        return np.concatenate([dustart, syNnext, siNnext, [1.0]])                # log.py:548
+
+    def satWeights(self, x, u, w0, ysp):                       # log.py:566-574
+        vals = self._eval_all(x, w0, ysp)
+        return np.array([1 / (V.gamma - vals[self.V.index(V)]) for V in self.VJ])

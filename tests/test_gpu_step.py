@@ -407,3 +407,42 @@ def test_host_buffer_entry_point_matches_device_engine():
             assert np.array_equal(hs.pesos.numpy(), eng.pesos.cpu().numpy())
             assert np.array_equal(hs.J.numpy(), eng.J.cpu().numpy())
             assert np.array_equal(hs.w_opt.numpy(), eng.w_opt.cpu().numpy())
+
+
+def test_log_variant_example_loop_matches_oracle():
+    """BASELINE configs[1]: the loop of example_distillation_log.py:63-135 on the drop-in log class
+    (sihmpc.ihmpccontroller_log) vs the log oracle; J within 1e-6 relative, du within 1e-6 of scale."""
+    from oracle.ihmpc_log_oracle import OracleIHMPCLog, declare_distillation_log
+    from sihmpc.ihmpccontroller_log import IHMPCController as LogController
+    sys_ = sc.distillation_system()
+    c = declare_distillation_log(LogController, sys_)
+    c.init_Qt                                                    # sic: example_distillation_log.py:61
+    orc = declare_distillation_log(OracleIHMPCLog, sys_)
+    assert [V.name for V in c.V] == [V.name for V in orc.V]
+    u = [1.95, 1.71]; x = np.append([96, 0.5], np.zeros(sys_.nx - 2)); ysp = [96, 0.5]
+    xo, uo = x.copy(), np.array(u)
+    w0 = []; lam_w0 = []; lam_g0 = []; w0o = []
+    scale = 0.0
+    for k in range(40):
+        if k > 5:
+            ysp = [96, 1]
+        if k > 25:
+            ysp = [95.5, 1]
+        sol = c.mpc(x0=x, ySP=ysp, w0=w0, u0=u, lam_w0=lam_w0, lam_g0=lam_g0, ViN_ant=[])
+        solo = orc.mpc(xo, ysp, w0o, uo, [], [], ViN_ant=[])
+        du = sol['du_opt'][:, 0].full()
+        scale = max(scale, np.max(np.abs(solo['du_opt'][:, 0])))
+        assert np.max(np.abs(du.reshape(-1) - solo['du_opt'][:, 0])) <= RTOL * max(scale, 1e-3), k
+        assert abs(float(sol['J']) - solo['J']) <= RTOL * abs(solo['J']), k
+        assert abs(float(sol['w_opt'][-1]) - solo['w_opt'][-1]) <= 1e-7
+        v = [float(V.F(x, u, sol['w_opt'][:], ysp)) for V in c.V]
+        vo = [orc.F(V, xo, uo, solo['w_opt'], ysp) for V in orc.V]
+        assert np.allclose(v, vo, rtol=1e-6, atol=1e-9)
+        res = c.dynF(x0=x, du0=du, u0=u)
+        x = res['xkp1'].full(); u = res['ukp1'].full()
+        r = orc.dynF(xo, uo, solo['du_opt'][:, 0]); xo, uo = r['xkp1'], r['ukp1']
+        w0 = c.warmStart(sol, ysp); w0o = orc.warmStart(solo, ysp)
+        lam_w0 = sol['lam_w']; lam_g0 = sol['lam_g']
+        assert np.allclose(c.satWeights(x, u, w0, ysp), orc.satWeights(xo, uo, w0o, ysp), rtol=1e-6)
+    assert abs(float(sol['w_opt'][-1]) - np.sqrt(2.0)) < 0.05        # ss* ~ sqrt(m/2) near steady state
+    assert len(sol['g'].full()) == 260                                 # SURVEY.md section 8 size table

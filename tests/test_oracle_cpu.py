@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 from scipy.optimize import minimize
 
-from oracle.ihmpc_oracle import OracleIHMPC, solve_qp_exact, closed_loop
+from oracle.ihmpc_oracle import OracleIHMPC, solve_qp_exact, closed_loop  # noqa: F401
 from sihmpc_b200 import scenarios as sc
 from tests.util import oracle_closed_loop
 
@@ -124,3 +124,45 @@ def test_golden_vectors_reproduce(sys_):
     b = oracle_closed_loop(sc.declare_distillation, sys_, scen, 1, 40, bounds=TIGHT)
     assert np.allclose(b["du"], g3["tight_du_1"][:40], rtol=0, atol=1e-12)
     assert g3["tight_nact_1"].max() > 0
+
+
+def test_log_oracle_stationarity_and_crosscheck(sys_):
+    """Log-barrier variant (ihmpccontroller_log.py): the oracle's point is a stationary point of the
+    literal objective Vt + ss^2 - sum log(ss*gamma_i - V_i) evaluated through fObj.F-style calls, an
+    independent scipy minimisation agrees, and at steady state ss* = sqrt(m/2)."""
+    from oracle.ihmpc_log_oracle import OracleIHMPCLog, declare_distillation_log
+    c = declare_distillation_log(OracleIHMPCLog, sys_)
+    assert [V.name for V in c.V][:2] == ['Vt', 'Vss'] and len(c.V) == 12 and len(c.VJ) == 4
+    x = np.append([96, 0.5], np.zeros(20)); u = np.array([1.95, 1.71])
+    sol = c.mpc(x, [96, 0.5], [], u, [], [], ViN_ant=[])
+    assert abs(sol['w_opt'][-1] - np.sqrt(2.0)) < 1e-9 and np.max(np.abs(sol['du_opt'])) < 1e-12
+    rng = np.random.default_rng(2)
+    x2 = x + rng.normal(size=22) * 0.05; x2[6:8] = 0
+    ysp = np.array([96.2, 0.8])
+    sol = c.mpc(x2, ysp, [], u, [], [], ViN_ant=[])
+    w = sol['w_opt']
+    gam = np.array([V.gamma for V in c.VJ])
+
+    def literal(v):                      # objective as written in log.py, slacks from the equalities
+        dU, ss = v[:20], v[20]
+        wq = np.concatenate([dU, np.zeros(4)])
+        xi = OracleIHMPC._xi(c, wq, x2, u, ysp) if False else None
+        XN = c.X_pred[-1]
+        base = np.zeros(c.nxi_); base[:20] = dU
+        base[c.o_x:c.o_x + 22] = x2; base[c.o_u:c.o_u + 2] = u; base[c.o_ysp:c.o_ysp + 2] = ysp; base[c.o_one] = 1
+        syN = XN[0:2] @ base - ysp; siN = XN[6:8] @ base
+        full = np.concatenate([dU, syN, siN, [ss]])
+        Vi = np.array([c.F(V, x2, u, full, ysp) for V in c.VJ])
+        d = ss * gam - Vi
+        if np.any(d <= 0):
+            return np.inf
+        return c.F(c.Vt, x2, u, full, ysp) + ss ** 2 - np.sum(np.log(d))
+
+    v = np.concatenate([w[:20], [w[-1]]])
+    f0 = literal(v)
+    assert abs(f0 - sol['J']) < 1e-10 * max(1.0, abs(f0))
+    g = np.array([(literal(v + 1e-6 * e) - literal(v - 1e-6 * e)) / 2e-6 for e in np.eye(21)])
+    assert np.max(np.abs(g)) < 1e-6
+    r = minimize(literal, v + 0.01 * rng.normal(size=21) * np.r_[np.ones(20) * 0.1, 1.0], method="BFGS",
+                 options=dict(gtol=1e-9, maxiter=2000))
+    assert r.fun >= f0 - 1e-9 and np.max(np.abs(r.x - v)) < 1e-4
