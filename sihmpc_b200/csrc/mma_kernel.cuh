@@ -76,28 +76,41 @@ struct MmaDims {
 };
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, const double a, const double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
 // c[T][.] += sum_t a[t] (x) B[T][t]     B tile element of this lane: cq[(T*KT + t)*32 + lane]
-template <int NT, int KT>
+// The k-tiles are dealt round-robin to NS independent accumulator sets (summed at the end) so that
+// NT*NS MMA chains are in flight: a single chain is bound by the DMMA latency, not by the pipe.
+template <int NT, int KT, int NS_ = 0>
 __device__ __forceinline__ void mma_block(const double *__restrict__ cq, const double (&a)[KT],
                                           double (&c)[NT][2], const int lane) {
-    if (NT == 1 && KT >= 4) {           // one output tile: two interleaved chains instead of one long one
-        double d0 = 0.0, d1 = 0.0;
+    constexpr int WANT = (NS_ > 0) ? NS_ : ((NT >= 8) ? 1 : (8 + NT - 1) / NT);
+    constexpr int NS = (WANT < KT) ? WANT : KT;
+    double p[NS][NT][2];
 #pragma unroll
-        for (int t = 0; t < KT; ++t) {
-            if (t & 1) dmma884(d0, d1, a[t], cq[t * 32 + lane]);
-            else dmma884(c[0][0], c[0][1], a[t], cq[t * 32 + lane]);
-        }
-        c[0][0] += d0; c[0][1] += d1;
-        return;
-    }
+    for (int s = 1; s < NS; ++s)
+#pragma unroll
+        for (int T = 0; T < NT; ++T) p[s][T][0] = p[s][T][1] = 0.0;
+#pragma unroll
+    for (int T = 0; T < NT; ++T) { p[0][T][0] = c[T][0]; p[0][T][1] = c[T][1]; }
+    double bq[KT][NT];
 #pragma unroll
     for (int t = 0; t < KT; ++t)
 #pragma unroll
-        for (int T = 0; T < NT; ++T) dmma884(c[T][0], c[T][1], a[t], cq[(T * KT + t) * 32 + lane]);
+        for (int T = 0; T < NT; ++T) bq[t][T] = cq[(T * KT + t) * 32 + lane];
+#pragma unroll
+    for (int t = 0; t < KT; ++t)
+#pragma unroll
+        for (int T = 0; T < NT; ++T) dmma884(p[t % NS][T][0], p[t % NS][T][1], a[t], bq[t][T]);
+#pragma unroll
+    for (int T = 0; T < NT; ++T) {
+        double s0 = p[0][T][0], s1 = p[0][T][1];
+#pragma unroll
+        for (int s = 1; s < NS; ++s) { s0 += p[s][T][0]; s1 += p[s][T][1]; }
+        c[T][0] = s0; c[T][1] = s1;
+    }
 }
 
 // host: B tiles of  out(T,n) = sum M[orow(T,n)][icol(t,k)] * in(t,k)   (negative index = padding)
@@ -281,8 +294,15 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
             }
             // ---------------- K2: factorisation + substitutions (registers, quad shuffles)
             int notpd = 0;
+#ifndef SIH_EXP_SKIP_CHOL
             chol_columns<D, 0>(L, fr, g, notpd);
+#ifndef SIH_EXP_SKIP_BACK
             back_rows<D, D::NV - 1>(L, fr, g);
+#endif
+#else
+#pragma unroll
+            for (int sl = 0; sl < SV; ++sl) fr[sl] = fr[sl] * 1e-3 + L[sl][0] * 1e-9;
+#endif
             // replicated dU (logical order) for the bound check, the outputs and the plant
 #pragma unroll
             for (int sl = 0; sl < SV; ++sl) bv[D::var_of(sl, g)] = fr[sl];
@@ -311,6 +331,9 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
             }
             viol = quad_max(viol);
             viol_abs = quad_max(viol_abs);
+#if defined(SIH_EXP_SKIP_CHOL) || defined(SIH_EXP_SKIP_BACK) || defined(SIH_EXP_SKIP_K3)
+            viol = 0.0; notpd = 0;         // timing experiments only: garbage moves must not hand over
+#endif
             if (alive && (viol > 1e-10 || notpd)) {
                 alive = false;             // hand over to the general kernel from this step on
                 if (g == 0) { start_step[s] = step; atomicAdd(n_handover, 1); }
@@ -443,6 +466,7 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
                 st_du2 += du2; st_viol = fmax(st_viol, viol_abs); st_J = Jval;
             }
             // ---------------- sub-objective values at the new state, weight update
+#ifndef SIH_EXP_SKIP_WEIGHTS
             if (io.flags & (SIHMPC_F_WEIGHTS_SAT2 | SIHMPC_F_WEIGHTS_SAT1)) {
                 double yp[TY][2];
 #pragma unroll
@@ -498,6 +522,7 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
                     }
                 }
             }
+#endif
         }  // steps
 
         __syncwarp();
