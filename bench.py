@@ -303,6 +303,11 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, ms_kernel = float(t[0]), float(t[1])
     status_or = int(agg[2, plan.ny + 3].item())
+    # scenarios whose loop raised a status bit (e.g. an unstable mismatched plant: 1 of the 1M of configs[4])
+    flagged = (eng.stats[:, plan.ny + 3] != 0).sum().to(torch.float64).reshape(1)
+    if world > 1:
+        dist.all_reduce(flagged, op=dist.ReduceOp.SUM)
+    flagged = int(flagged.item())
     value = world * batch * K / (ms_total * 1e-3)
 
     # ---- end-to-end through the host-buffer C-ABI call (pinned host state, H2D + D2H every step)
@@ -382,7 +387,7 @@ def main():
                              "and written once per launch, everything else stays on chip",
                        "includes": "final on-device statistics reduction" + (" + NCCL all-reduce" if world > 1 else "")},
             "clocks": clocks, "e2e": e2e, "gpu_launches": n_launch + 1, "roofline": roofline,
-            "cpu_baseline": cpu, "latency_batch1": lat, "status_or": status_or,
+            "cpu_baseline": cpu, "latency_batch1": lat, "status_or": status_or, "flagged_scenarios": flagged,
             "fp64_peak_tflops_measured": fp64_peak / 1e12}
     print(json.dumps(line))
     if world > 1:
