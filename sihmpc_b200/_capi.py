@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsihmpc_b200.so")
+LIB_PATH = os.environ.get("SIHMPC_B200_LIB") or os.path.join(HERE, "libsihmpc_b200.so")   # override: A/B builds only
 
 ABI_VERSION = 1
 F_ADVANCE, F_UPDATE_VIN, F_WEIGHTS_SAT2, F_WEIGHTS_SAT1 = 1, 2, 4, 8

@@ -174,6 +174,119 @@ __device__ __forceinline__ void back_rows(double (&L)[D::SV][D::NV], double (&fr
     }
 }
 
+// ---- block LDL^T with 2x2 pivots (default solver of the fast paths) ------------------------------
+// H = L D L^T, D block diagonal (2x2 blocks), L unit block-lower.  Ten sequential rounds instead of
+// twenty, no square roots, and the exchange of the two pivot columns does not depend on the
+// reciprocal of the block determinant, so it overlaps with that chain.  Positive definiteness is
+// checked through the leading minors of every block (a > 0, det > 0).
+// Storage after block B (columns k = 2B, k+1; slot s = B/2, lanes g0 = 2(B%2), g0+1):
+//   rows below the block:  L[t][k] = w1, L[t][k+1] = w2     (W = [p q] D^-1)
+//   pivot rows:            lane g0: L[s][k] = D^-1_11 ; lane g0+1: L[s][k] = D^-1_21, L[s][k+1] = D^-1_22
+__device__ __forceinline__ double fast_rcp(const double d) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    double e = fma(-d, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-d, y, 1.0);
+    y = fma(y, e, y);
+    return y;
+}
+
+template <typename D, int B>
+__device__ __forceinline__ void ldl_blocks(double (&L)[D::SV][D::NV], double (&fr)[D::SV], const int g, int &notpd) {
+    if constexpr (2 * B < D::NV) {
+        constexpr int SV = D::SV, NV = D::NV;
+        constexpr int k = 2 * B, s = B / 2, g0 = 2 * (B % 2);
+        double a = quad_bcast(L[s][k], g0);
+        const double bb = quad_bcast(L[s][k], g0 + 1);
+        const double c = quad_bcast(L[s][k + 1], g0 + 1);
+        const double yk = quad_bcast(fr[s], g0), yk1 = quad_bcast(fr[s], g0 + 1);
+        double det = fma(a, c, -bb * bb);
+        if (!(a > 0.0) || !(det > 0.0)) { notpd = 1; det = 1e300; a = 1.0; }
+        const double idet = fast_rcp(det);
+        const double d11 = c * idet, d21 = -bb * idet, d22 = a * idet;
+        double pq[SV][2], w[SV][2];
+#pragma unroll
+        for (int t = 0; t < SV; ++t) { pq[t][0] = pq[t][1] = 0.0; w[t][0] = w[t][1] = 0.0; }
+#pragma unroll
+        for (int t = s; t < SV; ++t)
+            if (4 * t + 3 > k + 1) {
+                const bool below = (4 * t + g > k + 1);
+                pq[t][0] = below ? L[t][k] : 0.0;
+                pq[t][1] = below ? L[t][k + 1] : 0.0;
+                w[t][0] = fma(pq[t][0], d11, pq[t][1] * d21);
+                w[t][1] = fma(pq[t][0], d21, pq[t][1] * d22);
+            }
+#pragma unroll
+        for (int j = k + 2; j < NV; ++j) {
+            const double pj = quad_bcast(pq[j >> 2][0], j & 3), qj = quad_bcast(pq[j >> 2][1], j & 3);
+#pragma unroll
+            for (int t = (j >> 2); t < SV; ++t) L[t][j] = fma(-w[t][1], qj, fma(-w[t][0], pj, L[t][j]));
+        }
+#pragma unroll
+        for (int t = s; t < SV; ++t)
+            if (4 * t + 3 > k + 1) {
+                fr[t] = fma(-w[t][1], yk1, fma(-w[t][0], yk, fr[t]));
+                if (4 * t + g > k + 1) { L[t][k] = w[t][0]; L[t][k + 1] = w[t][1]; }
+            }
+        if (g == g0) L[s][k] = d11;
+        if (g == g0 + 1) { L[s][k] = d21; L[s][k + 1] = d22; }
+        ldl_blocks<D, B + 1>(L, fr, g, notpd);
+    }
+}
+
+// z' = D^-1 y for both blocks of every slot at once (partners exchange with one xor-shuffle)
+template <typename D>
+__device__ __forceinline__ void ldl_dsolve(double (&L)[D::SV][D::NV], double (&fr)[D::SV], const int g) {
+#pragma unroll
+    for (int s = 0; s < D::SV; ++s) {
+        const bool hi = (g & 2) != 0, odd = (g & 1) != 0;
+        const double Lk = hi ? L[s][4 * s + 2] : L[s][4 * s];
+        const double Lk1 = hi ? L[s][4 * s + 3] : L[s][4 * s + 1];
+        const double py = __shfl_xor_sync(0xffffffffu, fr[s], 1);
+        const double pL = __shfl_xor_sync(0xffffffffu, Lk, 1);
+        // even lane: z' = D11 y + D21 y_partner ; odd lane: z' = D21 y_partner + D22 y
+        fr[s] = odd ? fma(Lk, py, Lk1 * fr[s]) : fma(Lk, fr[s], pL * py);
+    }
+}
+
+// L^T z = z', blocks from last to first
+template <typename D, int B>
+__device__ __forceinline__ void ldl_back(double (&L)[D::SV][D::NV], double (&fr)[D::SV], const int g) {
+    if constexpr (B >= 0) {
+        constexpr int SV = D::SV;
+        constexpr int k = 2 * B, s = B / 2, g0 = 2 * (B % 2);
+        double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+        for (int t = SV - 1; t >= s; --t)
+            if (4 * t + 3 > k + 1) {
+                const bool below = (4 * t + g > k + 1);
+                s1 = fma(below ? L[t][k] : 0.0, fr[t], s1);
+                s2 = fma(below ? L[t][k + 1] : 0.0, fr[t], s2);
+            }
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+        if (g == g0) fr[s] -= s1;
+        if (g == g0 + 1) fr[s] -= s2;
+        ldl_back<D, B - 1>(L, fr, g);
+    }
+}
+
+// fr <- H^{-1} fr   (H in L, lower triangle, rows cyclic over the quad)
+template <typename D>
+__device__ __forceinline__ void quad_solve_spd(double (&L)[D::SV][D::NV], double (&fr)[D::SV], const int g, int &notpd) {
+#ifdef SIH_SOLVER_CHOLESKY
+    chol_columns<D, 0>(L, fr, g, notpd);
+    back_rows<D, D::NV - 1>(L, fr, g);
+#else
+    ldl_blocks<D, 0>(L, fr, g, notpd);
+    ldl_dsolve<D>(L, fr, g);
+    ldl_back<D, D::NV / 2 - 1>(L, fr, g);
+#endif
+}
+
 template <typename D, int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 quad_step_kernel(const DevPlan P, const QuadConst Q, const double *__restrict__ qbuf, const sihmpc_io io,
@@ -316,8 +429,7 @@ quad_step_kernel(const DevPlan P, const QuadConst Q, const double *__restrict__ 
             // backward substitution (compile-time column index: template recursion, so that L
             // never leaves the register file)
             int notpd = 0;
-            chol_columns<D, 0>(L, fr, g, notpd);
-            back_rows<D, D::NV - 1>(L, fr, g);
+            quad_solve_spd<D>(L, fr, g, notpd);
             // all-gather dU
 #pragma unroll
             for (int t = 0; t < SV; ++t)

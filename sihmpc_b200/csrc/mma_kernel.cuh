@@ -294,15 +294,7 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
             }
             // ---------------- K2: factorisation + substitutions (registers, quad shuffles)
             int notpd = 0;
-#ifndef SIH_EXP_SKIP_CHOL
-            chol_columns<D, 0>(L, fr, g, notpd);
-#ifndef SIH_EXP_SKIP_BACK
-            back_rows<D, D::NV - 1>(L, fr, g);
-#endif
-#else
-#pragma unroll
-            for (int sl = 0; sl < SV; ++sl) fr[sl] = fr[sl] * 1e-3 + L[sl][0] * 1e-9;
-#endif
+            quad_solve_spd<D>(L, fr, g, notpd);
             // replicated dU (logical order) for the bound check, the outputs and the plant
 #pragma unroll
             for (int sl = 0; sl < SV; ++sl) bv[D::var_of(sl, g)] = fr[sl];
@@ -331,9 +323,6 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
             }
             viol = quad_max(viol);
             viol_abs = quad_max(viol_abs);
-#if defined(SIH_EXP_SKIP_CHOL) || defined(SIH_EXP_SKIP_BACK) || defined(SIH_EXP_SKIP_K3)
-            viol = 0.0; notpd = 0;         // timing experiments only: garbage moves must not hand over
-#endif
             if (alive && (viol > 1e-10 || notpd)) {
                 alive = false;             // hand over to the general kernel from this step on
                 if (g == 0) { start_step[s] = step; atomicAdd(n_handover, 1); }
@@ -466,7 +455,6 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
                 st_du2 += du2; st_viol = fmax(st_viol, viol_abs); st_J = Jval;
             }
             // ---------------- sub-objective values at the new state, weight update
-#ifndef SIH_EXP_SKIP_WEIGHTS
             if (io.flags & (SIHMPC_F_WEIGHTS_SAT2 | SIHMPC_F_WEIGHTS_SAT1)) {
                 double yp[TY][2];
 #pragma unroll
@@ -522,7 +510,6 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
                     }
                 }
             }
-#endif
         }  // steps
 
         __syncwarp();
