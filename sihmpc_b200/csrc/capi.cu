@@ -13,6 +13,7 @@
 #include "step_kernel.cuh"
 #include "dist_kernel.cuh"
 #include "mma_kernel.cuh"
+#include "tile_kernel.cuh"
 #include "log_kernel.cuh"
 
 namespace {
@@ -50,7 +51,9 @@ struct sihmpc_plan {
     int max_grid;
     sih::QuadPlan quad;      // register-tiled fast path v2 (dist_kernel.cuh), shape<0: none
     sih::MmaPlan mma;        // register-tiled + FP64 tensor-core fast path v3 (mma_kernel.cuh), shape<0: none
-    int use_fast;            // 0: general kernel only, 1: quad, 2: mma (default; SIHMPC_NO_FAST=1 / SIHMPC_FAST=quad for A/B)
+    sih::TilePlan tile;      // CTA-cooperative tile path v4 for mid-size controllers (tile_kernel.cuh), ok=0: none
+    int use_fast;            // 0: general kernel only, 1: quad, 2: mma where it matches, else tile (default), 3: tile
+                             // (SIHMPC_NO_FAST=1 / SIHMPC_FAST=quad|tile for A/B)
     std::vector<void *> allocs;
     // host-buffer entry point: copy streams + events for the chunked pipeline, pinned pack buffer
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
@@ -165,6 +168,7 @@ int sihmpc_plan_destroy(sihmpc_plan *plan) {
     for (void *q : plan->allocs) cudaFree(q);
     sih::quad_destroy(&plan->quad);
     sih::mma_destroy(&plan->mma);
+    sih::tile_destroy(&plan->tile);
     for (cudaEvent_t e : plan->events) cudaEventDestroy(e);
     if (plan->s_h2d) cudaStreamDestroy(plan->s_h2d);
     if (plan->s_d2h) cudaStreamDestroy(plan->s_d2h);
@@ -189,6 +193,7 @@ int sihmpc_plan_create(const sihmpc_plan_desc *d, sihmpc_plan **out) {
     sihmpc_plan *p = new sihmpc_plan();
     p->quad.shape = -1;
     p->mma.shape = -1;
+    memset(&p->tile, 0, sizeof p->tile);
     int rc = 0;
     auto bail = [&](int code) { sihmpc_plan_destroy(p); return code; };
     if (cudaGetDevice(&p->device) != cudaSuccess) return bail(fail(SIHMPC_E_CUDA, "cudaGetDevice failed%s"));
@@ -272,10 +277,13 @@ int sihmpc_plan_create(const sihmpc_plan_desc *d, sihmpc_plan **out) {
         if (qe != cudaSuccess) return bail(fail(SIHMPC_E_CUDA, "fast-path configuration failed: %s", cudaGetErrorString(qe)));
         qe = sih::mma_configure(d, p->d, &p->mma);
         if (qe != cudaSuccess) return bail(fail(SIHMPC_E_CUDA, "tensor fast-path configuration failed: %s", cudaGetErrorString(qe)));
+        qe = sih::tile_configure(d, p->d, &p->tile);
+        if (qe != cudaSuccess) return bail(fail(SIHMPC_E_CUDA, "tile fast-path configuration failed: %s", cudaGetErrorString(qe)));
         const char *nf = getenv("SIHMPC_NO_FAST");
         const char *ff = getenv("SIHMPC_FAST");
         p->use_fast = 2;
         if (ff && !strcmp(ff, "quad")) p->use_fast = 1;
+        if (ff && !strcmp(ff, "tile")) p->use_fast = 3;
         if (nf && nf[0] == '1') p->use_fast = 0;
     }
     *out = p;
@@ -300,7 +308,16 @@ int sihmpc_step(sihmpc_plan *plan, const sihmpc_io *io, int64_t batch, int32_t n
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     double *scratch = reinterpret_cast<double *>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     const int *start_step = nullptr, *n_handover = nullptr;
-    if (plan->use_fast == 2 && plan->mma.shape >= 0) {
+    const bool want_tile = plan->tile.ok && (plan->use_fast == 3 || (plan->use_fast == 2 && plan->mma.shape < 0));
+    if (want_tile) {
+        cudaError_t e = sih::tile_ensure_capacity(&plan->tile, batch);
+        if (e == cudaSuccess) e = cudaMemsetAsync(plan->tile.n_handover, 0x7f, (size_t)(batch + 1) * sizeof(int), st);
+        if (e == cudaSuccess) e = sih::tile_launch(plan->tile, plan->d, *io, batch, n_steps, plan->sm_count, st);
+        if (e != cudaSuccess) return fail(SIHMPC_E_CUDA, "tile fast-path launch failed: %s", cudaGetErrorString(e));
+        if (!(plan->d.has_box || plan->d.has_cum)) return 0;      // nothing can be handed over
+        start_step = plan->tile.start_step;
+        n_handover = plan->tile.n_handover;
+    } else if (plan->use_fast == 2 && plan->mma.shape >= 0) {
         cudaError_t e = sih::mma_ensure_capacity(&plan->mma, batch);
         if (e == cudaSuccess) e = cudaMemsetAsync(plan->mma.n_handover, 0x7f, (size_t)(batch + 1) * sizeof(int), st);
         if (e == cudaSuccess) e = sih::mma_launch(plan->mma, plan->d, *io, batch, n_steps, plan->sm_count, st);
@@ -308,7 +325,7 @@ int sihmpc_step(sihmpc_plan *plan, const sihmpc_io *io, int64_t batch, int32_t n
         if (!(plan->d.has_box || plan->d.has_cum)) return 0;      // nothing can be handed over
         start_step = plan->mma.start_step;
         n_handover = plan->mma.n_handover;
-    } else if (plan->use_fast && sih::quad_supported(plan->quad, *io)) {
+    } else if (plan->use_fast == 1 && sih::quad_supported(plan->quad, *io)) {
         cudaError_t e = sih::quad_ensure_capacity(&plan->quad, batch);
         if (e == cudaSuccess) e = cudaMemsetAsync(plan->quad.n_handover, 0x7f, (size_t)(batch + 1) * sizeof(int), st);
         if (e == cudaSuccess) e = sih::quad_launch(plan->quad, plan->d, *io, batch, n_steps, plan->sm_count, st);
