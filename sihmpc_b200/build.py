@@ -1,5 +1,6 @@
 # -*- coding: utf-8 -*-
-"""In-tree build of libsihmpc_b200.so for sm_100a (nvcc cross-compiles without a GPU)."""
+"""In-tree build of libsihmpc_b200.so for sm_100a (nvcc cross-compiles without a GPU).
+The translation units are compiled in parallel and linked into one shared library."""
 from __future__ import annotations
 
 import os
@@ -8,9 +9,11 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libsihmpc_b200.so")
+UNITS = ["capi.cu", "tile_kernel.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC"]
 
 
 def _sources():
@@ -26,17 +29,28 @@ def needs_build() -> bool:
     return any(os.path.getmtime(s) > t for s in _sources())
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, extra=()) -> str:
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", LIB, os.path.join(CSRC, "capi.cu")]
-    r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    os.makedirs(OBJ, exist_ok=True)
+    procs = []
+    for u in UNITS:
+        obj = os.path.join(OBJ, u.replace(".cu", ".o"))
+        cmd = [nvcc] + NVCC_FLAGS + list(extra) + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, os.path.join(CSRC, u)]
+        procs.append((u, obj, subprocess.Popen(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
+    objs = []
+    for u, obj, pr in procs:
+        out, err = pr.communicate()
+        if pr.returncode != 0:
+            raise RuntimeError("nvcc failed on %s:\n%s%s" % (u, out, err))
+        if verbose:
+            sys.stderr.write(err)
+        objs.append(obj)
+    r = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs,
+                       cwd=CSRC, capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
-    if verbose:
-        sys.stderr.write(r.stderr)
+        raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
     return LIB
 
 

@@ -13,7 +13,7 @@
 #include "step_kernel.cuh"
 #include "dist_kernel.cuh"
 #include "mma_kernel.cuh"
-#include "tile_kernel.cuh"
+#include "tile_api.h"
 #include "log_kernel.cuh"
 
 namespace {

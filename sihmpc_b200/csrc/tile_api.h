@@ -1,0 +1,46 @@
+// tile_api.h -- host interface of the tile fast path v4 (tile_kernel.cu), see there.
+#pragma once
+#include <cuda_runtime.h>
+#include "devplan.h"
+
+namespace sih {
+
+constexpr int TL_WARPS = 8;          // == scenarios per CTA == M of the MMA
+constexpr int TL_NTMAX = 8;          // tile rows of the augmented matrix: nv + 1 <= 64
+constexpr int TL_KHMAX = 6;          // k-tiles of the Hessian product: 1 + max(hj_index) + 1 <= 24
+
+struct TileCfg {
+    const int *ptr;                  // per matrix: segment range [ptr[T], ptr[T+1]) of output tile T
+    const int *seg;                  // segments (runs of consecutive k-tiles): {4*k_first, n_tiles, first stored tile}
+    const int *hrows;                // Hessian product: real rows (0..8) of packed tile t
+    const double *B;                 // stored tiles, 32 doubles each, B-fragment order
+    const double *BH;                // Hessian constants, dense: [tile][row][k-tile][32]
+    int KH, ntile;                   // k-tiles of [1 ; pesos] that carry Hessian blocks; packed tiles
+    int me, mw, mdu, mf, mh, mr, my, myp, mvn, mpl;  // offsets of the row-pointer arrays in ptr[]
+    int n_x;                         // output tiles of the shared-plant product (0: CSR path)
+    int n_r, n_v, n_f, n_h, n_y, n_yp, n_m;          // output tile counts
+    int NT, NP, Ib, rb, HS;
+    int S_sv, S_r, S_v, S_p, S_q, S_m, S_sc;         // per-scenario strides (doubles; == 4 mod 16 where read as A)
+    int o_H, o_sv, o_e, o_om, o_t, o_omdu, o_pes, o_sq, o_vn, o_z, o_y, o_sc;
+    int total;                       // doubles of shared memory per CTA
+};
+
+struct TilePlan {
+    int ok;                  // 1: the tile path can run this controller
+    TileCfg cfg;
+    int *ibuf;               // device: ptr | kt | hmap
+    double *dbuf;            // device: stored tiles
+    int *start_step;
+    int *n_handover;
+    long long capacity;
+    size_t smem_bytes;
+    int n_tiles;
+};
+
+cudaError_t tile_configure(const sihmpc_plan_desc *d, const DevPlan &P, TilePlan *tp);
+cudaError_t tile_ensure_capacity(TilePlan *tp, long long batch);
+cudaError_t tile_launch(const TilePlan &tp, const DevPlan &P, const sihmpc_io &io, long long batch, int n_steps,
+                        int sm_count, cudaStream_t st);
+void tile_destroy(TilePlan *tp);
+
+}  // namespace sih

@@ -1,4 +1,4 @@
-// tile_kernel.cuh -- fast path v4 for MID-SIZE controllers (N*nu + 1 <= 64, any nx / R / m):
+// tile_kernel.cu -- fast path v4 for MID-SIZE controllers (N*nu + 1 <= 64, any nx / R / m):
 // CTA-cooperative, everything that multiplies on the FP64 TENSOR pipe (DMMA.8x8x4).
 //
 // One CTA = 8 warps = 8 scenarios (an "octet"), state resident in shared memory for all n_steps.
@@ -25,60 +25,87 @@
 //
 // Reference semantics replaced: the same as step_kernel.cuh (ihmpccontroller.py:567-604, 534-564,
 // 619-636, 93-113; example_distillation.py:81-113).
-#pragma once
 #include <cuda_runtime.h>
 #include <vector>
 #include <functional>
 #include <string.h>
 #include <stdlib.h>
 #include "devplan.h"
-#include "step_kernel.cuh"
-#include "mma_kernel.cuh"
+#include <math.h>
+#include "tile_api.h"
+
+#define SIH_FULL 0xffffffffu
+#define SIH_INF (__longlong_as_double(0x7ff0000000000000LL))
 
 namespace sih {
 
-constexpr int TL_WARPS = 8;          // == scenarios per CTA == M of the MMA
-constexpr int TL_NTMAX = 8;          // tile rows of the augmented matrix: nv + 1 <= 64
-
-struct TileCfg {
-    const int *ptr;                  // row pointers of every tile matrix (absolute tile indices)
-    const int *kt;                   // k-tile of every stored tile
-    const int *hmap;                 // Hessian product: destination (tile*64 + row*8) of output tile T
-    const double *B;                 // stored tiles, 32 doubles each, B-fragment order
-    int me, mw, mdu, mf, mh, mr, my, myp, mvn;       // offsets of the row-pointer arrays in ptr[]
-    int n_r, n_v, n_f, n_h, n_y, n_yp, n_m;          // output tile counts
-    int NT, NP, Ib, rb, HS;
-    int S_sv, S_r, S_v, S_p, S_q, S_m, S_sc;         // per-scenario strides (doubles; == 4 mod 16 where read as A)
-    int o_H, o_sv, o_e, o_om, o_t, o_omdu, o_pes, o_sq, o_vn, o_z, o_y, o_sc;
-    int total;                       // doubles of shared memory per CTA
-};
+namespace {
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(SIH_FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(SIH_FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ void dmma884(double &c0, double &c1, const double a, const double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+        : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+// 1/sqrt(d) for a positive normal d: MUFU.RSQ64H seed + two Newton steps (see dist_kernel.cuh)
+__device__ __forceinline__ double fast_rsqrt(const double d) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    double t = d * y;
+    double e = fma(-t, y, 1.0);
+    y = fma(0.5 * y, e, y);
+    t = d * y;
+    e = fma(-t, y, 1.0);
+    y = fma(0.5 * y, e, y);
+    return y;
+}
+}  // namespace
 
 __host__ __device__ __forceinline__ int tl_tid(int I, int J) { return (I * (I + 1)) / 2 + J; }
 
-// accumulators of output tile T of one tile-CSR matrix; in_q = in + q*S + g (A-fragment base of this lane)
+// accumulators of output tile T of one tile-CSR matrix; in_q = in + q*S + g (A-fragment base of this lane).
+// A row is a short list of RUNS of consecutive k-tiles: inside a run the A address and the B address
+// advance by constants, the next four B tiles are fetched while the current four multiply.
 __device__ __forceinline__ void tile_row(const TileCfg &C, const int poff, const int T, const double *in_q,
                                          const int lane, double &r0, double &r1) {
-    const int i0 = C.ptr[poff + T], i1 = C.ptr[poff + T + 1];
+    const int s0 = __ldg(C.ptr + poff + T), s1 = __ldg(C.ptr + poff + T + 1);
     double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
-    for (int base = i0; base < i1; base += 32) {
-        const int n = (i1 - base < 32) ? (i1 - base) : 32;
-        const int ktv = (lane < n) ? __ldg(C.kt + base + lane) : 0;
-        const double *Bp = C.B + (size_t)base * 32 + lane;
-        int j = 0;
-        for (; j + 4 <= n; j += 4) {
-            const int k0 = __shfl_sync(SIH_FULL, ktv, j), k1 = __shfl_sync(SIH_FULL, ktv, j + 1);
-            const int k2 = __shfl_sync(SIH_FULL, ktv, j + 2), k3 = __shfl_sync(SIH_FULL, ktv, j + 3);
-            const double b0 = __ldg(Bp + (j) * 32), b1 = __ldg(Bp + (j + 1) * 32);
-            const double b2 = __ldg(Bp + (j + 2) * 32), b3 = __ldg(Bp + (j + 3) * 32);
-            const double a0 = in_q[4 * k0], a1 = in_q[4 * k1], a2 = in_q[4 * k2], a3 = in_q[4 * k3];
+    for (int sgi = s0; sgi < s1; ++sgi) {
+        const int koff = __ldg(C.seg + 3 * sgi), n = __ldg(C.seg + 3 * sgi + 1), bi = __ldg(C.seg + 3 * sgi + 2);
+        const double *Bp = C.B + (size_t)bi * 32 + lane;
+        const double *ap = in_q + koff;
+        int t = 0;
+        double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+        if (n >= 4) { b0 = __ldg(Bp); b1 = __ldg(Bp + 32); b2 = __ldg(Bp + 64); b3 = __ldg(Bp + 96); }
+        for (; t + 4 <= n; t += 4) {
+            const bool more = (t + 8 <= n);
+            double n0 = 0.0, n1 = 0.0, n2 = 0.0, n3 = 0.0;
+            if (more) {
+                n0 = __ldg(Bp + (t + 4) * 32); n1 = __ldg(Bp + (t + 5) * 32);
+                n2 = __ldg(Bp + (t + 6) * 32); n3 = __ldg(Bp + (t + 7) * 32);
+            }
+            const double a0 = ap[4 * t], a1 = ap[4 * t + 4], a2 = ap[4 * t + 8], a3 = ap[4 * t + 12];
             dmma884(c0, c1, a0, b0);
             dmma884(d0, d1, a1, b1);
             dmma884(c0, c1, a2, b2);
             dmma884(d0, d1, a3, b3);
+            b0 = n0; b1 = n1; b2 = n2; b3 = n3;
         }
-        for (; j < n; ++j) {
-            const int k0 = __shfl_sync(SIH_FULL, ktv, j);
-            dmma884(c0, c1, in_q[4 * k0], __ldg(Bp + j * 32));
+        if (t < n) {
+            const int rem = n - t;                       // 1..3
+            const double e0 = __ldg(Bp + t * 32);
+            const double e1 = (rem > 1) ? __ldg(Bp + (t + 1) * 32) : 0.0;
+            const double e2 = (rem > 2) ? __ldg(Bp + (t + 2) * 32) : 0.0;
+            dmma884(c0, c1, ap[4 * t], e0);
+            if (rem > 1) dmma884(d0, d1, ap[4 * t + 4], e1);
+            if (rem > 2) dmma884(c0, c1, ap[4 * t + 8], e2);
         }
     }
     r0 = c0 + d0; r1 = c1 + d1;
@@ -89,98 +116,124 @@ __device__ __forceinline__ double tl_rsqrt(const double d) { return fast_rsqrt(d
 // Right-looking tiled Cholesky of the augmented matrix [H ; b^T] of ONE scenario by ONE warp.
 // A: packed lower 8x8 tiles (row-major 64 doubles each) in shared memory.  On exit the strictly
 // lower part holds L, every 4x4 pivot block holds W = L11^-1 (lower), yv[0..nv) = L^-1 b.
-template <int NTMAX>
-__device__ int tile_factor(double *A, const int NT, const int NP, const int nv, const int Ib, const int rb,
-                           const int lane, double *yv) {
-    const int q = lane >> 2, g = lane & 3;
-    int notpd = 0;
-    for (int p = 0; p < NP; ++p) {
-        const int J = p >> 1, c0 = (p & 1) * 4;
-        double *D = A + tl_tid(J, J) * 64 + c0 * 8 + c0;          // pivot block, element (r,c) at D[r*8+c]
-        const int nreal = (nv - 4 * p < 4) ? (nv - 4 * p) : 4;    // columns >= nreal of the block: identity
-        double a00 = D[0], a10 = D[8], a11 = D[9], a20 = D[16], a21 = D[17], a22 = D[18];
-        double a30 = D[24], a31 = D[25], a32 = D[26], a33 = D[27];
-        if (!(a00 > 0.0)) { notpd = 1; a00 = 1.0; }
-        const double i00 = tl_rsqrt(a00);
-        const double l10 = a10 * i00, l20 = a20 * i00, l30 = a30 * i00;
-        double d1 = fma(-l10, l10, a11);
-        if (nreal < 2) d1 = 1.0; else if (!(d1 > 0.0)) { notpd = 1; d1 = 1.0; }
-        const double i11 = tl_rsqrt(d1);
-        const double l21 = (nreal < 2) ? 0.0 : fma(-l20, l10, a21) * i11;
-        const double l31 = (nreal < 2) ? 0.0 : fma(-l30, l10, a31) * i11;
-        double d2 = fma(-l21, l21, fma(-l20, l20, a22));
-        if (nreal < 3) d2 = 1.0; else if (!(d2 > 0.0)) { notpd = 1; d2 = 1.0; }
-        const double i22 = tl_rsqrt(d2);
-        const double l32 = (nreal < 3) ? 0.0 : fma(-l31, l21, fma(-l30, l20, a32)) * i22;
-        double d3 = fma(-l32, l32, fma(-l31, l31, fma(-l30, l30, a33)));
-        if (nreal < 4) d3 = 1.0; else if (!(d3 > 0.0)) { notpd = 1; d3 = 1.0; }
-        const double i33 = tl_rsqrt(d3);
-        // W = L11^-1
-        const double w10 = -l10 * i00 * i11;
-        const double w21 = -l21 * i11 * i22;
-        const double w32 = -l32 * i22 * i33;
-        const double w20 = -fma(l21, w10, l20 * i00) * i22;
-        const double w31 = -fma(l32, w21, l31 * i11) * i33;
-        const double w30 = -fma(l32, w20, fma(l31, w10, l30 * i00)) * i33;
-        // element (r,c) of W for this lane's (q,g) resp. (lane>>2, lane&3)
-        double wqg;
-        {
-            const double r0 = (g == 0) ? i00 : 0.0;
-            const double r1 = (g == 0) ? w10 : ((g == 1) ? i11 : 0.0);
-            const double r2 = (g == 0) ? w20 : ((g == 1) ? w21 : ((g == 2) ? i22 : 0.0));
-            const double r3 = (g == 0) ? w30 : ((g == 1) ? w31 : ((g == 2) ? w32 : i33));
-            wqg = (q == 0) ? r0 : ((q == 1) ? r1 : ((q == 2) ? r2 : ((q == 3) ? r3 : 0.0)));
-            if (q >= nreal) wqg = 0.0;
-        }
-        // panel solve  L21 = A21 W^T  for every row tile (rows in or above the pivot block are skipped)
-        for (int I = J; I < NT; ++I) {
-            double *tile = A + tl_tid(I, J) * 64;
-            double a = tile[q * 8 + c0 + g];
-            const bool skip = (I == J) && (q < c0 + 4);
-            if (skip) a = 0.0;
-            double o0 = 0.0, o1 = 0.0;
-            dmma884(o0, o1, a, wqg);
-            if (g < 2 && !skip) *reinterpret_cast<double2 *>(tile + q * 8 + c0 + 2 * g) = make_double2(o0, o1);
-        }
-        // y of these columns when the right-hand-side row sits inside the pivot block
-        if (nreal < 4) {
-            if (lane < nreal) {
+//
+// Everything is compile-time (NT tile rows, panel P): the trailing matrix lives in REGISTERS as MMA C
+// fragments (c[tile]), so a trailing update is one DMMA and nothing else; only the four columns of the
+// current panel go through shared memory (C layout -> A/B layout), which is also where L is kept for
+// the backward substitution.
+template <int NT, int P>
+__device__ __forceinline__ void tfs_panel(double2 (&c)[NT * (NT + 1) / 2], double *A, double *yv, const int nv,
+                                          const int rb, const int lane, int &notpd) {
+    if constexpr (P < 2 * NT) {
+        constexpr int J = P >> 1, c0 = (P & 1) * 4, Ib = NT - 1;
+        if (4 * P < nv) {                                              // uniform
+            const int q = lane >> 2, g = lane & 3;
+            // (a) the panel's four columns of every tile (I,J): registers -> home
+            if ((g >> 1) == (c0 >> 2)) {
+#pragma unroll
+                for (int I = J; I < NT; ++I)
+                    *reinterpret_cast<double2 *>(A + (I * (I + 1) / 2 + J) * 64 + q * 8 + 2 * g) = c[I * (I + 1) / 2 + J];
+            }
+            __syncwarp();
+            // (b) 4x4 pivot block, factorised and inverted redundantly by every lane
+            double *D = A + (J * (J + 1) / 2 + J) * 64 + c0 * 8 + c0;     // element (r,c) at D[r*8+c]
+            const int nreal = (nv - 4 * P < 4) ? (nv - 4 * P) : 4;        // columns >= nreal: identity
+            double a00 = D[0], a10 = D[8], a11 = D[9], a20 = D[16], a21 = D[17], a22 = D[18];
+            double a30 = D[24], a31 = D[25], a32 = D[26], a33 = D[27];
+            if (!(a00 > 0.0)) { notpd = 1; a00 = 1.0; }
+            const double i00 = tl_rsqrt(a00);
+            const double l10 = a10 * i00, l20 = a20 * i00, l30 = a30 * i00;
+            double d1 = fma(-l10, l10, a11);
+            if (nreal < 2) d1 = 1.0; else if (!(d1 > 0.0)) { notpd = 1; d1 = 1.0; }
+            const double i11 = tl_rsqrt(d1);
+            const double l21 = (nreal < 2) ? 0.0 : fma(-l20, l10, a21) * i11;
+            const double l31 = (nreal < 2) ? 0.0 : fma(-l30, l10, a31) * i11;
+            double d2 = fma(-l21, l21, fma(-l20, l20, a22));
+            if (nreal < 3) d2 = 1.0; else if (!(d2 > 0.0)) { notpd = 1; d2 = 1.0; }
+            const double i22 = tl_rsqrt(d2);
+            const double l32 = (nreal < 3) ? 0.0 : fma(-l31, l21, fma(-l30, l20, a32)) * i22;
+            double d3 = fma(-l32, l32, fma(-l31, l31, fma(-l30, l30, a33)));
+            if (nreal < 4) d3 = 1.0; else if (!(d3 > 0.0)) { notpd = 1; d3 = 1.0; }
+            const double i33 = tl_rsqrt(d3);
+            const double w10 = -l10 * i00 * i11;
+            const double w21 = -l21 * i11 * i22;
+            const double w32 = -l32 * i22 * i33;
+            const double w20 = -fma(l21, w10, l20 * i00) * i22;
+            const double w31 = -fma(l32, w21, l31 * i11) * i33;
+            const double w30 = -fma(l32, w20, fma(l31, w10, l30 * i00)) * i33;
+            double wqg;                                                // W[q][g], zero outside the block
+            {
+                const double r0 = (g == 0) ? i00 : 0.0;
+                const double r1 = (g == 0) ? w10 : ((g == 1) ? i11 : 0.0);
+                const double r2 = (g == 0) ? w20 : ((g == 1) ? w21 : ((g == 2) ? i22 : 0.0));
+                const double r3 = (g == 0) ? w30 : ((g == 1) ? w31 : ((g == 2) ? w32 : i33));
+                wqg = (q == 0) ? r0 : ((q == 1) ? r1 : ((q == 2) ? r2 : ((q == 3) ? r3 : 0.0)));
+                if (q >= nreal) wqg = 0.0;
+            }
+            // (c,d) panel solve  L21 = A21 W^T : A fragments from home, results (C layout, lanes g<2) back home
+            double pl[NT];
+#pragma unroll
+            for (int I = J; I < NT; ++I) {
+                double v = A[(I * (I + 1) / 2 + J) * 64 + q * 8 + c0 + g];
+                if (I == J && q < c0 + 4) v = 0.0;                     // rows in or above the pivot block
+                pl[I] = v;
+            }
+            {
+                double o[NT][2];
+#pragma unroll
+                for (int I = J; I < NT; ++I) { o[I][0] = o[I][1] = 0.0; dmma884(o[I][0], o[I][1], pl[I], wqg); }
+                if (g < 2) {
+#pragma unroll
+                    for (int I = J; I < NT; ++I)
+                        if (!(I == J && q < c0 + 4))
+                            *reinterpret_cast<double2 *>(A + (I * (I + 1) / 2 + J) * 64 + q * 8 + c0 + 2 * g) = make_double2(o[I][0], o[I][1]);
+                }
+            }
+            if (nreal < 4 && lane < nreal) {                           // right-hand-side row inside the pivot block
                 const double y0 = (nreal == 1) ? l10 : ((nreal == 2) ? l20 : l30);
                 const double y1 = (nreal == 2) ? l21 : l31;
-                yv[4 * p + lane] = (lane == 0) ? y0 : ((lane == 1) ? y1 : l32);
+                yv[4 * P + lane] = (lane == 0) ? y0 : ((lane == 1) ? y1 : l32);
             }
-        }
-        if (lane < 16 && g <= q && q < nreal) D[q * 8 + g] = wqg;     // (q,g) = (lane>>2, lane&3) for lane < 16
-        __syncwarp();
-        if (nreal == 4 && lane < 4) yv[4 * p + lane] = A[tl_tid(Ib, J) * 64 + rb * 8 + c0 + lane];
-        // trailing update: tile(I,K) -= L21_I L21_K^T  (A fragment of I, B fragment of K: the same layout)
-        double pa[NTMAX];
+            if (lane < 16 && g <= q && q < nreal) D[q * 8 + g] = wqg;     // (q,g) = (row, col) of W for lane < 16
+            __syncwarp();
+            if (nreal == 4 && lane < 4) yv[4 * P + lane] = A[(Ib * (Ib + 1) / 2 + J) * 64 + rb * 8 + c0 + lane];
+            // (e) trailing update on the register tiles: c(I,K) -= L21_I L21_K^T
+            if constexpr (P + 1 < 2 * NT) {
 #pragma unroll
-        for (int I = 0; I < NTMAX; ++I) {
-            double v = 0.0;
-            if (I >= J && I < NT) {
-                v = A[tl_tid(I, J) * 64 + q * 8 + c0 + g];
-                if (I == J && q < c0 + 4) v = 0.0;
-            }
-            pa[I] = v;
-        }
-        const int K0 = J + (c0 ? 1 : 0);
+                for (int I = J; I < NT; ++I) {
+                    double v = A[(I * (I + 1) / 2 + J) * 64 + q * 8 + c0 + g];
+                    if (I == J && q < c0 + 4) v = 0.0;
+                    pl[I] = v;
+                }
 #pragma unroll
-        for (int K = 0; K < NTMAX; ++K) {
-            if (K < K0 || K >= NT) continue;
-            const double bK = pa[K];
+                for (int K = J + (c0 ? 1 : 0); K < NT; ++K) {
 #pragma unroll
-            for (int I = K; I < NTMAX; ++I) {
-                if (I < NT) {
-                    double2 *cp = reinterpret_cast<double2 *>(A + tl_tid(I, K) * 64 + q * 8 + 2 * g);
-                    double2 c = *cp;
-                    dmma884(c.x, c.y, -pa[I], bK);
-                    *cp = c;
+                    for (int I = K; I < NT; ++I)
+                        dmma884(c[I * (I + 1) / 2 + K].x, c[I * (I + 1) / 2 + K].y, -pl[I], pl[K]);
                 }
             }
         }
-        __syncwarp();
+        tfs_panel<NT, P + 1>(c, A, yv, nv, rb, lane, notpd);
     }
+}
+
+template <int NT>
+__device__ __forceinline__ int tile_factor(double *A, const double *omdu_w, const int nv, const int rb,
+                                           const int lane, double *yv) {
+    constexpr int NTILES = NT * (NT + 1) / 2;
+    const int q = lane >> 2, g = lane & 3;
+    double2 c[NTILES];
+#pragma unroll
+    for (int t = 0; t < NTILES; ++t) c[t] = *reinterpret_cast<const double2 *>(A + t * 64 + q * 8 + 2 * g);
+    // + 2 omega_du on the diagonal (ihmpccontroller.py:200,212: the du sub-objectives)
+#pragma unroll
+    for (int J = 0; J < NT; ++J) {
+        const double od = 2.0 * omdu_w[8 * J + q];               // zero beyond nv
+        if (q == 2 * g) c[J * (J + 1) / 2 + J].x += od;
+        if (q == 2 * g + 1) c[J * (J + 1) / 2 + J].y += od;
+    }
+    int notpd = 0;
+    tfs_panel<NT, 0>(c, A, yv, nv, rb, lane, notpd);
     return notpd;
 }
 
@@ -210,7 +263,7 @@ __device__ void tile_backsolve(const double *A, const int NP, const int nv, cons
     }
 }
 
-template <int NTMAX>
+template <int NT>
 __global__ void __launch_bounds__(TL_WARPS * 32, 1)
 tile_step_kernel(const DevPlan P, const TileCfg C, const sihmpc_io io, const long long batch, const int n_steps,
                  int *__restrict__ start_step, int *__restrict__ n_handover) {
@@ -230,6 +283,8 @@ tile_step_kernel(const DevPlan P, const TileCfg C, const sihmpc_io io, const lon
     double *zw = sm + C.o_z + w * 64, *yw = sm + C.o_y + w * 64, *scw = scb + w * C.S_sc;
     double *uw = scw + 2, *stw = scw + 2 + nu;
     double *xtw = omw;                                // plant scratch: omega is dead after the cost
+    double *tbw = tb + w * C.S_r;
+    const bool shared_plant = (io.plant_val == nullptr) && C.n_x > 0;
     const int o_ysp = nx + nv, o_one = nx + nv + ny;
     const int nsq = Ny + 2 * ny;
 
@@ -242,7 +297,7 @@ tile_step_kernel(const DevPlan P, const TileCfg C, const sihmpc_io io, const lon
         // ---------------- load the scenario
         for (int i = lane; i < nx; i += 32) svw[i] = io.x[sl * nx + i];
         for (int i = lane; i < nv; i += 32) svw[nx + i] = 0.0;
-        for (int i = lane; i < m; i += 32) pw[i] = io.pesos[sl * m + i];
+        for (int i = lane; i < m; i += 32) pw[1 + i] = io.pesos[sl * m + i];     // k-space [1 ; pesos]
         for (int i = lane; i < nu; i += 32) uw[i] = io.u[sl * nu + i];
         for (int i = lane; i < nstat; i += 32) stw[i] = io.stats ? io.stats[sl * nstat + i] : 0.0;
         int seg = 0, next_start = 0x7fffffff, dstep = -1;
@@ -254,7 +309,7 @@ tile_step_kernel(const DevPlan P, const TileCfg C, const sihmpc_io io, const lon
         if (io.dist_step) dstep = io.dist_step[sl];
         for (int i = lane; i < ny; i += 32)
             svw[o_ysp + i] = io.ysp_seq ? io.ysp_seq[(sl * io.n_seg + seg) * ny + i] : io.ysp[sl * ny + i];
-        if (lane == 0) { svw[o_one] = 1.0; pw[m] = 1.0; scw[1] = alive ? 1.0 : 0.0; }
+        if (lane == 0) { svw[o_one] = 1.0; pw[0] = 1.0; scw[1] = alive ? 1.0 : 0.0; }
         const double *pv = io.plant_val ? io.plant_val + (size_t)sl * P.pl_nnz : P.pl_val;
 
         for (int step = 0; step < n_steps; ++step) {
@@ -280,10 +335,28 @@ tile_step_kernel(const DevPlan P, const TileCfg C, const sihmpc_io io, const lon
                 tile_row(C, C.mdu, T, pes + q * C.S_p + g, lane, o0, o1);
                 *reinterpret_cast<double2 *>(omdu + q * C.S_v + 8 * T + 2 * g) = make_double2(o0, o1);
             }
-            for (int T = w; T < C.n_h; T += TL_WARPS) {
-                double h0, h1;
-                tile_row(C, C.mh, T, pes + q * C.S_p + g, lane, h0, h1);
-                *reinterpret_cast<double2 *>(Hs + (size_t)q * C.HS + __ldg(C.hmap + T) + 2 * g) = make_double2(h0, h1);
+            // Hessian tiles  H = Ht + sum_a pesos_a HJ_a : dense k-tiles [0,KH) of [1 ; pesos], half a tile per unit
+            for (int u = w; u < 2 * C.ntile; u += TL_WARPS) {
+                const int tid = u >> 1, r0 = (u & 1) * 4;
+                const int nrow = __ldg(C.hrows + tid);
+                double a[TL_KHMAX];
+#pragma unroll
+                for (int t = 0; t < TL_KHMAX; ++t) a[t] = (t < C.KH) ? pes[q * C.S_p + 4 * t + g] : 0.0;
+                const double *Bp = C.BH + ((size_t)(tid * 8 + r0) * C.KH) * 32 + lane;
+                double h[4][2];
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) {
+                    h[rr][0] = h[rr][1] = 0.0;
+                    if (r0 + rr < nrow) {
+#pragma unroll
+                        for (int t = 0; t < TL_KHMAX; ++t)
+                            if (t < C.KH) dmma884(h[rr][0], h[rr][1], a[t], __ldg(Bp + (rr * C.KH + t) * 32));
+                    }
+                }
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr)
+                    if (r0 + rr < nrow)
+                        *reinterpret_cast<double2 *>(Hs + (size_t)q * C.HS + tid * 64 + (r0 + rr) * 8 + 2 * g) = make_double2(h[rr][0], h[rr][1]);
             }
             __syncthreads();                              // [B]
             // ---------------- P2: right-hand side b = -2 E^T t into row nv of the augmented matrix
@@ -294,7 +367,7 @@ tile_step_kernel(const DevPlan P, const TileCfg C, const sihmpc_io io, const lon
             }
             __syncthreads();                              // [C]
             // ---------------- P3 (warp per scenario): factorise, solve, check the boxes
-            const int notpd = tile_factor<NTMAX>(Hw, C.NT, C.NP, nv, C.Ib, C.rb, lane, yw);
+            const int notpd = tile_factor<NT>(Hw, omduw, nv, C.rb, lane, yw);
             tile_backsolve(Hw, C.NP, nv, lane, yw, zw);
             for (int i = lane; i < nv; i += 32) svw[nx + i] = zw[i];
             double viol = 0.0, viol_abs = 0.0;
@@ -321,7 +394,7 @@ tile_step_kernel(const DevPlan P, const TileCfg C, const sihmpc_io io, const lon
                 if (lane == 0) { start_step[s] = step; atomicAdd(n_handover, 1); scw[1] = 0.0; }
                 for (int i = lane; i < nx; i += 32) io.x[s * nx + i] = svw[i];
                 for (int i = lane; i < nu; i += 32) io.u[s * nu + i] = uw[i];
-                for (int i = lane; i < m; i += 32) io.pesos[s * m + i] = pw[i];
+                for (int i = lane; i < m; i += 32) io.pesos[s * m + i] = pw[1 + i];
                 if (io.stats) for (int i = lane; i < nstat; i += 32) io.stats[s * nstat + i] = stw[i];
             }
             if (lane == 0) scw[0] = 0.0;
@@ -340,6 +413,12 @@ tile_step_kernel(const DevPlan P, const TileCfg C, const sihmpc_io io, const lon
                 part += __shfl_xor_sync(SIH_FULL, part, 2);
                 if (g == 0) atomicAdd(scb + q * C.S_sc, part);
             }
+            if (shared_plant && advance)                  // x+ = [A|B][x ; du] on the tensor pipe (t is dead)
+                for (int T = (w + 2) & 7; T < C.n_x; T += TL_WARPS) {
+                    double x0, x1;
+                    tile_row(C, C.mpl, T, sv + q * C.S_sv + g, lane, x0, x1);
+                    *reinterpret_cast<double2 *>(tb + q * C.S_r + 8 * T + 2 * g) = make_double2(x0, x1);
+                }
             __syncthreads();                              // [E]
             // ---------------- P5 (warp per scenario): cost, outputs, plant, shifted-plan inputs
             double Jval;
@@ -376,14 +455,18 @@ tile_step_kernel(const DevPlan P, const TileCfg C, const sihmpc_io io, const lon
             }
             if (!advance) continue;                       // uniform: n_steps == 1
             // plant x+ = [A|B][x ; du]  (du = first nu entries of dU, which follow x in the buffer)
-            for (int i = lane; i < nx; i += 32) {
-                double a = 0.0;
-                const int p1 = P.pl_rowptr[i + 1];
-                for (int pp = P.pl_rowptr[i]; pp < p1; ++pp) a = fma(pv[pp], svw[P.pl_col[pp]], a);
-                xtw[i] = a;
+            if (shared_plant) {
+                for (int i = lane; i < nx; i += 32) svw[i] = tbw[i];
+            } else {
+                for (int i = lane; i < nx; i += 32) {
+                    double a = 0.0;
+                    const int p1 = P.pl_rowptr[i + 1];
+                    for (int pp = P.pl_rowptr[i]; pp < p1; ++pp) a = fma(pv[pp], svw[P.pl_col[pp]], a);
+                    xtw[i] = a;
+                }
+                __syncwarp();
+                for (int i = lane; i < nx; i += 32) svw[i] = xtw[i];
             }
-            __syncwarp();
-            for (int i = lane; i < nx; i += 32) svw[i] = xtw[i];
             if (kabs == dstep) {
                 __syncwarp();
                 for (int i = lane; i < ny; i += 32) svw[i] += io.dist[sl * ny + i];
@@ -451,12 +534,12 @@ tile_step_kernel(const DevPlan P, const TileCfg C, const sihmpc_io io, const lon
                     for (int i = lane; i < m; i += 32) {
                         const double g0 = P.gamma[i];
                         const double g1 = fmax(g0, g0 * smax + 1e-6);
-                        pw[i] = io.alfa * pw[i] + (1.0 - io.alfa) * (1.0 / (g1 - vnw[i]));
+                        pw[1 + i] = io.alfa * pw[1 + i] + (1.0 - io.alfa) * (1.0 / (g1 - vnw[i]));
                     }
                 } else {
                     for (int i = lane; i < m; i += 32) {
                         const double g0 = P.gamma[i];
-                        pw[i] = 1.0 / (g0 - fmin(fmax(vnw[i], 0.0), 0.99 * g0));
+                        pw[1 + i] = 1.0 / (g0 - fmin(fmax(vnw[i], 0.0), 0.99 * g0));
                     }
                 }
             }
@@ -466,7 +549,7 @@ tile_step_kernel(const DevPlan P, const TileCfg C, const sihmpc_io io, const lon
         if (alive && advance) {
             for (int i = lane; i < nx; i += 32) io.x[s * nx + i] = svw[i];
             for (int i = lane; i < nu; i += 32) io.u[s * nu + i] = uw[i];
-            for (int i = lane; i < m; i += 32) io.pesos[s * m + i] = pw[i];
+            for (int i = lane; i < m; i += 32) io.pesos[s * m + i] = pw[1 + i];
             if (io.stats) for (int i = lane; i < nstat; i += 32) io.stats[s * nstat + i] = stw[i];
         }
         __syncthreads();
@@ -474,48 +557,66 @@ tile_step_kernel(const DevPlan P, const TileCfg C, const sihmpc_io io, const lon
 }
 
 // ---- host side ----------------------------------------------------------------------------------
-struct TilePlan {
-    int ok;                  // 1: the tile path can run this controller
-    TileCfg cfg;
-    int *ibuf;               // device: ptr | kt | hmap
-    double *dbuf;            // device: stored tiles
-    int *start_step;
-    int *n_handover;
-    long long capacity;
-    size_t smem_bytes;
-    int n_tiles;
-};
-
 struct TileBuilder {
-    std::vector<int> ptr, kt, hmap;
+    std::vector<int> ptr, seg, hmap;
     std::vector<double> B;
-    // adds a matrix with nT output tiles; M(r,c) over rows [0, 8 nT) and k-space [0, nc); returns the ptr offset
+    int n_stored = 0;
+    // one output tile: fill(t, tile[32]) writes k-tile t in B-fragment order and returns true if non-zero.
+    // Non-zero k-tiles are grouped into runs; a gap of one zero tile is bridged (a zero MMA is cheaper
+    // than a new run).
+    void row(int KT, const std::function<bool(int, double *)> &fill) {
+        ptr.push_back((int)seg.size() / 3);
+        std::vector<double> tiles((size_t)KT * 32);
+        std::vector<char> nz(KT, 0);
+        for (int t = 0; t < KT; ++t) nz[t] = fill(t, tiles.data() + (size_t)t * 32) ? 1 : 0;
+        int t = 0;
+        while (t < KT) {
+            if (!nz[t]) { ++t; continue; }
+            int e = t;                                   // extend the run [t, e]
+            while (true) {
+                if (e + 1 < KT && nz[e + 1]) { ++e; continue; }
+                if (e + 2 < KT && nz[e + 2]) { e += 2; continue; }
+                break;
+            }
+            seg.push_back(4 * t); seg.push_back(e - t + 1); seg.push_back(n_stored);
+            B.insert(B.end(), tiles.begin() + (size_t)t * 32, tiles.begin() + (size_t)(e + 1) * 32);
+            n_stored += e - t + 1;
+            t = e + 1;
+        }
+    }
+    void close() { ptr.push_back((int)seg.size() / 3); }
+    // a matrix with nT output tiles; M(r,c) over rows [0, 8 nT) and k-space [0, nc); returns the ptr offset
     int add(int nT, int nc, const std::function<double(int, int)> &M) {
         const int off = (int)ptr.size();
         const int KT = (nc + 3) / 4;
-        for (int T = 0; T < nT; ++T) {
-            ptr.push_back((int)kt.size());
-            for (int t = 0; t < KT; ++t) {
-                double tile[32];
+        for (int T = 0; T < nT; ++T)
+            row(KT, [&](int t, double *tile) {
                 bool nz = false;
                 for (int lane = 0; lane < 32; ++lane) {
-                    const int n = lane >> 2, k = lane & 3;
-                    const int c = 4 * t + k;
+                    const int n = lane >> 2, k = lane & 3, c = 4 * t + k;
                     const double v = (c < nc) ? M(8 * T + n, c) : 0.0;
                     tile[lane] = v;
                     if (v != 0.0) nz = true;
                 }
-                if (nz) { kt.push_back(t); B.insert(B.end(), tile, tile + 32); }
-            }
-        }
-        ptr.push_back((int)kt.size());
+                return nz; });
+        close();
         return off;
     }
 };
 
+static cudaError_t tile_set_smem(int NT, size_t bytes) {
+#define SIH_TL_ATTR(N_) case N_: return cudaFuncSetAttribute(tile_step_kernel<N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    switch (NT) {
+        SIH_TL_ATTR(1) SIH_TL_ATTR(2) SIH_TL_ATTR(3) SIH_TL_ATTR(4)
+        SIH_TL_ATTR(5) SIH_TL_ATTR(6) SIH_TL_ATTR(7) SIH_TL_ATTR(8)
+        default: return cudaErrorInvalidValue;
+    }
+#undef SIH_TL_ATTR
+}
+
 inline int tl_stride(int n) { int s = (n + 3) & ~3; while (s % 16 != 4) s += 4; return s; }
 
-inline cudaError_t tile_configure(const sihmpc_plan_desc *d, const DevPlan &P, TilePlan *tp) {
+cudaError_t tile_configure(const sihmpc_plan_desc *d, const DevPlan &P, TilePlan *tp) {
     memset(tp, 0, sizeof *tp);
     const int nx = d->nx, nu = d->nu, ny = d->ny, nv = P.nv, m = d->m, R = d->R, Ny = P.Ny, N = d->N;
     if (nv + 1 > 8 * TL_NTMAX || d->ncd > 0 || P.eval_term) return cudaSuccess;
@@ -525,8 +626,9 @@ inline cudaError_t tile_configure(const sihmpc_plan_desc *d, const DevPlan &P, T
     C.HS = ntiles * 64; while (C.HS % 16 != 8) C.HS += 2;
     const int RE = R + ny, K_sv = nx + nv + ny + 1, nsq = Ny + 2 * ny;
     C.n_r = (RE + 7) / 8; C.n_v = (nv + 7) / 8; C.n_f = C.NT; C.n_y = (ny + 7) / 8; C.n_yp = (Ny + 7) / 8; C.n_m = (m + 7) / 8;
-    int SR = 8 * C.n_r; if (SR < nx) SR = nx;
-    C.S_sv = tl_stride(K_sv); C.S_r = tl_stride(SR); C.S_v = tl_stride(8 * C.n_v); C.S_p = tl_stride(m + 1);
+    C.n_x = (nx + 7) / 8;
+    int SR = 8 * C.n_r; if (SR < 8 * C.n_x) SR = 8 * C.n_x;
+    C.S_sv = tl_stride(K_sv); C.S_r = tl_stride(SR); C.S_v = tl_stride(8 * C.NT); C.S_p = tl_stride(m + 1);
     C.S_q = tl_stride(nsq + nv); C.S_m = tl_stride(8 * C.n_m); C.S_sc = (2 + nu + ny + SIHMPC_NSTATS_EXTRA + 1) & ~1;
     int o = 0;
     auto take = [&](int n) { int r = o; o += (n + 1) & ~1; return r; };
@@ -547,50 +649,47 @@ inline cudaError_t tile_configure(const sihmpc_plan_desc *d, const DevPlan &P, T
         if (c >= o_ysp && c < o_one) return r < R ? d->Py[(size_t)r * ny + (c - o_ysp)] : 0.0;
         if (c == o_one) return r < R ? d->e0[r] : 0.0;
         return 0.0; });
-    // omega = [Wrow | w0row][pesos ; 1]
+    // omega = [w0row | Wrow][1 ; pesos]
     C.mw = tb.add(C.n_r, m + 1, [&](int r, int c) -> double {
         if (r >= R) return 0.0;
-        return c < m ? d->Wrow[(size_t)r * m + c] : d->w0row[r]; });
+        return c == 0 ? d->w0row[r] : d->Wrow[(size_t)r * m + (c - 1)]; });
     // omega_du = Wdu pesos
     C.mdu = tb.add(C.n_v, m + 1, [&](int r, int c) -> double {
-        return (r < nv && c < m) ? d->Wdu[(size_t)r * m + c] : 0.0; });
+        return (r < nv && c >= 1) ? d->Wdu[(size_t)r * m + (c - 1)] : 0.0; });
     // b = -2 E^T t
     C.mf = tb.add(C.n_f, R, [&](int r, int c) -> double {
         return r < nv ? -2.0 * d->E[(size_t)c * nv + r] : 0.0; });
-    // Hessian tiles (lower), k-space [pesos ; 1]
+    // Hessian tiles (lower), k-space [1 ; pesos]: Ht at k = 0, HJ_a at k = 1 + hj_index[a]  (dense k-tiles)
+    std::vector<double> BH;
+    std::vector<int> hrows;
     {
-        C.mh = (int)tb.ptr.size();
-        const int KT = (m + 1 + 3) / 4;
+        int kmax = 0;
+        for (int a = 0; a < d->mh; ++a) if (1 + d->hj_index[a] > kmax) kmax = 1 + d->hj_index[a];
+        C.KH = (kmax + 1 + 3) / 4;
+        if (C.KH > TL_KHMAX) return cudaSuccess;
+        C.ntile = ntiles;
+        BH.assign((size_t)ntiles * 8 * C.KH * 32, 0.0);
+        hrows.assign(ntiles, 0);
         for (int I = 0; I < C.NT; ++I)
-            for (int J = 0; J <= I; ++J)
-                for (int r = 0; r < 8; ++r) {
-                    const int row = 8 * I + r;
-                    if (row >= nv) continue;
-                    tb.hmap.push_back(tl_tid(I, J) * 64 + r * 8);
-                    tb.ptr.push_back((int)tb.kt.size());
-                    for (int t = 0; t < KT; ++t) {
-                        double tile[32];
-                        bool nz = false;
+            for (int J = 0; J <= I; ++J) {
+                const int tid = tl_tid(I, J);
+                int nr = nv - 8 * I; if (nr < 0) nr = 0; if (nr > 8) nr = 8;
+                hrows[tid] = nr;
+                for (int r = 0; r < nr; ++r)
+                    for (int t = 0; t < C.KH; ++t)
                         for (int lane = 0; lane < 32; ++lane) {
                             const int n = lane >> 2, k = lane & 3;
-                            const int col = 8 * J + n, kk = 4 * t + k;
+                            const int row = 8 * I + r, col = 8 * J + n, kk = 4 * t + k;
                             double v = 0.0;
                             if (col <= row && col < nv && kk <= m) {
-                                if (kk == m) v = d->Ht[(size_t)row * nv + col];
-                                else {
+                                if (kk == 0) v = d->Ht[(size_t)row * nv + col];
+                                else
                                     for (int a = 0; a < d->mh; ++a)
-                                        if (d->hj_index[a] == kk) v += d->HJ[((size_t)a * nv + row) * nv + col];
-                                    if (col == row) v += 2.0 * d->Wdu[(size_t)row * m + kk];
-                                }
+                                        if (d->hj_index[a] == kk - 1) v += d->HJ[((size_t)a * nv + row) * nv + col];
                             }
-                            tile[lane] = v;
-                            if (v != 0.0) nz = true;
+                            BH[(((size_t)tid * 8 + r) * C.KH + t) * 32 + lane] = v;
                         }
-                        if (nz) { tb.kt.push_back(t); tb.B.insert(tb.B.end(), tile, tile + 32); }
-                    }
-                }
-        tb.ptr.push_back((int)tb.kt.size());
-        C.n_h = (int)tb.hmap.size();
+            }
     }
     // r += [E ; Mi1u] dU
     C.mr = tb.add(C.n_r, K_sv, [&](int r, int c) -> double {
@@ -614,31 +713,39 @@ inline cudaError_t tile_configure(const sihmpc_plan_desc *d, const DevPlan &P, T
         if (c < nsq) return d->Wrow[(size_t)c * m + i];
         const int v = c - nsq;
         return v >= nu ? d->Wdu[(size_t)(v - nu) * m + i] : 0.0; });
+    // x+ = [A | B][x ; du]  (shared plant; per-scenario plant values use the CSR path)
+    C.mpl = tb.add(C.n_x, K_sv, [&](int r, int c) -> double {
+        if (r >= nx || c >= nx + nu) return 0.0;
+        for (int pp = d->pl_rowptr[r]; pp < d->pl_rowptr[r + 1]; ++pp)
+            if (d->pl_col[pp] == c) return d->pl_val[pp];
+        return 0.0; });
     (void)N;
 
-    const size_t np = tb.ptr.size(), nk = tb.kt.size(), nh = tb.hmap.size();
+    const size_t np = tb.ptr.size(), nk = tb.seg.size(), nh = hrows.size();
     std::vector<int> ib(np + nk + nh);
     memcpy(ib.data(), tb.ptr.data(), np * sizeof(int));
-    memcpy(ib.data() + np, tb.kt.data(), nk * sizeof(int));
-    memcpy(ib.data() + np + nk, tb.hmap.data(), nh * sizeof(int));
+    memcpy(ib.data() + np, tb.seg.data(), nk * sizeof(int));
+    memcpy(ib.data() + np + nk, hrows.data(), nh * sizeof(int));
     cudaError_t e = cudaMalloc(&tp->ibuf, ib.size() * sizeof(int));
     if (e != cudaSuccess) return e;
     e = cudaMemcpy(tp->ibuf, ib.data(), ib.size() * sizeof(int), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return e;
-    e = cudaMalloc(&tp->dbuf, (tb.B.size() + 32) * sizeof(double));
+    const size_t nB = (tb.B.size() + 31) & ~(size_t)31;
+    e = cudaMalloc(&tp->dbuf, (nB + BH.size() + 32) * sizeof(double));
     if (e != cudaSuccess) return e;
     e = cudaMemcpy(tp->dbuf, tb.B.data(), tb.B.size() * sizeof(double), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return e;
-    C.ptr = tp->ibuf; C.kt = tp->ibuf + np; C.hmap = tp->ibuf + np + nk; C.B = tp->dbuf;
-    tp->n_tiles = (int)nk;
-    auto kern = tile_step_kernel<TL_NTMAX>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp->smem_bytes);
+    e = cudaMemcpy(tp->dbuf + nB, BH.data(), BH.size() * sizeof(double), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return e;
+    C.ptr = tp->ibuf; C.seg = tp->ibuf + np; C.hrows = tp->ibuf + np + nk; C.B = tp->dbuf; C.BH = tp->dbuf + nB;
+    tp->n_tiles = tb.n_stored;
+    e = tile_set_smem(C.NT, tp->smem_bytes);
     if (e != cudaSuccess) return e;
     tp->ok = 1;
     return cudaSuccess;
 }
 
-inline cudaError_t tile_ensure_capacity(TilePlan *tp, long long batch) {
+cudaError_t tile_ensure_capacity(TilePlan *tp, long long batch) {
     if (tp->capacity >= batch) return cudaSuccess;
     if (tp->n_handover) cudaFree(tp->n_handover);
     tp->n_handover = nullptr; tp->start_step = nullptr; tp->capacity = 0;
@@ -647,7 +754,7 @@ inline cudaError_t tile_ensure_capacity(TilePlan *tp, long long batch) {
     return e;
 }
 
-inline cudaError_t tile_launch(const TilePlan &tp, const DevPlan &P, const sihmpc_io &io, long long batch,
+cudaError_t tile_launch(const TilePlan &tp, const DevPlan &P, const sihmpc_io &io, long long batch,
                                int n_steps, int sm_count, cudaStream_t st) {
     const long long n_oct = (batch + TL_WARPS - 1) / TL_WARPS;
     int per_sm = (int)((227 * 1024) / (tp.smem_bytes + 1024));
@@ -655,12 +762,17 @@ inline cudaError_t tile_launch(const TilePlan &tp, const DevPlan &P, const sihmp
     if (per_sm > 4) per_sm = 4;
     const long long cap = (long long)sm_count * per_sm;
     const int grid = (int)(n_oct < cap ? n_oct : cap);
-    tile_step_kernel<TL_NTMAX><<<grid, TL_WARPS * 32, tp.smem_bytes, st>>>(P, tp.cfg, io, batch, n_steps,
-                                                                            tp.start_step, tp.n_handover);
+#define SIH_TL_LAUNCH(N_) case N_: tile_step_kernel<N_><<<grid, TL_WARPS * 32, tp.smem_bytes, st>>>(P, tp.cfg, io, batch, n_steps, tp.start_step, tp.n_handover); break;
+    switch (tp.cfg.NT) {
+        SIH_TL_LAUNCH(1) SIH_TL_LAUNCH(2) SIH_TL_LAUNCH(3) SIH_TL_LAUNCH(4)
+        SIH_TL_LAUNCH(5) SIH_TL_LAUNCH(6) SIH_TL_LAUNCH(7) SIH_TL_LAUNCH(8)
+        default: return cudaErrorInvalidValue;
+    }
+#undef SIH_TL_LAUNCH
     return cudaGetLastError();
 }
 
-inline void tile_destroy(TilePlan *tp) {
+void tile_destroy(TilePlan *tp) {
     if (tp->ibuf) cudaFree(tp->ibuf);
     if (tp->dbuf) cudaFree(tp->dbuf);
     if (tp->n_handover) cudaFree(tp->n_handover);
