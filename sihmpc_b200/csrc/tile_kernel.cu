@@ -113,14 +113,28 @@ __device__ __forceinline__ void tile_row(const TileCfg &C, const int poff, const
 
 __device__ __forceinline__ double tl_rsqrt(const double d) { return fast_rsqrt(d); }
 
-// Right-looking tiled Cholesky of the augmented matrix [H ; b^T] of ONE scenario by ONE warp.
-// A: packed lower 8x8 tiles (row-major 64 doubles each) in shared memory.  On exit the strictly
-// lower part holds L, every 4x4 pivot block holds W = L11^-1 (lower), yv[0..nv) = L^-1 b.
+// Right-looking BLOCK elimination (block LDL^T with 4x4 pivot blocks) of the augmented matrix
+// [H ; b^T] of ONE scenario by ONE warp.  A: packed lower 8x8 tiles (row-major 64 doubles each) in
+// shared memory.  For every panel of four columns:  M = A11^-1 (closed form through two 2x2 blocks:
+// two reciprocals, no square roots),  X = A21 M  (one DMMA per row tile),  C -= X A21^T (one DMMA per
+// trailing tile: A fragment = X, B fragment = the panel itself).  H = L D L^T with L = X unit block
+// lower and D = blockdiag(A11), so with the right-hand side riding along as row nv:
+//     w = D^-1 L^-1 b = the X values of row nv,      z_blk = w_blk - sum_{i below} X[i][blk] z_i.
+// On exit the strictly-lower part of A holds X and yv[0..nv) = w.
 //
 // Everything is compile-time (NT tile rows, panel P): the trailing matrix lives in REGISTERS as MMA C
 // fragments (c[tile]), so a trailing update is one DMMA and nothing else; only the four columns of the
-// current panel go through shared memory (C layout -> A/B layout), which is also where L is kept for
-// the backward substitution.
+// current panel go through shared memory (C layout -> A/B layout).
+__device__ __forceinline__ double tl_rcp(const double d) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    double e = fma(-d, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-d, y, 1.0);
+    y = fma(y, e, y);
+    return y;
+}
+
 template <int NT, int P>
 __device__ __forceinline__ void tfs_panel(double2 (&c)[NT * (NT + 1) / 2], double *A, double *yv, const int nv,
                                           const int rb, const int lane, int &notpd) {
@@ -135,81 +149,76 @@ __device__ __forceinline__ void tfs_panel(double2 (&c)[NT * (NT + 1) / 2], doubl
                     *reinterpret_cast<double2 *>(A + (I * (I + 1) / 2 + J) * 64 + q * 8 + 2 * g) = c[I * (I + 1) / 2 + J];
             }
             __syncwarp();
-            // (b) 4x4 pivot block, factorised and inverted redundantly by every lane
-            double *D = A + (J * (J + 1) / 2 + J) * 64 + c0 * 8 + c0;     // element (r,c) at D[r*8+c]
             const int nreal = (nv - 4 * P < 4) ? (nv - 4 * P) : 4;        // columns >= nreal: identity
-            double a00 = D[0], a10 = D[8], a11 = D[9], a20 = D[16], a21 = D[17], a22 = D[18];
-            double a30 = D[24], a31 = D[25], a32 = D[26], a33 = D[27];
-            if (!(a00 > 0.0)) { notpd = 1; a00 = 1.0; }
-            const double i00 = tl_rsqrt(a00);
-            const double l10 = a10 * i00, l20 = a20 * i00, l30 = a30 * i00;
-            double d1 = fma(-l10, l10, a11);
-            if (nreal < 2) d1 = 1.0; else if (!(d1 > 0.0)) { notpd = 1; d1 = 1.0; }
-            const double i11 = tl_rsqrt(d1);
-            const double l21 = (nreal < 2) ? 0.0 : fma(-l20, l10, a21) * i11;
-            const double l31 = (nreal < 2) ? 0.0 : fma(-l30, l10, a31) * i11;
-            double d2 = fma(-l21, l21, fma(-l20, l20, a22));
-            if (nreal < 3) d2 = 1.0; else if (!(d2 > 0.0)) { notpd = 1; d2 = 1.0; }
-            const double i22 = tl_rsqrt(d2);
-            const double l32 = (nreal < 3) ? 0.0 : fma(-l31, l21, fma(-l30, l20, a32)) * i22;
-            double d3 = fma(-l32, l32, fma(-l31, l31, fma(-l30, l30, a33)));
-            if (nreal < 4) d3 = 1.0; else if (!(d3 > 0.0)) { notpd = 1; d3 = 1.0; }
-            const double i33 = tl_rsqrt(d3);
-            const double w10 = -l10 * i00 * i11;
-            const double w21 = -l21 * i11 * i22;
-            const double w32 = -l32 * i22 * i33;
-            const double w20 = -fma(l21, w10, l20 * i00) * i22;
-            const double w31 = -fma(l32, w21, l31 * i11) * i33;
-            const double w30 = -fma(l32, w20, fma(l31, w10, l30 * i00)) * i33;
-            double wqg;                                                // W[q][g], zero outside the block
-            {
-                const double r0 = (g == 0) ? i00 : 0.0;
-                const double r1 = (g == 0) ? w10 : ((g == 1) ? i11 : 0.0);
-                const double r2 = (g == 0) ? w20 : ((g == 1) ? w21 : ((g == 2) ? i22 : 0.0));
-                const double r3 = (g == 0) ? w30 : ((g == 1) ? w31 : ((g == 2) ? w32 : i33));
-                wqg = (q == 0) ? r0 : ((q == 1) ? r1 : ((q == 2) ? r2 : ((q == 3) ? r3 : 0.0)));
-                if (q >= nreal) wqg = 0.0;
-            }
-            // (c,d) panel solve  L21 = A21 W^T : A fragments from home, results (C layout, lanes g<2) back home
+            // the panel in A/B layout (rows of the pivot block itself do not take part)
             double pl[NT];
 #pragma unroll
             for (int I = J; I < NT; ++I) {
                 double v = A[(I * (I + 1) / 2 + J) * 64 + q * 8 + c0 + g];
-                if (I == J && q < c0 + 4) v = 0.0;                     // rows in or above the pivot block
+                if (I == J && q < c0 + nreal) v = 0.0;
                 pl[I] = v;
             }
+            // (b) M = A11^-1, redundantly in every lane
+            const double *D = A + (J * (J + 1) / 2 + J) * 64 + c0 * 8 + c0;   // element (r,c) at D[r*8+c]
+            double a00 = D[0], a10 = D[8], a11 = D[9], a20 = D[16], a21 = D[17], a22 = D[18];
+            double a30 = D[24], a31 = D[25], a32 = D[26], a33 = D[27];
+            if (nreal < 4) { a30 = a31 = a32 = 0.0; a33 = 1.0; }
+            if (nreal < 3) { a20 = a21 = 0.0; a22 = 1.0; }
+            if (nreal < 2) { a10 = 0.0; a11 = 1.0; }
+            double detp = fma(a00, a11, -a10 * a10);
+            if (!(a00 > 0.0) || !(detp > 0.0)) { notpd = 1; detp = 1.0; }
+            const double ip = tl_rcp(detp);
+            const double p00 = a11 * ip, p10 = -a10 * ip, p11 = a00 * ip;
+            const double t00 = fma(a20, p00, a21 * p10), t01 = fma(a20, p10, a21 * p11);
+            const double t10 = fma(a30, p00, a31 * p10), t11 = fma(a30, p10, a31 * p11);
+            const double s00 = a22 - fma(t00, a20, t01 * a21);
+            const double s10 = a32 - fma(t10, a20, t11 * a21);
+            const double s11 = a33 - fma(t10, a30, t11 * a31);
+            double dets = fma(s00, s11, -s10 * s10);
+            if (!(s00 > 0.0) || !(dets > 0.0)) { notpd = 1; dets = 1.0; }
+            const double is = tl_rcp(dets);
+            const double m22 = s11 * is, m32 = -s10 * is, m33 = s00 * is;
+            const double u00 = fma(m22, t00, m32 * t10), u01 = fma(m22, t01, m32 * t11);
+            const double u10 = fma(m32, t00, m33 * t10), u11 = fma(m32, t01, m33 * t11);
+            const double m00 = p00 + fma(t00, u00, t10 * u10);
+            const double m10 = p10 + fma(t01, u00, t11 * u10);
+            const double m11 = p11 + fma(t01, u01, t11 * u11);
+            double mqg;                                                // M[q][g] (symmetric), zero for q >= 4
+            {
+                const double r0 = (g == 0) ? m00 : ((g == 1) ? m10 : ((g == 2) ? -u00 : -u10));
+                const double r1 = (g == 0) ? m10 : ((g == 1) ? m11 : ((g == 2) ? -u01 : -u11));
+                const double r2 = (g == 0) ? -u00 : ((g == 1) ? -u01 : ((g == 2) ? m22 : m32));
+                const double r3 = (g == 0) ? -u10 : ((g == 1) ? -u11 : ((g == 2) ? m32 : m33));
+                mqg = (q == 0) ? r0 : ((q == 1) ? r1 : ((q == 2) ? r2 : ((q == 3) ? r3 : 0.0)));
+            }
+            // (c) X = A21 M : results (C layout, lanes g<2) back home
             {
                 double o[NT][2];
 #pragma unroll
-                for (int I = J; I < NT; ++I) { o[I][0] = o[I][1] = 0.0; dmma884(o[I][0], o[I][1], pl[I], wqg); }
+                for (int I = J; I < NT; ++I) { o[I][0] = o[I][1] = 0.0; dmma884(o[I][0], o[I][1], pl[I], mqg); }
                 if (g < 2) {
 #pragma unroll
                     for (int I = J; I < NT; ++I)
-                        if (!(I == J && q < c0 + 4))
+                        if (!(I == J && q < c0 + nreal))
                             *reinterpret_cast<double2 *>(A + (I * (I + 1) / 2 + J) * 64 + q * 8 + c0 + 2 * g) = make_double2(o[I][0], o[I][1]);
                 }
             }
-            if (nreal < 4 && lane < nreal) {                           // right-hand-side row inside the pivot block
-                const double y0 = (nreal == 1) ? l10 : ((nreal == 2) ? l20 : l30);
-                const double y1 = (nreal == 2) ? l21 : l31;
-                yv[4 * P + lane] = (lane == 0) ? y0 : ((lane == 1) ? y1 : l32);
-            }
-            if (lane < 16 && g <= q && q < nreal) D[q * 8 + g] = wqg;     // (q,g) = (row, col) of W for lane < 16
             __syncwarp();
-            if (nreal == 4 && lane < 4) yv[4 * P + lane] = A[(Ib * (Ib + 1) / 2 + J) * 64 + rb * 8 + c0 + lane];
-            // (e) trailing update on the register tiles: c(I,K) -= L21_I L21_K^T
+            if (lane < nreal) yv[4 * P + lane] = A[(Ib * (Ib + 1) / 2 + J) * 64 + rb * 8 + c0 + lane];
+            // (d) trailing update on the register tiles: c(I,K) -= X_I A21_K^T
             if constexpr (P + 1 < 2 * NT) {
+                double xa[NT];
 #pragma unroll
                 for (int I = J; I < NT; ++I) {
                     double v = A[(I * (I + 1) / 2 + J) * 64 + q * 8 + c0 + g];
                     if (I == J && q < c0 + 4) v = 0.0;
-                    pl[I] = v;
+                    xa[I] = -v;
                 }
 #pragma unroll
                 for (int K = J + (c0 ? 1 : 0); K < NT; ++K) {
 #pragma unroll
                     for (int I = K; I < NT; ++I)
-                        dmma884(c[I * (I + 1) / 2 + K].x, c[I * (I + 1) / 2 + K].y, -pl[I], pl[K]);
+                        dmma884(c[I * (I + 1) / 2 + K].x, c[I * (I + 1) / 2 + K].y, xa[I], pl[K]);
                 }
             }
         }
@@ -237,29 +246,30 @@ __device__ __forceinline__ int tile_factor(double *A, const double *omdu_w, cons
     return notpd;
 }
 
-// L^T z = y with the stored W blocks: zv[0..nv)
-__device__ void tile_backsolve(const double *A, const int NP, const int nv, const int lane, const double *yv,
-                               double *zv) {
-    const int rq = lane >> 2, cg = lane & 3;
-    for (int p = NP - 1; p >= 0; --p) {
-        const int J = p >> 1, c0 = (p & 1) * 4;
-        const int nreal = (nv - 4 * p < 4) ? (nv - 4 * p) : 4;
-        double acc = 0.0;
-        for (int i = 4 * p + 4 + rq; i < nv; i += 8)
-            acc = fma(A[tl_tid(i >> 3, J) * 64 + (i & 7) * 8 + c0 + cg], zv[i], acc);
-        acc += __shfl_xor_sync(SIH_FULL, acc, 4);
-        acc += __shfl_xor_sync(SIH_FULL, acc, 8);
-        acc += __shfl_xor_sync(SIH_FULL, acc, 16);
-        const double t = (cg < nreal) ? yv[4 * p + cg] - acc : 0.0;
-        const double *D = A + tl_tid(J, J) * 64 + c0 * 8 + c0;
-        double z = 0.0;
+// backward substitution  z_blk = w_blk - sum_{i below} X[i][blk] z_i ; zv[nv..8NT) must be zero
+template <int NT, int P>
+__device__ __forceinline__ void tbs_panel(const double *A, const int nv, const int lane, const double *yv, double *zv) {
+    if constexpr (P >= 0) {
+        constexpr int J = P >> 1, c0 = (P & 1) * 4;
+        if (4 * P < nv) {
+            const int rq = lane >> 2, cg = lane & 3;
+            double acc = 0.0;
+            constexpr int NJ = c0 ? (NT - J - 1) : (NT - J);
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const double tr = __shfl_sync(SIH_FULL, t, r, 4);
-            if (r >= cg && r < nreal) z = fma(D[r * 8 + cg], tr, z);
+            for (int j = 0; j < NJ; ++j) {
+                // rows i = 4P + 4 + rq + 8j
+                int T, row;
+                if (c0) { T = J + 1 + j; row = rq; }
+                else { T = J + j + (rq >> 2); row = (rq + 4) & 7; }
+                if (T < NT) acc = fma(A[(T * (T + 1) / 2 + J) * 64 + row * 8 + c0 + cg], zv[8 * T + row], acc);
+            }
+            acc += __shfl_xor_sync(SIH_FULL, acc, 4);
+            acc += __shfl_xor_sync(SIH_FULL, acc, 8);
+            acc += __shfl_xor_sync(SIH_FULL, acc, 16);
+            if (rq == 0 && 4 * P + cg < nv) zv[4 * P + cg] = yv[4 * P + cg] - acc;
+            __syncwarp();
         }
-        if (rq == 0 && cg < nreal) zv[4 * p + cg] = z;
-        __syncwarp();
+        tbs_panel<NT, P - 1>(A, nv, lane, yv, zv);
     }
 }
 
@@ -368,7 +378,7 @@ tile_step_kernel(const DevPlan P, const TileCfg C, const sihmpc_io io, const lon
             __syncthreads();                              // [C]
             // ---------------- P3 (warp per scenario): factorise, solve, check the boxes
             const int notpd = tile_factor<NT>(Hw, omduw, nv, C.rb, lane, yw);
-            tile_backsolve(Hw, C.NP, nv, lane, yw, zw);
+            tbs_panel<NT, 2 * NT - 1>(Hw, nv, lane, yw, zw);
             for (int i = lane; i < nv; i += 32) svw[nx + i] = zw[i];
             double viol = 0.0, viol_abs = 0.0;
             if (P.has_box)
