@@ -552,6 +552,8 @@ tile_step_kernel(const DevPlan P, const TileCfg C, const sihmpc_io io, const lon
                         pw[1 + i] = 1.0 / (g0 - fmin(fmax(vnw[i], 0.0), 0.99 * g0));
                     }
                 }
+            } else {
+                __syncthreads();                          // the owners may not touch ysp before every y tile is done
             }
         }  // steps
 
