@@ -82,54 +82,96 @@ def algorithmic_bytes(plan):
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
+    """SM clock, power and throttle reasons sampled DURING the timed region: NVML from a thread (about
+    1 ms per sample, so a 50 ms region still gets tens of samples); nvidia-smi as the fall-back."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index, period_ms=20):
-        self.samples = []
+    def __init__(self, index, uuid=None, period_s=0.001):
+        self.samples = []          # (t, sm_mhz, sm_max_mhz, power_w, [hw, hw_thermal, sw_thermal, sw_power_cap])
         self.proc = None
-        self.t = None
+        self.stop_flag = False
+        self.source = None
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", str(period_ms)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml as N
+            N.nvmlInit()
+            h = None
+            if uuid:
+                for cand in (uuid, "GPU-" + uuid):
+                    try:
+                        h = N.nvmlDeviceGetHandleByUUID(cand if isinstance(cand, bytes) else cand.encode())
+                        break
+                    except Exception:
+                        h = None
+            if h is None:
+                h = N.nvmlDeviceGetHandleByIndex(index)
+            self.N, self.h = N, h
+            self.max_sm = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+            self.period = period_s
+            self.source = "nvml"
+            self.t = threading.Thread(target=self._poll, daemon=True)
             self.t.start()
         except Exception:
-            self.proc = None
+            self.source = None
+        if self.source is None:
+            try:
+                self.proc = subprocess.Popen(
+                    ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                     "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self.source = "nvidia-smi"
+                self.t = threading.Thread(target=self._read, daemon=True)
+                self.t.start()
+            except Exception:
+                self.proc = None
+
+    def _poll(self):
+        N, h = self.N, self.h
+        bits = [getattr(N, "nvmlClocksEventReasonHwSlowdown", 0x8), getattr(N, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                getattr(N, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), getattr(N, "nvmlClocksEventReasonSwPowerCap", 0x4)]
+        get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            try:
+                sm = float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM))
+                pw = N.nvmlDeviceGetPowerUsage(h) / 1000.0
+                r = int(get_reasons(h))
+                self.samples.append((time.time(), sm, self.max_sm, pw, [bool(r & b) for b in bits]))
+            except Exception:
+                pass
+            time.sleep(self.period)
 
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append((time.time(), line.strip()))
-
-    def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.05)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        rows = []
-        for ts, line in self.samples:
             f = [x.strip() for x in line.split(",")]
             if len(f) < 7:
                 continue
             try:
-                rows.append((ts, float(f[0]), float(f[1]), float(f[2]), f[3:7]))
+                self.samples.append((time.time(), float(f[0]), float(f[1]), float(f[2]),
+                                     [x.lower().startswith("active") for x in f[3:7]]))
             except ValueError:
                 continue
-        inside = [r for r in rows if t0 - 0.02 <= r[0] <= t1 + 0.02]
+
+    def stop(self, t0, t1):
+        if self.source is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML / nvidia-smi"]}
+        time.sleep(0.01)
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        rows = list(self.samples)
+        inside = [r for r in rows if t0 <= r[0] <= t1]
         use = inside if len(inside) >= 2 else [r for r in rows if r[3] > 250.0] or rows
         if not use:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in use for i in range(4) if r[4][i].lower().startswith("active")})
+        reasons = sorted({names[i] for r in use for i in range(4) if r[4][i]})
         return {"sm_mhz": float(np.median([r[1] for r in use])), "sm_max_mhz": use[0][2],
                 "power_w_max": max(r[3] for r in use), "samples": len(use),
-                "samples_in_timed_region": len(inside), "reasons": reasons}
+                "samples_in_timed_region": len(inside), "source": self.source, "reasons": reasons}
 
 
 # ----------------------------------------------------------------------------- CPU arm (oracle port)
@@ -279,7 +321,13 @@ def main():
     eng.reduce_stats()
     torch.cuda.synchronize(dev)
     flush.fill_(1)                                     # L2 flush before the timed region
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = None
+    if rank == 0:
+        try:
+            uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+        except Exception:
+            uuid = None
+        sampler = ClockSampler(local_rank, uuid)
     barrier()
     # ---- timed region: EXACTLY K control steps (+ the statistics reduction / NCCL exchange)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
@@ -361,10 +409,20 @@ def main():
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    # DRAM traffic of the same kernel from the committed ncu --set full capture (profiles/ncu_traffic.json:
+    # bytes per scenario per launch, measured at the listed batch), scaled to this launch; None if not captured
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        ent = tj.get(eng.dp.kernel_name() + ":" + args.workload)
+        if ent:
+            traffic = float(ent["dram_bytes_per_scenario_launch"]) * batch
+    except Exception:
+        pass
     roofline = {"bound": "fp64", "achieved": achieved_tflops, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
-                "frac": achieved_tflops / (fp64_peak / 1e12), "traffic": None,
+                "frac": achieved_tflops / (fp64_peak / 1e12), "traffic": traffic,
                 "peak_source": "measured in this run (sihmpc_fp64_peak: dependent-free DFMA loop, all SMs)",
-                "flop_per_scenario_step": F_alg, "kernel": "sih::ihmpc_step_kernel",
+                "flop_per_scenario_step": F_alg, "kernel": "sih::" + eng.dp.kernel_name(),
                 "kernel_ms_per_launch": per_launch_s * 1e3, "launches": n_launch,
                 "hbm": {"achieved": B_alg * batch / per_launch_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "bytes_per_scenario_launch": B_alg,

@@ -154,6 +154,11 @@ int sihmpc_device_count(void);                        /* 0 without a usable CUDA
 int sihmpc_plan_create(const sihmpc_plan_desc *desc, sihmpc_plan **out);
 int sihmpc_plan_destroy(sihmpc_plan *plan);
 size_t sihmpc_workspace_bytes(const sihmpc_plan *plan, int64_t batch);
+/* Name of the kernel that serves sihmpc_step for this plan: "mma_step_kernel" (register quads + DMMA,
+ * distillation shape), "tile_step_kernel" (tile-CSR DMMA products + tiled block LDL^T, N*nu < 64),
+ * "quad_step_kernel" or "ihmpc_step_kernel" (general warp-per-scenario active set; also the second pass
+ * for scenarios a fast path hands over).  Static string, never NULL. */
+const char *sihmpc_plan_kernel(const sihmpc_plan *plan);
 
 /* -- the hot path --------------------------------------------------------------------------- */
 /* replaces: IHMPCController.mpc (ihmpccontroller.py:567-604) for `batch` scenarios at once and,

@@ -296,6 +296,14 @@ size_t sihmpc_workspace_bytes(const sihmpc_plan *plan, int64_t batch) {
     return (size_t)plan->max_grid * plan->wpb * scratch_doubles_per_warp(plan->d.nv) * sizeof(double) + 256;
 }
 
+const char *sihmpc_plan_kernel(const sihmpc_plan *plan) {
+    if (!plan) return "none";
+    if (plan->tile.ok && (plan->use_fast == 3 || (plan->use_fast == 2 && plan->mma.shape < 0))) return "tile_step_kernel";
+    if (plan->use_fast == 2 && plan->mma.shape >= 0) return "mma_step_kernel";
+    if (plan->use_fast == 1 && plan->quad.shape >= 0) return "quad_step_kernel";
+    return "ihmpc_step_kernel";
+}
+
 int sihmpc_step(sihmpc_plan *plan, const sihmpc_io *io, int64_t batch, int32_t n_steps,
                 void *workspace, size_t workspace_bytes, void *stream) {
     if (!plan || !io) return fail(SIHMPC_E_INVALID, "NULL argument%s");

@@ -282,8 +282,6 @@ tile_step_kernel(const DevPlan P, const TileCfg C, const sihmpc_io io, const lon
     const int nx = P.nx, nu = P.nu, ny = P.ny, nv = P.nv, m = P.m, R = P.R, Ny = P.Ny;
     const int nstat = ny + SIHMPC_NSTATS_EXTRA;
     const bool advance = (io.flags & SIHMPC_F_ADVANCE) != 0;
-    for (int i = threadIdx.x; i < C.total; i += blockDim.x) sm[i] = 0.0;
-    __syncthreads();
     double *Hs = sm + C.o_H, *sv = sm + C.o_sv, *eb = sm + C.o_e, *omb = sm + C.o_om, *tb = sm + C.o_t;
     double *omdu = sm + C.o_omdu, *pes = sm + C.o_pes, *sq = sm + C.o_sq, *vn = sm + C.o_vn;
     double *scb = sm + C.o_sc;
@@ -300,6 +298,10 @@ tile_step_kernel(const DevPlan P, const TileCfg C, const sihmpc_io io, const lon
 
     const long long n_oct = (batch + TL_WARPS - 1) / TL_WARPS;
     for (long long oct = blockIdx.x; oct < n_oct; oct += gridDim.x) {
+        // every slot starts from clean buffers: padding entries are never rewritten inside the loop, and a
+        // scenario that was handed over keeps stepping unconstrained in its slot and may leave Inf/NaN there
+        for (int i = threadIdx.x; i < C.total; i += blockDim.x) sm[i] = 0.0;
+        __syncthreads();
         const long long s = oct * TL_WARPS + w;
         const bool valid = s < batch;
         const long long sl = valid ? s : batch - 1;

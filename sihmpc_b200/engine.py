@@ -47,6 +47,10 @@ class DevicePlan:
             self._ws_bytes = need
         return self._ws, self._ws_bytes
 
+    def kernel_name(self) -> str:
+        """Kernel that serves sihmpc_step for this plan (sihmpc_plan_kernel)."""
+        return self.lib.sihmpc_plan_kernel(self.handle).decode()
+
     def close(self):
         if self.handle:
             self.lib.sihmpc_plan_destroy(self.handle)
