@@ -49,6 +49,7 @@ struct sihmpc_plan {
     int blocks_per_sm;
     size_t smem_bytes;
     int max_grid;
+    int scratch_in_smem;     // general kernel: active-set workspace in shared memory (small controllers)
     sih::QuadPlan quad;      // register-tiled fast path v2 (dist_kernel.cuh), shape<0: none
     sih::MmaPlan mma;        // register-tiled + FP64 tensor-core fast path v3 (mma_kernel.cuh), shape<0: none
     sih::TilePlan tile;      // CTA-cooperative tile path v4 for mid-size controllers (tile_kernel.cuh), ok=0: none
@@ -114,6 +115,13 @@ int configure(sihmpc_plan *p) {
     while (wpb > 2 && per_warp * wpb > limit / 2) wpb >>= 1;
     p->wpb = wpb;
     p->smem_bytes = per_warp * wpb;
+    // small controllers: the active-set workspace lives in shared memory as well
+    const size_t sbytes = scratch_doubles_per_warp(p->d.nv) * sizeof(double);
+    p->scratch_in_smem = 0;
+    if ((per_warp + sbytes) * wpb <= limit / 2) {
+        p->scratch_in_smem = 1;
+        p->smem_bytes += sbytes * wpb;
+    }
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));
     int occ = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpb * 32, p->smem_bytes));
@@ -132,7 +140,7 @@ int launch_step(sihmpc_plan *p, const sihmpc_io &io, long long batch, int n_step
     const int max_outer = 8 * (2 * p->d.nv + p->d.ncd) + 16;
     sih::ihmpc_step_kernel<NVR><<<grid, p->wpb * 32, p->smem_bytes, st>>>(p->d, io, batch, n_steps,
                                                                            scratch, max_outer, start_step,
-                                                                           n_handover);
+                                                                           n_handover, p->scratch_in_smem);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

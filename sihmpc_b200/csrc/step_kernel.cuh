@@ -106,9 +106,9 @@ __device__ void warp_trsv_lower_T(const double *L, int ld, const double *dinv, i
                                   double (&acc)[NVR], int lane) {
 #pragma unroll
     for (int t = NVR - 1; t >= 0; --t) {
-        for (int jj = 31; jj >= 0; --jj) {
+        const int jj0 = (n - 1 - 32 * t < 31) ? (n - 1 - 32 * t) : 31;
+        for (int jj = jj0; jj >= 0; --jj) {
             const int j = t * 32 + jj;
-            if (j >= n) continue;
             const double zj = __shfl_sync(SIH_FULL, acc[t], jj) * dinv[j];
             if (lane == jj) acc[t] = zj;
 #pragma unroll
@@ -267,16 +267,23 @@ __device__ void eval_subobjectives(const DevPlan &P, const double *xs, const dou
 // ------------------------------------------------------------------------------------------
 template <int NVR>
 __global__ void __launch_bounds__(256, (NVR == 1 ? 2 : 1))
-ihmpc_step_kernel(const DevPlan P, const sihmpc_io io, const long long batch, const int n_steps,
+ihmpc_step_kernel(const DevPlan P_in, const sihmpc_io io, const long long batch, const int n_steps,
                   double *__restrict__ scratch, const int max_outer,
-                  const int *__restrict__ start_step, const int *__restrict__ n_handover) {
-    // second pass after the quad fast path: only scenarios it handed over (start_step < n_steps)
+                  const int *__restrict__ start_step, const int *__restrict__ n_handover,
+                  const int scratch_in_smem) {
+    // second pass after a fast path: only scenarios it handed over (start_step < n_steps)
     if (n_handover && *n_handover == 0x7f7f7f7f) return;     // counter baseline: the buffer is memset to 0x7f
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const long long gw = (long long)blockIdx.x * wpb + wib;
     const long long nwarps = (long long)gridDim.x * wpb;
+    const DevPlan &P = P_in;
     const WarpLayout lay = make_layout(P);
+    if (start_step) {                                        // a CTA without any handed-over scenario leaves at once
+        int any = 0;
+        for (long long s = gw; s < batch; s += nwarps) any |= (start_step[s] < n_steps);
+        if (!__syncthreads_or(any)) return;
+    }
     double *W = smem + (size_t)wib * lay.total;
     double *Ls = W + lay.L, *dinv = W + lay.dinv, *xin = W + lay.xin, *xnew = W + lay.xnew;
     double *uu = W + lay.uu, *ysp = W + lay.ysp, *pes = W + lay.pes, *vin = W + lay.vin;
@@ -287,7 +294,10 @@ ihmpc_step_kernel(const DevPlan P, const sihmpc_io io, const long long batch, co
 
     const int nx = P.nx, nu = P.nu, ny = P.ny, nv = P.nv, m = P.m, R = P.R, ld = P.ld;
     const int lds = nv | 1;
-    double *scr = scratch + (size_t)gw * scratch_doubles_per_warp(nv);
+    // active-set workspace: in shared memory when it fits (a handed-over scenario is stepped by ONE warp on a
+    // nearly idle machine: its S = Y Y^T refactorisations are chains of dependent loads), else global scratch
+    double *scr = scratch_in_smem ? smem + (size_t)wpb * lay.total + (size_t)wib * scratch_doubles_per_warp(nv)
+                                  : scratch + (size_t)gw * scratch_doubles_per_warp(nv);
     double *Ya = scr;                               // [nv][nv]
     double *Sa = Ya + (size_t)nv * nv;              // [nv][lds]
     double *Rf = Sa + (size_t)nv * lds;             // [nv][lds]
@@ -400,11 +410,73 @@ ihmpc_step_kernel(const DevPlan P, const sihmpc_io io, const long long batch, co
             __syncwarp();
 
             // dual active set (Goldfarb-Idnani, range-space form)
+            const int q_prev = q;                   // active rows at the optimum of the previous step of this scenario
             q = 0;
             int outer = 0;
             RowScan sc;
             const bool any_rows = P.has_box || P.has_cum || P.ncd > 0;
             sc.rel = 0.0; sc.abs = 0.0; sc.code = -1;
+            // Warm start: a scenario that sits on a bound keeps (almost) the same active set from step to step.
+            // Solve the equality-constrained problem on the previous set in one go: Y = L^-1 N_A, S = Y Y^T,
+            // S lam = b_A - N_A^T v0, v = v0 + L^-T Y^T lam.  With every lam >= 0 this (v, A, lam) is an S-pair,
+            // i.e. a valid state of the dual method, which then only adds what is still violated; otherwise
+            // the cold start below runs unchanged.  Either way the loop ends at the unique optimum.
+            if (any_rows && q_prev > 0 && q_prev <= nv) {
+                for (int a = 0; a < q_prev; ++a) {
+                    const int code = act[a];
+                    const double bp = load_normal(P, code, uu, glo, ghi, nrm, lane);
+                    double dot = 0.0;
+                    for (int i = lane; i < nv; i += 32) dot = fma(nrm[i], v[i], dot);
+                    dot = warp_sum(dot);
+                    if (lane == 0) cbuf[a] = bp - dot;
+                    load_acc<NVR>(acc, nrm, nv, lane, 1.0);
+                    warp_trsv_lower<NVR>(Ls, ld, dinv, nv, acc, lane);
+                    store_acc<NVR>(acc, Ya + (size_t)a * nv, nv, lane);
+                    __syncwarp();
+                }
+                for (int idx = lane; idx < q_prev * q_prev; idx += 32) {
+                    const int a = idx / q_prev, b = idx % q_prev;
+                    if (b <= a) {
+                        double c = 0.0;
+                        for (int i = 0; i < nv; ++i) c = fma(Ya[(size_t)a * nv + i], Ya[(size_t)b * nv + i], c);
+                        Sa[(size_t)a * lds + b] = c; Sa[(size_t)b * lds + a] = c;
+                        Rf[(size_t)a * lds + b] = c;
+                    }
+                }
+                __syncwarp();
+                bool ok = !warp_cholesky<NVR>(Rf, lds, q_prev, rdinv, lane);
+                double ra[NVR];
+                load_acc<NVR>(ra, cbuf, q_prev, lane, 1.0);
+                warp_trsv_lower<NVR>(Rf, lds, rdinv, q_prev, ra, lane);
+                warp_trsv_lower_T<NVR>(Rf, lds, rdinv, q_prev, ra, lane);
+                bool neg = false;
+#pragma unroll
+                for (int t = 0; t < NVR; ++t) {
+                    const int a = lane + 32 * t;
+                    if (a < q_prev && !(ra[t] >= 0.0)) neg = true;
+                }
+                ok = ok && !__any_sync(SIH_FULL, neg);
+                if (ok) {
+                    store_acc<NVR>(ra, lam, q_prev, lane);
+                    __syncwarp();
+                    for (int i = lane; i < nv; i += 32) {
+                        double d = 0.0;
+                        for (int a = 0; a < q_prev; ++a) d = fma(Ya[(size_t)a * nv + i], lam[a], d);
+                        dbuf[i] = d;
+                    }
+                    __syncwarp();
+                    load_acc<NVR>(acc, dbuf, nv, lane, 1.0);
+                    warp_trsv_lower_T<NVR>(Ls, ld, dinv, nv, acc, lane);
+#pragma unroll
+                    for (int tt = 0; tt < NVR; ++tt) {
+                        const int i = lane + 32 * tt;
+                        if (i < nv) v[i] += acc[tt];
+                    }
+                    q = q_prev;
+                    ++iters_total;
+                }
+                __syncwarp();
+            }
             while (any_rows) {
                 sc = scan_rows(P, v, uu, glo, ghi, lane);
                 if (sc.rel <= 1e-10 || sc.code < 0) break;
