@@ -36,14 +36,18 @@ namespace sih {
 
 struct MmaConst {            // offsets in doubles into the packed block
     int be, bw, w0c, bf, br, bh, bomdu, by, byp, bvn, tau, gamma, bounds, vinq, ell_val, total_d;
-    int ell_col, ell_csr, hj_idx, vin_row, total_i;
+    int ell_col, ell_csr, hj_idx, vin_row, vlive, vdead, total_i;
     int ell_w;
 };
 
-template <int NX_, int NU_, int NY_, int ND_, int N_, int M_>
+// NVE_: number of QP variables that are actually eliminated.  Moves whose dead time pushes their whole
+// effect past the horizon have a zero column in E, Ht, HJ: their optimum is exactly 0 (presolve on the
+// host, mma_dead_variables), so the factorisation runs on the NVE_ live ones only; 0 = all of them.
+template <int NX_, int NU_, int NY_, int ND_, int N_, int M_, int NVE_ = 0>
 struct MmaDims {
     static constexpr int NX = NX_, NU = NU_, NY = NY_, ND = ND_, N = N_, M = M_;
-    static constexpr int NV = N * NU;
+    static constexpr int NVL = N * NU;                 // logical QP variables (w_opt layout)
+    static constexpr int NV = NVE_ > 0 ? NVE_ : NVL;   // live variables = dimension of the factorisation
     static constexpr int NYP = N * NY;
     static constexpr int R = NYP + 2 * NY + ND;
     static constexpr int RE = R + NY;
@@ -61,7 +65,7 @@ struct MmaDims {
     static constexpr int KH = 1;                       // k-tile [1 ; pesos of <= 3 dense Hessian blocks]
     static constexpr int KD = (NU + 3) / 4;            // k-tiles of du
     static constexpr int HPAIRS = SV * (SV + 1);
-    static constexpr int BX = 8 * TX, BV = NV;
+    static constexpr int BX = 8 * TX, BV = NVL;
     static constexpr int BRAW = BX + NU + (NU & 1) + BV;
     static constexpr int BS = BRAW + ((2 - BRAW % 4 + 4) % 4);
     static constexpr int WELL = 4;                     // ELL width of the plant map (rows with more non-zeros: no fast path)
@@ -69,7 +73,7 @@ struct MmaDims {
     static constexpr int WARP_DOUBLES = 8 * BS + 8 * PV;
     static_assert(NV % 4 == 0, "N*nu must be a multiple of 4 for the MMA fast path");
     static_assert(M <= 8 && NY <= 4 && NU <= 4, "shape outside the MMA fast path");
-    // variable held by (slot s, lane g) of the factorisation
+    // elimination position held by (slot s, lane g) of the factorisation (live[position] = logical variable)
     __host__ __device__ static constexpr int var_of(int s, int g) {
         return (NV % 8 == 4 && s == SV - 1) ? (NV - 4 + g) : (8 * (s / 2) + 2 * g + (s % 2));
     }
@@ -151,6 +155,11 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
     double *bv = bx + D::BX + NU + (NU & 1);  // replicated dU (logical order)
     double *pval = wbase + 8 * BS + q * D::PV;   // this scenario's plant values in ELL order
 
+    int vlog[SV];                             // logical variable of (slot, this lane)
+#pragma unroll
+    for (int sl = 0; sl < SV; ++sl) vlog[sl] = cint[Q.vlive + D::var_of(sl, g)];
+    for (int e = g; e < D::NVL; e += 4) bv[e] = 0.0;      // presolved moves stay exactly zero
+    __syncwarp();
     const long long gq = ((long long)blockIdx.x * WARPS + wib) * 8 + q;
     const long long nq = (long long)gridDim.x * WARPS * 8;
     const long long rounds = (batch + nq - 1) / nq;
@@ -297,14 +306,14 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
             quad_solve_spd<D>(L, fr, g, notpd);
             // replicated dU (logical order) for the bound check, the outputs and the plant
 #pragma unroll
-            for (int sl = 0; sl < SV; ++sl) bv[D::var_of(sl, g)] = fr[sl];
+            for (int sl = 0; sl < SV; ++sl) bv[vlog[sl]] = fr[sl];
             __syncwarp();
             // ---------------- feasibility of the unconstrained optimum
             double viol = 0.0, viol_abs = 0.0;
             if (P.has_box) {
 #pragma unroll
                 for (int sl = 0; sl < SV; ++sl) {
-                    const int j = D::var_of(sl, g) % NU;
+                    const int j = vlog[sl] % NU;
                     const double lo = cst[Q.bounds + j], hi = cst[Q.bounds + NU + j];
                     if (lo > -SIH_INF) { const double a = lo - fr[sl]; viol_abs = fmax(viol_abs, a); viol = fmax(viol, a / (1.0 + fabs(lo))); }
                     if (hi < SIH_INF) { const double a = fr[sl] - hi; viol_abs = fmax(viol_abs, a); viol = fmax(viol, a / (1.0 + fabs(hi))); }
@@ -375,12 +384,13 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
                 if (last_step) {
                     if (io.du) for (int j = g; j < NU; j += 4) io.du[s * NU + j] = bv[j];
                     if (io.w_opt) {
-                        constexpr int nw = NV + 2 * NY;
+                        constexpr int nw = D::NVL + 2 * NY;
 #pragma unroll
-                        for (int sl = 0; sl < SV; ++sl) io.w_opt[s * nw + D::var_of(sl, g)] = fr[sl];
+                        for (int sl = 0; sl < SV; ++sl) io.w_opt[s * nw + vlog[sl]] = fr[sl];
+                        for (int i = g; i < D::NVL - NV; i += 4) io.w_opt[s * nw + cint[Q.vdead + i]] = 0.0;
                         if (g == 0) {
 #pragma unroll
-                            for (int i = 0; i < 2 * NY; ++i) io.w_opt[s * nw + NV + i] = syv[i];
+                            for (int i = 0; i < 2 * NY; ++i) io.w_opt[s * nw + D::NVL + i] = syv[i];
                         }
                     }
                     if (g == 0) {
@@ -549,24 +559,58 @@ struct MmaPlan {
 };
 
 using DistillationMma = MmaDims<22, 2, 2, 4, 10, 4>;
+using DistillationMma16 = MmaDims<22, 2, 2, 4, 10, 4, 16>;     // four presolved moves (Wood & Berry dead times)
 constexpr int MMA_WARPS = 4;
 #ifndef SIH_MMA_MINB
 #define SIH_MMA_MINB 2
 #endif
 constexpr int MMA_MINB = SIH_MMA_MINB;
 
+// presolve: variable v is dead when nothing but its own move weight depends on it (zero column in E, Mi1u,
+// Ht, HJ), that weight is positive and 0 lies inside its move box: dU_v = 0 exactly
+inline std::vector<int> mma_dead_variables(const DevPlan &P, const sihmpc_plan_desc *d) {
+    std::vector<int> dead;
+    const int nv = P.nv, R = d->R, m = d->m, ny = d->ny, nu = d->nu;
+    for (int v = 0; v < nv; ++v) {
+        bool z = true;
+        for (int r = 0; r < R && z; ++r) z = (d->E[(size_t)r * nv + v] == 0.0);
+        for (int r = 0; r < ny && z; ++r) z = (d->Mi1u[(size_t)r * nv + v] == 0.0);
+        for (int c = 0; c < nv && z; ++c) z = (d->Ht[(size_t)v * nv + c] == 0.0 && d->Ht[(size_t)c * nv + v] == 0.0);
+        for (int a = 0; a < d->mh && z; ++a)
+            for (int c = 0; c < nv && z; ++c)
+                z = (d->HJ[((size_t)a * nv + v) * nv + c] == 0.0 && d->HJ[((size_t)a * nv + c) * nv + v] == 0.0);
+        bool w = false;
+        for (int i = 0; i < m; ++i) { if (d->Wdu[(size_t)v * m + i] > 0.0) w = true; if (d->Wdu[(size_t)v * m + i] < 0.0) z = false; }
+        const int j = v % nu;
+        if (z && w && d->dulb[j] <= 0.0 && d->duub[j] >= 0.0) dead.push_back(v);
+    }
+    return dead;
+}
+
+// 0: all 20 variables live, 1: four presolved moves (16 live), -1: no MMA fast path
 inline int mma_match_shape(const DevPlan &P, const sihmpc_plan_desc *d) {
     for (int i = 0; i < P.nx; ++i)
         if (d->pl_rowptr[i + 1] - d->pl_rowptr[i] > 4) return -1;      // ELL width of the fast path
-    if (P.nx == 22 && P.nu == 2 && P.ny == 2 && P.nd == 4 && P.N == 10 && P.m == 4 && P.ncd == 0 && P.mh <= 3) return 0;
+    if (P.nx == 22 && P.nu == 2 && P.ny == 2 && P.nd == 4 && P.N == 10 && P.m == 4 && P.ncd == 0 && P.mh <= 3) {
+        if (getenv("SIHMPC_NO_PRESOLVE")) return 0;
+        return mma_dead_variables(P, d).size() >= 4 ? 1 : 0;
+    }
     return -1;
 }
 
 template <typename D>
-inline void mma_build_constants(const sihmpc_plan_desc *d, MmaConst &qc, std::vector<double> &buf,
+inline void mma_build_constants(const sihmpc_plan_desc *d, const DevPlan &P, MmaConst &qc, std::vector<double> &buf,
                                 std::vector<int> &ibuf) {
-    constexpr int NX = D::NX, NU = D::NU, NY = D::NY, M = D::M, NV = D::NV, R = D::R, RE = D::RE, NYP = D::NYP;
+    constexpr int NX = D::NX, NU = D::NU, NY = D::NY, M = D::M, NV = D::NV, NVL = D::NVL, R = D::R, RE = D::RE, NYP = D::NYP;
     constexpr int SV = D::SV;
+    // live[position] = logical variable; the last NVL-NV dead variables are presolved
+    std::vector<int> live, deadv;
+    {
+        std::vector<int> dd = mma_dead_variables(P, d);
+        std::vector<char> drop(NVL, 0);
+        for (int i = 0; i < NVL - NV; ++i) drop[dd[dd.size() - 1 - i]] = 1;
+        for (int v = 0; v < NVL; ++v) (drop[v] ? deadv : live).push_back(v);
+    }
     int o = 0;
     auto take = [&](int n) { int r = o; o += (n + 1) & ~1; return r; };
     qc.be = take(D::TR * (D::KX + D::KA) * 32);
@@ -592,10 +636,10 @@ inline void mma_build_constants(const sihmpc_plan_desc *d, MmaConst &qc, std::ve
     // index maps
     auto crow = [](int lim) { return [lim](int T, int n) { int r = 8 * T + n; return r < lim ? r : -1; }; };
     auto ccol = [](int lim) { return [lim](int t, int k) { int r = 8 * (t / 2) + 2 * k + (t % 2); return r < lim ? r : -1; }; };
-    auto vcol = [](int t, int k) { return (t < SV) ? D::var_of(t, k) : -1; };              // dU in factorisation slots
-    auto vrow = [](int T, int n) {                                                            // gradient tiles -> slots
-        if (NV % 8 == 4 && T == D::TV - 1) return (n % 2 == 0) ? (NV - 4 + n / 2) : -1;
-        int r = 8 * T + n; return r < NV ? r : -1;
+    auto vcol = [&](int t, int k) { return (t < SV) ? live[D::var_of(t, k)] : -1; };       // dU in factorisation slots
+    auto vrow = [&](int T, int n) {                                                            // gradient tiles -> slots
+        if (NV % 8 == 4 && T == D::TV - 1) return (n % 2 == 0) ? live[NV - 4 + n / 2] : -1;
+        int r = 8 * T + n; return r < NV ? live[r] : -1;
     };
     // e = [Px | Py | e0] [x ; ysp ; 1], rows R.. = xi(N+1) map (Mi1x)
     mma_pack(buf, qc.be, D::TR, D::KX + D::KA, crow(RE),
@@ -614,10 +658,10 @@ inline void mma_build_constants(const sihmpc_plan_desc *d, MmaConst &qc, std::ve
             for (int h = 0; h < 2; ++h) { int r = 8 * T + 2 * g + h; if (r < R) buf[qc.w0c + (T * 4 + g) * 2 + h] = d->w0row[r]; }
     // f = 2 E^T t : out = variables (slot order), in = residual rows (C-layout)
     mma_pack(buf, qc.bf, D::TV, 2 * D::TR, vrow, ccol(R),
-             [&](int v, int r) { return 2.0 * d->E[(size_t)r * NV + v]; });
+             [&](int v, int r) { return 2.0 * d->E[(size_t)r * NVL + v]; });
     // r += E_ext dU
     mma_pack(buf, qc.br, D::TR, SV, crow(RE), vcol,
-             [&](int r, int v) { return r < R ? d->E[(size_t)r * NV + v] : d->Mi1u[(size_t)(r - R) * NV + v]; });
+             [&](int r, int v) { return r < R ? d->E[(size_t)r * NVL + v] : d->Mi1u[(size_t)(r - R) * NVL + v]; });
     // omega_du = Wdu pesos  (delivered in factorisation slots)
     mma_pack(buf, qc.bomdu, D::TV, D::KP, vrow,
              [&](int t, int k) { int e = 4 * t + k; return e < M ? e : -1; },
@@ -634,8 +678,8 @@ inline void mma_build_constants(const sihmpc_plan_desc *d, MmaConst &qc, std::ve
                              const int gq = n / 2, h = n % 2;
                              const int prow = 4 * t + gq, pcol = 2 * jp + h;      // positions in elimination order
                              if (pcol > prow) return 0.0;
-                             const int vi = D::var_of(prow / 4, prow % 4), vj = D::var_of(pcol / 4, pcol % 4);
-                             return e == 0 ? d->Ht[(size_t)vi * NV + vj] : d->HJ[((size_t)(e - 1) * NV + vi) * NV + vj]; });
+                             const int vi = live[D::var_of(prow / 4, prow % 4)], vj = live[D::var_of(pcol / 4, pcol % 4)];
+                             return e == 0 ? d->Ht[(size_t)vi * NVL + vj] : d->HJ[((size_t)(e - 1) * NVL + vi) * NVL + vj]; });
             }
     }
     // y = [C | D] [x+ ; du]
@@ -646,13 +690,13 @@ inline void mma_build_constants(const sihmpc_plan_desc *d, MmaConst &qc, std::ve
     // Y' = Myx x+ + Myu shift(dU): column v of the shifted map is Myu[:, v - NU]
     mma_pack(buf, qc.byp, D::TY, D::KX + SV, crow(NYP),
              [&](int t, int k) { if (t < D::KX) { int c = 8 * (t / 2) + 2 * k + (t % 2); return c < NX ? c : -1; }
-                                 return NX + D::var_of(t - D::KX, k); },
+                                 return NX + live[D::var_of(t - D::KX, k)]; },
              [&](int r, int c) { if (c < NX) return d->Myx[(size_t)r * NX + c];
-                                 int v = c - NX; return v >= NU ? d->Myu[(size_t)r * NV + (v - NU)] : 0.0; });
+                                 int v = c - NX; return v >= NU ? d->Myu[(size_t)r * NVL + (v - NU)] : 0.0; });
     // V_i = sum_r Wrow[r][i] sq_r + sum_v Wdu[v-NU][i] dU_v^2
     mma_pack(buf, qc.bvn, D::TM, 2 * D::TQ + SV, crow(M),
              [&](int t, int k) { if (t < 2 * D::TQ) { int r = 8 * (t / 2) + 2 * k + (t % 2); return r < NYP + 2 * NY ? r : -1; }
-                                 return 1000 + D::var_of(t - 2 * D::TQ, k); },
+                                 return 1000 + live[D::var_of(t - 2 * D::TQ, k)]; },
              [&](int i, int c) { if (c < 1000) return d->Wrow[(size_t)c * M + i];
                                  int v = c - 1000; return v >= NU ? d->Wdu[(size_t)(v - NU) * M + i] : 0.0; });
     for (int T = 0; T < D::TY; ++T)
@@ -670,8 +714,12 @@ inline void mma_build_constants(const sihmpc_plan_desc *d, MmaConst &qc, std::ve
     qc.ell_csr = takei(D::TX * 2 * W * 4);
     qc.hj_idx = takei(M);
     qc.vin_row = takei(d->n_vin > 0 ? d->n_vin : 1);
+    qc.vlive = takei(NV);
+    qc.vdead = takei(NVL - NV > 0 ? NVL - NV : 1);
     qc.total_i = io_;
     ibuf.assign(io_, 0);
+    for (int i = 0; i < NV; ++i) ibuf[qc.vlive + i] = live[i];
+    for (int i = 0; i < NVL - NV; ++i) ibuf[qc.vdead + i] = deadv[i];
     for (int T = 0; T < D::TX; ++T)
         for (int h = 0; h < 2; ++h)
             for (int g = 0; g < 4; ++g) {
@@ -699,13 +747,10 @@ inline size_t mma_smem_bytes(const MmaConst &qc) {
     return ((size_t)qc.total_d + (((qc.total_i + 3) >> 2) << 1) + (size_t)MMA_WARPS * D::WARP_DOUBLES) * sizeof(double);
 }
 
-inline cudaError_t mma_configure(const sihmpc_plan_desc *d, const DevPlan &P, MmaPlan *qp) {
-    memset(qp, 0, sizeof *qp);
-    qp->shape = mma_match_shape(P, d);
-    if (qp->shape < 0) return cudaSuccess;
-    using D = DistillationMma;
+template <typename D>
+inline cudaError_t mma_configure_shape(const sihmpc_plan_desc *d, const DevPlan &P, MmaPlan *qp) {
     std::vector<double> buf; std::vector<int> ibuf;
-    mma_build_constants<D>(d, qp->qc, buf, ibuf);
+    mma_build_constants<D>(d, P, qp->qc, buf, ibuf);
     const size_t nd = buf.size(), ni = ibuf.size();
     std::vector<double> all(nd + ((ni + 1) >> 1), 0.0);
     memcpy(all.data(), buf.data(), nd * sizeof(double));
@@ -727,6 +772,13 @@ inline cudaError_t mma_configure(const sihmpc_plan_desc *d, const DevPlan &P, Mm
     return cudaSuccess;
 }
 
+inline cudaError_t mma_configure(const sihmpc_plan_desc *d, const DevPlan &P, MmaPlan *qp) {
+    memset(qp, 0, sizeof *qp);
+    qp->shape = mma_match_shape(P, d);
+    if (qp->shape < 0) return cudaSuccess;
+    return qp->shape == 1 ? mma_configure_shape<DistillationMma16>(d, P, qp) : mma_configure_shape<DistillationMma>(d, P, qp);
+}
+
 inline cudaError_t mma_ensure_capacity(MmaPlan *qp, long long batch) {
     if (qp->capacity >= batch) return cudaSuccess;
     if (qp->n_handover) cudaFree(qp->n_handover);      // one buffer: [counter | start_step[batch]]
@@ -738,14 +790,17 @@ inline cudaError_t mma_ensure_capacity(MmaPlan *qp, long long batch) {
 
 inline cudaError_t mma_launch(const MmaPlan &qp, const DevPlan &P, const sihmpc_io &io, long long batch,
                               int n_steps, int sm_count, cudaStream_t st) {
-    using D = DistillationMma;
     const long long per_block = MMA_WARPS * 8;
     long long need = (batch + per_block - 1) / per_block;
     const long long cap = (long long)sm_count * qp.blocks_per_sm;
     int grid = (int)(need < cap ? need : cap);
     if (const char *gv = getenv("SIHMPC_QUAD_GRID")) { int gg = atoi(gv); if (gg > 0 && gg < grid) grid = gg; }
-    mma_step_kernel<D, MMA_WARPS, MMA_MINB><<<grid, MMA_WARPS * 32, qp.smem_bytes, st>>>(
-        P, qp.qc, qp.qbuf, io, batch, n_steps, qp.start_step, qp.n_handover);
+    if (qp.shape == 1)
+        mma_step_kernel<DistillationMma16, MMA_WARPS, MMA_MINB><<<grid, MMA_WARPS * 32, qp.smem_bytes, st>>>(
+            P, qp.qc, qp.qbuf, io, batch, n_steps, qp.start_step, qp.n_handover);
+    else
+        mma_step_kernel<DistillationMma, MMA_WARPS, MMA_MINB><<<grid, MMA_WARPS * 32, qp.smem_bytes, st>>>(
+            P, qp.qc, qp.qbuf, io, batch, n_steps, qp.start_step, qp.n_handover);
     return cudaGetLastError();
 }
 
