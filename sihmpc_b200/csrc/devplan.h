@@ -33,7 +33,7 @@ struct DevPlan {
 // per-warp shared-memory layout (offsets in doubles)
 struct WarpLayout {
     int L, dinv, xin, xnew, uu, ysp, pes, vin, e, om, omdu, f, v, nrm, ybuf, dbuf, rbuf, cbuf,
-        sy, yout, glo, ghi, vn, st, total;
+        sy, yout, glo, ghi, vn, st, te, pwh, total;
 };
 
 __host__ __device__ inline WarpLayout make_layout(const DevPlan &P) {
@@ -64,6 +64,8 @@ __host__ __device__ inline WarpLayout make_layout(const DevPlan &P) {
     SIH_TAKE(ghi, P.ncd > 0 ? P.ncd : 1);
     SIH_TAKE(vn, P.m > 0 ? P.m : 1);
     SIH_TAKE(st, P.ny + SIHMPC_NSTATS_EXTRA);
+    SIH_TAKE(te, P.R);
+    SIH_TAKE(pwh, P.mh > 0 ? P.mh : 1);
 #undef SIH_TAKE
     w.total = o;
     return w;

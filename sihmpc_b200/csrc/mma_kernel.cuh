@@ -560,7 +560,10 @@ struct MmaPlan {
 
 using DistillationMma = MmaDims<22, 2, 2, 4, 10, 4>;
 using DistillationMma16 = MmaDims<22, 2, 2, 4, 10, 4, 16>;     // four presolved moves (Wood & Berry dead times)
-constexpr int MMA_WARPS = 4;
+#ifndef SIH_MMA_WARPS
+#define SIH_MMA_WARPS 4
+#endif
+constexpr int MMA_WARPS = SIH_MMA_WARPS;
 #ifndef SIH_MMA_MINB
 #define SIH_MMA_MINB 2
 #endif

@@ -120,6 +120,24 @@ __device__ void warp_trsv_lower_T(const double *L, int ld, const double *dinv, i
     }
 }
 
+// sum_{j<n} M[j*stride] * x[j] with four independent accumulators and eight loads in flight: a handed-over
+// scenario is stepped by one warp on a nearly idle SM, where the latency of the constant loads (L1/L2) is
+// what the matrix-vector loops cost
+__device__ __forceinline__ double strided_dot(const double *__restrict__ M, const size_t stride,
+                                              const double *__restrict__ x, const int n, double a0) {
+    double a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int j = 0;
+    for (; j + 8 <= n; j += 8) {
+        const double m0 = M[(size_t)j * stride], m1 = M[(size_t)(j + 1) * stride], m2 = M[(size_t)(j + 2) * stride],
+                     m3 = M[(size_t)(j + 3) * stride], m4 = M[(size_t)(j + 4) * stride], m5 = M[(size_t)(j + 5) * stride],
+                     m6 = M[(size_t)(j + 6) * stride], m7 = M[(size_t)(j + 7) * stride];
+        a0 = fma(m0, x[j], a0); a1 = fma(m1, x[j + 1], a1); a2 = fma(m2, x[j + 2], a2); a3 = fma(m3, x[j + 3], a3);
+        a0 = fma(m4, x[j + 4], a0); a1 = fma(m5, x[j + 5], a1); a2 = fma(m6, x[j + 6], a2); a3 = fma(m7, x[j + 7], a3);
+    }
+    for (; j < n; ++j) a0 = fma(M[(size_t)j * stride], x[j], a0);
+    return (a0 + a1) + (a2 + a3);
+}
+
 template <int NVR>
 __device__ __forceinline__ void load_acc(double (&acc)[NVR], const double *v, int n, int lane, double scale) {
 #pragma unroll
@@ -221,21 +239,10 @@ __device__ void eval_subobjectives(const DevPlan &P, const double *xs, const dou
                                    double *vn, int lane) {
     const int Ny = P.Ny, ny = P.ny, nx = P.nx, nv = P.nv, m = P.m;
     for (int r = lane; r < Ny; r += 32) {
-        double a0 = 0.0, a1 = 0.0;
-        int j = 0;
-        for (; j + 1 < nx; j += 2) {
-            a0 = fma(P.MyxT[(size_t)j * Ny + r], xs[j], a0);
-            a1 = fma(P.MyxT[(size_t)(j + 1) * Ny + r], xs[j + 1], a1);
-        }
-        if (j < nx) a0 = fma(P.MyxT[(size_t)j * Ny + r], xs[j], a0);
-        int c = 0;
-        for (; c + 1 < nv; c += 2) {
-            a0 = fma(P.MyuT[(size_t)c * Ny + r], dv[c], a0);
-            a1 = fma(P.MyuT[(size_t)(c + 1) * Ny + r], dv[c + 1], a1);
-        }
-        if (c < nv) a0 = fma(P.MyuT[(size_t)c * Ny + r], dv[c], a0);
+        double a0 = strided_dot(P.MyxT + r, Ny, xs, nx, 0.0);
+        a0 = strided_dot(P.MyuT + r, Ny, dv, nv, a0);
         const int i = r % ny, k = r / ny;
-        const double rr = (a0 + a1) - ysp[i] - sy[i] - P.tau[k] * sy[ny + i];
+        const double rr = a0 - ysp[i] - sy[i] - P.tau[k] * sy[ny + i];
         sq[r] = rr * rr;
     }
     for (int i = lane; i < ny; i += 32) {
@@ -247,19 +254,16 @@ __device__ void eval_subobjectives(const DevPlan &P, const double *xs, const dou
     if (P.eval_term) {   // terminal rows Lbar^T xd(N): no slack dependence (ihmpccontroller.py:340)
         const int R = P.R;
         for (int r = P.o_t + lane; r < R; r += 32) {
-            double a = P.e0[r];
-            for (int j = 0; j < nx; ++j) a = fma(P.PxT[(size_t)j * R + r], xs[j], a);
-            for (int c = 0; c < nv; ++c) a = fma(P.ET[(size_t)c * R + r], dv[c], a);
+            double a = strided_dot(P.PxT + r, R, xs, nx, P.e0[r]);
+            a = strided_dot(P.ET + r, R, dv, nv, a);
             sq[r] = a * a;
         }
         nr = R;
     }
     __syncwarp();
     for (int i = lane; i < m; i += 32) {
-        double a = 0.0;
-        for (int r = 0; r < nr; ++r) a = fma(P.Wrow[(size_t)r * m + i], sq[r], a);
-        for (int j = 0; j < nv; ++j) a = fma(P.Wdu[(size_t)j * m + i], sqdu[j], a);
-        vn[i] = a;
+        double a = strided_dot(P.Wrow + i, m, sq, nr, 0.0);
+        vn[i] = strided_dot(P.Wdu + i, m, sqdu, nv, a);
     }
     __syncwarp();
 }
@@ -291,6 +295,7 @@ ihmpc_step_kernel(const DevPlan P_in, const sihmpc_io io, const long long batch,
     double *nrm = W + lay.nrm, *ybuf = W + lay.ybuf, *dbuf = W + lay.dbuf, *rbuf = W + lay.rbuf;
     double *cbuf = W + lay.cbuf, *sy = W + lay.sy, *yout = W + lay.yout;
     double *glo = W + lay.glo, *ghi = W + lay.ghi, *vn = W + lay.vn, *st = W + lay.st;
+    double *cbuf2 = W + lay.te, *pw_hj = W + lay.pwh;
 
     const int nx = P.nx, nu = P.nu, ny = P.ny, nv = P.nv, m = P.m, R = P.R, ld = P.ld;
     const int lds = nv | 1;
@@ -335,25 +340,16 @@ ihmpc_step_kernel(const DevPlan P_in, const sihmpc_io io, const long long batch,
             }
             __syncwarp();
 
+            for (int a = lane; a < P.mh; a += 32) pw_hj[a] = pes[P.hj_index[a]];
             // ---------------- K1: residual offsets, row weights
             for (int r = lane; r < R; r += 32) {
-                double a0 = P.e0[r], a1 = 0.0;
-                int j = 0;
-                for (; j + 1 < nx; j += 2) {
-                    a0 = fma(P.PxT[(size_t)j * R + r], xin[j], a0);
-                    a1 = fma(P.PxT[(size_t)(j + 1) * R + r], xin[j + 1], a1);
-                }
-                if (j < nx) a0 = fma(P.PxT[(size_t)j * R + r], xin[j], a0);
-                for (int c = 0; c < ny; ++c) a0 = fma(P.PyT[(size_t)c * R + r], ysp[c], a0);
-                double o = P.w0row[r];
-                for (int i = 0; i < m; ++i) o = fma(P.WrowT[(size_t)i * R + r], pes[i], o);
-                e[r] = a0 + a1;
-                om[r] = o;
+                double a0 = strided_dot(P.PxT + r, R, xin, nx, P.e0[r]);
+                a0 = strided_dot(P.PyT + r, R, ysp, ny, a0);
+                e[r] = a0;
+                om[r] = strided_dot(P.WrowT + r, R, pes, m, P.w0row[r]);
             }
             for (int j = lane; j < nv; j += 32) {
-                double o = 0.0;
-                for (int i = 0; i < m; ++i) o = fma(P.WduT[(size_t)i * nv + j], pes[i], o);
-                omdu[j] = o;
+                omdu[j] = strided_dot(P.WduT + j, nv, pes, m, 0.0);
             }
             // dense-row bounds of this step
             for (int r = lane; r < P.ncd; r += 32) {
@@ -371,16 +367,9 @@ ihmpc_step_kernel(const DevPlan P_in, const sihmpc_io io, const long long batch,
             }
             __syncwarp();
             // gradient f = 2 E^T (omega o e)
-            for (int c = lane; c < nv; c += 32) {
-                double a0 = 0.0, a1 = 0.0;
-                int r = 0;
-                for (; r + 1 < R; r += 2) {
-                    a0 = fma(P.E[(size_t)r * nv + c], om[r] * e[r], a0);
-                    a1 = fma(P.E[(size_t)(r + 1) * nv + c], om[r + 1] * e[r + 1], a1);
-                }
-                if (r < R) a0 = fma(P.E[(size_t)r * nv + c], om[r] * e[r], a0);
-                f[c] = 2.0 * (a0 + a1);
-            }
+            for (int r = lane; r < R; r += 32) cbuf2[r] = om[r] * e[r];
+            __syncwarp();
+            for (int c = lane; c < nv; c += 32) f[c] = 2.0 * strided_dot(P.E + c, nv, cbuf2, R, 0.0);
             // Hessian, lower triangle
             {
                 int i = 0, j = lane;
@@ -388,9 +377,7 @@ ihmpc_step_kernel(const DevPlan P_in, const sihmpc_io io, const long long batch,
                 const int nn = nv * nv;
                 for (int idx = lane; idx < nn; idx += 32) {
                     if (j <= i) {
-                        double h = P.Ht[idx];
-                        for (int a = 0; a < P.mh; ++a)
-                            h = fma(pes[P.hj_index[a]], P.HJ[(size_t)a * nn + idx], h);
+                        double h = strided_dot(P.HJ + idx, nn, pw_hj, P.mh, P.Ht[idx]);
                         if (i == j) h += 2.0 * omdu[i];
                         Ls[i * ld + j] = h;
                     }
@@ -631,14 +618,7 @@ ihmpc_step_kernel(const DevPlan P_in, const sihmpc_io io, const long long batch,
             // ---------------- K3: residual, cost, slacks
             double Jacc = 0.0;
             for (int r = lane; r < R; r += 32) {
-                double a0 = e[r], a1 = 0.0;
-                int c = 0;
-                for (; c + 1 < nv; c += 2) {
-                    a0 = fma(P.ET[(size_t)c * R + r], v[c], a0);
-                    a1 = fma(P.ET[(size_t)(c + 1) * R + r], v[c + 1], a1);
-                }
-                if (c < nv) a0 = fma(P.ET[(size_t)c * R + r], v[c], a0);
-                const double rr = a0 + a1;
+                const double rr = strided_dot(P.ET + r, R, v, nv, e[r]);
                 e[r] = rr;
                 Jacc = fma(om[r], rr * rr, Jacc);
             }
@@ -648,9 +628,8 @@ ihmpc_step_kernel(const DevPlan P_in, const sihmpc_io io, const long long batch,
 
             // siN_next = xi(N+1) with a zero move appended; syN kept (ihmpccontroller.py:543-560)
             for (int i = lane; i < ny; i += 32) {
-                double a = 0.0;
-                for (int j = 0; j < nx; ++j) a = fma(P.Mi1xT[(size_t)j * ny + i], xin[j], a);
-                for (int c = 0; c < nv; ++c) a = fma(P.Mi1uT[(size_t)c * ny + i], v[c], a);
+                double a = strided_dot(P.Mi1xT + i, ny, xin, nx, 0.0);
+                a = strided_dot(P.Mi1uT + i, ny, v, nv, a);
                 sy[i] = e[P.o_sy + i];
                 sy[ny + i] = a;
             }
@@ -700,9 +679,8 @@ ihmpc_step_kernel(const DevPlan P_in, const sihmpc_io io, const long long batch,
                 __syncwarp();
                 // measured output y = C x+ + D du (:107)
                 for (int i = lane; i < ny; i += 32) {
-                    double a = 0.0;
-                    for (int j = 0; j < nx; ++j) a = fma(P.CT[(size_t)j * ny + i], xnew[j], a);
-                    for (int j = 0; j < nu; ++j) a = fma(P.DT[(size_t)j * ny + i], v[j], a);
+                    double a = strided_dot(P.CT + i, ny, xnew, nx, 0.0);
+                    a = strided_dot(P.DT + i, ny, v, nu, a);
                     yout[i] = a;
                     const double err = a - ysp[i];
                     st[i] += err * err;
