@@ -243,7 +243,20 @@ def cpu_arm(workload, per_core, n_steps, warm, cores=None):
 
 
 # ----------------------------------------------------------------------------- main
+def _emit(line):
+    """The ONE JSON line goes to the real stdout; everything else a library prints to fd 1 (NCCL's
+    version banner, ...) has been redirected to stderr by main()."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -280,7 +293,7 @@ def main():
                                  "p50_step_latency_us": r["p50_us"]},
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        _emit(line)
         return 0
 
     if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
@@ -447,7 +460,7 @@ def main():
             "clocks": clocks, "e2e": e2e, "gpu_launches": n_launch + 1, "roofline": roofline,
             "cpu_baseline": cpu, "latency_batch1": lat, "status_or": status_or, "flagged_scenarios": flagged,
             "fp64_peak_tflops_measured": fp64_peak / 1e12}
-    print(json.dumps(line))
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
