@@ -24,6 +24,13 @@ to the previous move).  One step:
     y   = xs + Psi xd                       (C = [I, Psi, 0, 0], D = 0)
 
 ``F = diag(exp(r*Ts))`` ordered output-major: index ``(i*nu + j)*na + a``.
+
+Under-damped channels: a complex-conjugate pole pair ``p, conj(p)`` with residues ``c, conj(c)``
+contributes ``2 Re(c exp(p t))`` to the step response.  It takes TWO real states (Re, Im of the
+complex mode ``xi+ = f xi + c f du``, ``f = exp(p Ts)``): ``F`` gets the block
+``[[Re f, -Im f], [Im f, Re f]]``, the input column ``(Re(c f), Im(c f))`` and ``Psi`` the weights
+``(2, 0)``.  ``F`` is then block diagonal instead of diagonal; the controller only needs it in the
+Lyapunov equation of the terminal weight (``ihmpccontroller.py:338-339``), which is general.
 """
 from __future__ import annotations
 
@@ -50,10 +57,10 @@ class TransferFunction(signal.TransferFunction):
     def step_coefficients(self, pole_tol=1e-9):
         """Partial fractions of G(s)/s -> (d0, [(dd_a, r_a)...], di).
 
-        Supported pole sets: distinct real stable poles plus at most one pole at
-        the origin (integrating channel).  Anything else raises
-        NotImplementedError (SURVEY.md section 8(f) item 2 -- not needed by the
-        named configurations).
+        Supported pole sets: distinct stable poles, real (``(dd, r)`` floats) or complex-conjugate
+        pairs (``(c, p)`` complex, one entry per pair, Im p > 0), plus at most one pole at the origin
+        (integrating channel).  Repeated or unstable poles raise NotImplementedError
+        (SURVEY.md section 8(f) item 2 -- not needed by the named configurations).
         """
         num = np.atleast_1d(np.asarray(self.num, dtype=float))
         den = np.atleast_1d(np.asarray(self.den, dtype=float))
@@ -61,25 +68,26 @@ class TransferFunction(signal.TransferFunction):
         r, p, k = signal.residue(num, np.polymul(den, [1.0, 0.0]))
         if len(np.atleast_1d(k)) and np.any(np.abs(k) > 0):
             raise NotImplementedError("improper transfer function (direct term in G(s)/s)")
-        if np.any(np.abs(np.imag(p)) > pole_tol):
-            raise NotImplementedError("complex poles are not supported by this OPOM builder")
-        p = np.real(p)
-        r = np.real(r)
         zero = np.abs(p) <= pole_tol
         nzero = int(np.sum(zero))
         if nzero > 2:
             raise NotImplementedError("more than one integrator per channel")
         stable = p[~zero]
-        if np.any(stable >= 0):
+        if np.any(np.real(stable) >= 0):
             raise NotImplementedError("unstable pole in channel")
         if len(stable) > 1 and np.min(np.abs(np.subtract.outer(stable, stable))
                                        + np.eye(len(stable)) * 1e9) <= pole_tol:
             raise NotImplementedError("repeated poles are not supported")
         # scipy.signal.residue orders repeated roots by ascending power: r/(s-p), r/(s-p)^2
-        rz = r[zero]
+        rz = np.real(r[zero])
         d0 = float(rz[0]) if nzero >= 1 else 0.0
         di = float(rz[1]) if nzero == 2 else 0.0
-        modes = [(float(rr), float(pp)) for rr, pp in zip(r[~zero], stable)]
+        modes = []
+        for rr, pp in zip(r[~zero], stable):
+            if abs(pp.imag) <= pole_tol:
+                modes.append((float(np.real(rr)), float(np.real(pp))))
+            elif pp.imag > 0:                       # one entry per conjugate pair
+                modes.append((complex(rr), complex(pp)))
         return d0, modes, di
 
 
@@ -102,7 +110,10 @@ class OPOM(object):
         ny, nu = self.ny, self.nu
 
         coeffs = [[Hm[i, j].step_coefficients() for j in range(nu)] for i in range(ny)]
-        self.na = max(1, max(len(coeffs[i][j][1]) for i in range(ny) for j in range(nu)))
+
+        def n_states(modes):
+            return sum(2 if isinstance(mm[1], complex) else 1 for mm in modes)
+        self.na = max(1, max(n_states(coeffs[i][j][1]) for i in range(ny) for j in range(nu)))
         na = self.na
         self.nd = ny * nu * na
 
@@ -121,23 +132,38 @@ class OPOM(object):
         # coefficient tables
         self.D0 = np.zeros((ny, nu))
         self.Di = np.zeros((ny, nu))
-        self.Dd = np.zeros(self.nd)          # diagonal of the Dd matrix
-        self.R = np.zeros(self.nd)           # poles
-        fdiag = np.zeros(self.nd)            # padded (non-existent) modes get F = 0
+        self.Dd = np.zeros(self.nd)          # diagonal of the Dd matrix (real modes)
+        self.R = np.zeros(self.nd)           # poles (real modes; real part of complex ones)
+        self.F = np.zeros((self.nd, self.nd))    # padded (non-existent) modes get F = 0
+        self._bd = np.zeros(self.nd)         # what a move adds to each xd state when its dead time is over
+        self.Psi = np.zeros((ny, self.nd))
         for i in range(ny):
             for j in range(nu):
                 d0, modes, di = coeffs[i][j]
                 self.D0[i, j] = d0
                 self.Di[i, j] = di
-                for a, (dd, r) in enumerate(modes):
+                a = 0
+                for dd, r in modes:
                     idx = (i * nu + j) * na + a
-                    self.Dd[idx] = dd
-                    self.R[idx] = r
-                    fdiag[idx] = np.exp(r * Ts)
-        self.F = np.diag(fdiag)
-        self.Psi = np.zeros((ny, self.nd))
-        for i in range(ny):
-            self.Psi[i, i * nu * na:(i + 1) * nu * na] = 1.0
+                    if isinstance(r, complex):
+                        f = np.exp(r * Ts)
+                        self.F[idx:idx + 2, idx:idx + 2] = [[f.real, -f.imag], [f.imag, f.real]]
+                        g = dd * f
+                        self._bd[idx], self._bd[idx + 1] = g.real, g.imag
+                        self.Psi[i, idx] = 2.0
+                        self.R[idx] = self.R[idx + 1] = r.real
+                        a += 2
+                    else:
+                        f = np.exp(r * Ts)
+                        self.Dd[idx] = dd
+                        self.R[idx] = r
+                        self.F[idx, idx] = f
+                        self._bd[idx] = dd * f
+                        self.Psi[i, idx] = 1.0
+                        a += 1
+                # states of this channel that no mode uses keep F = 0, Psi = 1 (they stay at zero)
+                for a2 in range(a, na):
+                    self.Psi[i, (i * nu + j) * na + a2] = 1.0
         self.N = np.zeros((self.nd, nu))
         for i in range(ny):
             for j in range(nu):
@@ -155,13 +181,12 @@ class OPOM(object):
         Bs = np.where(mask, self.D0 + Ts * self.Di, 0.0)
         Bi = np.where(mask, self.Di, 0.0)
         Bd = np.zeros((self.nd, nu))
-        f = np.diag(self.F)
         for i in range(ny):
             for j in range(nu):
                 if mask[i, j]:
                     for a in range(na):
                         idx = (i * nu + j) * na + a
-                        Bd[idx, j] = self.Dd[idx] * f[idx]
+                        Bd[idx, j] = self._bd[idx]
         return Bs, Bd, Bi
 
     def _state_space(self):

@@ -93,6 +93,22 @@ def test_tile_equals_general_on_random_shapes(ny, nu, N, dmax, monkeypatch):
     assert np.max(np.abs(t["J"][:, 3] - ref["J"]) / np.maximum(np.abs(ref["J"]), 1e-6)) <= 10 * RTOL
 
 
+def test_tile_underdamped_plant_matches_oracle(monkeypatch):
+    """Complex pole pairs in the model (block-diagonal F, nd = 12): tile path vs the oracle and the general kernel."""
+    from tests.test_plan_cpu import _underdamped_system
+    sys_, _ = _underdamped_system()
+    declare = lambda cls, s, **b: sc.declare_mimo10(cls, s, N=6, **(b or dict(ulb=[-3.0, -3.0], uub=[3.0, 3.0])))
+    scen = _scenarios(24, sys_, 21)
+    t = _run(monkeypatch, "tile", declare, sys_, scen, 40)
+    g = _run(monkeypatch, "general", declare, sys_, scen, 40)
+    assert (t["stats"][:, 2 + 3] == 0).all()
+    _close(t, g)
+    for idx in (1, 17):
+        ref = oracle_closed_loop(declare, sys_, scen, idx, 40)
+        assert np.max(np.abs(t["du"][:, idx] - ref["du"])) <= RTOL * np.max(np.abs(ref["du"]))
+        assert np.max(np.abs(t["y"][:, idx] - ref["y"])) <= RTOL * max(1.0, np.max(np.abs(ref["y"])))
+
+
 def test_tile_path_on_distillation_with_handover(monkeypatch):
     """Forced tile path on the distillation controller with bounds that make a good share of the
     scenarios hand over to the exact active-set kernel mid-loop: equals the general kernel alone

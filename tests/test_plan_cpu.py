@@ -32,6 +32,62 @@ def test_opom_matches_analytic_step_responses():
     assert np.max(np.abs(y - ana)) < 1e-12
 
 
+def _underdamped_system():
+    """2x2 plant with complex pole pairs (under-damped second order), a third-order channel and dead times."""
+    from sihmpc_b200.opom import OPOM, TransferFunction
+    wn, z = 0.5, 0.3
+    h = [[TransferFunction([2.0 * wn * wn], np.polymul([1, 2 * z * wn, wn * wn], [4.0, 1.0]), delay=2),
+          TransferFunction([1.5], [3.0, 1.0], delay=0)],
+         [TransferFunction([0.7], [1.0, 0.4, 0.29], delay=1),
+          TransferFunction([-1.0], [5.0, 1.0], delay=3)]]
+    return OPOM(h, 1.0), h
+
+
+def test_opom_complex_poles_match_continuous_step_responses():
+    """Under-damped channels: two real states per conjugate pair, F block diagonal."""
+    from scipy import signal
+    m, h = _underdamped_system()
+    assert m.na == 3 and m.nd == 12 and m.nx == 2 * 2 + 12 + 2 * 3
+    assert not np.allclose(m.F, np.diag(np.diag(m.F)))           # genuinely block diagonal
+    n = 80
+    t = np.arange(0, n + 1) * 1.0
+    for j in range(2):
+        y = m.step_response(n, j)
+        for i in range(2):
+            _, yy = signal.step(signal.TransferFunction(h[i][j].num, h[i][j].den), T=t)
+            d = int(h[i][j].delay)
+            ref = np.concatenate([np.zeros(d), yy[:n + 1 - d]])
+            assert np.max(np.abs(y[:, i] - ref)) <= 1e-12
+
+
+def test_plan_with_complex_poles_reproduces_oracle_problem():
+    """The compiled plan of a controller on the under-damped plant == the oracle's un-condensed problem."""
+    from oracle.ihmpc_oracle import OracleIHMPC
+    from sihmpc_b200 import scenarios as sc
+    from sihmpc_b200.ihmpccontroller import IHMPCController
+    m, _ = _underdamped_system()
+    declare = lambda cls: sc.declare_mimo10(cls, m, N=6, ulb=[-3.0, -3.0], uub=[3.0, 3.0])
+    c, orc = declare(IHMPCController), declare(OracleIHMPC)
+    plan = c.compile()
+    rng = np.random.default_rng(4)
+    x = rng.normal(size=m.nx) * 0.1
+    x[2 + m.nd:4 + m.nd] = 0.0
+    u = rng.normal(size=2) * 0.1
+    ysp = np.array([0.4, -0.3])
+    pesos = np.asarray(c.init_pesos(), float) * (1 + rng.random(plan.m))
+    sol = orc.mpc(x, ysp, [], u, pesos)
+    dU = sol["w_opt"][:plan.nv]
+    # condensed cost of the plan at the oracle's optimum == the oracle's cost; gradient vanishes (no bound active)
+    e = plan.Px @ x + plan.Py @ ysp + plan.e0
+    om = plan.Wrow @ pesos + plan.w0row
+    r = plan.E @ dU + e
+    J = float(om @ (r * r) + (plan.Wdu @ pesos) @ (dU * dU))
+    assert abs(J - sol["J"]) <= 1e-9 * max(1.0, abs(sol["J"]))
+    if sol["info"]["n_active"] == 0:
+        g = 2 * plan.E.T @ (om * r) + 2 * (plan.Wdu @ pesos) * dU
+        assert np.max(np.abs(g)) <= 1e-8 * max(1.0, np.max(np.abs(2 * plan.E.T @ (om * e))))
+
+
 def test_constructor_asserts_like_reference():
     s = sc.distillation_system()
     with pytest.raises(AssertionError):
