@@ -199,6 +199,17 @@ int sihmpc_subobjectives(sihmpc_plan *plan, const double *x, const double *w, co
 int sihmpc_log_step(sihmpc_plan *plan, const double *x, const double *u, const double *ysp, const double *w0,
                     int64_t batch, double *w_opt, double *J, int32_t *status, int32_t *iters, void *stream);
 
+/* The driver loop of the log-barrier variant (example_distillation_log.py:85-135) for `batch` scenarios and
+ * n_steps consecutive control steps in ONE launch: mpc (ihmpccontroller_log.py:552-563), first move to the
+ * plant (dynF :103-123), warmStart (:518-549: shifted moves, ss = 1).  `io` as for sihmpc_step (DEVICE
+ * pointers; x, u in/out with SIHMPC_F_ADVANCE; ysp or ysp_seq/seg_start; optional dist, plant_val, du, J,
+ * status, stats, traj_*; io.w_opt is [batch][nv+2ny+1] here; pesos/vinant are not used).  w_warm
+ * [batch][nv+2ny+1] is the warm start on entry and the shifted plan on exit (NULL: cold start, not
+ * returned).  iters [batch]: Newton iterations of the last step (NULL skips); io.stats[ny+4] accumulates
+ * them.                                                                                              */
+int sihmpc_log_loop(sihmpc_plan *plan, const sihmpc_io *io, double *w_warm, int64_t batch, int32_t n_steps,
+                    int32_t *iters, void *stream);
+
 /* On-device reduction of the per-scenario statistics block to aggregate moments
  * out[3][nstat] = {sum, sum of squares, max} (feeds one NCCL all-reduce). */
 int sihmpc_stats_reduce(const double *stats, int64_t batch, int32_t nstat, double *out,

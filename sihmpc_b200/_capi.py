@@ -56,7 +56,7 @@ EXPORTS = [
     "sihmpc_abi_version", "sihmpc_last_error", "sihmpc_device_count", "sihmpc_plan_create",
     "sihmpc_plan_destroy", "sihmpc_workspace_bytes", "sihmpc_step", "sihmpc_step_host",
     "sihmpc_host_staging_bytes", "sihmpc_predict", "sihmpc_subobjectives", "sihmpc_stats_reduce",
-    "sihmpc_fp64_peak", "sihmpc_log_step", "sihmpc_plan_kernel",
+    "sihmpc_fp64_peak", "sihmpc_log_step", "sihmpc_log_loop", "sihmpc_plan_kernel",
 ]
 
 _lib = None
@@ -102,6 +102,8 @@ def load():
     lib.sihmpc_stats_reduce.restype = C.c_int
     lib.sihmpc_log_step.argtypes = [C.c_void_p] + [C.c_void_p] * 4 + [C.c_int64] + [C.c_void_p] * 5
     lib.sihmpc_log_step.restype = C.c_int
+    lib.sihmpc_log_loop.argtypes = [C.c_void_p, C.POINTER(IO), C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.sihmpc_log_loop.restype = C.c_int
     lib.sihmpc_plan_kernel.argtypes = [C.c_void_p]
     lib.sihmpc_plan_kernel.restype = C.c_char_p
     lib.sihmpc_fp64_peak.argtypes = [C.POINTER(C.c_double)]

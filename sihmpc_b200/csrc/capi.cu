@@ -548,10 +548,8 @@ int sihmpc_stats_reduce(const double *stats, int64_t batch, int32_t nstat, doubl
     return 0;
 }
 
-int sihmpc_log_step(sihmpc_plan *plan, const double *x, const double *u, const double *ysp, const double *w0,
-                    int64_t batch, double *w_opt, double *J, int32_t *status, int32_t *iters, void *stream) {
-    if (!plan || !x || !u || !ysp || !w_opt) return fail(SIHMPC_E_INVALID, "NULL argument%s");
-    if (batch <= 0) return batch == 0 ? 0 : fail(SIHMPC_E_INVALID, "negative batch%s");
+static int log_launch(sihmpc_plan *plan, const sihmpc_io &io, const double *w0, double *w_warm, int64_t batch,
+                      int32_t n_steps, int32_t *iters, void *stream) {
     if (plan->d.ncd > 0) return fail(SIHMPC_E_INVALID, "log variant: dense inequality rows are not supported%s");
     const sih::LogLayout lay = sih::make_log_layout(plan->d);
     int wpb = 4;
@@ -563,13 +561,36 @@ int sihmpc_log_step(sihmpc_plan *plan, const double *x, const double *u, const d
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (plan->d.nv + 1 <= 32) {
         CUDA_TRY(cudaFuncSetAttribute(sih::ihmpc_log_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        sih::ihmpc_log_kernel<1><<<(int)blocks, wpb * 32, smem, st>>>(plan->d, x, u, ysp, w0, batch, w_opt, J, status, iters, 100);
+        sih::ihmpc_log_kernel<1><<<(int)blocks, wpb * 32, smem, st>>>(plan->d, io, w0, w_warm, batch, n_steps, iters, 100);
     } else {
         CUDA_TRY(cudaFuncSetAttribute(sih::ihmpc_log_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        sih::ihmpc_log_kernel<2><<<(int)blocks, wpb * 32, smem, st>>>(plan->d, x, u, ysp, w0, batch, w_opt, J, status, iters, 100);
+        sih::ihmpc_log_kernel<2><<<(int)blocks, wpb * 32, smem, st>>>(plan->d, io, w0, w_warm, batch, n_steps, iters, 100);
     }
     CUDA_TRY(cudaGetLastError());
     return 0;
+}
+
+int sihmpc_log_step(sihmpc_plan *plan, const double *x, const double *u, const double *ysp, const double *w0,
+                    int64_t batch, double *w_opt, double *J, int32_t *status, int32_t *iters, void *stream) {
+    if (!plan || !x || !u || !ysp || !w_opt) return fail(SIHMPC_E_INVALID, "NULL argument%s");
+    if (batch <= 0) return batch == 0 ? 0 : fail(SIHMPC_E_INVALID, "negative batch%s");
+    sihmpc_io io;
+    memset(&io, 0, sizeof io);
+    io.x = const_cast<double *>(x); io.u = const_cast<double *>(u); io.ysp = ysp;    // read only: no SIHMPC_F_ADVANCE
+    io.w_opt = w_opt; io.J = J; io.status = status;
+    return log_launch(plan, io, w0, nullptr, batch, 1, iters, stream);
+}
+
+int sihmpc_log_loop(sihmpc_plan *plan, const sihmpc_io *io, double *w_warm, int64_t batch, int32_t n_steps,
+                    int32_t *iters, void *stream) {
+    if (!plan || !io) return fail(SIHMPC_E_INVALID, "NULL argument%s");
+    if (batch <= 0) return batch == 0 ? 0 : fail(SIHMPC_E_INVALID, "negative batch%s");
+    if (!io->x || !io->u) return fail(SIHMPC_E_INVALID, "io.x and io.u are required%s");
+    if (!io->ysp && !(io->ysp_seq && io->seg_start && io->n_seg > 0))
+        return fail(SIHMPC_E_INVALID, "io.ysp or io.ysp_seq/seg_start is required%s");
+    if (n_steps < 1) return fail(SIHMPC_E_INVALID, "n_steps must be >= 1%s");
+    if (n_steps > 1 && !(io->flags & SIHMPC_F_ADVANCE)) return fail(SIHMPC_E_INVALID, "n_steps > 1 needs SIHMPC_F_ADVANCE%s");
+    return log_launch(plan, *io, w_warm, w_warm, batch, n_steps, iters, stream);
 }
 
 int sihmpc_fp64_peak(double *flops_per_s) {

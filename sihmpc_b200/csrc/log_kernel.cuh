@@ -18,13 +18,13 @@
 
 namespace sih {
 
-struct LogLayout { int H, dinv, x, ysp, e, r, v, g, p, gi, d, Vi, vt, total; };
+struct LogLayout { int H, dinv, x, xn, uu, ysp, e, r, v, g, p, gi, d, Vi, vt, total; };
 
 __host__ __device__ inline LogLayout make_log_layout(const DevPlan &P) {
     LogLayout w; int o = 0;
     const int n = P.nv + 1, ld = n | 1;
 #define SIH_TAKE(field, cnt) do { w.field = o; o += ((cnt) + 1) & ~1; } while (0)
-    SIH_TAKE(H, n * ld); SIH_TAKE(dinv, n); SIH_TAKE(x, P.nx); SIH_TAKE(ysp, P.ny); SIH_TAKE(e, P.R);
+    SIH_TAKE(H, n * ld); SIH_TAKE(dinv, n); SIH_TAKE(x, P.nx + P.nu); SIH_TAKE(xn, P.nx); SIH_TAKE(uu, P.nu); SIH_TAKE(ysp, P.ny); SIH_TAKE(e, P.R);
     SIH_TAKE(r, P.R); SIH_TAKE(v, n); SIH_TAKE(g, n); SIH_TAKE(p, n); SIH_TAKE(gi, P.m * P.nv);
     SIH_TAKE(d, P.m); SIH_TAKE(Vi, P.m); SIH_TAKE(vt, n);
 #undef SIH_TAKE
@@ -59,11 +59,14 @@ __device__ double log_eval(const DevPlan &P, const double *vv, const double *e, 
     return bad > 0.0 ? SIH_INF : phi;
 }
 
+// One launch = n_steps control steps of every scenario.  n_steps == 1 without SIHMPC_F_ADVANCE is mpc() of
+// the log controller (ihmpccontroller_log.py:552-563); with SIHMPC_F_ADVANCE the body of the driver loop
+// (example_distillation_log.py:85-135: mpc, first move to the plant, warmStart with ss = 1, log.py:518-549)
+// runs in place with the state resident in shared memory.
 template <int NVR>
 __global__ void __launch_bounds__(128)
-ihmpc_log_kernel(const DevPlan P, const double *__restrict__ x, const double *__restrict__ u,
-                 const double *__restrict__ ysp, const double *__restrict__ w0, const long long batch,
-                 double *w_opt, double *J, int *status, int *iters_out, const int max_iter) {
+ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__ w0, double *__restrict__ w_warm,
+                 const long long batch, const int n_steps, int *iters_out, const int max_iter) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const long long gw = (long long)blockIdx.x * wpb + wib, nwarps = (long long)gridDim.x * wpb;
@@ -71,15 +74,37 @@ ihmpc_log_kernel(const DevPlan P, const double *__restrict__ x, const double *__
     double *W = smem + (size_t)wib * lay.total;
     double *Hm = W + lay.H, *dinv = W + lay.dinv, *xs = W + lay.x, *ys = W + lay.ysp, *e = W + lay.e;
     double *r = W + lay.r, *v = W + lay.v, *g = W + lay.g, *gi = W + lay.gi, *d = W + lay.d, *Vi = W + lay.Vi;
-    double *vt = W + lay.vt;
+    double *vt = W + lay.vt, *xn = W + lay.xn, *uu = W + lay.uu;
     const int nx = P.nx, nu = P.nu, ny = P.ny, nv = P.nv, m = P.m, R = P.R;
     const int n = nv + 1, ld = n | 1, nw = nv + 2 * ny + 1;
+    const int nstat = ny + SIHMPC_NSTATS_EXTRA;
+    const bool advance = (io.flags & SIHMPC_F_ADVANCE) != 0;
+    double *const w_opt = io.w_opt;
+    double *const J = io.J;
+    int *const status = io.status;
 
     for (long long s = gw; s < batch; s += nwarps) {
-        for (int i = lane; i < nx; i += 32) xs[i] = x[s * nx + i];
-        for (int i = lane; i < ny; i += 32) ys[i] = ysp[s * ny + i];
+        for (int i = lane; i < nx; i += 32) xs[i] = io.x[s * nx + i];
+        for (int i = lane; i < nu; i += 32) uu[i] = io.u[s * nu + i];
         for (int i = lane; i < nv; i += 32) v[i] = w0 ? w0[s * nw + i] : 0.0;
         if (lane == 0) v[nv] = w0 ? w0[s * nw + nw - 1] : 1.0;
+        double st_ise = 0.0, st_du2 = 0.0, st_J = 0.0;      // lane i < ny holds the ISE of output i
+        int st_or = 0, it_total = 0;
+        if (io.stats) {
+            if (lane < ny) st_ise = io.stats[s * nstat + lane];
+            st_du2 = io.stats[s * nstat + ny]; st_or = (int)io.stats[s * nstat + ny + 3];
+            it_total = (int)io.stats[s * nstat + ny + 4];
+        }
+      for (int step = 0; step < n_steps; ++step) {
+        const int kabs = io.k0 + step;
+        if (io.ysp_seq) {
+            int seg = 0;
+            for (int a = 1; a < io.n_seg; ++a)
+                if (io.seg_start[s * io.n_seg + a] <= kabs) seg = a;
+            for (int i = lane; i < ny; i += 32) ys[i] = io.ysp_seq[(s * io.n_seg + seg) * ny + i];
+        } else {
+            for (int i = lane; i < ny; i += 32) ys[i] = io.ysp[s * ny + i];
+        }
         __syncwarp();
         for (int k = lane; k < R; k += 32) {
             double a = P.e0[k];
@@ -171,8 +196,10 @@ ihmpc_log_kernel(const DevPlan P, const double *__restrict__ x, const double *__
             }
             __syncwarp();
             for (int i = lane; i < n; i += 32) v[i] = vt[i];
+            const bool flat = (phi - phin) <= 1e-15 * (1.0 + fabs(phi));    // decrease at rounding level: converged
             phi = phin;
             __syncwarp();
+            if (flat) break;
         }
         if (it > max_iter) st |= SIHMPC_ST_MAXITER;
         // ---- explicit inequalities of the reference NLP must be strictly inactive
@@ -183,7 +210,7 @@ ihmpc_log_kernel(const DevPlan P, const double *__restrict__ x, const double *__
                 for (int i = 0; i < m; ++i) marg = fmin(marg, d[i] - 0.01);
             }
             for (int j = lane; j < nu; j += 32) {
-                double cs = u[s * nu + j];
+                double cs = uu[j];
                 for (int k = 0; k < P.N; ++k) {
                     const double dv = v[k * nu + j];
                     cs += dv;
@@ -194,16 +221,85 @@ ihmpc_log_kernel(const DevPlan P, const double *__restrict__ x, const double *__
             marg = -warp_max(-marg);
             if (!(marg > 1e-9)) st |= SIHMPC_ST_ACTIVE_UNSUPPORTED;
         }
-        for (int i = lane; i < nv; i += 32) w_opt[s * nw + i] = v[i];
-        for (int i = lane; i < ny; i += 32) {
-            w_opt[s * nw + nv + i] = r[P.o_sy + i];
-            w_opt[s * nw + nv + ny + i] = r[P.o_si + i];
+        st_or |= st; it_total += it; st_J = phi;
+        const bool last_step = (step == n_steps - 1);
+        if (last_step) {
+            if (io.du) for (int j = lane; j < nu; j += 32) io.du[s * nu + j] = v[j];
+            if (w_opt) {
+                for (int i = lane; i < nv; i += 32) w_opt[s * nw + i] = v[i];
+                for (int i = lane; i < ny; i += 32) {
+                    w_opt[s * nw + nv + i] = r[P.o_sy + i];
+                    w_opt[s * nw + nv + ny + i] = r[P.o_si + i];
+                }
+                if (lane == 0) w_opt[s * nw + nw - 1] = v[nv];
+            }
+            if (lane == 0) {
+                if (J) J[s] = phi;
+                if (status) status[s] = st;
+                if (iters_out) iters_out[s] = it;
+            }
         }
-        if (lane == 0) {
-            w_opt[s * nw + nw - 1] = v[nv];
-            if (J) J[s] = phi;
-            if (status) status[s] = st;
-            if (iters_out) iters_out[s] = it;
+        if (io.traj_du) for (int j = lane; j < nu; j += 32) io.traj_du[((long long)step * batch + s) * nu + j] = v[j];
+        if (io.traj_J && lane == 0) io.traj_J[(long long)step * batch + s] = phi;
+        __syncwarp();
+        if (!advance) continue;
+        // ---- plant x+ = [A|B][x ; du], u+ = u + du, measured output, statistics
+        for (int j = lane; j < nu; j += 32) xs[nx + j] = v[j];
+        __syncwarp();
+        {
+            const double *pv = io.plant_val ? io.plant_val + (size_t)s * P.pl_nnz : P.pl_val;
+            for (int i = lane; i < nx; i += 32) {
+                double a = 0.0;
+                const int p1 = P.pl_rowptr[i + 1];
+                for (int pp = P.pl_rowptr[i]; pp < p1; ++pp) a = fma(pv[pp], xs[P.pl_col[pp]], a);
+                xn[i] = a;
+            }
+        }
+        __syncwarp();
+        if (io.dist_step && io.dist_step[s] == kabs)
+            for (int i = lane; i < ny; i += 32) xn[i] += io.dist[s * ny + i];
+        {
+            double d2 = 0.0;
+            for (int j = lane; j < nu; j += 32) { const double dj = v[j]; uu[j] += dj; d2 = fma(dj, dj, d2); }
+            st_du2 += warp_sum(d2);
+        }
+        __syncwarp();
+        if (lane < ny) {
+            double a = 0.0;
+            for (int j = 0; j < nx; ++j) a = fma(P.CT[(size_t)j * ny + lane], xn[j], a);
+            for (int j = 0; j < nu; ++j) a = fma(P.DT[(size_t)j * ny + lane], v[j], a);
+            const double err = a - ys[lane];
+            st_ise = fma(err, err, st_ise);
+            if (io.traj_y) io.traj_y[((long long)step * batch + s) * ny + lane] = a;
+        }
+        __syncwarp();
+        for (int i = lane; i < nx; i += 32) xs[i] = xn[i];
+        // ---- warm start of the next step (log.py:518-549): shifted moves, ss = 1
+        {
+            double sh[NVR];
+#pragma unroll
+            for (int t = 0; t < NVR; ++t) { const int i = lane + 32 * t; sh[t] = (i + nu < nv) ? v[i + nu] : 0.0; }
+            __syncwarp();
+#pragma unroll
+            for (int t = 0; t < NVR; ++t) { const int i = lane + 32 * t; if (i < nv) v[i] = sh[t]; }
+            if (lane == 0) v[nv] = 1.0;
+        }
+        __syncwarp();
+      }  // steps
+        if (advance) {
+            for (int i = lane; i < nx; i += 32) io.x[s * nx + i] = xs[i];
+            for (int i = lane; i < nu; i += 32) io.u[s * nu + i] = uu[i];
+            if (w_warm) {
+                for (int i = lane; i < nv; i += 32) w_warm[s * nw + i] = v[i];
+                if (lane == 0) w_warm[s * nw + nw - 1] = v[nv];
+            }
+        }
+        if (io.stats) {
+            if (lane < ny) io.stats[s * nstat + lane] = st_ise;
+            if (lane == 0) {
+                io.stats[s * nstat + ny] = st_du2; io.stats[s * nstat + ny + 2] = st_J;
+                io.stats[s * nstat + ny + 3] = (double)st_or; io.stats[s * nstat + ny + 4] = (double)it_total;
+            }
         }
         __syncwarp();
     }

@@ -198,6 +198,86 @@ class BatchedEngine:
         return out
 
 
+class LogBatchedEngine:
+    """Batched closed loop of the LOG-BARRIER controller (sihmpc_log_loop): `batch` scenarios of the
+    driver loop of /root/reference/example_distillation_log.py:85-135 (mpc, first move to the plant,
+    warmStart with ss = 1) stepping in lockstep, `n_steps` per launch."""
+
+    def __init__(self, plan: Plan, batch: int, device=None):
+        self.dp = DevicePlan(plan, device)
+        self.plan = plan
+        self.batch = int(batch)
+        self.device = self.dp.device
+        dev, f64 = self.device, torch.float64
+        B, p = self.batch, plan
+        self.nw = p.nv + 2 * p.ny + 1
+        self.nstat = p.ny + _capi.NSTATS_EXTRA
+        self.x = torch.zeros(B, p.nx, dtype=f64, device=dev)
+        self.u = torch.zeros(B, p.nu, dtype=f64, device=dev)
+        self.ysp = torch.zeros(B, p.ny, dtype=f64, device=dev)
+        self.du = torch.zeros(B, p.nu, dtype=f64, device=dev)
+        self.J = torch.zeros(B, dtype=f64, device=dev)
+        self.w_opt = torch.zeros(B, self.nw, dtype=f64, device=dev)
+        self.w_warm = torch.zeros(B, self.nw, dtype=f64, device=dev)
+        self.w_warm[:, -1] = 1.0
+        self.status = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.iters = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.stats = torch.zeros(B, self.nstat, dtype=f64, device=dev)
+        self.ysp_seq = self.seg_start = self.dist_step = self.dist = self.plant_val = None
+        self.k = 0
+
+    def set_state(self, x, u):
+        self.x.copy_(torch.as_tensor(np.asarray(x, dtype=np.float64)).reshape(self.batch, -1))
+        self.u.copy_(torch.as_tensor(np.asarray(u, dtype=np.float64)).reshape(self.batch, -1))
+        self.w_warm.zero_(); self.w_warm[:, -1] = 1.0
+        self.k = 0
+        self.stats.zero_()
+
+    set_schedule = BatchedEngine.set_schedule
+    set_disturbance = BatchedEngine.set_disturbance
+    set_plant_values = BatchedEngine.set_plant_values
+
+    def run(self, n_steps: int, steps_per_launch: Optional[int] = None, record: bool = False):
+        spl = n_steps if steps_per_launch is None else int(steps_per_launch)
+        traj_all = None
+        if record:
+            traj_all = {
+                "du": torch.zeros(n_steps, self.batch, self.plan.nu, dtype=torch.float64, device=self.device),
+                "J": torch.zeros(n_steps, self.batch, dtype=torch.float64, device=self.device),
+                "y": torch.zeros(n_steps, self.batch, self.plan.ny, dtype=torch.float64, device=self.device),
+            }
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        done = 0
+        with torch.cuda.device(self.device):
+            while done < n_steps:
+                n = min(spl, n_steps - done)
+                io = _capi.IO()
+                io.x, io.u = self.x.data_ptr(), self.u.data_ptr()
+                if self.ysp_seq is not None:
+                    io.ysp_seq, io.seg_start = self.ysp_seq.data_ptr(), self.seg_start.data_ptr()
+                    io.n_seg = int(self.ysp_seq.shape[1])
+                else:
+                    io.ysp = self.ysp.data_ptr()
+                if self.dist_step is not None:
+                    io.dist_step, io.dist = self.dist_step.data_ptr(), self.dist.data_ptr()
+                if self.plant_val is not None:
+                    io.plant_val = self.plant_val.data_ptr()
+                io.du, io.J, io.w_opt = self.du.data_ptr(), self.J.data_ptr(), self.w_opt.data_ptr()
+                io.status, io.stats = self.status.data_ptr(), self.stats.data_ptr()
+                if record:
+                    io.traj_du = traj_all["du"][done:done + n].data_ptr()
+                    io.traj_J = traj_all["J"][done:done + n].data_ptr()
+                    io.traj_y = traj_all["y"][done:done + n].data_ptr()
+                io.flags = _capi.F_ADVANCE
+                io.k0 = self.k
+                _capi.check(self.dp.lib.sihmpc_log_loop(self.dp.handle, C.byref(io), C.c_void_p(self.w_warm.data_ptr()),
+                                                        self.batch, n, C.c_void_p(self.iters.data_ptr()), C.c_void_p(st)),
+                            "sihmpc_log_loop")
+                self.k += n
+                done += n
+        return traj_all
+
+
 class HostStepper:
     """The host-buffer entry point (sihmpc_step_host): numpy/pinned in, numpy/pinned out."""
 

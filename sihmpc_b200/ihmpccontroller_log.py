@@ -106,7 +106,9 @@ class IHMPCController(_Weighted):
         return self._plan
 
     def engine(self, batch, **kw):
-        raise NotImplementedError("batched closed loops exist for the weighted controller only")
+        """Batched closed loop of the log controller on the device (sihmpc_log_loop)."""
+        from .engine import LogBatchedEngine
+        return LogBatchedEngine(self.compile(), batch, **kw)
 
     # ---- step (log.py:552-563)
     def mpc(self, x0, ySP, w0, u0, lam_w0, lam_g0, ViN_ant=None):

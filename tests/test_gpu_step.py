@@ -446,3 +446,38 @@ def test_log_variant_example_loop_matches_oracle():
         assert np.allclose(c.satWeights(x, u, w0, ysp), orc.satWeights(xo, uo, w0o, ysp), rtol=1e-6)
     assert abs(float(sol['w_opt'][-1]) - np.sqrt(2.0)) < 0.05        # ss* ~ sqrt(m/2) near steady state
     assert len(sol['g'].full()) == 260                                 # SURVEY.md section 8 size table
+
+
+def test_log_variant_batched_closed_loop_matches_oracle():
+    """sihmpc_log_loop: 24 scenarios of the log-variant driver loop (example_distillation_log.py:85-135: mpc,
+    first move to the plant, warmStart with ss = 1) in one launch vs the log oracle run scenario by scenario."""
+    from oracle.ihmpc_log_oracle import OracleIHMPCLog, declare_distillation_log
+    from sihmpc.ihmpccontroller_log import IHMPCController as LogController
+    sys_ = sc.distillation_system()
+    c = declare_distillation_log(LogController, sys_)
+    B, T = 24, 30
+    scen = sc.distillation_scenarios(B)
+    scen["seg_start"][:, 1] = 4; scen["seg_start"][:, 2] = 18
+    eng = c.engine(B)
+    eng.set_state(scen["x0"], scen["u0"])
+    eng.set_schedule(scen["ysp_seq"], scen["seg_start"])
+    tr = eng.run(T, steps_per_launch=11, record=True)
+    du = tr["du"].cpu().numpy(); J = tr["J"].cpu().numpy(); y = tr["y"].cpu().numpy()
+    assert (eng.stats[:, sys_.ny + 3].cpu().numpy() == 0).all()
+    assert (eng.stats[:, sys_.ny + 4].cpu().numpy() > 0).all()          # Newton iterations were counted
+    f = schedule_fn
+    for idx in (0, 9, 23):
+        orc = declare_distillation_log(OracleIHMPCLog, sys_)
+        xo, uo, w0o = scen["x0"][idx].copy(), scen["u0"][idx].copy(), []
+        ysp_of = f(scen["ysp_seq"][idx], scen["seg_start"][idx])
+        scale = 1e-3
+        for k in range(T):
+            ysp = np.asarray(ysp_of(k), float)
+            solo = orc.mpc(xo, ysp, w0o, uo, [], [], ViN_ant=[])
+            scale = max(scale, np.max(np.abs(solo['du_opt'][:, 0])))
+            assert np.max(np.abs(du[k, idx] - solo['du_opt'][:, 0])) <= RTOL * scale, (idx, k)
+            assert abs(J[k, idx] - solo['J']) <= RTOL * abs(solo['J']), (idx, k)
+            r = orc.dynF(xo, uo, solo['du_opt'][:, 0]); xo, uo = r['xkp1'], r['ukp1']
+            assert np.max(np.abs(y[k, idx] - r['ykp1'])) <= RTOL * 100.0
+            w0o = orc.warmStart(solo, ysp)
+        assert np.max(np.abs(eng.x[idx].cpu().numpy() - xo)) <= RTOL * 100.0
