@@ -63,6 +63,10 @@ struct sihmpc_plan {
     size_t h_stage_bytes = 0;
     // host copies needed by the host-buffer entry point
     int nw;
+    // zero-copy path: pinned host pointers seen so far and their device aliases
+    void *pinned_host[16];
+    void *pinned_dev[16];
+    int n_pinned = 0;
 };
 
 namespace {
@@ -423,6 +427,41 @@ int sihmpc_step_host(sihmpc_plan *plan, const sihmpc_io *h, int64_t batch, void 
                  by = (size_t)P.ny * 8, bw = (size_t)plan->nw * 8;
 
     if (batch <= 512) {
+        // ---- small batch, every buffer pinned (cudaHostAlloc / cudaHostRegister): ZERO-COPY.  The kernel reads
+        // the caller's arrays over PCIe through their device aliases and writes the results straight back:
+        // no staging copies, no memcpy launches -- the latency of a step is one kernel plus one synchronise.
+        {
+            void *hp[10] = {h->x, h->u, h->pesos, want_vin ? h->vinant : nullptr, const_cast<double *>(h->ysp),
+                            h->du, h->J, h->w_opt, h->status, h->n_active};
+            void *dp[10];
+            bool all = true;
+            for (int i = 0; i < 10 && all; ++i) {
+                dp[i] = nullptr;
+                if (!hp[i]) continue;
+                int hit = -1;
+                for (int k = 0; k < plan->n_pinned; ++k)
+                    if (plan->pinned_host[k] == hp[i]) { hit = k; break; }
+                if (hit >= 0) { dp[i] = plan->pinned_dev[hit]; continue; }
+                cudaPointerAttributes at;
+                if (cudaPointerGetAttributes(&at, hp[i]) != cudaSuccess) { cudaGetLastError(); all = false; break; }
+                if (at.type != cudaMemoryTypeHost || !at.devicePointer) { all = false; break; }
+                dp[i] = at.devicePointer;
+                if (plan->n_pinned < 16) {
+                    plan->pinned_host[plan->n_pinned] = hp[i]; plan->pinned_dev[plan->n_pinned] = dp[i]; ++plan->n_pinned;
+                }
+            }
+            if (all && !getenv("SIHMPC_NO_ZEROCOPY") && h->du && h->J && h->status && h->n_active) {
+                sihmpc_io z = d;
+                z.x = static_cast<double *>(dp[0]); z.u = static_cast<double *>(dp[1]); z.pesos = static_cast<double *>(dp[2]);
+                z.vinant = static_cast<double *>(dp[3]); z.ysp = static_cast<double *>(dp[4]);
+                z.du = static_cast<double *>(dp[5]); z.J = static_cast<double *>(dp[6]); z.w_opt = static_cast<double *>(dp[7]);
+                z.status = static_cast<int32_t *>(dp[8]); z.n_active = static_cast<int32_t *>(dp[9]);
+                int rc = sihmpc_step(plan, &z, batch, 1, workspace, wsb, stream);
+                if (rc) return rc;
+                CUDA_TRY(cudaStreamSynchronize(st));
+                return 0;
+            }
+        }
         // ---- small batch (latency path): pack on the host, ONE upload, ONE download
         if (plan->h_stage_bytes < stage_bytes) {
             if (plan->h_stage) cudaFreeHost(plan->h_stage);
