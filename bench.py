@@ -394,7 +394,7 @@ def main():
         e2e = {"value": world * batch * args.e2e_steps / float(tt[0]), "unit": UNIT,
                "h2d_bytes_per_step": hs.h2d_bytes(), "d2h_bytes_per_step": hs.d2h_bytes(advance=True, want_w_opt=False),
                "steps": args.e2e_steps, "api": "sihmpc_step_host (pinned host buffers; in: x,u,pesos,ViNant,ysp; out: du,J,status,ViNant + advanced x,u,pesos; "
-                      "chunked upload / kernel / download pipeline)"}
+                      "zero-copy: the step kernel reads and writes the pinned arrays over PCIe)"}
         if rank == 0:
             h1 = HostStepper(plan, 1, device=dev)
             h1.x.copy_(torch.as_tensor(scen["x0"][:1])); h1.u.copy_(torch.as_tensor(scen["u0"][:1]))
