@@ -160,6 +160,11 @@ size_t sihmpc_workspace_bytes(const sihmpc_plan *plan, int64_t batch);
  * for scenarios a fast path hands over).  Static string, never NULL. */
 const char *sihmpc_plan_kernel(const sihmpc_plan *plan);
 
+/* Diagnostics of the LAST sihmpc_step launch of this plan (synchronises `stream`): how many scenarios a fast
+ * path handed over to the general active-set kernel, and how many scenario-steps with active bounds the
+ * tensor fast path resolved itself (mma_active_set).  Either pointer may be NULL.                       */
+int sihmpc_plan_counters(sihmpc_plan *plan, int64_t *handed_over, int64_t *solved_in_kernel, void *stream);
+
 /* -- the hot path --------------------------------------------------------------------------- */
 /* replaces: IHMPCController.mpc (ihmpccontroller.py:567-604) for `batch` scenarios at once and,
  * with SIHMPC_F_ADVANCE, the rest of the driver-loop body (example_distillation.py:98-113:

@@ -56,7 +56,7 @@ EXPORTS = [
     "sihmpc_abi_version", "sihmpc_last_error", "sihmpc_device_count", "sihmpc_plan_create",
     "sihmpc_plan_destroy", "sihmpc_workspace_bytes", "sihmpc_step", "sihmpc_step_host",
     "sihmpc_host_staging_bytes", "sihmpc_predict", "sihmpc_subobjectives", "sihmpc_stats_reduce",
-    "sihmpc_fp64_peak", "sihmpc_log_step", "sihmpc_log_loop", "sihmpc_plan_kernel",
+    "sihmpc_fp64_peak", "sihmpc_log_step", "sihmpc_log_loop", "sihmpc_plan_kernel", "sihmpc_plan_counters",
 ]
 
 _lib = None
@@ -106,6 +106,8 @@ def load():
     lib.sihmpc_log_loop.restype = C.c_int
     lib.sihmpc_plan_kernel.argtypes = [C.c_void_p]
     lib.sihmpc_plan_kernel.restype = C.c_char_p
+    lib.sihmpc_plan_counters.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_void_p]
+    lib.sihmpc_plan_counters.restype = C.c_int
     lib.sihmpc_fp64_peak.argtypes = [C.POINTER(C.c_double)]
     lib.sihmpc_fp64_peak.restype = C.c_int
     if lib.sihmpc_abi_version() != ABI_VERSION:

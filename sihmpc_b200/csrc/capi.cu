@@ -316,6 +316,26 @@ const char *sihmpc_plan_kernel(const sihmpc_plan *plan) {
     return "ihmpc_step_kernel";
 }
 
+int sihmpc_plan_counters(sihmpc_plan *plan, int64_t *handed_over, int64_t *solved_in_kernel, void *stream) {
+    if (!plan) return fail(SIHMPC_E_INVALID, "NULL argument%s");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaStreamSynchronize(st);
+    int h = 0x7f7f7f7f, k = 0;
+    const int *hp = nullptr;
+    const bool want_tile = plan->tile.ok && (plan->use_fast == 3 || (plan->use_fast == 2 && plan->mma.shape < 0));
+    if (want_tile) hp = plan->tile.n_handover;
+    else if (plan->use_fast == 2 && plan->mma.shape >= 0)
+        hp = sih::mma_has_resume(plan->mma) ? plan->mma.n_fail : plan->mma.n_handover;
+    else if (plan->use_fast == 1 && plan->quad.shape >= 0) hp = plan->quad.n_handover;
+    if (e == cudaSuccess && hp) e = cudaMemcpy(&h, hp, sizeof(int), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && !want_tile && plan->use_fast == 2 && plan->mma.shape >= 0 && plan->mma.n_inkernel)
+        e = cudaMemcpy(&k, plan->mma.n_inkernel, sizeof(int), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return fail(SIHMPC_E_CUDA, "reading the fast-path counters failed: %s", cudaGetErrorString(e));
+    if (handed_over) *handed_over = (int64_t)h - 0x7f7f7f7f;
+    if (solved_in_kernel) *solved_in_kernel = k;
+    return 0;
+}
+
 int sihmpc_step(sihmpc_plan *plan, const sihmpc_io *io, int64_t batch, int32_t n_steps,
                 void *workspace, size_t workspace_bytes, void *stream) {
     if (!plan || !io) return fail(SIHMPC_E_INVALID, "NULL argument%s");
@@ -339,12 +359,12 @@ int sihmpc_step(sihmpc_plan *plan, const sihmpc_io *io, int64_t batch, int32_t n
         n_handover = plan->tile.n_handover;
     } else if (plan->use_fast == 2 && plan->mma.shape >= 0) {
         cudaError_t e = sih::mma_ensure_capacity(&plan->mma, batch);
-        if (e == cudaSuccess) e = cudaMemsetAsync(plan->mma.n_handover, 0x7f, (size_t)(batch + 1) * sizeof(int), st);
+        if (e == cudaSuccess) e = sih::mma_reset(plan->mma, batch, st);
         if (e == cudaSuccess) e = sih::mma_launch(plan->mma, plan->d, *io, batch, n_steps, plan->sm_count, st);
         if (e != cudaSuccess) return fail(SIHMPC_E_CUDA, "tensor fast-path launch failed: %s", cudaGetErrorString(e));
         if (!(plan->d.has_box || plan->d.has_cum)) return 0;      // nothing can be handed over
         start_step = plan->mma.start_step;
-        n_handover = plan->mma.n_handover;
+        n_handover = sih::mma_has_resume(plan->mma) ? plan->mma.n_fail : plan->mma.n_handover;
     } else if (plan->use_fast == 1 && sih::quad_supported(plan->quad, *io)) {
         cudaError_t e = sih::quad_ensure_capacity(&plan->quad, batch);
         if (e == cudaSuccess) e = cudaMemsetAsync(plan->quad.n_handover, 0x7f, (size_t)(batch + 1) * sizeof(int), st);

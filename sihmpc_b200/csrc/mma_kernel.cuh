@@ -38,6 +38,10 @@ struct MmaConst {            // offsets in doubles into the packed block
     int be, bw, w0c, bf, br, bh, bomdu, by, byp, bvn, tau, gamma, bounds, vinq, ell_val, total_d;
     int ell_col, ell_csr, hj_idx, vin_row, vlive, vdead, total_i;
     int ell_w;
+    // in-kernel active set on simple bounds (mma_active_set): gradient / Hessian / difference maps in the space
+    // where the bounds are simple (cspace 1: cumulative moves c = cumsum(dU), input box; 0: dU itself, move box;
+    // -1: not available, a violated bound hands the scenario over)
+    int bfc, bhc, bdp, bdpt, du_idx, n_du, cspace;
 };
 
 // NVE_: number of QP variables that are actually eliminated.  Moves whose dead time pushes their whole
@@ -64,6 +68,7 @@ struct MmaDims {
     static constexpr int KP = (M + 3) / 4;             // k-tiles of pesos
     static constexpr int KH = 1;                       // k-tile [1 ; pesos of <= 3 dense Hessian blocks]
     static constexpr int KD = (NU + 3) / 4;            // k-tiles of du
+    static constexpr int KHC = 2;                      // k-tiles [1 ; pesos of dense blocks ; pesos of move weights] (bound space)
     static constexpr int HPAIRS = SV * (SV + 1);
     static constexpr int BX = 8 * TX, BV = NVL;
     static constexpr int BRAW = BX + NU + (NU & 1) + BV;
@@ -130,11 +135,201 @@ inline void mma_pack(std::vector<double> &buf, int off, int NT, int KT,
             }
 }
 
-template <typename D, int WARPS, int MINB>
+// value of factorisation slot sl in a C-layout tile set [TV][2]
+template <typename D>
+__device__ __forceinline__ double mma_slot(const double (&c)[D::TV][2], const int sl) {
+    return (D::NV % 8 == 4 && sl == D::SV - 1) ? c[D::TV - 1][0] : c[sl / 2][sl % 2];
+}
+
+// gradient of the step cost in the bound space at the point v (slots):  g = S^T (2 E^T (omega o (e + E S v)) + 2 omega_du o S v),
+// S = the map from bound-space variables to moves (difference operator for cumulative moves, identity for the move box)
+template <typename D>
+__device__ __forceinline__ void mma_bound_gradient(const double *__restrict__ cst, const MmaConst &Q,
+                                                   const double (&e)[D::TR][2], const double (&om)[D::TR][2],
+                                                   const double (&od)[D::SV], const double (&v)[D::SV],
+                                                   double (&gout)[D::SV], double (&dv)[D::SV], const int lane) {
+    constexpr int SV = D::SV, TR = D::TR, TV = D::TV;
+    double t0[TV][2];
+#pragma unroll
+    for (int T = 0; T < TV; ++T) t0[T][0] = t0[T][1] = 0.0;
+    mma_block<TV, SV>(cst + Q.bdp, v, t0, lane);
+#pragma unroll
+    for (int sl = 0; sl < SV; ++sl) dv[sl] = mma_slot<D>(t0, sl);
+    double r[TR][2];
+#pragma unroll
+    for (int T = 0; T < TR; ++T) { r[T][0] = e[T][0]; r[T][1] = e[T][1]; }
+    mma_block<TR, SV>(cst + Q.br, dv, r, lane);
+    double at[2 * TR];
+#pragma unroll
+    for (int T = 0; T < TR; ++T) { at[2 * T] = om[T][0] * r[T][0]; at[2 * T + 1] = om[T][1] * r[T][1]; }
+#pragma unroll
+    for (int T = 0; T < TV; ++T) t0[T][0] = t0[T][1] = 0.0;
+    mma_block<TV, 2 * TR>(cst + Q.bfc, at, t0, lane);
+    double wd[SV];
+#pragma unroll
+    for (int sl = 0; sl < SV; ++sl) wd[sl] = 2.0 * od[sl] * dv[sl];
+    mma_block<TV, SV>(cst + Q.bdpt, wd, t0, lane);
+#pragma unroll
+    for (int sl = 0; sl < SV; ++sl) gout[sl] = mma_slot<D>(t0, sl);
+}
+
+// In-kernel active set for the scenarios of this warp whose unconstrained optimum violates a bound (`need`).
+// The QP is restated in the space where the violated family of bounds is SIMPLE (cumulative moves for the input
+// box ihmpccontroller.py:420-424, the moves themselves for the move box :42-43), so an active bound is a fixed
+// variable: its row and column of the Hessian are replaced by the identity (per-scenario bit masks, the register
+// resident factorisation stays static and the eight scenarios of the warp stay in lockstep).  Violated free
+// variables are fixed, fixed variables whose multiplier has the wrong sign are released, until the KKT conditions
+// hold -- which certifies the optimum of this strictly convex problem whatever path led there; a scenario that
+// does not get there in MAXIT rounds returns false and is handed over to the general kernel as before.
+// mlo/mhi: bit p = elimination position p fixed at its lower/upper bound (replicated over the quad); kept by the
+// caller as the warm start of the next step.  On success fr = the optimal moves in factorisation slots.
+template <typename D>
+__device__ __forceinline__ bool mma_active_set(const double *__restrict__ cst, const int *__restrict__ cint,
+                                               const MmaConst &Q, const double (&e)[D::TR][2],
+                                               const double (&om)[D::TR][2], const double (&apes)[D::KP],
+                                               const double (&pes)[D::M], const double (&uu)[D::NU],
+                                               const int (&vlog)[D::SV], unsigned &mlo, unsigned &mhi, const bool need,
+                                               double (&fr)[D::SV], const int lane, const int g, const int mh) {
+    constexpr int SV = D::SV, TV = D::TV, NU = D::NU, M = D::M, KP = D::KP, KHC = D::KHC;
+    constexpr int MAXIT = 8;
+    double blo[SV], bhi[SV], tlo[SV], thi[SV], od[SV];
+#pragma unroll
+    for (int sl = 0; sl < SV; ++sl) {
+        const int j = vlog[sl] % NU;
+        const double off = (Q.cspace == 1) ? sel<NU>(uu, j) : 0.0;
+        const int bo = (Q.cspace == 1) ? 2 * NU : 0;
+        const double lo = cst[Q.bounds + bo + j], hi = cst[Q.bounds + bo + NU + j];
+        blo[sl] = lo - off; bhi[sl] = hi - off;
+        tlo[sl] = 1e-10 * (1.0 + fabs(lo)); thi[sl] = 1e-10 * (1.0 + fabs(hi));
+    }
+    {
+        double omdu[TV][2];
+#pragma unroll
+        for (int T = 0; T < TV; ++T) omdu[T][0] = omdu[T][1] = 0.0;
+        mma_block<TV, KP>(cst + Q.bomdu, apes, omdu, lane);
+#pragma unroll
+        for (int sl = 0; sl < SV; ++sl) od[sl] = mma_slot<D>(omdu, sl);
+    }
+    double ahc[KHC];
+#pragma unroll
+    for (int t = 0; t < KHC; ++t) {
+        const int el = 4 * t + g;                          // 0 -> 1 ; 1+a -> dense block a ; 1+mh+b -> move weight b
+        double v = (el == 0) ? 1.0 : 0.0;
+        if (el >= 1 && el - 1 < mh) v = sel<M>(pes, cint[Q.hj_idx + el - 1]);
+        else if (el >= 1 + mh && el - 1 - mh < Q.n_du) v = sel<M>(pes, cint[Q.du_idx + el - 1 - mh]);
+        ahc[t] = v;
+    }
+    bool done = !need, ok = false;
+    double cres[SV];
+#pragma unroll
+    for (int sl = 0; sl < SV; ++sl) cres[sl] = 0.0;
+    if (!need) mlo = mhi = 0u;
+    for (int it = 0; it < MAXIT; ++it) {
+        if (!__any_sync(0xffffffffu, !done)) break;
+        const unsigned mf = mlo | mhi;
+        double z[SV], rhs[SV], dv[SV];
+#pragma unroll
+        for (int sl = 0; sl < SV; ++sl) {
+            const int p = 4 * sl + g;
+            z[sl] = ((mlo >> p) & 1u) ? blo[sl] : (((mhi >> p) & 1u) ? bhi[sl] : 0.0);
+        }
+        mma_bound_gradient<D>(cst, Q, e, om, od, z, rhs, dv, lane);
+#pragma unroll
+        for (int sl = 0; sl < SV; ++sl) rhs[sl] = ((mf >> (4 * sl + g)) & 1u) ? 0.0 : -rhs[sl];
+        // Hessian in the bound space, fixed rows/columns replaced by the identity
+        double L[SV][D::NV];
+        {
+            int pp = 0;
+#pragma unroll
+            for (int t = 0; t < SV; ++t) {
+                const bool rowfix = ((mf >> (4 * t + g)) & 1u) != 0u;
+#pragma unroll
+                for (int jp = 0; jp < (4 * t + 4) / 2; ++jp) {
+                    double h[1][2];
+                    h[0][0] = h[0][1] = 0.0;
+                    mma_block<1, KHC>(cst + Q.bhc + (size_t)pp * KHC * 32, ahc, h, lane);
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int j = 2 * jp + hh;
+                        const bool fix = rowfix || (((mf >> j) & 1u) != 0u);
+                        L[t][j] = fix ? ((j == 4 * t + g) ? 1.0 : 0.0) : h[0][hh];
+                    }
+                    ++pp;
+                }
+            }
+        }
+        int npd = 0;
+        quad_solve_spd<D>(L, rhs, g, npd);
+        double c[SV];
+        unsigned vlo = 0u, vhi = 0u, wrel = 0u;
+#pragma unroll
+        for (int sl = 0; sl < SV; ++sl) {
+            const int p = 4 * sl + g;
+            const bool fixed = ((mf >> p) & 1u) != 0u;
+            c[sl] = fixed ? z[sl] : rhs[sl];
+            if (!fixed && c[sl] < blo[sl] - tlo[sl]) vlo |= 1u << p;
+            if (!fixed && c[sl] > bhi[sl] + thi[sl]) vhi |= 1u << p;
+        }
+        if (__any_sync(0xffffffffu, mf != 0u)) {           // multipliers of the fixed variables = gradient there
+            double gc[SV];
+            mma_bound_gradient<D>(cst, Q, e, om, od, c, gc, dv, lane);
+            double gs = 0.0;
+#pragma unroll
+            for (int sl = 0; sl < SV; ++sl) gs = fmax(gs, fabs(gc[sl]));
+            gs = 1e-12 * (1.0 + quad_max(gs));
+#pragma unroll
+            for (int sl = 0; sl < SV; ++sl) {
+                const int p = 4 * sl + g;
+                if (((mlo >> p) & 1u) && gc[sl] < -gs) wrel |= 1u << p;
+                if (((mhi >> p) & 1u) && gc[sl] > gs) wrel |= 1u << p;
+            }
+        }
+        vlo |= __shfl_xor_sync(0xffffffffu, vlo, 1); vlo |= __shfl_xor_sync(0xffffffffu, vlo, 2);
+        vhi |= __shfl_xor_sync(0xffffffffu, vhi, 1); vhi |= __shfl_xor_sync(0xffffffffu, vhi, 2);
+        wrel |= __shfl_xor_sync(0xffffffffu, wrel, 1); wrel |= __shfl_xor_sync(0xffffffffu, wrel, 2);
+        npd |= __shfl_xor_sync(0xffffffffu, npd, 1); npd |= __shfl_xor_sync(0xffffffffu, npd, 2);
+        if (!done) {
+            if ((vlo | vhi | wrel) == 0u && !npd) {
+                done = true; ok = true;
+#pragma unroll
+                for (int sl = 0; sl < SV; ++sl) cres[sl] = c[sl];
+            } else {
+                mlo = (mlo | vlo) & ~wrel;
+                mhi = (mhi | vhi) & ~wrel;
+            }
+        }
+    }
+    {   // moves of the accepted point
+        double t0[TV][2];
+#pragma unroll
+        for (int T = 0; T < TV; ++T) t0[T][0] = t0[T][1] = 0.0;
+        mma_block<TV, SV>(cst + Q.bdp, cres, t0, lane);
+        if (need && ok) {
+#pragma unroll
+            for (int sl = 0; sl < SV; ++sl) fr[sl] = mma_slot<D>(t0, sl);
+        }
+    }
+    return ok;
+}
+
+// MODE 0: first pass.  Unconstrained optimum + bound check; a scenario that violates a bound is appended to `list`
+//         and leaves the kernel (the active set inlined here cost the hot loop 20 %: register pressure).
+// MODE 1: resume pass over the scenarios of `list` (n_list = their counter), each from its own start_step, with the
+//         in-kernel active set (mma_active_set); eight listed scenarios per warp, every quad on its own step index.
+//         What it cannot resolve is flagged in start_step / n_handover for the general kernel (third pass).
+// MODE 2: first pass with the active set inline (workloads where most scenarios sit on bounds).
+template <typename D, int WARPS, int MINB, int MODE>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qbuf, const sihmpc_io io,
                 const long long batch, const int n_steps, int *__restrict__ start_step,
-                int *__restrict__ n_handover) {
+                int *__restrict__ n_handover, int *__restrict__ n_inkernel, int *__restrict__ list,
+                const int *__restrict__ n_list) {
+    constexpr bool AS = (MODE != 0), RESUME = (MODE == 1);
+    long long n_work = batch;
+    if constexpr (RESUME) {
+        n_work = (long long)(*n_list) - 0x7f7f7f7f;
+        if ((long long)blockIdx.x * WARPS * 8 >= n_work) return;
+    }
     constexpr int NX = D::NX, NU = D::NU, NY = D::NY, M = D::M, NV = D::NV, NYP = D::NYP, R = D::R;
     constexpr int SV = D::SV, TX = D::TX, TR = D::TR, TV = D::TV, TY = D::TY, TQ = D::TQ, TC = D::TC, TM = D::TM;
     constexpr int KX = D::KX, KA = D::KA, KP = D::KP, KH = D::KH, KD = D::KD;
@@ -162,14 +357,23 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
     __syncwarp();
     const long long gq = ((long long)blockIdx.x * WARPS + wib) * 8 + q;
     const long long nq = (long long)gridDim.x * WARPS * 8;
-    const long long rounds = (batch + nq - 1) / nq;
+    const long long rounds = (n_work + nq - 1) / nq;
     const int nstat = NY + SIHMPC_NSTATS_EXTRA;
     const bool advance = (io.flags & SIHMPC_F_ADVANCE) != 0;
     const int mh = P.mh;
 
     for (long long rd = 0; rd < rounds; ++rd) {
-        const long long s = gq + rd * nq;
-        const bool valid = s < batch;
+        long long s = gq + rd * nq;
+        const bool valid = s < n_work;
+        int st0 = 0, n_iter = n_steps;
+        if constexpr (RESUME) {
+            s = valid ? list[s] : 0;
+            st0 = valid ? start_step[s] : n_steps;
+            if (st0 < 0 || st0 > n_steps) st0 = n_steps;
+            n_iter = __reduce_max_sync(0xffffffffu, n_steps - st0);
+            __syncwarp();
+            if (valid && g == 0) start_step[s] = 0x7f7f7f7f;    // resolved here unless flagged again below
+        }
         const long long sc = valid ? s : 0;
         bool alive = valid;
         // ---- plant values of this scenario (nominal or per-scenario), staged once per round
@@ -204,6 +408,7 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
         double uu[NU], pes[M], ise[2];
         double st_du2 = 0.0, st_viol = 0.0, st_J = 0.0;
         int st_or = 0;
+        unsigned mlo = 0u, mhi = 0u;         // warm start of the in-kernel active set (bound masks of the last step)
 #pragma unroll
         for (int j = 0; j < NU; ++j) uu[j] = io.u[sc * NU + j];
 #pragma unroll
@@ -216,7 +421,31 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
             st_J = io.stats[sc * nstat + NY + 2]; st_or = (int)io.stats[sc * nstat + NY + 3];
         }
 
-        for (int step = 0; step < n_steps; ++step) {
+        // state of an alive scenario back to global memory (end of the launch, or hand-over)
+        auto write_state = [&]() {
+#pragma unroll
+            for (int T = 0; T < TX; ++T)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) { const int r = 8 * T + 2 * g + h; if (r < NX) io.x[s * NX + r] = xr[T][h]; }
+            if (g == 0) {
+#pragma unroll
+                for (int j = 0; j < NU; ++j) io.u[s * NU + j] = uu[j];
+#pragma unroll
+                for (int i = 0; i < M; ++i) io.pesos[s * M + i] = pes[i];
+            }
+            if (io.stats) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) if (2 * g + h < NY) io.stats[s * nstat + 2 * g + h] = ise[h];
+                if (g == 0) {
+                    io.stats[s * nstat + NY] = st_du2; io.stats[s * nstat + NY + 1] = st_viol;
+                    io.stats[s * nstat + NY + 2] = st_J; io.stats[s * nstat + NY + 3] = (double)st_or;
+                }
+            }
+        };
+
+        for (int it = 0; it < n_iter; ++it) {
+            const int step = st0 + it;
+            if constexpr (RESUME) { if (step >= n_steps) alive = false; }
             const int kabs = io.k0 + step;
             if (kabs >= next_start) {                    // rare: the schedule switches segment
                 while (seg + 1 < io.n_seg && io.seg_start[sc * io.n_seg + seg + 1] <= kabs) ++seg;
@@ -332,27 +561,36 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
             }
             viol = quad_max(viol);
             viol_abs = quad_max(viol_abs);
-            if (alive && (viol > 1e-10 || notpd)) {
-                alive = false;             // hand over to the general kernel from this step on
-                if (g == 0) { start_step[s] = step; atomicAdd(n_handover, 1); }
+            int nact = 0;
+            if constexpr (AS) {
+                if (Q.cspace >= 0) {           // bound violated: active set on the register-resident problem
+                    const bool need = alive && !notpd && viol > 1e-10;
+                    if (__any_sync(0xffffffffu, need)) {
+                        const bool ok = mma_active_set<D>(cst, cint, Q, er, om, apes, pes, uu, vlog, mlo, mhi, need, fr,
+                                                          lane, g, mh);
+                        __syncwarp();
+                        if (need && ok) {
 #pragma unroll
-                for (int T = 0; T < TX; ++T)
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) { const int r = 8 * T + 2 * g + h; if (r < NX) io.x[s * NX + r] = xr[T][h]; }
-                if (g == 0) {
-#pragma unroll
-                    for (int j = 0; j < NU; ++j) io.u[s * NU + j] = uu[j];
-#pragma unroll
-                    for (int i = 0; i < M; ++i) io.pesos[s * M + i] = pes[i];
-                }
-                if (io.stats) {
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) if (2 * g + h < NY) io.stats[s * nstat + 2 * g + h] = ise[h];
-                    if (g == 0) {
-                        io.stats[s * nstat + NY] = st_du2; io.stats[s * nstat + NY + 1] = st_viol;
-                        io.stats[s * nstat + NY + 2] = st_J; io.stats[s * nstat + NY + 3] = (double)st_or;
+                            for (int sl = 0; sl < SV; ++sl) bv[vlog[sl]] = fr[sl];
+                            viol = 0.0; viol_abs = 0.0;
+                            nact = __popc(mlo | mhi);
+                            if (g == 0) atomicAdd(n_inkernel, 1);
+                        }
+                        __syncwarp();
+                    } else {
+                        mlo = mhi = 0u;
                     }
                 }
+            }
+            if (alive && (viol > 1e-10 || notpd)) {
+                alive = false;             // hand over from this step on (MODE 0: resume pass; else: general kernel)
+                mlo = mhi = 0u;
+                if (g == 0) {
+                    start_step[s] = step;
+                    const int slot = atomicAdd(n_handover, 1) - 0x7f7f7f7f;
+                    if constexpr (MODE == 0) list[slot] = (int)s;
+                }
+                write_state();
             }
             // ---------------- K3: r = e + E dU, cost, slacks
             double syv[3 * NY];
@@ -396,7 +634,7 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
                     if (g == 0) {
                         if (io.J) io.J[s] = Jval;
                         if (io.status) io.status[s] = 0;
-                        if (io.n_active) io.n_active[s] = 0;
+                        if (io.n_active) io.n_active[s] = nact;
                     }
                 }
                 if (io.traj_du) for (int j = g; j < NU; j += 4) io.traj_du[((long long)step * batch + s) * NU + j] = bv[j];
@@ -520,28 +758,14 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
                     }
                 }
             }
+            if constexpr (RESUME) {
+                if (alive && last_step) { write_state(); alive = false; }
+            }
         }  // steps
 
         __syncwarp();
-        if (alive && advance) {
-#pragma unroll
-            for (int T = 0; T < TX; ++T)
-#pragma unroll
-                for (int h = 0; h < 2; ++h) { const int r = 8 * T + 2 * g + h; if (r < NX) io.x[s * NX + r] = xr[T][h]; }
-            if (g == 0) {
-#pragma unroll
-                for (int j = 0; j < NU; ++j) io.u[s * NU + j] = uu[j];
-#pragma unroll
-                for (int i = 0; i < M; ++i) io.pesos[s * M + i] = pes[i];
-            }
-            if (io.stats) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) if (2 * g + h < NY) io.stats[s * nstat + 2 * g + h] = ise[h];
-                if (g == 0) {
-                    io.stats[s * nstat + NY] = st_du2; io.stats[s * nstat + NY + 1] = st_viol;
-                    io.stats[s * nstat + NY + 2] = st_J; io.stats[s * nstat + NY + 3] = (double)st_or;
-                }
-            }
+        if (!RESUME && alive && advance) {
+            write_state();
         }
     }
 }
@@ -551,8 +775,12 @@ struct MmaPlan {
     int shape;
     MmaConst qc;
     double *qbuf;
+    int *ctr;                // one device buffer: [n_handover | n_fail | n_inkernel | pad | start_step[cap] | list[cap]]
     int *start_step;
-    int *n_handover;
+    int *n_handover;         // scenarios the first pass appended to `list` (counter baseline 0x7f7f7f7f)
+    int *n_fail;             // scenarios the resume pass could not resolve either: left to the general kernel
+    int *n_inkernel;         // scenario-steps of the last launch whose active bounds were resolved by mma_active_set
+    int *list;
     long long capacity;
     int blocks_per_sm;
     size_t smem_bytes;
@@ -633,6 +861,10 @@ inline void mma_build_constants(const sihmpc_plan_desc *d, const DevPlan &P, Mma
     const int W = D::WELL;
     qc.ell_w = W;
     qc.ell_val = take(D::TX * 2 * W * 4);
+    qc.bfc = take(D::TV * 2 * D::TR * 32);
+    qc.bhc = take(D::HPAIRS * D::KHC * 32);
+    qc.bdp = take(D::TV * SV * 32);
+    qc.bdpt = take(D::TV * SV * 32);
     qc.total_d = o;
     buf.assign(o, 0.0);
 
@@ -702,6 +934,85 @@ inline void mma_build_constants(const sihmpc_plan_desc *d, const DevPlan &P, Mma
                                  return 1000 + live[D::var_of(t - 2 * D::TQ, k)]; },
              [&](int i, int c) { if (c < 1000) return d->Wrow[(size_t)c * M + i];
                                  int v = c - 1000; return v >= NU ? d->Wdu[(size_t)(v - NU) * M + i] : 0.0; });
+    // ---- bound space of the in-kernel active set (mma_active_set): variables c = one per live move, dU_live = S c
+    // with S = difference operator along the horizon per input (c = cumulative move: the input box becomes a simple
+    // bound; presolved moves are zero, so the predecessor of a live move is the nearest earlier live move of the same
+    // input) or S = I (move box).  Indices below are LIVE indices (position in `live`).
+    std::vector<int> du_w;                                   // weights that act on the moves
+    for (int i = 0; i < M; ++i) {
+        bool any = false;
+        for (int v = 0; v < NVL && !any; ++v) any = (d->Wdu[(size_t)v * M + i] != 0.0);
+        if (any) du_w.push_back(i);
+    }
+    qc.n_du = (int)du_w.size();
+    qc.cspace = (P.has_cum && !P.has_box) ? 1 : ((P.has_box && !P.has_cum) ? 0 : -1);
+    if (1 + d->mh + qc.n_du > 4 * D::KHC || getenv("SIHMPC_NO_INKERNEL_AS")) qc.cspace = -1;
+    {
+        std::vector<double> S((size_t)NV * NV, 0.0);        // dU_live[a] = sum_b S[a][b] c[b]
+        for (int a = 0; a < NV; ++a) {
+            S[(size_t)a * NV + a] = 1.0;
+            if (qc.cspace == 1) {
+                int prev = -1;
+                for (int b = 0; b < NV; ++b)
+                    if (live[b] % NU == live[a] % NU && live[b] < live[a] && (prev < 0 || live[b] > live[prev])) prev = b;
+                if (prev >= 0) S[(size_t)a * NV + prev] = -1.0;
+            }
+        }
+        auto lcol = [&](int t, int k) { return (t < SV) ? D::var_of(t, k) : -1; };
+        auto lrow = [&](int T, int n) {
+            if (NV % 8 == 4 && T == D::TV - 1) return (n % 2 == 0) ? NV - 4 + n / 2 : -1;
+            int r = 8 * T + n; return r < NV ? r : -1;
+        };
+        mma_pack(buf, qc.bdp, D::TV, SV, lrow, lcol, [&](int a, int b) { return S[(size_t)a * NV + b]; });
+        mma_pack(buf, qc.bdpt, D::TV, SV, lrow, lcol, [&](int a, int b) { return S[(size_t)b * NV + a]; });
+        // gradient map: 2 (E_live S)^T
+        std::vector<double> Ec((size_t)R * NV, 0.0);
+        for (int r = 0; r < R; ++r)
+            for (int b = 0; b < NV; ++b) {
+                double acc = 0.0;
+                for (int a = 0; a < NV; ++a) acc += d->E[(size_t)r * NVL + live[a]] * S[(size_t)a * NV + b];
+                Ec[(size_t)r * NV + b] = acc;
+            }
+        mma_pack(buf, qc.bfc, D::TV, 2 * D::TR, lrow, ccol(R), [&](int b, int r) { return 2.0 * Ec[(size_t)r * NV + b]; });
+        // Hessian blocks S^T X S for X = Ht, HJ_a, 2 diag(Wdu[:, i])
+        const int nblk = 1 + d->mh + qc.n_du;
+        std::vector<double> Hc((size_t)nblk * NV * NV, 0.0), X((size_t)NV * NV), XS((size_t)NV * NV);
+        for (int e = 0; e < nblk; ++e) {
+            for (int a = 0; a < NV; ++a)
+                for (int b = 0; b < NV; ++b) {
+                    const int va = live[a], vb = live[b];
+                    double x;
+                    if (e == 0) x = d->Ht[(size_t)va * NVL + vb];
+                    else if (e <= d->mh) x = d->HJ[((size_t)(e - 1) * NVL + va) * NVL + vb];
+                    else x = (a == b) ? 2.0 * d->Wdu[(size_t)va * M + du_w[e - 1 - d->mh]] : 0.0;
+                    X[(size_t)a * NV + b] = x;
+                }
+            for (int a = 0; a < NV; ++a)
+                for (int b = 0; b < NV; ++b) {
+                    double acc = 0.0;
+                    for (int k = 0; k < NV; ++k) acc += X[(size_t)a * NV + k] * S[(size_t)k * NV + b];
+                    XS[(size_t)a * NV + b] = acc;
+                }
+            for (int a = 0; a < NV; ++a)
+                for (int b = 0; b < NV; ++b) {
+                    double acc = 0.0;
+                    for (int k = 0; k < NV; ++k) acc += S[(size_t)k * NV + a] * XS[(size_t)k * NV + b];
+                    Hc[((size_t)e * NV + a) * NV + b] = acc;
+                }
+        }
+        int pp = 0;
+        for (int t = 0; t < SV; ++t)
+            for (int jp = 0; jp < (4 * t + 4) / 2; ++jp, ++pp)
+                mma_pack(buf, qc.bhc + pp * D::KHC * 32, 1, D::KHC,
+                         [&](int, int n) { return n; },
+                         [&](int tt, int k) { int e = 4 * tt + k; return e < nblk && e < 4 * D::KHC ? e : -1; },
+                         [&](int n, int e) {
+                             const int gq = n / 2, h = n % 2;
+                             const int prow = 4 * t + gq, pcol = 2 * jp + h;
+                             if (pcol > prow) return 0.0;
+                             const int a = D::var_of(prow / 4, prow % 4), b = D::var_of(pcol / 4, pcol % 4);
+                             return Hc[((size_t)e * NV + a) * NV + b]; });
+    }
     for (int T = 0; T < D::TY; ++T)
         for (int g = 0; g < 4; ++g)
             for (int h = 0; h < 2; ++h) { int r = 8 * T + 2 * g + h; if (r < NYP) buf[qc.tau + (T * 4 + g) * 2 + h] = d->tau[r / NY]; }
@@ -719,8 +1030,10 @@ inline void mma_build_constants(const sihmpc_plan_desc *d, const DevPlan &P, Mma
     qc.vin_row = takei(d->n_vin > 0 ? d->n_vin : 1);
     qc.vlive = takei(NV);
     qc.vdead = takei(NVL - NV > 0 ? NVL - NV : 1);
+    qc.du_idx = takei(M);
     qc.total_i = io_;
     ibuf.assign(io_, 0);
+    for (int i = 0; i < qc.n_du; ++i) ibuf[qc.du_idx + i] = du_w[i];
     for (int i = 0; i < NV; ++i) ibuf[qc.vlive + i] = live[i];
     for (int i = 0; i < NVL - NV; ++i) ibuf[qc.vdead + i] = deadv[i];
     for (int T = 0; T < D::TX; ++T)
@@ -764,13 +1077,17 @@ inline cudaError_t mma_configure_shape(const sihmpc_plan_desc *d, const DevPlan 
     if (e != cudaSuccess) return e;
     qp->smem_bytes = mma_smem_bytes<D>(qp->qc);
     if (qp->smem_bytes > 227 * 1024) { qp->shape = -1; return cudaSuccess; }
-    auto kern = mma_step_kernel<D, MMA_WARPS, MMA_MINB>;
+    auto kern = mma_step_kernel<D, MMA_WARPS, MMA_MINB, 0>;
+    auto kern_resume = mma_step_kernel<D, MMA_WARPS, MMA_MINB, 1>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qp->smem_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern_resume, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qp->smem_bytes);
     if (e != cudaSuccess) return e;
-    int occ = 0;
+    int occ = 0, occ_r = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, MMA_WARPS * 32, qp->smem_bytes);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_r, kern_resume, MMA_WARPS * 32, qp->smem_bytes);
     if (e != cudaSuccess) return e;
     if (occ < 1) { qp->shape = -1; return cudaSuccess; }
+    if (occ_r < 1) qp->qc.cspace = -1;
     qp->blocks_per_sm = occ;
     return cudaSuccess;
 }
@@ -784,11 +1101,36 @@ inline cudaError_t mma_configure(const sihmpc_plan_desc *d, const DevPlan &P, Mm
 
 inline cudaError_t mma_ensure_capacity(MmaPlan *qp, long long batch) {
     if (qp->capacity >= batch) return cudaSuccess;
-    if (qp->n_handover) cudaFree(qp->n_handover);      // one buffer: [counter | start_step[batch]]
-    qp->n_handover = nullptr; qp->start_step = nullptr; qp->capacity = 0;
-    cudaError_t e = cudaMalloc(&qp->n_handover, (size_t)(batch + 1) * sizeof(int));
-    if (e == cudaSuccess) { qp->start_step = qp->n_handover + 1; qp->capacity = batch; }
+    if (qp->ctr) cudaFree(qp->ctr);
+    qp->ctr = qp->n_handover = qp->n_fail = qp->n_inkernel = qp->start_step = qp->list = nullptr; qp->capacity = 0;
+    cudaError_t e = cudaMalloc(&qp->ctr, (size_t)(4 + 2 * batch) * sizeof(int));
+    if (e == cudaSuccess) {
+        qp->n_handover = qp->ctr; qp->n_fail = qp->ctr + 1; qp->n_inkernel = qp->ctr + 2;
+        qp->start_step = qp->ctr + 4; qp->list = qp->ctr + 4 + batch; qp->capacity = batch;
+    }
     return e;
+}
+
+// counters and start_step back to "nothing handed over" (baseline 0x7f7f7f7f), n_inkernel to 0
+inline cudaError_t mma_reset(const MmaPlan &qp, long long batch, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(qp.ctr, 0x7f, (size_t)(4 + batch) * sizeof(int), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(qp.n_inkernel, 0, sizeof(int), st);
+    return e;
+}
+
+inline bool mma_has_resume(const MmaPlan &qp) { return qp.qc.cspace >= 0; }
+
+template <typename D>
+inline cudaError_t mma_launch_shape(const MmaPlan &qp, const DevPlan &P, const sihmpc_io &io, long long batch,
+                                    int n_steps, int grid, cudaStream_t st) {
+    mma_step_kernel<D, MMA_WARPS, MMA_MINB, 0><<<grid, MMA_WARPS * 32, qp.smem_bytes, st>>>(
+        P, qp.qc, qp.qbuf, io, batch, n_steps, qp.start_step, qp.n_handover, qp.n_inkernel, qp.list, nullptr);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess || !mma_has_resume(qp)) return e;
+    // resume pass over the listed scenarios (their number is only known on the device: blocks beyond it leave at once)
+    mma_step_kernel<D, MMA_WARPS, MMA_MINB, 1><<<grid, MMA_WARPS * 32, qp.smem_bytes, st>>>(
+        P, qp.qc, qp.qbuf, io, batch, n_steps, qp.start_step, qp.n_fail, qp.n_inkernel, qp.list, qp.n_handover);
+    return cudaGetLastError();
 }
 
 inline cudaError_t mma_launch(const MmaPlan &qp, const DevPlan &P, const sihmpc_io &io, long long batch,
@@ -798,18 +1140,13 @@ inline cudaError_t mma_launch(const MmaPlan &qp, const DevPlan &P, const sihmpc_
     const long long cap = (long long)sm_count * qp.blocks_per_sm;
     int grid = (int)(need < cap ? need : cap);
     if (const char *gv = getenv("SIHMPC_QUAD_GRID")) { int gg = atoi(gv); if (gg > 0 && gg < grid) grid = gg; }
-    if (qp.shape == 1)
-        mma_step_kernel<DistillationMma16, MMA_WARPS, MMA_MINB><<<grid, MMA_WARPS * 32, qp.smem_bytes, st>>>(
-            P, qp.qc, qp.qbuf, io, batch, n_steps, qp.start_step, qp.n_handover);
-    else
-        mma_step_kernel<DistillationMma, MMA_WARPS, MMA_MINB><<<grid, MMA_WARPS * 32, qp.smem_bytes, st>>>(
-            P, qp.qc, qp.qbuf, io, batch, n_steps, qp.start_step, qp.n_handover);
-    return cudaGetLastError();
+    return qp.shape == 1 ? mma_launch_shape<DistillationMma16>(qp, P, io, batch, n_steps, grid, st)
+                         : mma_launch_shape<DistillationMma>(qp, P, io, batch, n_steps, grid, st);
 }
 
 inline void mma_destroy(MmaPlan *qp) {
     if (qp->qbuf) cudaFree(qp->qbuf);
-    if (qp->n_handover) cudaFree(qp->n_handover);
+    if (qp->ctr) cudaFree(qp->ctr);
     memset(qp, 0, sizeof *qp);
     qp->shape = -1;
 }

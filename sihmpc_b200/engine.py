@@ -51,6 +51,16 @@ class DevicePlan:
         """Kernel that serves sihmpc_step for this plan (sihmpc_plan_kernel)."""
         return self.lib.sihmpc_plan_kernel(self.handle).decode()
 
+    def counters(self, stream=None):
+        """(scenarios handed over to the general kernel, scenario-steps with active bounds solved inside the
+        fast path) of the last sihmpc_step launch (sihmpc_plan_counters; synchronises the stream)."""
+        h, k = C.c_int64(0), C.c_int64(0)
+        st = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        rc = self.lib.sihmpc_plan_counters(self.handle, C.byref(h), C.byref(k), C.c_void_p(st))
+        if rc:
+            raise _capi.SihmpcError(self.lib.sihmpc_last_error().decode())
+        return int(h.value), int(k.value)
+
     def close(self):
         if self.handle:
             self.lib.sihmpc_plan_destroy(self.handle)

@@ -227,6 +227,7 @@ def test_fast_path_handover_many_rounds(monkeypatch):
 
     def run(no_fast, grid):
         monkeypatch.setenv("SIHMPC_NO_FAST", "1" if no_fast else "0")
+        monkeypatch.setenv("SIHMPC_NO_INKERNEL_AS", "1")     # this test is about the hand-over itself
         if grid:
             monkeypatch.setenv("SIHMPC_QUAD_GRID", str(grid))
         else:
@@ -243,6 +244,7 @@ def test_fast_path_handover_many_rounds(monkeypatch):
     du_g, x_g, st_g = run(True, 0)
     monkeypatch.delenv("SIHMPC_QUAD_GRID", raising=False)
     monkeypatch.delenv("SIHMPC_NO_FAST", raising=False)
+    monkeypatch.delenv("SIHMPC_NO_INKERNEL_AS", raising=False)
     assert (st_f[:, 5] == 0).all() and (st_g[:, 5] == 0).all()
     n_constrained = int((st_g[:, 6] > 0).sum())
     assert 0.05 * B < n_constrained < 0.95 * B          # both paths are exercised
@@ -253,6 +255,49 @@ def test_fast_path_handover_many_rounds(monkeypatch):
     ref = oracle_closed_loop(sc.declare_distillation, sys_, scen, idx, T, bounds=bounds)
     assert ref["n_active"].max() > 0
     assert np.max(np.abs(du_f[:, idx] - ref["du"])) <= RTOL * np.max(np.abs(ref["du"]))
+
+
+@pytest.mark.parametrize("bname,bounds", [
+    ("input_box", dict(ulb=[1.80, 1.62], uub=[2.02, 1.78])),          # cumulative moves are the simple variables
+    ("example_ulb", dict(ulb=[1.9, 1.55])),
+    ("move_box", dict(dulb=[-0.01, -0.03], duub=[0.015, 0.02])),      # the moves themselves
+])
+def test_inkernel_active_set_matches_general_and_oracle(bname, bounds, monkeypatch):
+    """Tensor fast path with bounds active: the scenarios are solved INSIDE mma_step_kernel (mma_active_set: the
+    bound family restated as simple bounds, fixed variables masked out of the register-resident factorisation, KKT
+    certificate), not handed over.  Must equal the general dual-active-set kernel and the oracle."""
+    sys_ = sc.distillation_system()
+    B, T = 512, 150
+    scen = sc.distillation_scenarios(B)
+
+    def run(no_fast):
+        monkeypatch.setenv("SIHMPC_NO_FAST", "1" if no_fast else "0")
+        c = sc.declare_distillation(IHMPCController, sys_, **bounds)
+        eng = c.engine(B)
+        eng.set_state(scen["x0"], scen["u0"])
+        eng.set_schedule(scen["ysp_seq"], scen["seg_start"])
+        eng.set_disturbance(scen["dist_step"], scen["dist"])
+        tr = eng.run(T, record=True)
+        return tr["du"].cpu().numpy(), eng.x.cpu().numpy(), eng.stats.cpu().numpy(), eng.dp.counters(), eng.dp.kernel_name()
+
+    du_f, x_f, st_f, cnt_f, name_f = run(False)
+    du_g, x_g, st_g, _, name_g = run(True)
+    monkeypatch.delenv("SIHMPC_NO_FAST", raising=False)
+    assert name_f == "mma_step_kernel" and name_g == "ihmpc_step_kernel"
+    handed, inkernel = cnt_f
+    n_constrained = int((st_g[:, 6] > 0).sum())
+    assert n_constrained > 0.05 * B
+    assert inkernel > 0 and handed <= 0.02 * B, (handed, inkernel, n_constrained)
+    assert (st_f[:, 5] == 0).all() and (st_g[:, 5] == 0).all()
+    assert st_f[:, 3].max() <= VIOL
+    # two exact methods with different (tiny) feasibility tolerances, 150 closed-loop steps apart
+    assert np.max(np.abs(du_f - du_g)) <= 2e-7 * np.max(np.abs(du_g))
+    assert np.max(np.abs(x_f - x_g)) <= 2e-7 * 100.0
+    assert np.allclose(st_f[:, :3], st_g[:, :3], rtol=1e-6, atol=1e-12)
+    worst = int(np.argmax(np.abs(du_f - du_g).max(axis=(0, 2))))
+    for idx in sorted({int(np.argmax(st_g[:, 6])), worst, 0}):
+        ref = oracle_closed_loop(sc.declare_distillation, sys_, scen, idx, T, bounds=bounds)
+        assert np.max(np.abs(du_f[:, idx] - ref["du"])) <= RTOL * np.max(np.abs(ref["du"])), idx
 
 
 def _siso_integrating():
