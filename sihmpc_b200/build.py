@@ -11,13 +11,16 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libsihmpc_b200.so")
-UNITS = ["capi.cu", "tile_kernel.cu"]
+# (source, extra defines, object, dependencies): the tile kernels are instantiated one tile-row count per unit
+_TILE_DEPS = ["tile_kernel.cu", "tile_active_set.inc", "tile_api.h", "devplan.h", "../../include/sihmpc_b200.h"]
+UNITS = [("capi.cu", [], "capi.o", None), ("tile_kernel.cu", [], "tile_host.o", _TILE_DEPS)] + [
+    ("tile_kernel.cu", ["-DSIH_TL_ONLY_NT=%d" % k], "tile_nt%d.o" % k, _TILE_DEPS) for k in range(1, 9)]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 
 
 def _sources():
-    out = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h"))]
+    out = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h", ".inc"))]
     out.append(os.path.join(HERE, "..", "include", "sihmpc_b200.h"))
     return out
 
@@ -29,24 +32,33 @@ def needs_build() -> bool:
     return any(os.path.getmtime(s) > t for s in _sources())
 
 
+def _stale(obj, deps) -> bool:
+    if not os.path.exists(obj):
+        return True
+    t = os.path.getmtime(obj)
+    srcs = _sources() if deps is None else [os.path.join(CSRC, d) for d in deps]
+    return any(os.path.getmtime(s) > t for s in srcs)
+
+
 def build(force: bool = False, verbose: bool = False, extra=()) -> str:
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
     os.makedirs(OBJ, exist_ok=True)
-    procs = []
-    for u in UNITS:
-        obj = os.path.join(OBJ, u.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + list(extra) + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, os.path.join(CSRC, u)]
-        procs.append((u, obj, subprocess.Popen(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
-    objs = []
-    for u, obj, pr in procs:
+    procs, objs = [], []
+    for src, defs, oname, deps in UNITS:
+        obj = os.path.join(OBJ, oname)
+        objs.append(obj)
+        if not force and not extra and not _stale(obj, deps):
+            continue
+        cmd = [nvcc] + NVCC_FLAGS + list(extra) + defs + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, os.path.join(CSRC, src)]
+        procs.append((oname, subprocess.Popen(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
+    for u, pr in procs:
         out, err = pr.communicate()
         if pr.returncode != 0:
             raise RuntimeError("nvcc failed on %s:\n%s%s" % (u, out, err))
         if verbose:
             sys.stderr.write(err)
-        objs.append(obj)
     r = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs,
                        cwd=CSRC, capture_output=True, text=True)
     if r.returncode != 0:

@@ -320,19 +320,22 @@ int sihmpc_plan_counters(sihmpc_plan *plan, int64_t *handed_over, int64_t *solve
     if (!plan) return fail(SIHMPC_E_INVALID, "NULL argument%s");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t e = cudaStreamSynchronize(st);
-    int h = 0x7f7f7f7f, k = 0;
-    const int *hp = nullptr;
+    // every counter starts a launch at the baseline 0x7f7f7f7f (one memset); a resume pass that ran counts what it
+    // could not resolve in n_fail, otherwise the first pass' own counter is what the general kernel received
+    const int base = 0x7f7f7f7f;
+    int c[3] = {base, base, base};          // n_handover, n_fail, n_inkernel
+    const int *ctr = nullptr;
     const bool want_tile = plan->tile.ok && (plan->use_fast == 3 || (plan->use_fast == 2 && plan->mma.shape < 0));
-    if (want_tile) hp = plan->tile.n_handover;
-    else if (plan->use_fast == 2 && plan->mma.shape >= 0)
-        hp = sih::mma_has_resume(plan->mma) ? plan->mma.n_fail : plan->mma.n_handover;
-    else if (plan->use_fast == 1 && plan->quad.shape >= 0) hp = plan->quad.n_handover;
-    if (e == cudaSuccess && hp) e = cudaMemcpy(&h, hp, sizeof(int), cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess && !want_tile && plan->use_fast == 2 && plan->mma.shape >= 0 && plan->mma.n_inkernel)
-        e = cudaMemcpy(&k, plan->mma.n_inkernel, sizeof(int), cudaMemcpyDeviceToHost);
+    bool resumed = false;
+    if (want_tile) { ctr = plan->tile.ctr; resumed = plan->tile.last_resumed != 0; }
+    else if (plan->use_fast == 2 && plan->mma.shape >= 0) { ctr = plan->mma.ctr; resumed = plan->mma.last_resumed != 0; }
+    else if (plan->use_fast == 1 && plan->quad.shape >= 0 && plan->quad.n_handover) {
+        if (e == cudaSuccess) e = cudaMemcpy(c, plan->quad.n_handover, sizeof(int), cudaMemcpyDeviceToHost);
+    }
+    if (e == cudaSuccess && ctr) e = cudaMemcpy(c, ctr, 3 * sizeof(int), cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) return fail(SIHMPC_E_CUDA, "reading the fast-path counters failed: %s", cudaGetErrorString(e));
-    if (handed_over) *handed_over = (int64_t)h - 0x7f7f7f7f;
-    if (solved_in_kernel) *solved_in_kernel = k;
+    if (handed_over) *handed_over = (int64_t)(resumed ? c[1] : c[0]) - base;
+    if (solved_in_kernel) *solved_in_kernel = (int64_t)c[2] - base;
     return 0;
 }
 
@@ -351,12 +354,12 @@ int sihmpc_step(sihmpc_plan *plan, const sihmpc_io *io, int64_t batch, int32_t n
     const bool want_tile = plan->tile.ok && (plan->use_fast == 3 || (plan->use_fast == 2 && plan->mma.shape < 0));
     if (want_tile) {
         cudaError_t e = sih::tile_ensure_capacity(&plan->tile, batch);
-        if (e == cudaSuccess) e = cudaMemsetAsync(plan->tile.n_handover, 0x7f, (size_t)(batch + 1) * sizeof(int), st);
+        if (e == cudaSuccess) e = sih::tile_reset(plan->tile, batch, st);
         if (e == cudaSuccess) e = sih::tile_launch(plan->tile, plan->d, *io, batch, n_steps, plan->sm_count, st);
         if (e != cudaSuccess) return fail(SIHMPC_E_CUDA, "tile fast-path launch failed: %s", cudaGetErrorString(e));
         if (!(plan->d.has_box || plan->d.has_cum)) return 0;      // nothing can be handed over
         start_step = plan->tile.start_step;
-        n_handover = plan->tile.n_handover;
+        n_handover = sih::tile_resumes(plan->tile, batch, n_steps) ? plan->tile.n_fail : plan->tile.n_handover;
     } else if (plan->use_fast == 2 && plan->mma.shape >= 0) {
         cudaError_t e = sih::mma_ensure_capacity(&plan->mma, batch);
         if (e == cudaSuccess) e = sih::mma_reset(plan->mma, batch, st);
@@ -364,7 +367,7 @@ int sihmpc_step(sihmpc_plan *plan, const sihmpc_io *io, int64_t batch, int32_t n
         if (e != cudaSuccess) return fail(SIHMPC_E_CUDA, "tensor fast-path launch failed: %s", cudaGetErrorString(e));
         if (!(plan->d.has_box || plan->d.has_cum)) return 0;      // nothing can be handed over
         start_step = plan->mma.start_step;
-        n_handover = sih::mma_has_resume(plan->mma) ? plan->mma.n_fail : plan->mma.n_handover;
+        n_handover = sih::mma_resumes(plan->mma, batch, n_steps) ? plan->mma.n_fail : plan->mma.n_handover;
     } else if (plan->use_fast == 1 && sih::quad_supported(plan->quad, *io)) {
         cudaError_t e = sih::quad_ensure_capacity(&plan->quad, batch);
         if (e == cudaSuccess) e = cudaMemsetAsync(plan->quad.n_handover, 0x7f, (size_t)(batch + 1) * sizeof(int), st);

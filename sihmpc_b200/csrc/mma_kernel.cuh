@@ -191,7 +191,7 @@ __device__ __forceinline__ bool mma_active_set(const double *__restrict__ cst, c
                                                const int (&vlog)[D::SV], unsigned &mlo, unsigned &mhi, const bool need,
                                                double (&fr)[D::SV], const int lane, const int g, const int mh) {
     constexpr int SV = D::SV, TV = D::TV, NU = D::NU, M = D::M, KP = D::KP, KHC = D::KHC;
-    constexpr int MAXIT = 8;
+    constexpr int MAXIT = 24;
     double blo[SV], bhi[SV], tlo[SV], thi[SV], od[SV];
 #pragma unroll
     for (int sl = 0; sl < SV; ++sl) {
@@ -270,32 +270,49 @@ __device__ __forceinline__ bool mma_active_set(const double *__restrict__ cst, c
             if (!fixed && c[sl] < blo[sl] - tlo[sl]) vlo |= 1u << p;
             if (!fixed && c[sl] > bhi[sl] + thi[sl]) vhi |= 1u << p;
         }
-        if (__any_sync(0xffffffffu, mf != 0u)) {           // multipliers of the fixed variables = gradient there
+        vlo |= __shfl_xor_sync(0xffffffffu, vlo, 1); vlo |= __shfl_xor_sync(0xffffffffu, vlo, 2);
+        vhi |= __shfl_xor_sync(0xffffffffu, vhi, 1); vhi |= __shfl_xor_sync(0xffffffffu, vhi, 2);
+        // multipliers of the fixed variables = gradient there (only looked at once the point is feasible: bounds
+        // are added all at once, released one at a time -- the variable with the worst multiplier)
+        if (__any_sync(0xffffffffu, mf != 0u && !done && (vlo | vhi) == 0u)) {
             double gc[SV];
             mma_bound_gradient<D>(cst, Q, e, om, od, c, gc, dv, lane);
             double gs = 0.0;
 #pragma unroll
             for (int sl = 0; sl < SV; ++sl) gs = fmax(gs, fabs(gc[sl]));
             gs = 1e-12 * (1.0 + quad_max(gs));
+            double worst = 0.0; int wp = -1;
 #pragma unroll
             for (int sl = 0; sl < SV; ++sl) {
                 const int p = 4 * sl + g;
-                if (((mlo >> p) & 1u) && gc[sl] < -gs) wrel |= 1u << p;
-                if (((mhi >> p) & 1u) && gc[sl] > gs) wrel |= 1u << p;
+                const double bad = ((mlo >> p) & 1u) ? -gc[sl] : (((mhi >> p) & 1u) ? gc[sl] : 0.0);
+                if (bad > gs && bad > worst) { worst = bad; wp = p; }
+            }
+            const double wmax = quad_max(worst);
+            int cand = (wp >= 0 && worst == wmax) ? wp : 0x7fffffff;     // lowest position among equals
+            cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, 1));
+            cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, 2));
+            if (cand != 0x7fffffff) wrel = 1u << cand;
+            if (it < MAXIT / 3) {                  // early rounds: all of them at once (few rounds when it works)
+#pragma unroll
+                for (int sl = 0; sl < SV; ++sl) {
+                    const int p = 4 * sl + g;
+                    if (((mlo >> p) & 1u) && gc[sl] < -gs) wrel |= 1u << p;
+                    if (((mhi >> p) & 1u) && gc[sl] > gs) wrel |= 1u << p;
+                }
+                wrel |= __shfl_xor_sync(0xffffffffu, wrel, 1); wrel |= __shfl_xor_sync(0xffffffffu, wrel, 2);
             }
         }
-        vlo |= __shfl_xor_sync(0xffffffffu, vlo, 1); vlo |= __shfl_xor_sync(0xffffffffu, vlo, 2);
-        vhi |= __shfl_xor_sync(0xffffffffu, vhi, 1); vhi |= __shfl_xor_sync(0xffffffffu, vhi, 2);
-        wrel |= __shfl_xor_sync(0xffffffffu, wrel, 1); wrel |= __shfl_xor_sync(0xffffffffu, wrel, 2);
         npd |= __shfl_xor_sync(0xffffffffu, npd, 1); npd |= __shfl_xor_sync(0xffffffffu, npd, 2);
         if (!done) {
             if ((vlo | vhi | wrel) == 0u && !npd) {
                 done = true; ok = true;
 #pragma unroll
                 for (int sl = 0; sl < SV; ++sl) cres[sl] = c[sl];
+            } else if ((vlo | vhi) != 0u) {
+                mlo |= vlo; mhi |= vhi;
             } else {
-                mlo = (mlo | vlo) & ~wrel;
-                mhi = (mhi | vhi) & ~wrel;
+                mlo &= ~wrel; mhi &= ~wrel;
             }
         }
     }
@@ -781,6 +798,7 @@ struct MmaPlan {
     int *n_fail;             // scenarios the resume pass could not resolve either: left to the general kernel
     int *n_inkernel;         // scenario-steps of the last launch whose active bounds were resolved by mma_active_set
     int *list;
+    int last_resumed;        // the last launch ran the resume pass (sihmpc_plan_counters)
     long long capacity;
     int blocks_per_sm;
     size_t smem_bytes;
@@ -1111,29 +1129,30 @@ inline cudaError_t mma_ensure_capacity(MmaPlan *qp, long long batch) {
     return e;
 }
 
-// counters and start_step back to "nothing handed over" (baseline 0x7f7f7f7f), n_inkernel to 0
+// counters and start_step back to "nothing handed over" (every counter counts up from the baseline 0x7f7f7f7f)
 inline cudaError_t mma_reset(const MmaPlan &qp, long long batch, cudaStream_t st) {
-    cudaError_t e = cudaMemsetAsync(qp.ctr, 0x7f, (size_t)(4 + batch) * sizeof(int), st);
-    if (e == cudaSuccess) e = cudaMemsetAsync(qp.n_inkernel, 0, sizeof(int), st);
-    return e;
+    return cudaMemsetAsync(qp.ctr, 0x7f, (size_t)(4 + batch) * sizeof(int), st);
 }
 
-inline bool mma_has_resume(const MmaPlan &qp) { return qp.qc.cspace >= 0; }
+// the resume pass is one more launch: only worth it when the call carries enough work (not the single-step host API)
+inline bool mma_resumes(const MmaPlan &qp, long long batch, int n_steps) { return qp.qc.cspace >= 0 && (n_steps > 1 || batch >= 4096); }
 
 template <typename D>
-inline cudaError_t mma_launch_shape(const MmaPlan &qp, const DevPlan &P, const sihmpc_io &io, long long batch,
+inline cudaError_t mma_launch_shape(MmaPlan &qp, const DevPlan &P, const sihmpc_io &io, long long batch,
                                     int n_steps, int grid, cudaStream_t st) {
     mma_step_kernel<D, MMA_WARPS, MMA_MINB, 0><<<grid, MMA_WARPS * 32, qp.smem_bytes, st>>>(
         P, qp.qc, qp.qbuf, io, batch, n_steps, qp.start_step, qp.n_handover, qp.n_inkernel, qp.list, nullptr);
     cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess || !mma_has_resume(qp)) return e;
+    qp.last_resumed = 0;
+    if (e != cudaSuccess || !mma_resumes(qp, batch, n_steps)) return e;
+    qp.last_resumed = 1;
     // resume pass over the listed scenarios (their number is only known on the device: blocks beyond it leave at once)
     mma_step_kernel<D, MMA_WARPS, MMA_MINB, 1><<<grid, MMA_WARPS * 32, qp.smem_bytes, st>>>(
         P, qp.qc, qp.qbuf, io, batch, n_steps, qp.start_step, qp.n_fail, qp.n_inkernel, qp.list, qp.n_handover);
     return cudaGetLastError();
 }
 
-inline cudaError_t mma_launch(const MmaPlan &qp, const DevPlan &P, const sihmpc_io &io, long long batch,
+inline cudaError_t mma_launch(MmaPlan &qp, const DevPlan &P, const sihmpc_io &io, long long batch,
                               int n_steps, int sm_count, cudaStream_t st) {
     const long long per_block = MMA_WARPS * 8;
     long long need = (batch + per_block - 1) / per_block;

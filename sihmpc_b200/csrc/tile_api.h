@@ -15,7 +15,10 @@ struct TileCfg {
     const int *hrows;                // Hessian product: real rows (0..8) of packed tile t
     const double *B;                 // stored tiles, 32 doubles each, B-fragment order
     const double *BH;                // Hessian constants, dense: [tile][row][k-tile][32]
+    const double *BHc;               // the same in the bound space of the in-kernel active set: S^T (Ht | HJ_a + 2 diag Wdu_a) S
     int KH, ntile;                   // k-tiles of [1 ; pesos] that carry Hessian blocks; packed tiles
+    int KHc;                         // k-tiles of BHc (every weight carries a block there)
+    int cspace;                      // 1: bound space = cumulative moves (input box), 0: moves (move box), -1: no in-kernel active set
     int me, mw, mdu, mf, mh, mr, my, myp, mvn, mpl;  // offsets of the row-pointer arrays in ptr[]
     int n_x;                         // output tiles of the shared-plant product (0: CSR path)
     int n_r, n_v, n_f, n_h, n_y, n_yp, n_m;          // output tile counts
@@ -30,8 +33,13 @@ struct TilePlan {
     TileCfg cfg;
     int *ibuf;               // device: ptr | kt | hmap
     double *dbuf;            // device: stored tiles
+    int *ctr;                // one device buffer: [n_handover | n_fail | n_inkernel | pad | start_step[cap] | list[cap]]
     int *start_step;
-    int *n_handover;
+    int *n_handover;         // scenarios the first pass appended to `list` (counter baseline 0x7f7f7f7f)
+    int *n_fail;             // scenarios the resume pass could not resolve: left to the general kernel
+    int *n_inkernel;         // scenario-steps with active bounds resolved by the in-kernel active set (last launch)
+    int *list;
+    int last_resumed;        // the last launch ran the resume pass (sihmpc_plan_counters)
     long long capacity;
     size_t smem_bytes;
     int n_tiles;
@@ -39,7 +47,10 @@ struct TilePlan {
 
 cudaError_t tile_configure(const sihmpc_plan_desc *d, const DevPlan &P, TilePlan *tp);
 cudaError_t tile_ensure_capacity(TilePlan *tp, long long batch);
-cudaError_t tile_launch(const TilePlan &tp, const DevPlan &P, const sihmpc_io &io, long long batch, int n_steps,
+cudaError_t tile_reset(const TilePlan &tp, long long batch, cudaStream_t st);
+// the resume pass is one more launch: only worth it when the call carries enough work (not the single-step host API)
+inline bool tile_resumes(const TilePlan &tp, long long batch, int n_steps) { return tp.cfg.cspace >= 0 && (n_steps > 1 || batch >= 4096); }
+cudaError_t tile_launch(TilePlan &tp, const DevPlan &P, const sihmpc_io &io, long long batch, int n_steps,
                         int sm_count, cudaStream_t st);
 void tile_destroy(TilePlan *tp);
 

@@ -32,6 +32,7 @@
 #include <stdlib.h>
 #include "devplan.h"
 #include <math.h>
+#include <stdio.h>
 #include "tile_api.h"
 
 #define SIH_FULL 0xffffffffu
@@ -226,7 +227,7 @@ __device__ __forceinline__ void tfs_panel(double2 (&c)[NT * (NT + 1) / 2], doubl
     }
 }
 
-template <int NT>
+template <int NT, bool ADD_DIAG = true>
 __device__ __forceinline__ int tile_factor(double *A, const double *omdu_w, const int nv, const int rb,
                                            const int lane, double *yv) {
     constexpr int NTILES = NT * (NT + 1) / 2;
@@ -235,11 +236,13 @@ __device__ __forceinline__ int tile_factor(double *A, const double *omdu_w, cons
 #pragma unroll
     for (int t = 0; t < NTILES; ++t) c[t] = *reinterpret_cast<const double2 *>(A + t * 64 + q * 8 + 2 * g);
     // + 2 omega_du on the diagonal (ihmpccontroller.py:200,212: the du sub-objectives)
+    if constexpr (ADD_DIAG) {
 #pragma unroll
-    for (int J = 0; J < NT; ++J) {
-        const double od = 2.0 * omdu_w[8 * J + q];               // zero beyond nv
-        if (q == 2 * g) c[J * (J + 1) / 2 + J].x += od;
-        if (q == 2 * g + 1) c[J * (J + 1) / 2 + J].y += od;
+        for (int J = 0; J < NT; ++J) {
+            const double od = 2.0 * omdu_w[8 * J + q];               // zero beyond nv
+            if (q == 2 * g) c[J * (J + 1) / 2 + J].x += od;
+            if (q == 2 * g + 1) c[J * (J + 1) / 2 + J].y += od;
+        }
     }
     int notpd = 0;
     tfs_panel<NT, 0>(c, A, yv, nv, rb, lane, notpd);
@@ -273,11 +276,52 @@ __device__ __forceinline__ void tbs_panel(const double *A, const int nv, const i
     }
 }
 
-template <int NT>
+// Hessian product: packed lower tiles of  sum_k a_k X_k  for the eight scenarios of the CTA (k-space [1 ; pesos]),
+// BHm = the blocks in B-fragment order (du space: Ht, HJ_a; bound space: S^T (Ht | HJ_a + 2 diag Wdu_a) S)
+__device__ __forceinline__ void tile_hessian(const TileCfg &C, const double *__restrict__ BHm, const int KHm,
+                                             const double *pes, double *Hs, const int w, const int lane) {
+    const int q = lane >> 2, g = lane & 3;
+    for (int u = w; u < 2 * C.ntile; u += TL_WARPS) {
+        const int tid = u >> 1, r0 = (u & 1) * 4;
+        const int nrow = __ldg(C.hrows + tid);
+        double a[TL_KHMAX];
+#pragma unroll
+        for (int t = 0; t < TL_KHMAX; ++t) a[t] = (t < KHm) ? pes[q * C.S_p + 4 * t + g] : 0.0;
+        const double *Bp = BHm + ((size_t)(tid * 8 + r0) * KHm) * 32 + lane;
+        double h[4][2];
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+            h[rr][0] = h[rr][1] = 0.0;
+            if (r0 + rr < nrow) {
+#pragma unroll
+                for (int t = 0; t < TL_KHMAX; ++t)
+                    if (t < KHm) dmma884(h[rr][0], h[rr][1], a[t], __ldg(Bp + (rr * KHm + t) * 32));
+            }
+        }
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr)
+            if (r0 + rr < nrow)
+                *reinterpret_cast<double2 *>(Hs + (size_t)q * C.HS + tid * 64 + (r0 + rr) * 8 + 2 * g) = make_double2(h[rr][0], h[rr][1]);
+    }
+}
+
+// MODE 0: first pass (unconstrained optimum + bound check; a scenario that violates a bound is appended to `list`).
+// MODE 1: resume pass over the listed scenarios, eight per CTA, each from its own start_step, with the in-kernel
+//         active set below; what it cannot resolve is flagged in start_step / n_handover for the general kernel.
+template <int NT, int MODE>
 __global__ void __launch_bounds__(TL_WARPS * 32, 1)
 tile_step_kernel(const DevPlan P, const TileCfg C, const sihmpc_io io, const long long batch, const int n_steps,
-                 int *__restrict__ start_step, int *__restrict__ n_handover) {
+                 int *__restrict__ start_step, int *__restrict__ n_handover, int *__restrict__ n_inkernel,
+                 int *__restrict__ list, const int *__restrict__ n_list) {
+    constexpr bool RESUME = (MODE == 1);
     extern __shared__ double sm[];
+    __shared__ long long s_sid[TL_WARPS];
+    __shared__ int s_stp[TL_WARPS], s_len[TL_WARPS];
+    long long n_work = batch;
+    if constexpr (RESUME) {
+        n_work = (long long)(*n_list) - 0x7f7f7f7f;
+        if ((long long)blockIdx.x * TL_WARPS >= n_work) return;
+    }
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, q = lane >> 2, g = lane & 3;
     const int nx = P.nx, nu = P.nu, ny = P.ny, nv = P.nv, m = P.m, R = P.R, Ny = P.Ny;
     const int nstat = ny + SIHMPC_NSTATS_EXTRA;
@@ -296,16 +340,33 @@ tile_step_kernel(const DevPlan P, const TileCfg C, const sihmpc_io io, const lon
     const int o_ysp = nx + nv, o_one = nx + nv + ny;
     const int nsq = Ny + 2 * ny;
 
-    const long long n_oct = (batch + TL_WARPS - 1) / TL_WARPS;
+    // active set scratch of this scenario: the point lives in the squares buffer (only used after the solve), the
+    // gradient in the forward-substitution output (dead outside factorisation + back substitution)
+    double *cw = sqw, *gw = yw;
+    const long long n_oct = (n_work + TL_WARPS - 1) / TL_WARPS;
     for (long long oct = blockIdx.x; oct < n_oct; oct += gridDim.x) {
         // every slot starts from clean buffers: padding entries are never rewritten inside the loop, and a
         // scenario that was handed over keeps stepping unconstrained in its slot and may leave Inf/NaN there
         for (int i = threadIdx.x; i < C.total; i += blockDim.x) sm[i] = 0.0;
         __syncthreads();
-        const long long s = oct * TL_WARPS + w;
-        const bool valid = s < batch;
+        long long s = oct * TL_WARPS + w;
+        const bool valid = s < n_work;
+        int st0 = 0, n_iter = n_steps;
+        if constexpr (RESUME) {
+            s = valid ? list[s] : batch - 1;
+            st0 = valid ? start_step[s] : n_steps;
+            if (st0 < 0 || st0 > n_steps) st0 = n_steps;
+            if (lane == 0) s_len[w] = n_steps - st0;
+            __syncthreads();
+            n_iter = 0;
+#pragma unroll
+            for (int i = 0; i < TL_WARPS; ++i) n_iter = max(n_iter, s_len[i]);
+            if (valid && lane == 0) start_step[s] = 0x7f7f7f7f;      // resolved here unless flagged again below
+        }
         const long long sl = valid ? s : batch - 1;
         bool alive = valid;
+        unsigned long long mlo = 0ull, mhi = 0ull;     // bound masks of the last step (warm start of the active set)
+        if (lane == 0) s_sid[w] = s;
         // ---------------- load the scenario
         for (int i = lane; i < nx; i += 32) svw[i] = io.x[sl * nx + i];
         for (int i = lane; i < nv; i += 32) svw[nx + i] = 0.0;
@@ -324,7 +385,19 @@ tile_step_kernel(const DevPlan P, const TileCfg C, const sihmpc_io io, const lon
         if (lane == 0) { svw[o_one] = 1.0; pw[0] = 1.0; scw[1] = alive ? 1.0 : 0.0; }
         const double *pv = io.plant_val ? io.plant_val + (size_t)sl * P.pl_nnz : P.pl_val;
 
-        for (int step = 0; step < n_steps; ++step) {
+        auto write_state = [&]() {
+            for (int i = lane; i < nx; i += 32) io.x[s * nx + i] = svw[i];
+            for (int i = lane; i < nu; i += 32) io.u[s * nu + i] = uw[i];
+            for (int i = lane; i < m; i += 32) io.pesos[s * m + i] = pw[1 + i];
+            if (io.stats) for (int i = lane; i < nstat; i += 32) io.stats[s * nstat + i] = stw[i];
+        };
+
+        for (int it = 0; it < n_iter; ++it) {
+            const int step = st0 + it;
+            if constexpr (RESUME) {
+                if (step >= n_steps && alive) { alive = false; if (lane == 0) scw[1] = 0.0; }
+            }
+            if (lane == 0) s_stp[w] = step;
             const int kabs = io.k0 + step;
             if (kabs >= next_start) {                     // rare: the schedule switches segment
                 while (seg + 1 < io.n_seg && io.seg_start[sl * io.n_seg + seg + 1] <= kabs) ++seg;
@@ -348,28 +421,7 @@ tile_step_kernel(const DevPlan P, const TileCfg C, const sihmpc_io io, const lon
                 *reinterpret_cast<double2 *>(omdu + q * C.S_v + 8 * T + 2 * g) = make_double2(o0, o1);
             }
             // Hessian tiles  H = Ht + sum_a pesos_a HJ_a : dense k-tiles [0,KH) of [1 ; pesos], half a tile per unit
-            for (int u = w; u < 2 * C.ntile; u += TL_WARPS) {
-                const int tid = u >> 1, r0 = (u & 1) * 4;
-                const int nrow = __ldg(C.hrows + tid);
-                double a[TL_KHMAX];
-#pragma unroll
-                for (int t = 0; t < TL_KHMAX; ++t) a[t] = (t < C.KH) ? pes[q * C.S_p + 4 * t + g] : 0.0;
-                const double *Bp = C.BH + ((size_t)(tid * 8 + r0) * C.KH) * 32 + lane;
-                double h[4][2];
-#pragma unroll
-                for (int rr = 0; rr < 4; ++rr) {
-                    h[rr][0] = h[rr][1] = 0.0;
-                    if (r0 + rr < nrow) {
-#pragma unroll
-                        for (int t = 0; t < TL_KHMAX; ++t)
-                            if (t < C.KH) dmma884(h[rr][0], h[rr][1], a[t], __ldg(Bp + (rr * C.KH + t) * 32));
-                    }
-                }
-#pragma unroll
-                for (int rr = 0; rr < 4; ++rr)
-                    if (r0 + rr < nrow)
-                        *reinterpret_cast<double2 *>(Hs + (size_t)q * C.HS + tid * 64 + (r0 + rr) * 8 + 2 * g) = make_double2(h[rr][0], h[rr][1]);
-            }
+            tile_hessian(C, C.BH, C.KH, pes, Hs, w, lane);
             __syncthreads();                              // [B]
             // ---------------- P2: right-hand side b = -2 E^T t into row nv of the augmented matrix
             for (int T = w; T < C.n_f; T += TL_WARPS) {
@@ -401,13 +453,21 @@ tile_step_kernel(const DevPlan P, const TileCfg C, const sihmpc_io io, const lon
                 }
             viol = warp_max(viol);
             viol_abs = warp_max(viol_abs);
+            int nact = 0;
+            if constexpr (MODE != 0) {
+                if (C.cspace >= 0) {
+#include "tile_active_set.inc"
+                }
+            }
             if (alive && (viol > 1e-10 || notpd)) {
-                alive = false;                            // hand over to the general kernel from this step on
-                if (lane == 0) { start_step[s] = step; atomicAdd(n_handover, 1); scw[1] = 0.0; }
-                for (int i = lane; i < nx; i += 32) io.x[s * nx + i] = svw[i];
-                for (int i = lane; i < nu; i += 32) io.u[s * nu + i] = uw[i];
-                for (int i = lane; i < m; i += 32) io.pesos[s * m + i] = pw[1 + i];
-                if (io.stats) for (int i = lane; i < nstat; i += 32) io.stats[s * nstat + i] = stw[i];
+                alive = false;                            // hand over from this step on (MODE 0: resume pass; else general kernel)
+                mlo = mhi = 0ull;
+                if (lane == 0) {
+                    start_step[s] = step; scw[1] = 0.0;
+                    const int slot = atomicAdd(n_handover, 1) - 0x7f7f7f7f;
+                    if constexpr (MODE == 0) list[slot] = (int)s;
+                }
+                write_state();
             }
             if (lane == 0) scw[0] = 0.0;
             __syncthreads();                              // [D]
@@ -454,7 +514,7 @@ tile_step_kernel(const DevPlan P, const TileCfg C, const sihmpc_io io, const lon
                     if (lane == 0) {
                         if (io.J) io.J[s] = Jval;
                         if (io.status) io.status[s] = 0;
-                        if (io.n_active) io.n_active[s] = 0;
+                        if (io.n_active) io.n_active[s] = nact;
                     }
                 }
                 if (io.traj_du) for (int j = lane; j < nu; j += 32) io.traj_du[((long long)step * batch + s) * nu + j] = zw[j];
@@ -510,8 +570,7 @@ tile_step_kernel(const DevPlan P, const TileCfg C, const sihmpc_io io, const lon
                         const double yv_ = h ? y1 : y0;
                         const double err = yv_ - sv[q * C.S_sv + o_ysp + i];
                         scb[q * C.S_sc + 2 + nu + i] += err * err;
-                        const long long sq_ = oct * TL_WARPS + q;
-                        if (io.traj_y && scb[q * C.S_sc + 1] != 0.0) io.traj_y[((long long)step * batch + sq_) * ny + i] = yv_;
+                        if (io.traj_y && scb[q * C.S_sc + 1] != 0.0) io.traj_y[((long long)s_stp[q] * batch + s_sid[q]) * ny + i] = yv_;
                     }
                 }
             }
@@ -557,20 +616,48 @@ tile_step_kernel(const DevPlan P, const TileCfg C, const sihmpc_io io, const lon
             } else {
                 __syncthreads();                          // the owners may not touch ysp before every y tile is done
             }
+            if constexpr (RESUME) {
+                if (alive && last_step) { write_state(); alive = false; if (lane == 0) scw[1] = 0.0; }
+            }
         }  // steps
 
         // ---------------- write back
-        if (alive && advance) {
-            for (int i = lane; i < nx; i += 32) io.x[s * nx + i] = svw[i];
-            for (int i = lane; i < nu; i += 32) io.u[s * nu + i] = uw[i];
-            for (int i = lane; i < m; i += 32) io.pesos[s * m + i] = pw[1 + i];
-            if (io.stats) for (int i = lane; i < nstat; i += 32) io.stats[s * nstat + i] = stw[i];
-        }
+        if (!RESUME && alive && advance) write_state();
         __syncthreads();
     }
 }
 
 // ---- host side ----------------------------------------------------------------------------------
+// The kernels are instantiated one tile-row count per translation unit (-DSIH_TL_ONLY_NT=k: only
+// tile_set_smem_k / tile_launch_k), compiled in parallel by build.py; the unit without the define holds the host
+// logic and dispatches over them.
+#define SIH_TL_CAT2(a, b) a##b
+#define SIH_TL_CAT(a, b) SIH_TL_CAT2(a, b)
+#ifdef SIH_TL_ONLY_NT
+cudaError_t SIH_TL_CAT(tile_set_smem_, SIH_TL_ONLY_NT)(size_t bytes) {
+    cudaError_t e = cudaFuncSetAttribute(tile_step_kernel<SIH_TL_ONLY_NT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    return e != cudaSuccess ? e : cudaFuncSetAttribute(tile_step_kernel<SIH_TL_ONLY_NT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+// mode 0: first pass (appends to `list`, counts in `counter`); mode 1: resume pass over `list` (n_list scenarios,
+// known on the device only: blocks beyond it leave at once), failures counted in `counter`
+cudaError_t SIH_TL_CAT(tile_launch_, SIH_TL_ONLY_NT)(const TilePlan &tp, const DevPlan &P, const sihmpc_io &io, long long batch,
+                                                     int n_steps, int grid, int mode, int *list, const int *n_list,
+                                                     int *counter, cudaStream_t st) {
+    if (mode == 0)
+        tile_step_kernel<SIH_TL_ONLY_NT, 0><<<grid, TL_WARPS * 32, tp.smem_bytes, st>>>(P, tp.cfg, io, batch, n_steps, tp.start_step,
+                                                                                         counter, tp.n_inkernel, list, nullptr);
+    else
+        tile_step_kernel<SIH_TL_ONLY_NT, 1><<<grid, TL_WARPS * 32, tp.smem_bytes, st>>>(P, tp.cfg, io, batch, n_steps, tp.start_step,
+                                                                                         counter, tp.n_inkernel, list, n_list);
+    return cudaGetLastError();
+}
+#else
+#define SIH_TL_DECL(N_) \
+    cudaError_t tile_set_smem_##N_(size_t bytes); \
+    cudaError_t tile_launch_##N_(const TilePlan &, const DevPlan &, const sihmpc_io &, long long, int, int, int, int *, const int *, int *, cudaStream_t);
+SIH_TL_DECL(1) SIH_TL_DECL(2) SIH_TL_DECL(3) SIH_TL_DECL(4) SIH_TL_DECL(5) SIH_TL_DECL(6) SIH_TL_DECL(7) SIH_TL_DECL(8)
+#undef SIH_TL_DECL
+
 struct TileBuilder {
     std::vector<int> ptr, seg, hmap;
     std::vector<double> B;
@@ -619,7 +706,7 @@ struct TileBuilder {
 };
 
 static cudaError_t tile_set_smem(int NT, size_t bytes) {
-#define SIH_TL_ATTR(N_) case N_: return cudaFuncSetAttribute(tile_step_kernel<N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+#define SIH_TL_ATTR(N_) case N_: return tile_set_smem_##N_(bytes);
     switch (NT) {
         SIH_TL_ATTR(1) SIH_TL_ATTR(2) SIH_TL_ATTR(3) SIH_TL_ATTR(4)
         SIH_TL_ATTR(5) SIH_TL_ATTR(6) SIH_TL_ATTR(7) SIH_TL_ATTR(8)
@@ -705,6 +792,49 @@ cudaError_t tile_configure(const sihmpc_plan_desc *d, const DevPlan &P, TilePlan
                         }
             }
     }
+    // Hessian blocks of the bound space (tile_active_set.inc): S^T X_k S with S = difference along the horizon per
+    // input (cumulative moves) or I (move box); X_0 = Ht, X_{1+i} = sum_{a: hj_index[a]=i} HJ_a + 2 diag(Wdu[:, i])
+    std::vector<double> BHc;
+    C.cspace = (P.has_cum && !P.has_box) ? 1 : ((P.has_box && !P.has_cum) ? 0 : -1);
+    C.KHc = (m + 1 + 3) / 4;
+    if (C.KHc > TL_KHMAX || getenv("SIHMPC_NO_INKERNEL_AS")) C.cspace = -1;
+    if (C.cspace >= 0) {
+        const bool cum = (C.cspace == 1);
+        std::vector<double> Xc((size_t)(m + 1) * nv * nv, 0.0), X((size_t)nv * nv), XS((size_t)nv * nv);
+        for (int k = 0; k <= m; ++k) {
+            for (int a = 0; a < nv; ++a)
+                for (int b = 0; b < nv; ++b) {
+                    double x = 0.0;
+                    if (k == 0) x = d->Ht[(size_t)a * nv + b];
+                    else {
+                        for (int h = 0; h < d->mh; ++h)
+                            if (d->hj_index[h] == k - 1) x += d->HJ[((size_t)h * nv + a) * nv + b];
+                        if (a == b) x += 2.0 * d->Wdu[(size_t)a * m + (k - 1)];
+                    }
+                    X[(size_t)a * nv + b] = x;
+                }
+            // (X S)[a][b] = X[a][b] - X[a][b+nu] ; (S^T Y)[a][b] = Y[a][b] - Y[a+nu][b]
+            for (int a = 0; a < nv; ++a)
+                for (int b = 0; b < nv; ++b)
+                    XS[(size_t)a * nv + b] = X[(size_t)a * nv + b] - ((cum && b + nu < nv) ? X[(size_t)a * nv + b + nu] : 0.0);
+            for (int a = 0; a < nv; ++a)
+                for (int b = 0; b < nv; ++b)
+                    Xc[((size_t)k * nv + a) * nv + b] = XS[(size_t)a * nv + b] - ((cum && a + nu < nv) ? XS[(size_t)(a + nu) * nv + b] : 0.0);
+        }
+        BHc.assign((size_t)ntiles * 8 * C.KHc * 32, 0.0);
+        for (int I = 0; I < C.NT; ++I)
+            for (int J = 0; J <= I; ++J) {
+                const int tid = tl_tid(I, J);
+                for (int r = 0; r < hrows[tid]; ++r)
+                    for (int t = 0; t < C.KHc; ++t)
+                        for (int lane = 0; lane < 32; ++lane) {
+                            const int n = lane >> 2, k = lane & 3;
+                            const int row = 8 * I + r, col = 8 * J + n, kk = 4 * t + k;
+                            if (col <= row && col < nv && kk <= m)
+                                BHc[(((size_t)tid * 8 + r) * C.KHc + t) * 32 + lane] = Xc[((size_t)kk * nv + row) * nv + col];
+                        }
+            }
+    }
     // r += [E ; Mi1u] dU
     C.mr = tb.add(C.n_r, K_sv, [&](int r, int c) -> double {
         if (r >= RE || c < o_v || c >= o_v + nv) return 0.0;
@@ -745,13 +875,19 @@ cudaError_t tile_configure(const sihmpc_plan_desc *d, const DevPlan &P, TilePlan
     e = cudaMemcpy(tp->ibuf, ib.data(), ib.size() * sizeof(int), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return e;
     const size_t nB = (tb.B.size() + 31) & ~(size_t)31;
-    e = cudaMalloc(&tp->dbuf, (nB + BH.size() + 32) * sizeof(double));
+    const size_t nBH = (BH.size() + 31) & ~(size_t)31;
+    e = cudaMalloc(&tp->dbuf, (nB + nBH + BHc.size() + 32) * sizeof(double));
     if (e != cudaSuccess) return e;
     e = cudaMemcpy(tp->dbuf, tb.B.data(), tb.B.size() * sizeof(double), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return e;
     e = cudaMemcpy(tp->dbuf + nB, BH.data(), BH.size() * sizeof(double), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return e;
+    if (!BHc.empty()) {
+        e = cudaMemcpy(tp->dbuf + nB + nBH, BHc.data(), BHc.size() * sizeof(double), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) return e;
+    }
     C.ptr = tp->ibuf; C.seg = tp->ibuf + np; C.hrows = tp->ibuf + np + nk; C.B = tp->dbuf; C.BH = tp->dbuf + nB;
+    C.BHc = tp->dbuf + nB + nBH;
     tp->n_tiles = tb.n_stored;
     e = tile_set_smem(C.NT, tp->smem_bytes);
     if (e != cudaSuccess) return e;
@@ -761,36 +897,60 @@ cudaError_t tile_configure(const sihmpc_plan_desc *d, const DevPlan &P, TilePlan
 
 cudaError_t tile_ensure_capacity(TilePlan *tp, long long batch) {
     if (tp->capacity >= batch) return cudaSuccess;
-    if (tp->n_handover) cudaFree(tp->n_handover);
-    tp->n_handover = nullptr; tp->start_step = nullptr; tp->capacity = 0;
-    cudaError_t e = cudaMalloc(&tp->n_handover, (size_t)(batch + 1) * sizeof(int));
-    if (e == cudaSuccess) { tp->start_step = tp->n_handover + 1; tp->capacity = batch; }
+    if (tp->ctr) cudaFree(tp->ctr);
+    tp->ctr = tp->n_handover = tp->n_fail = tp->n_inkernel = tp->start_step = tp->list = nullptr; tp->capacity = 0;
+    cudaError_t e = cudaMalloc(&tp->ctr, (size_t)(4 + 2 * batch) * sizeof(int));
+    if (e == cudaSuccess) {
+        tp->n_handover = tp->ctr; tp->n_fail = tp->ctr + 1; tp->n_inkernel = tp->ctr + 2;
+        tp->start_step = tp->ctr + 4; tp->list = tp->ctr + 4 + batch; tp->capacity = batch;
+    }
     return e;
 }
 
-cudaError_t tile_launch(const TilePlan &tp, const DevPlan &P, const sihmpc_io &io, long long batch,
-                               int n_steps, int sm_count, cudaStream_t st) {
+// counters and start_step back to "nothing handed over" (every counter counts up from the baseline 0x7f7f7f7f)
+cudaError_t tile_reset(const TilePlan &tp, long long batch, cudaStream_t st) {
+    return cudaMemsetAsync(tp.ctr, 0x7f, (size_t)(4 + batch) * sizeof(int), st);
+}
+
+static int tile_grid(const TilePlan &tp, long long batch, int sm_count) {
     const long long n_oct = (batch + TL_WARPS - 1) / TL_WARPS;
     int per_sm = (int)((227 * 1024) / (tp.smem_bytes + 1024));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 4) per_sm = 4;
     const long long cap = (long long)sm_count * per_sm;
-    const int grid = (int)(n_oct < cap ? n_oct : cap);
-#define SIH_TL_LAUNCH(N_) case N_: tile_step_kernel<N_><<<grid, TL_WARPS * 32, tp.smem_bytes, st>>>(P, tp.cfg, io, batch, n_steps, tp.start_step, tp.n_handover); break;
+    return (int)(n_oct < cap ? n_oct : cap);
+}
+
+static cudaError_t tile_dispatch(const TilePlan &tp, const DevPlan &P, const sihmpc_io &io, long long batch, int n_steps,
+                                 int grid, int mode, int *list, const int *n_list, int *counter, cudaStream_t st) {
+#define SIH_TL_LAUNCH(N_) case N_: return tile_launch_##N_(tp, P, io, batch, n_steps, grid, mode, list, n_list, counter, st);
     switch (tp.cfg.NT) {
         SIH_TL_LAUNCH(1) SIH_TL_LAUNCH(2) SIH_TL_LAUNCH(3) SIH_TL_LAUNCH(4)
         SIH_TL_LAUNCH(5) SIH_TL_LAUNCH(6) SIH_TL_LAUNCH(7) SIH_TL_LAUNCH(8)
         default: return cudaErrorInvalidValue;
     }
 #undef SIH_TL_LAUNCH
-    return cudaGetLastError();
+}
+
+// first pass over the whole batch, then (bounds present, in-kernel active set available, enough work to pay for one
+// more launch) the resume pass over the scenarios it listed; what that cannot resolve is counted in n_fail with
+// start_step set
+cudaError_t tile_launch(TilePlan &tp, const DevPlan &P, const sihmpc_io &io, long long batch,
+                               int n_steps, int sm_count, cudaStream_t st) {
+    const int grid = tile_grid(tp, batch, sm_count);
+    tp.last_resumed = 0;
+    cudaError_t e = tile_dispatch(tp, P, io, batch, n_steps, grid, 0, tp.list, nullptr, tp.n_handover, st);
+    if (e != cudaSuccess || !tile_resumes(tp, batch, n_steps) || !(P.has_box || P.has_cum)) return e;
+    tp.last_resumed = 1;
+    return tile_dispatch(tp, P, io, batch, n_steps, grid, 1, tp.list, tp.n_handover, tp.n_fail, st);
 }
 
 void tile_destroy(TilePlan *tp) {
     if (tp->ibuf) cudaFree(tp->ibuf);
     if (tp->dbuf) cudaFree(tp->dbuf);
-    if (tp->n_handover) cudaFree(tp->n_handover);
+    if (tp->ctr) cudaFree(tp->ctr);
     memset(tp, 0, sizeof *tp);
 }
+#endif  // SIH_TL_ONLY_NT
 
 }  // namespace sih

@@ -32,9 +32,12 @@ def _scenarios(B, sys_, seed):
                 dist_step=rng.integers(5, 25, size=B).astype(np.int32), dist=rng.normal(0, 0.1, size=(B, ny)))
 
 
-def _run(monkeypatch, mode, declare, sys_, scen, T, bounds=None, spl=None, weights="sat2", alfa=0.0):
+def _run(monkeypatch, mode, declare, sys_, scen, T, bounds=None, spl=None, weights="sat2", alfa=0.0, inkernel=True):
     monkeypatch.delenv("SIHMPC_NO_FAST", raising=False)
     monkeypatch.delenv("SIHMPC_FAST", raising=False)
+    monkeypatch.delenv("SIHMPC_NO_INKERNEL_AS", raising=False)
+    if not inkernel:
+        monkeypatch.setenv("SIHMPC_NO_INKERNEL_AS", "1")
     if mode == "general":
         monkeypatch.setenv("SIHMPC_NO_FAST", "1")
     elif mode == "tile":
@@ -51,7 +54,8 @@ def _run(monkeypatch, mode, declare, sys_, scen, T, bounds=None, spl=None, weigh
     tr = eng.run(T, steps_per_launch=spl, record=True)
     out = dict(du=tr["du"].cpu().numpy(), J=tr["J"].cpu().numpy(), y=tr["y"].cpu().numpy(),
                x=eng.x.cpu().numpy(), u=eng.u.cpu().numpy(), pesos=eng.pesos.cpu().numpy(),
-               stats=eng.stats.cpu().numpy(), w=eng.w_opt.cpu().numpy())
+               stats=eng.stats.cpu().numpy(), w=eng.w_opt.cpu().numpy(), cnt=eng.dp.counters())
+    monkeypatch.delenv("SIHMPC_NO_INKERNEL_AS", raising=False)
     monkeypatch.delenv("SIHMPC_NO_FAST", raising=False)
     monkeypatch.delenv("SIHMPC_FAST", raising=False)
     return out
@@ -109,20 +113,27 @@ def test_tile_underdamped_plant_matches_oracle(monkeypatch):
         assert np.max(np.abs(t["y"][:, idx] - ref["y"])) <= RTOL * max(1.0, np.max(np.abs(ref["y"])))
 
 
-def test_tile_path_on_distillation_with_handover(monkeypatch):
-    """Forced tile path on the distillation controller with bounds that make a good share of the
-    scenarios hand over to the exact active-set kernel mid-loop: equals the general kernel alone
-    and the oracle."""
+@pytest.mark.parametrize("inkernel", [False, True])
+def test_tile_path_on_distillation_with_handover(inkernel, monkeypatch):
+    """Forced tile path on the distillation controller with bounds that bind for a good share of the scenarios.
+    inkernel=False: they are handed over to the exact active-set kernel mid-loop; inkernel=True: the resume pass of
+    the tile kernel resolves them itself (tile_active_set.inc).  Either way: equals the general kernel alone and
+    the oracle."""
     sys_ = sc.distillation_system()
     bounds = dict(ulb=[1.80, 1.62], uub=[2.02, 1.78])
     B, T = 500, 120
     scen = sc.distillation_scenarios(B)
-    t = _run(monkeypatch, "tile", sc.declare_distillation, sys_, scen, T, bounds=bounds, spl=50)
+    t = _run(monkeypatch, "tile", sc.declare_distillation, sys_, scen, T, bounds=bounds, spl=50, inkernel=inkernel)
     g = _run(monkeypatch, "general", sc.declare_distillation, sys_, scen, T, bounds=bounds, spl=50)
     assert (t["stats"][:, 5] == 0).all()
     n_constrained = int((g["stats"][:, 6] > 0).sum())
     assert 0.05 * B < n_constrained < 0.95 * B
-    _close(t, g)
+    handed, solved = t["cnt"]                              # of the last launch (steps 100..119)
+    if inkernel:
+        assert solved > 0 and handed <= 0.05 * B, (handed, solved)
+    else:
+        assert solved == 0 and handed > 0, (handed, solved)
+    _close(t, g, tol=1e-8 if not inkernel else 2e-7)
     idx = int(np.argmax(g["stats"][:, 6]))
     ref = oracle_closed_loop(sc.declare_distillation, sys_, scen, idx, T, bounds=bounds)
     assert ref["n_active"].max() > 0
@@ -148,7 +159,26 @@ def test_tile_mimo10_with_active_bounds(monkeypatch):
     t = _run(monkeypatch, "tile", sc.declare_mimo10, sys_, scen, T, bounds=bounds)
     g = _run(monkeypatch, "general", sc.declare_mimo10, sys_, scen, T, bounds=bounds)
     assert int((g["stats"][:, -1] > 0).sum()) > 0
-    _close(t, g)
+    handed, solved = t["cnt"]
+    assert solved > 0 and handed <= 2, (handed, solved)      # resolved inside the tile kernel, not handed over
+    _close(t, g, tol=2e-7)
+    idx = int(np.argmax(g["stats"][:, -1]))
+    ref = oracle_closed_loop(sc.declare_mimo10, sys_, scen, idx, T, bounds=bounds)
+    assert ref["n_active"].max() > 0
+    assert np.max(np.abs(t["du"][:, idx] - ref["du"])) <= RTOL * np.max(np.abs(ref["du"]))
+
+
+def test_tile_move_box_inkernel(monkeypatch):
+    """Move box only (bound space = the moves themselves) on a 3x3 plant: resume pass == general kernel."""
+    sys_ = _plant(3, 3, 9, 2)
+    declare = lambda cls, s, **b: sc.declare_mimo10(cls, s, N=4, **(b or dict(dulb=[-0.03] * 3, duub=[0.04] * 3)))
+    scen = _scenarios(50, sys_, 11)
+    t = _run(monkeypatch, "tile", declare, sys_, scen, 30)
+    g = _run(monkeypatch, "general", declare, sys_, scen, 30)
+    assert int((g["stats"][:, -1] > 0).sum()) > 0
+    handed, solved = t["cnt"]
+    assert solved > 0 and handed <= 2, (handed, solved)
+    _close(t, g, tol=2e-7)
 
 
 @pytest.mark.parametrize("B", [1, 7, 9, 1000])
