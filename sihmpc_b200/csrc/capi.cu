@@ -137,14 +137,17 @@ int configure(sihmpc_plan *p) {
 
 template <int NVR>
 int launch_step(sihmpc_plan *p, const sihmpc_io &io, long long batch, int n_steps, double *scratch,
-                cudaStream_t st, const int *start_step = nullptr, const int *n_handover = nullptr) {
+                cudaStream_t st, int *start_step = nullptr, const int *n_handover = nullptr,
+                int *bounce_list = nullptr, int *n_bounce = nullptr, unsigned long long *warm_mask = nullptr,
+                int bounce_steps = 0, int bounce_space = -1) {
     long long need = (batch + p->wpb - 1) / p->wpb;
     int grid = (int)(need < p->max_grid ? need : p->max_grid);
     if (grid < 1) grid = 1;
     const int max_outer = 8 * (2 * p->d.nv + p->d.ncd) + 16;
     sih::ihmpc_step_kernel<NVR><<<grid, p->wpb * 32, p->smem_bytes, st>>>(p->d, io, batch, n_steps,
                                                                            scratch, max_outer, start_step,
-                                                                           n_handover, p->scratch_in_smem);
+                                                                           n_handover, p->scratch_in_smem, bounce_list,
+                                                                           n_bounce, warm_mask, bounce_steps, bounce_space);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -327,13 +330,19 @@ int sihmpc_plan_counters(sihmpc_plan *plan, int64_t *handed_over, int64_t *solve
     const int *ctr = nullptr;
     const bool want_tile = plan->tile.ok && (plan->use_fast == 3 || (plan->use_fast == 2 && plan->mma.shape < 0));
     bool resumed = false;
-    if (want_tile) { ctr = plan->tile.ctr; resumed = plan->tile.last_resumed != 0; }
+    int final_tile = base;
+    if (want_tile) {
+        ctr = plan->tile.ctr; resumed = plan->tile.last_resumed != 0;
+        if (resumed && plan->tile.last_final && e == cudaSuccess)
+            e = cudaMemcpy(&final_tile, plan->tile.last_final, sizeof(int), cudaMemcpyDeviceToHost);
+    }
     else if (plan->use_fast == 2 && plan->mma.shape >= 0) { ctr = plan->mma.ctr; resumed = plan->mma.last_resumed != 0; }
     else if (plan->use_fast == 1 && plan->quad.shape >= 0 && plan->quad.n_handover) {
         if (e == cudaSuccess) e = cudaMemcpy(c, plan->quad.n_handover, sizeof(int), cudaMemcpyDeviceToHost);
     }
     if (e == cudaSuccess && ctr) e = cudaMemcpy(c, ctr, 3 * sizeof(int), cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) return fail(SIHMPC_E_CUDA, "reading the fast-path counters failed: %s", cudaGetErrorString(e));
+    if (want_tile && resumed && plan->tile.last_final) c[1] = final_tile;      // after the bounce rounds
     if (handed_over) *handed_over = (int64_t)(resumed ? c[1] : c[0]) - base;
     if (solved_in_kernel) *solved_in_kernel = (int64_t)c[2] - base;
     return 0;
@@ -350,7 +359,8 @@ int sihmpc_step(sihmpc_plan *plan, const sihmpc_io *io, int64_t batch, int32_t n
         return fail(SIHMPC_E_WORKSPACE, "workspace smaller than sihmpc_workspace_bytes()%s");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     double *scratch = reinterpret_cast<double *>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-    const int *start_step = nullptr, *n_handover = nullptr;
+    int *start_step = nullptr;
+    const int *n_handover = nullptr;
     const bool want_tile = plan->tile.ok && (plan->use_fast == 3 || (plan->use_fast == 2 && plan->mma.shape < 0));
     if (want_tile) {
         cudaError_t e = sih::tile_ensure_capacity(&plan->tile, batch);
@@ -359,7 +369,30 @@ int sihmpc_step(sihmpc_plan *plan, const sihmpc_io *io, int64_t batch, int32_t n
         if (e != cudaSuccess) return fail(SIHMPC_E_CUDA, "tile fast-path launch failed: %s", cudaGetErrorString(e));
         if (!(plan->d.has_box || plan->d.has_cum)) return 0;      // nothing can be handed over
         start_step = plan->tile.start_step;
-        n_handover = sih::tile_resumes(plan->tile, batch, n_steps) ? plan->tile.n_fail : plan->tile.n_handover;
+        n_handover = plan->tile.n_handover;
+        if (sih::tile_resumes(plan->tile, batch, n_steps)) {
+            // What the resume pass gave up on (large changes of the active set right after a set-point change): the
+            // general kernel solves ONE step of those scenarios and sends them back with the active set it found, the
+            // tile kernel resumes them from there -- TL_BOUNCES rounds, every launch of a round leaves at once when its
+            // list is empty -- and the final general pass below takes what is still flagged.
+            n_handover = plan->tile.n_fail;
+            // Measured on the 10x10 workload (65536 x 200): three rounds resolve 23155 constrained scenario-steps
+            // instead of 2437 and leave 1316 instead of 1871 scenarios to the final pass, but every round is two more
+            // latency-bound launches and the launch got slower (791 vs 745 ms): opt-in (SIHMPC_BOUNCE=1).
+            const int rounds = getenv("SIHMPC_BOUNCE") ? sih::TL_BOUNCES : 0;
+            for (int r = 0; r < rounds; ++r) {
+                int *nb = sih::tile_bounce_counter(plan->tile, r);
+                rc = (plan->nvr == 1) ? launch_step<1>(plan, *io, batch, n_steps, scratch, st, start_step, n_handover, plan->tile.list2, nb,
+                                                       plan->tile.warm_mask, 1, plan->tile.cfg.cspace)
+                                      : launch_step<2>(plan, *io, batch, n_steps, scratch, st, start_step, n_handover, plan->tile.list2, nb,
+                                                       plan->tile.warm_mask, 1, plan->tile.cfg.cspace);
+                if (rc) return rc;
+                e = sih::tile_launch_bounced(plan->tile, plan->d, *io, batch, n_steps, plan->sm_count, r, st);
+                if (e != cudaSuccess) return fail(SIHMPC_E_CUDA, "tile resume launch failed: %s", cudaGetErrorString(e));
+                n_handover = sih::tile_fail_counter(plan->tile, r);
+            }
+            plan->tile.last_final = n_handover;
+        }
     } else if (plan->use_fast == 2 && plan->mma.shape >= 0) {
         cudaError_t e = sih::mma_ensure_capacity(&plan->mma, batch);
         if (e == cudaSuccess) e = sih::mma_reset(plan->mma, batch, st);

@@ -273,8 +273,17 @@ template <int NVR>
 __global__ void __launch_bounds__(256, (NVR == 1 ? 2 : 1))
 ihmpc_step_kernel(const DevPlan P_in, const sihmpc_io io, const long long batch, const int n_steps,
                   double *__restrict__ scratch, const int max_outer,
-                  const int *__restrict__ start_step, const int *__restrict__ n_handover,
-                  const int scratch_in_smem) {
+                  int *start_step, const int *__restrict__ n_handover,
+                  const int scratch_in_smem, int *__restrict__ bounce_list = nullptr,
+                  int *__restrict__ n_bounce = nullptr, unsigned long long *__restrict__ warm_mask = nullptr,
+                  const int bounce_steps = 0, const int bounce_space = -1) {
+    // bounce mode (bounce_list != NULL): this pass carries a handed-over scenario only through the steps the
+    // in-kernel active set of the tile fast path gave up on (large changes of the active set right after a set-point
+    // change).  After bounce_steps steps the scenario goes back to the fast path: start_step = the next step, the
+    // ACTIVE SET of the last solve exported as bound masks in the fast path's bound space (bit i of warm_mask[2s] /
+    // [2s+1] = variable i at its lower / upper bound; bounce_space 1: cumulative input rows, 0: move box) -- the warm
+    // start that lets the resume pass certify the next optimum in a round or two.  A scenario that ends here is
+    // marked done so that the final pass skips it.
     // second pass after a fast path: only scenarios it handed over (start_step < n_steps)
     if (n_handover && *n_handover == 0x7f7f7f7f) return;     // counter baseline: the buffer is memset to 0x7f
     extern __shared__ double smem[];
@@ -325,6 +334,7 @@ ihmpc_step_kernel(const DevPlan P_in, const sihmpc_io io, const long long batch,
 
         double Jval = 0.0;
         int status = 0, q = 0, iters_total = 0;
+        bool bounced = false;
         double viol_abs = 0.0;
 
         for (int step = step0; step < n_steps; ++step) {
@@ -724,8 +734,29 @@ ihmpc_step_kernel(const DevPlan P_in, const sihmpc_io io, const long long batch,
                     }
                 }
                 __syncwarp();
+                if (bounce_list && step + 1 < n_steps && step + 1 - step0 >= bounce_steps) {      // warp-uniform
+                    if (lane == 0) {
+                        unsigned long long lo_m = 0ull, hi_m = 0ull;
+                        bool expressible = true;
+                        for (int a = 0; a < q; ++a) {
+                            const int row = act[a] >> 1, side = act[a] & 1;
+                            int bit = -1;
+                            if (bounce_space == 0 && row < nv) bit = row;
+                            if (bounce_space == 1 && row >= nv && row < 2 * nv) bit = row - nv;
+                            if (bit < 0) { expressible = false; continue; }
+                            if (side) hi_m |= 1ull << bit; else lo_m |= 1ull << bit;
+                        }
+                        if (!expressible) { lo_m = 0ull; hi_m = 0ull; }
+                        warm_mask[2 * s] = lo_m; warm_mask[2 * s + 1] = hi_m;
+                        start_step[s] = step + 1;
+                        bounce_list[atomicAdd(n_bounce, 1) - 0x7f7f7f7f] = (int)s;
+                    }
+                    bounced = true;
+                    break;
+                }
             }
         }  // steps
+        if (bounce_list && !bounced && lane == 0) start_step[s] = 0x7f7f7f7f;     // done: the later passes skip it
 
         // ---------------- write back
         if (advance) {

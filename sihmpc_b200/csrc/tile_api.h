@@ -7,6 +7,8 @@ namespace sih {
 
 constexpr int TL_WARPS = 8;          // == scenarios per CTA == M of the MMA
 constexpr int TL_NTMAX = 8;          // tile rows of the augmented matrix: nv + 1 <= 64
+constexpr int TL_BOUNCES = 3;        // rounds of (general kernel: one hard step) -> (resume pass with its active set)
+constexpr int TL_CTR = 4 + 2 * TL_BOUNCES + (2 * TL_BOUNCES) % 4;      // counter words in front of start_step[]
 constexpr int TL_KHMAX = 6;          // k-tiles of the Hessian product: 1 + max(hj_index) + 1 <= 24
 
 struct TileCfg {
@@ -33,13 +35,15 @@ struct TilePlan {
     TileCfg cfg;
     int *ibuf;               // device: ptr | kt | hmap
     double *dbuf;            // device: stored tiles
-    int *ctr;                // one device buffer: [n_handover | n_fail | n_inkernel | pad | start_step[cap] | list[cap]]
+    int *ctr;                // one device buffer: [n_handover | n_fail | n_inkernel | pad | (n_bounce, n_fail2) x TL_BOUNCES | start_step[cap] | list[cap] | list2[cap]]
     int *start_step;
     int *n_handover;         // scenarios the first pass appended to `list` (counter baseline 0x7f7f7f7f)
     int *n_fail;             // scenarios the resume pass could not resolve: left to the general kernel
     int *n_inkernel;         // scenario-steps with active bounds resolved by the in-kernel active set (last launch)
-    int *list;
+    int *list, *list2;       // scenarios listed by the first pass / sent back by the general kernel (bounce rounds)
+    unsigned long long *warm_mask;   // [cap][2] active set exported by the general kernel for a scenario it sends back
     int last_resumed;        // the last launch ran the resume pass (sihmpc_plan_counters)
+    const int *last_final;   // counter the final general pass of the last launch was given
     long long capacity;
     size_t smem_bytes;
     int n_tiles;
@@ -52,6 +56,10 @@ cudaError_t tile_reset(const TilePlan &tp, long long batch, cudaStream_t st);
 inline bool tile_resumes(const TilePlan &tp, long long batch, int n_steps) { return tp.cfg.cspace >= 0 && (n_steps > 1 || batch >= 4096); }
 cudaError_t tile_launch(TilePlan &tp, const DevPlan &P, const sihmpc_io &io, long long batch, int n_steps,
                         int sm_count, cudaStream_t st);
+inline int *tile_bounce_counter(const TilePlan &tp, int round) { return tp.ctr + 4 + 2 * round; }
+inline int *tile_fail_counter(const TilePlan &tp, int round) { return tp.ctr + 4 + 2 * round + 1; }
+cudaError_t tile_launch_bounced(const TilePlan &tp, const DevPlan &P, const sihmpc_io &io, long long batch, int n_steps,
+                                int sm_count, int round, cudaStream_t st);
 void tile_destroy(TilePlan *tp);
 
 }  // namespace sih

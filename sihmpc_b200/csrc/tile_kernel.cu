@@ -312,7 +312,8 @@ template <int NT, int MODE>
 __global__ void __launch_bounds__(TL_WARPS * 32, 1)
 tile_step_kernel(const DevPlan P, const TileCfg C, const sihmpc_io io, const long long batch, const int n_steps,
                  int *__restrict__ start_step, int *__restrict__ n_handover, int *__restrict__ n_inkernel,
-                 int *__restrict__ list, const int *__restrict__ n_list) {
+                 int *__restrict__ list, const int *__restrict__ n_list,
+                 const unsigned long long *__restrict__ warm_mask) {
     constexpr bool RESUME = (MODE == 1);
     extern __shared__ double sm[];
     __shared__ long long s_sid[TL_WARPS];
@@ -366,6 +367,9 @@ tile_step_kernel(const DevPlan P, const TileCfg C, const sihmpc_io io, const lon
         const long long sl = valid ? s : batch - 1;
         bool alive = valid;
         unsigned long long mlo = 0ull, mhi = 0ull;     // bound masks of the last step (warm start of the active set)
+        if constexpr (RESUME) {                        // scenario sent back by the general kernel: its last active set
+            if (warm_mask && valid) { mlo = warm_mask[2 * s]; mhi = warm_mask[2 * s + 1]; }
+        }
         if (lane == 0) s_sid[w] = s;
         // ---------------- load the scenario
         for (int i = lane; i < nx; i += 32) svw[i] = io.x[sl * nx + i];
@@ -642,19 +646,20 @@ cudaError_t SIH_TL_CAT(tile_set_smem_, SIH_TL_ONLY_NT)(size_t bytes) {
 // known on the device only: blocks beyond it leave at once), failures counted in `counter`
 cudaError_t SIH_TL_CAT(tile_launch_, SIH_TL_ONLY_NT)(const TilePlan &tp, const DevPlan &P, const sihmpc_io &io, long long batch,
                                                      int n_steps, int grid, int mode, int *list, const int *n_list,
-                                                     int *counter, cudaStream_t st) {
+                                                     int *counter, const unsigned long long *warm, cudaStream_t st) {
     if (mode == 0)
         tile_step_kernel<SIH_TL_ONLY_NT, 0><<<grid, TL_WARPS * 32, tp.smem_bytes, st>>>(P, tp.cfg, io, batch, n_steps, tp.start_step,
-                                                                                         counter, tp.n_inkernel, list, nullptr);
+                                                                                         counter, tp.n_inkernel, list, nullptr, nullptr);
     else
         tile_step_kernel<SIH_TL_ONLY_NT, 1><<<grid, TL_WARPS * 32, tp.smem_bytes, st>>>(P, tp.cfg, io, batch, n_steps, tp.start_step,
-                                                                                         counter, tp.n_inkernel, list, n_list);
+                                                                                         counter, tp.n_inkernel, list, n_list, warm);
     return cudaGetLastError();
 }
 #else
 #define SIH_TL_DECL(N_) \
     cudaError_t tile_set_smem_##N_(size_t bytes); \
-    cudaError_t tile_launch_##N_(const TilePlan &, const DevPlan &, const sihmpc_io &, long long, int, int, int, int *, const int *, int *, cudaStream_t);
+    cudaError_t tile_launch_##N_(const TilePlan &, const DevPlan &, const sihmpc_io &, long long, int, int, int, int *, const int *, int *, \
+                                 const unsigned long long *, cudaStream_t);
 SIH_TL_DECL(1) SIH_TL_DECL(2) SIH_TL_DECL(3) SIH_TL_DECL(4) SIH_TL_DECL(5) SIH_TL_DECL(6) SIH_TL_DECL(7) SIH_TL_DECL(8)
 #undef SIH_TL_DECL
 
@@ -898,18 +903,22 @@ cudaError_t tile_configure(const sihmpc_plan_desc *d, const DevPlan &P, TilePlan
 cudaError_t tile_ensure_capacity(TilePlan *tp, long long batch) {
     if (tp->capacity >= batch) return cudaSuccess;
     if (tp->ctr) cudaFree(tp->ctr);
-    tp->ctr = tp->n_handover = tp->n_fail = tp->n_inkernel = tp->start_step = tp->list = nullptr; tp->capacity = 0;
-    cudaError_t e = cudaMalloc(&tp->ctr, (size_t)(4 + 2 * batch) * sizeof(int));
+    if (tp->warm_mask) cudaFree(tp->warm_mask);
+    tp->ctr = tp->n_handover = tp->n_fail = tp->n_inkernel = tp->start_step = tp->list = tp->list2 = nullptr;
+    tp->warm_mask = nullptr; tp->capacity = 0;
+    cudaError_t e = cudaMalloc(&tp->ctr, (size_t)(TL_CTR + 3 * batch) * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&tp->warm_mask, (size_t)2 * batch * sizeof(unsigned long long));
     if (e == cudaSuccess) {
         tp->n_handover = tp->ctr; tp->n_fail = tp->ctr + 1; tp->n_inkernel = tp->ctr + 2;
-        tp->start_step = tp->ctr + 4; tp->list = tp->ctr + 4 + batch; tp->capacity = batch;
+        tp->start_step = tp->ctr + TL_CTR; tp->list = tp->ctr + TL_CTR + batch; tp->list2 = tp->ctr + TL_CTR + 2 * batch;
+        tp->capacity = batch;
     }
     return e;
 }
 
 // counters and start_step back to "nothing handed over" (every counter counts up from the baseline 0x7f7f7f7f)
 cudaError_t tile_reset(const TilePlan &tp, long long batch, cudaStream_t st) {
-    return cudaMemsetAsync(tp.ctr, 0x7f, (size_t)(4 + batch) * sizeof(int), st);
+    return cudaMemsetAsync(tp.ctr, 0x7f, (size_t)(TL_CTR + batch) * sizeof(int), st);
 }
 
 static int tile_grid(const TilePlan &tp, long long batch, int sm_count) {
@@ -922,8 +931,9 @@ static int tile_grid(const TilePlan &tp, long long batch, int sm_count) {
 }
 
 static cudaError_t tile_dispatch(const TilePlan &tp, const DevPlan &P, const sihmpc_io &io, long long batch, int n_steps,
-                                 int grid, int mode, int *list, const int *n_list, int *counter, cudaStream_t st) {
-#define SIH_TL_LAUNCH(N_) case N_: return tile_launch_##N_(tp, P, io, batch, n_steps, grid, mode, list, n_list, counter, st);
+                                 int grid, int mode, int *list, const int *n_list, int *counter,
+                                 const unsigned long long *warm, cudaStream_t st) {
+#define SIH_TL_LAUNCH(N_) case N_: return tile_launch_##N_(tp, P, io, batch, n_steps, grid, mode, list, n_list, counter, warm, st);
     switch (tp.cfg.NT) {
         SIH_TL_LAUNCH(1) SIH_TL_LAUNCH(2) SIH_TL_LAUNCH(3) SIH_TL_LAUNCH(4)
         SIH_TL_LAUNCH(5) SIH_TL_LAUNCH(6) SIH_TL_LAUNCH(7) SIH_TL_LAUNCH(8)
@@ -939,16 +949,25 @@ cudaError_t tile_launch(TilePlan &tp, const DevPlan &P, const sihmpc_io &io, lon
                                int n_steps, int sm_count, cudaStream_t st) {
     const int grid = tile_grid(tp, batch, sm_count);
     tp.last_resumed = 0;
-    cudaError_t e = tile_dispatch(tp, P, io, batch, n_steps, grid, 0, tp.list, nullptr, tp.n_handover, st);
+    cudaError_t e = tile_dispatch(tp, P, io, batch, n_steps, grid, 0, tp.list, nullptr, tp.n_handover, nullptr, st);
     if (e != cudaSuccess || !tile_resumes(tp, batch, n_steps) || !(P.has_box || P.has_cum)) return e;
     tp.last_resumed = 1;
-    return tile_dispatch(tp, P, io, batch, n_steps, grid, 1, tp.list, tp.n_handover, tp.n_fail, st);
+    return tile_dispatch(tp, P, io, batch, n_steps, grid, 1, tp.list, tp.n_handover, tp.n_fail, nullptr, st);
+}
+
+// resume pass number `round` (0..TL_BOUNCES-1) over the scenarios the general kernel carried through one hard step and
+// sent back with their active set (list2 / tile_bounce_counter(round)); failures counted in tile_fail_counter(round)
+cudaError_t tile_launch_bounced(const TilePlan &tp, const DevPlan &P, const sihmpc_io &io, long long batch,
+                                int n_steps, int sm_count, int round, cudaStream_t st) {
+    return tile_dispatch(tp, P, io, batch, n_steps, tile_grid(tp, batch, sm_count), 1, tp.list2, tile_bounce_counter(tp, round),
+                         tile_fail_counter(tp, round), tp.warm_mask, st);
 }
 
 void tile_destroy(TilePlan *tp) {
     if (tp->ibuf) cudaFree(tp->ibuf);
     if (tp->dbuf) cudaFree(tp->dbuf);
     if (tp->ctr) cudaFree(tp->ctr);
+    if (tp->warm_mask) cudaFree(tp->warm_mask);
     memset(tp, 0, sizeof *tp);
 }
 #endif  // SIH_TL_ONLY_NT

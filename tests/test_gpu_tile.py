@@ -168,6 +168,26 @@ def test_tile_mimo10_with_active_bounds(monkeypatch):
     assert np.max(np.abs(t["du"][:, idx] - ref["du"])) <= RTOL * np.max(np.abs(ref["du"]))
 
 
+def test_tile_bounce_rounds(monkeypatch):
+    """Opt-in bounce rounds (SIHMPC_BOUNCE=1): scenarios the resume pass gives up on are carried through one step by
+    the general kernel and sent back with the active set it found as the warm start of the in-kernel active set."""
+    sys_ = sc.mimo10_system()
+    bounds = dict(ulb=[-0.6] * 10, uub=[0.6] * 10)
+    B, T = 64, 40
+    scen = sc.mimo10_scenarios(B, sys_)
+    scen["seg_start"][:, 1] = 3; scen["seg_start"][:, 2] = 20
+    scen["dist_step"][:] = np.minimum(scen["dist_step"], 25)
+    monkeypatch.setenv("SIHMPC_BOUNCE", "1")
+    t = _run(monkeypatch, "tile", sc.declare_mimo10, sys_, scen, T, bounds=bounds)
+    monkeypatch.delenv("SIHMPC_BOUNCE", raising=False)
+    n = _run(monkeypatch, "tile", sc.declare_mimo10, sys_, scen, T, bounds=bounds)
+    g = _run(monkeypatch, "general", sc.declare_mimo10, sys_, scen, T, bounds=bounds)
+    assert int((g["stats"][:, -1] > 0).sum()) > 0
+    assert t["cnt"][1] >= n["cnt"][1]                      # at least as many constrained steps resolved in the kernel
+    _close(t, g, tol=2e-7)
+    _close(n, g, tol=2e-7)
+
+
 def test_tile_move_box_inkernel(monkeypatch):
     """Move box only (bound space = the moves themselves) on a 3x3 plant: resume pass == general kernel."""
     sys_ = _plant(3, 3, 9, 2)
