@@ -197,10 +197,13 @@ int sihmpc_subobjectives(sihmpc_plan *plan, const double *x, const double *w, co
  * The plan is compiled from the log controller's declarations (its weighted list VJ defines V_i and
  * gamma_i; `pesos` are not used).  DEVICE pointers: x [batch][nx], u [batch][nu], ysp [batch][ny],
  * w0 [batch][nv+2ny+1] warm start or NULL, w_opt [batch][nv+2ny+1] = [dU ; syN ; siN ; ss], J [batch],
- * status [batch] (SIHMPC_ST_* bits; bit 8 = an explicit inequality of the reference NLP -- ss >= 1,
- * ss*gamma_i - V_i >= 0.01, input/move boxes -- is active at the minimiser: not supported yet),
+ * status [batch] (SIHMPC_ST_* bits).  When an explicit inequality of the reference NLP -- ss >= 1,
+ * ss*gamma_i - V_i >= 0.01, input/move boxes (ihmpccontroller_log.py:390-392,420-424,435-440) -- is not strictly
+ * inactive at that minimiser the step is solved again as an interior-point problem (a barrier -mu log c_j per
+ * inequality, mu 1e-1 ... 1e-14); bit 8 is only left set when no strictly feasible start exists (u outside its
+ * box, 0 outside the move box).
  * iters [batch] Newton iterations.  NULL outputs are skipped.                                      */
-#define SIHMPC_ST_ACTIVE_UNSUPPORTED 8
+#define SIHMPC_ST_ACTIVE_UNSUPPORTED 8   /* log variant: active inequality and no strictly feasible start */
 int sihmpc_log_step(sihmpc_plan *plan, const double *x, const double *u, const double *ysp, const double *w0,
                     int64_t batch, double *w_opt, double *J, int32_t *status, int32_t *iters, void *stream);
 

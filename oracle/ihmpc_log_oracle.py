@@ -10,10 +10,11 @@ Problem handed to IPOPT by the reference (log.py:349-461):
     g = [X_pred ; U_pred ; xi(N)-siN ; xs(N)-ysp-syN ; V_l for all l ; ss*gamma_i - V_i >= 0.01]
                                                                (log.py:394-440)
 This oracle eliminates the terminal equalities like the weighted one, runs a damped Newton method
-on (dU, ss) for the smooth convex objective and then CHECKS that every explicit inequality
+on (dU, ss) for the smooth convex objective and then checks whether every explicit inequality
 (ss >= 1, ss*gamma_i - V_i >= 0.01, input/move boxes) is strictly inactive at the minimiser --
 which is the case for the reference's own example (stationary ss = sqrt(m/2)).
-If one is active it raises NotImplementedError instead of returning an approximate point.
+If one is active the constrained problem is solved with SciPy's trust-constr and polished by Newton steps on the
+identified active set (_solve_constrained; KKT stationarity kept in last_kkt).
 The sub-objective forms, prediction recursion and V ordering come from OracleIHMPC.
 """
 from __future__ import annotations
@@ -173,7 +174,17 @@ class OracleIHMPCLog(OracleIHMPC):
                   float(np.min(u_pred - self.ulb)), float(np.min(self.uub - u_pred)),
                   float(np.min(dU.reshape(N, nu) - self.dulb)), float(np.min(self.duub - dU.reshape(N, nu)))]
         if min(margin) <= 1e-9:
-            raise NotImplementedError("an explicit inequality is active at the log-variant optimum: %r" % (margin,))
+            # an explicit inequality of the NLP is active: solve the constrained problem with SciPy's trust-constr
+            # (its own interior point / SQP machinery -- independent of the product's barrier continuation), from a
+            # strictly feasible start, then polish and certify through the KKT conditions below.
+            v, kkt = self._solve_constrained(evaluate, phi, Rt, Wt, gam, u0, nv, N, nu, m)
+            Vt, Vi, d, gi, Hi, rt = evaluate(v)
+            dU, ss = v[:nv], v[nv]
+            u_pred = np.asarray(u0)[None, :] + np.cumsum(dU.reshape(N, nu), axis=0)
+            margin = [ss - 1.0, float(np.min(d - 0.01)),
+                      float(np.min(u_pred - self.ulb)), float(np.min(self.uub - u_pred)),
+                      float(np.min(dU.reshape(N, nu) - self.dulb)), float(np.min(self.duub - dU.reshape(N, nu)))]
+            self.last_kkt = kkt
         w = np.concatenate([T @ dU + t0, [ss]])
         xi = self._xi(w, x0, u0, ySP)
         J = float(Vt + ss ** 2 - np.sum(np.log(d)))
@@ -189,6 +200,107 @@ class OracleIHMPCLog(OracleIHMPC):
         for i, V in enumerate(self.F_ViN):
             self.ViNant[i] = self.F(V, [0] * self.nx, [0] * self.nu, warm, [0] * self.ny)
         return sol
+
+    def _solve_constrained(self, evaluate, phi, Rt, Wt, gam, u0, nv, N, nu, m):
+        """min phi(v) s.t. ss >= 1, ss*gamma_i - V_i >= 0.01, ulb <= u0 + cumsum(dU) <= uub, dulb <= dU <= duub
+        (log.py:390-392,420-424,435-440).  Returns (v, kkt) with kkt = dict(stationarity, min multiplier)."""
+        from scipy.optimize import minimize, LinearConstraint, NonlinearConstraint, Bounds
+        n = nv + 1
+
+        def fgh(v):
+            Vt, Vi, d, gi, Hi, rt = evaluate(v)
+            g = np.zeros(n); H = np.zeros((n, n))
+            g[:nv] = 2 * Rt.T @ Wt @ rt; H[:nv, :nv] = 2 * Rt.T @ Wt @ Rt
+            g[nv] = 2 * v[nv]; H[nv, nv] = 2.0
+            for i in range(m):
+                a = gi[i].copy(); a[nv] = -gam[i]
+                g += a / d[i]; H[:nv, :nv] += Hi[i] / d[i]; H += np.outer(a, a) / d[i] ** 2
+            return g, H
+        # linear rows: cumulative input box and move box
+        Tc = np.kron(np.tril(np.ones((N, N))), np.eye(nu))
+        A = np.zeros((2 * nv, n)); A[:nv, :nv] = Tc; A[nv:, :nv] = np.eye(nv)
+        lo = np.concatenate([np.tile(self.ulb - u0, N), np.tile(self.dulb, N)])
+        hi = np.concatenate([np.tile(self.uub - u0, N), np.tile(self.duub, N)])
+
+        def dfun(v):
+            return evaluate(v)[2] - 0.01
+
+        def djac(v):
+            _, _, _, gi, _, _ = evaluate(v)
+            J = -gi.copy(); J[:, nv] = gam
+            return J
+        # strictly feasible start: no moves, ss large
+        v0 = np.zeros(n)
+        Vi0 = evaluate(v0)[1]
+        v0[nv] = max(2.0, 1.1 * float(np.max((Vi0 + 0.02) / gam)) + 0.1)
+        big = 1e30
+
+        def fsafe(v):
+            f = phi(v)
+            return f if np.isfinite(f) else big
+        res = minimize(fsafe, v0, jac=lambda v: fgh(v)[0], hess=lambda v: fgh(v)[1], method='trust-constr',
+                       bounds=Bounds(np.r_[np.full(nv, -np.inf), 1.0], np.full(n, np.inf), keep_feasible=True),
+                       constraints=[LinearConstraint(A, lo, hi),      # (a state on a bound up to rounding: no keep_feasible)
+                                    NonlinearConstraint(dfun, 0.0, np.inf, jac=djac, keep_feasible=True)],
+                       options=dict(gtol=1e-8, xtol=1e-12, barrier_tol=1e-9, maxiter=400, initial_barrier_parameter=0.1))
+        v = res.x
+        # polish: primal active-set Newton from there.  Rows: ('lin', k, +1/-1) of A v >= lo / <= hi, ('ss',), ('d', i).
+        cs = A @ v
+        active = []
+        for k in range(2 * nv):
+            if np.isfinite(lo[k]) and cs[k] - lo[k] < 1e-7: active.append(('lin', k, 1.0))
+            elif np.isfinite(hi[k]) and hi[k] - cs[k] < 1e-7: active.append(('lin', k, -1.0))
+        if v[nv] - 1.0 < 1e-7: active.append(('ss', 0, 1.0))
+        for i in range(m):
+            if dfun(v)[i] < 1e-7: active.append(('d', i, 1.0))
+        lam = np.zeros(0); stat = np.inf
+        for _ in range(400):
+            g, H = fgh(v)
+            dj = djac(v); dv_ = dfun(v); cs = A @ v
+            rows, rhs = [], []
+            for kind, k, sg in active:
+                if kind == 'lin': rows.append(A[k]); rhs.append((lo[k] if sg > 0 else hi[k]) - cs[k])
+                elif kind == 'ss': e_ = np.zeros(n); e_[nv] = 1.0; rows.append(e_); rhs.append(1.0 - v[nv])
+                else: rows.append(dj[k]); rhs.append(-dv_[k])
+            Aa = np.array(rows).reshape(-1, n); ba = np.array(rhs)
+            K = np.block([[H, Aa.T], [Aa, np.zeros((len(ba), len(ba)))]])
+            sol_ = np.linalg.lstsq(K, np.r_[-g, ba], rcond=None)[0]
+            step = sol_[:n]; lam = -sol_[n:]
+            # longest feasible fraction of the step; the blocking row joins the active set
+            t, block = 1.0, None
+            act_lin = {(k, sg) for kind, k, sg in active if kind == 'lin'}
+            ds = A @ step
+            for k in range(2 * nv):
+                if np.isfinite(lo[k]) and (k, 1.0) not in act_lin and ds[k] < -1e-16:
+                    tk = (lo[k] - cs[k]) / ds[k]
+                    if tk < t: t, block = max(tk, 0.0), ('lin', k, 1.0)
+                if np.isfinite(hi[k]) and (k, -1.0) not in act_lin and ds[k] > 1e-16:
+                    tk = (hi[k] - cs[k]) / ds[k]
+                    if tk < t: t, block = max(tk, 0.0), ('lin', k, -1.0)
+            if ('ss', 0, 1.0) not in active and step[nv] < -1e-16:
+                tk = (1.0 - v[nv]) / step[nv]
+                if tk < t: t, block = max(tk, 0.0), ('ss', 0, 1.0)
+            while t > 1e-10:                                   # barrier domain and d_i >= 0.01 (nonlinear): backtrack
+                vn = v + t * step
+                dn = dfun(vn)
+                inact = [i for i in range(m) if ('d', i, 1.0) not in active]
+                if np.isfinite(phi(vn)) and all(dn[i] >= -1e-13 for i in inact):
+                    break
+                t *= 0.5; block = None
+            v = v + t * step
+            if block is not None:
+                active.append(block)
+                continue
+            stat = float(np.max(np.abs(g - Aa.T @ lam))) if len(ba) else float(np.max(np.abs(g)))
+            if np.linalg.norm(t * step) < 1e-13 * (1 + np.linalg.norm(v)):
+                sg = np.array([a_[2] for a_ in active])
+                if len(active) and np.min(sg * lam) < -1e-10:
+                    active.pop(int(np.argmin(sg * lam)))     # wrong-sign multiplier: release that row
+                    continue
+                break
+        sg = np.array([a_[2] for a_ in active])
+        lam_min = float(np.min(sg * lam)) if len(active) else 0.0       # >= 0: multipliers have the KKT sign
+        return v, dict(stationarity=stat, n_active=len(active), lam=lam, lam_min=lam_min)
 
     def warmStart(self, sol, ysp):                                # log.py:518-549
         w0 = np.asarray(sol['w_opt']).reshape(-1)

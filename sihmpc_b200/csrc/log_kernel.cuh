@@ -10,15 +10,23 @@
 //   H_dU,ss = - sum gamma_i a_i / d_i^2                                       H_ss,ss = 2 + sum gamma_i^2 / d_i^2
 // Damped Newton (in-shared-memory Cholesky of the (nv+1)x(nv+1) system, backtracking that keeps every
 // d_i > 0).  The explicit inequalities of the reference NLP (ss >= 1, ss*gamma_i - V_i >= 0.01,
-// input and move boxes; log.py:390-392,420-424,435-440) are CHECKED at the minimiser: if one is
-// not strictly inactive the scenario is flagged SIHMPC_ST_ACTIVE_UNSUPPORTED instead of returning an
-// approximate point (they are inactive in the reference's own example: ss* = sqrt(m/2) > 1).
+// input and move boxes; log.py:390-392,420-424,435-440) are checked at that minimiser (they are inactive in the
+// reference's own example: ss* = sqrt(m/2) > 1).  If one is not strictly inactive the step is solved again as an
+// INTERIOR-POINT problem, the way the reference's IPOPT treats them: every explicit inequality c_j(v) >= 0 gets
+// its own barrier  -mu log c_j  (bounds relaxed by 1e-10 max(1,|b|) -- IPOPT relaxes by 1e-8, bound_relax_factor -- so a point on
+// a bound is strictly interior), Newton on phi_mu with the same machinery, mu from 1e-1 down to 1e-14 (a weakly
+// active row with multiplier 1e-4 is then within 1e-10 of its bound).  The extra
+// terms: ss >= 1 and the shifted d_i - 0.01 change the weights 1/d_i, 1/d_i^2 of the existing blocks; a row of the
+// input box (cumulative moves of one input up to step k) adds t1 = -mu/s_lo + mu/s_hi to the gradient of every
+// move of that input up to k and t2 = mu/s_lo^2 + mu/s_hi^2 to every pair of them (suffix sums S1, S2 over k);
+// the move box adds diagonal terms.  SIHMPC_ST_ACTIVE_UNSUPPORTED is only left set when that solve fails
+// (no strictly feasible start: u outside its box, 0 outside the move box).
 #pragma once
 #include "step_kernel.cuh"
 
 namespace sih {
 
-struct LogLayout { int H, dinv, x, xn, uu, ysp, e, r, v, g, p, gi, d, Vi, vt, total; };
+struct LogLayout { int H, dinv, x, xn, uu, ysp, e, r, v, g, p, gi, d, Vi, vt, s1, s2, b1, b2, total; };
 
 __host__ __device__ inline LogLayout make_log_layout(const DevPlan &P) {
     LogLayout w; int o = 0;
@@ -27,6 +35,7 @@ __host__ __device__ inline LogLayout make_log_layout(const DevPlan &P) {
     SIH_TAKE(H, n * ld); SIH_TAKE(dinv, n); SIH_TAKE(x, P.nx + P.nu); SIH_TAKE(xn, P.nx); SIH_TAKE(uu, P.nu); SIH_TAKE(ysp, P.ny); SIH_TAKE(e, P.R);
     SIH_TAKE(r, P.R); SIH_TAKE(v, n); SIH_TAKE(g, n); SIH_TAKE(p, n); SIH_TAKE(gi, P.m * P.nv);
     SIH_TAKE(d, P.m); SIH_TAKE(Vi, P.m); SIH_TAKE(vt, n);
+    SIH_TAKE(s1, n); SIH_TAKE(s2, n); SIH_TAKE(b1, n); SIH_TAKE(b2, n);
 #undef SIH_TAKE
     w.total = o;
     return w;
@@ -59,6 +68,50 @@ __device__ double log_eval(const DevPlan &P, const double *vv, const double *e, 
     return bad > 0.0 ? SIH_INF : phi;
 }
 
+__device__ __forceinline__ double log_relax(const double b, const double sgn) {       // cf. IPOPT bound_relax_factor (1e-8 there)
+    return b + sgn * 1e-10 * fmax(1.0, fabs(b));
+}
+
+// barrier of the explicit inequalities at vv (d[] from log_eval at the same point):  -mu sum log c_j, inf outside.
+// With `deriv` the first/second derivative coefficients are left in shared memory: S1/S2[k*nu+j] = suffix sums
+// over the horizon of the input-box rows of input j, b1/b2 = move-box terms per variable.
+__device__ double log_barrier(const DevPlan &P, const double *vv, const double *uu, const double *d, const double mu,
+                              const bool deriv, double *S1, double *S2, double *b1, double *b2, int lane) {
+    const int nv = P.nv, nu = P.nu, m = P.m, N = P.N;
+    double acc = 0.0, bad = 0.0;
+    if (lane == 0) {
+        const double s = vv[nv] - log_relax(1.0, -1.0);
+        if (!(s > 0.0)) bad = 1.0; else acc -= log(s);
+        for (int i = 0; i < m; ++i) {
+            const double si = d[i] - log_relax(0.01, -1.0);
+            if (!(si > 0.0)) bad = 1.0; else acc -= log(si);
+        }
+    }
+    for (int j = lane; j < nu; j += 32) {
+        const bool hl = P.ulb[j] > -SIH_INF, hh = P.uub[j] < SIH_INF, dl = P.dulb[j] > -SIH_INF, dh = P.duub[j] < SIH_INF;
+        const double lo = hl ? log_relax(P.ulb[j], -1.0) : 0.0, hi = hh ? log_relax(P.uub[j], 1.0) : 0.0;
+        const double dlo = dl ? log_relax(P.dulb[j], -1.0) : 0.0, dhi = dh ? log_relax(P.duub[j], 1.0) : 0.0;
+        double cs = uu[j];
+        for (int k = 0; k < N; ++k) {
+            const int c = k * nu + j;
+            const double dv = vv[c];
+            cs += dv;
+            double t1 = 0.0, t2 = 0.0, u1 = 0.0, u2 = 0.0;
+            if (hl) { const double sl = cs - lo; if (!(sl > 0.0)) bad = 1.0; else { acc -= log(sl); t1 -= 1.0 / sl; t2 += 1.0 / (sl * sl); } }
+            if (hh) { const double sl = hi - cs; if (!(sl > 0.0)) bad = 1.0; else { acc -= log(sl); t1 += 1.0 / sl; t2 += 1.0 / (sl * sl); } }
+            if (dl) { const double sl = dv - dlo; if (!(sl > 0.0)) bad = 1.0; else { acc -= log(sl); u1 -= 1.0 / sl; u2 += 1.0 / (sl * sl); } }
+            if (dh) { const double sl = dhi - dv; if (!(sl > 0.0)) bad = 1.0; else { acc -= log(sl); u1 += 1.0 / sl; u2 += 1.0 / (sl * sl); } }
+            if (deriv) { S1[c] = mu * t1; S2[c] = mu * t2; b1[c] = mu * u1; b2[c] = mu * u2; }
+        }
+        if (deriv)
+            for (int k = N - 2; k >= 0; --k) { S1[k * nu + j] += S1[(k + 1) * nu + j]; S2[k * nu + j] += S2[(k + 1) * nu + j]; }
+    }
+    acc = warp_sum(acc);
+    bad = warp_max(bad);
+    __syncwarp();
+    return bad > 0.0 ? SIH_INF : mu * acc;
+}
+
 // One launch = n_steps control steps of every scenario.  n_steps == 1 without SIHMPC_F_ADVANCE is mpc() of
 // the log controller (ihmpccontroller_log.py:552-563); with SIHMPC_F_ADVANCE the body of the driver loop
 // (example_distillation_log.py:85-135: mpc, first move to the plant, warmStart with ss = 1, log.py:518-549)
@@ -75,6 +128,7 @@ ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__
     double *Hm = W + lay.H, *dinv = W + lay.dinv, *xs = W + lay.x, *ys = W + lay.ysp, *e = W + lay.e;
     double *r = W + lay.r, *v = W + lay.v, *g = W + lay.g, *gi = W + lay.gi, *d = W + lay.d, *Vi = W + lay.Vi;
     double *vt = W + lay.vt, *xn = W + lay.xn, *uu = W + lay.uu;
+    double *S1 = W + lay.s1, *S2 = W + lay.s2, *b1 = W + lay.b1, *b2 = W + lay.b2;
     const int nx = P.nx, nu = P.nu, ny = P.ny, nv = P.nv, m = P.m, R = P.R;
     const int n = nv + 1, ld = n | 1, nw = nv + 2 * ny + 1;
     const int nstat = ny + SIHMPC_NSTATS_EXTRA;
@@ -124,7 +178,14 @@ ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__
             __syncwarp();
             phi = log_eval(P, v, e, r, Vi, d, lane);
         }
-        for (it = 1; it <= max_iter; ++it) {
+        // Newton on phi (mu = 0) or phi_mu = phi - mu sum log c_j (interior-point rounds), at most `lim` iterations
+        auto newton = [&](const double mu, const int lim) {
+            auto w1f = [&](const int i) { return 1.0 / d[i] + (mu > 0.0 ? mu / (d[i] - log_relax(0.01, -1.0)) : 0.0); };
+            auto w2f = [&](const int i) { const double di = d[i], si = d[i] - log_relax(0.01, -1.0);
+                                          return 1.0 / (di * di) + (mu > 0.0 ? mu / (si * si) : 0.0); };
+        for (int itn = 1; itn <= lim; ++itn) {
+            ++it;
+            if (mu > 0.0) log_barrier(P, v, uu, d, mu, true, S1, S2, b1, b2, lane);     // derivative coefficients at v
             // ---- gradients a_i = grad_dU V_i (rows of gi), lanes over variables
             for (int c = lane; c < nv; c += 32) {
                 for (int i = 0; i < m; ++i) {
@@ -135,12 +196,14 @@ ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__
                 double a = 0.0;
                 for (int k = 0; k < R; ++k) a = fma(P.E[(size_t)k * nv + c], P.w0row[k] * r[k], a);
                 double gc = 2.0 * a;
-                for (int i = 0; i < m; ++i) gc += gi[i * nv + c] / d[i];
+                for (int i = 0; i < m; ++i) gc += gi[i * nv + c] * w1f(i);
+                if (mu > 0.0) gc += S1[c] + b1[c];
                 g[c] = gc;
             }
             if (lane == 0) {
                 double gs = 2.0 * v[nv];
-                for (int i = 0; i < m; ++i) gs -= P.gamma[i] / d[i];
+                for (int i = 0; i < m; ++i) gs -= P.gamma[i] * w1f(i);
+                if (mu > 0.0) gs -= mu / (v[nv] - log_relax(1.0, -1.0));
                 g[nv] = gs;
             }
             __syncwarp();
@@ -151,18 +214,22 @@ ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__
                 double h;
                 if (a < nv) {
                     h = P.Ht[a * nv + b];
-                    for (int q = 0; q < P.mh; ++q) h = fma(1.0 / d[P.hj_index[q]], P.HJ[((size_t)q * nv + a) * nv + b], h);
+                    for (int q = 0; q < P.mh; ++q) h = fma(w1f(P.hj_index[q]), P.HJ[((size_t)q * nv + a) * nv + b], h);
                     for (int i = 0; i < m; ++i) {
-                        const double di = d[i];
-                        h = fma(gi[i * nv + a], gi[i * nv + b] / (di * di), h);
-                        if (a == b) h = fma(2.0 * P.Wdu[(size_t)a * m + i], 1.0 / di, h);
+                        h = fma(gi[i * nv + a], gi[i * nv + b] * w2f(i), h);
+                        if (a == b) h = fma(2.0 * P.Wdu[(size_t)a * m + i], w1f(i), h);
+                    }
+                    if (mu > 0.0) {
+                        if ((a % nu) == (b % nu)) h += S2[a];          // a >= b: rows k >= k_a cover both moves
+                        if (a == b) h += b2[a];
                     }
                 } else if (b < nv) {
                     h = 0.0;
-                    for (int i = 0; i < m; ++i) h -= P.gamma[i] * gi[i * nv + b] / (d[i] * d[i]);
+                    for (int i = 0; i < m; ++i) h -= P.gamma[i] * gi[i * nv + b] * w2f(i);
                 } else {
                     h = 2.0;
-                    for (int i = 0; i < m; ++i) h += P.gamma[i] * P.gamma[i] / (d[i] * d[i]);
+                    for (int i = 0; i < m; ++i) h += P.gamma[i] * P.gamma[i] * w2f(i);
+                    if (mu > 0.0) { const double sl = v[nv] - log_relax(1.0, -1.0); h += mu / (sl * sl); }
                 }
                 Hm[a * ld + b] = h;
             }
@@ -176,7 +243,7 @@ ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__
 #pragma unroll
             for (int t = 0; t < NVR; ++t) { const int i = lane + 32 * t; if (i < n) dec = fma(-g[i], acc[t], dec); }
             dec = warp_sum(dec);
-            if (!(dec > 1e-18 * (1.0 + fabs(phi)))) break;
+            if (!(dec > (mu > 0.0 ? fmin(1e-16 * (1.0 + fabs(phi)), 1e-2 * mu) : 1e-18 * (1.0 + fabs(phi))))) break;
             // ---- backtracking on phi (keeps every d_i > 0)
             double t_ = 1.0, phin = SIH_INF;
             bool ok = false;
@@ -185,6 +252,7 @@ ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__
                 for (int t = 0; t < NVR; ++t) { const int i = lane + 32 * t; if (i < n) vt[i] = fma(t_, acc[t], v[i]); }
                 __syncwarp();
                 phin = log_eval(P, vt, e, r, Vi, d, lane);
+                if (mu > 0.0 && phin < SIH_INF) phin += log_barrier(P, vt, uu, d, mu, false, S1, S2, b1, b2, lane);
                 if (phin <= phi - 1e-4 * t_ * dec) { ok = true; break; }
                 t_ *= 0.5;
                 __syncwarp();
@@ -192,16 +260,20 @@ ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__
             if (!ok) {                     // rounding level: restore the state of v and stop
                 __syncwarp();
                 phi = log_eval(P, v, e, r, Vi, d, lane);
+                if (mu > 0.0) phi += log_barrier(P, v, uu, d, mu, false, S1, S2, b1, b2, lane);
                 break;
             }
             __syncwarp();
             for (int i = lane; i < n; i += 32) v[i] = vt[i];
-            const bool flat = (phi - phin) <= 1e-15 * (1.0 + fabs(phi));    // decrease at rounding level: converged
+            const double flat_tol = (mu > 0.0) ? fmin(1e-15 * (1.0 + fabs(phi)), 1e-3 * mu) : 1e-15 * (1.0 + fabs(phi));
+            const bool flat = (phi - phin) <= flat_tol;                      // decrease at rounding level: converged
             phi = phin;
             __syncwarp();
             if (flat) break;
         }
-        if (it > max_iter) st |= SIHMPC_ST_MAXITER;
+        };
+        newton(0.0, max_iter);
+        if (it >= max_iter) st |= SIHMPC_ST_MAXITER;
         // ---- explicit inequalities of the reference NLP must be strictly inactive
         {
             double marg = SIH_INF;
@@ -219,7 +291,32 @@ ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__
                 }
             }
             marg = -warp_max(-marg);
-            if (!(marg > 1e-9)) st |= SIHMPC_ST_ACTIVE_UNSUPPORTED;
+            if (!(marg > 1e-9)) {
+                // ---- interior point on the explicit inequalities (see the header): strictly feasible start = no moves,
+                // ss large enough for every barrier
+                __syncwarp();
+                for (int i = lane; i < nv; i += 32) v[i] = 0.0;
+                if (lane == 0) v[nv] = 2.0;
+                __syncwarp();
+                log_eval(P, v, e, r, Vi, d, lane);
+                {
+                    double smax = 0.0;
+                    for (int i = 0; i < m; ++i) smax = fmax(smax, (Vi[i] + 0.02) / P.gamma[i]);
+                    __syncwarp();
+                    if (lane == 0) v[nv] = fmax(2.0, 1.1 * smax + 0.1);
+                    __syncwarp();
+                }
+                bool fail_ip = false;
+                for (double mu = 1e-1; mu >= 0.99e-14; mu *= 0.1) {
+                    phi = log_eval(P, v, e, r, Vi, d, lane);
+                    const double bar = log_barrier(P, v, uu, d, mu, false, S1, S2, b1, b2, lane);
+                    if (!(phi < SIH_INF) || !(bar < SIH_INF)) { fail_ip = true; break; }
+                    phi += bar;
+                    newton(mu, 60);
+                }
+                phi = log_eval(P, v, e, r, Vi, d, lane);         // the cost the reference reports: without the barriers
+                if (fail_ip) st |= SIHMPC_ST_ACTIVE_UNSUPPORTED;
+            }
         }
         st_or |= st; it_total += it; st_J = phi;
         const bool last_step = (step == n_steps - 1);

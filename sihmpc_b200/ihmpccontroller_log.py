@@ -147,7 +147,8 @@ class IHMPCController(_Weighted):
         self.newton_iters = int(itd.cpu().numpy()[0])
         if self.status & _capi.ST_ACTIVE_UNSUPPORTED:
             raise NotImplementedError("an explicit inequality of the log NLP (ss >= 1, ss*gamma_i - V_i >= 0.01, "
-                                      "input/move boxes) is active at the minimiser: not supported yet")
+                                      "input/move boxes) is active and the interior-point solve found no strictly "
+                                      "feasible start (u0 outside its box, or 0 outside the move box)")
         x_pred, y_pred, u_pred = self._predict(x, u, w[:nv])
         vals = self._eval_all(x, w, ysp)
         XN = x_pred[-nx:]

@@ -526,3 +526,75 @@ def test_log_variant_batched_closed_loop_matches_oracle():
             assert np.max(np.abs(y[k, idx] - r['ykp1'])) <= RTOL * 100.0
             w0o = orc.warmStart(solo, ysp)
         assert np.max(np.abs(eng.x[idx].cpu().numpy() - xo)) <= RTOL * 100.0
+
+
+def _declare_log(cls, s, **b):
+    N = 10
+    c = cls(s, N, **b)
+    c.subObjComposed(y=[0], Q=1, sat=N * 0.5 ** 2)
+    c.subObjComposed(y=[1], Q=1, sat=N * 2.0 ** 2)
+    c.subObj(du=[0], Q=1, sat=N * 0.3 ** 2)
+    c.subObj(du=[1], Q=1, sat=N * 0.3 ** 2)
+    c.subObj(siN=[0], Q=1, addJ=False)
+    c.subObj(siN=[1], Q=1, addJ=False)
+    return c
+
+
+@pytest.mark.parametrize("bname,bounds", [
+    ("input_box", dict(ulb=[1.93, 1.60], uub=[2.2, 1.9])),
+    ("move_box", dict(ulb=[0, 0], dulb=[-0.01, -0.01], duub=[0.01, 0.01])),
+])
+def test_log_variant_active_inequalities_match_oracle(bname, bounds):
+    """Log-barrier variant with explicit inequalities of the reference NLP ACTIVE at the optimum (input box
+    log.py:420-424, move box :375-389): the kernel's interior-point rounds vs the oracle's KKT-certified constrained
+    optimum (SciPy trust-constr + active-set Newton polish), closed loop of example_distillation_log.py:85-135."""
+    from oracle.ihmpc_log_oracle import OracleIHMPCLog
+    from sihmpc.ihmpccontroller_log import IHMPCController as LogController
+    sys_ = sc.distillation_system()
+    c = _declare_log(LogController, sys_, **bounds)
+    orc = _declare_log(OracleIHMPCLog, sys_, **bounds)
+    u = [1.95, 1.71]; x = np.append([96, 0.5], np.zeros(sys_.nx - 2)); ysp = [96, 0.5]
+    xo, uo = x.copy(), np.array(u)
+    w0 = []; w0o = []
+    scale, n_constrained = 0.0, 0
+    for k in range(12):
+        if k > 1:
+            ysp = [96, 1]
+        sol = c.mpc(x0=x, ySP=ysp, w0=w0, u0=u, lam_w0=[], lam_g0=[], ViN_ant=[])
+        solo = orc.mpc(xo, ysp, w0o, uo, [], [], ViN_ant=[])
+        if min(solo['info']['margins']) <= 1e-8:
+            n_constrained += 1
+            assert orc.last_kkt['stationarity'] <= 1e-8 and orc.last_kkt['lam_min'] >= -1e-9
+        assert c.status == 0
+        du = sol['du_opt'][:, 0].full().reshape(-1)
+        scale = max(scale, np.max(np.abs(solo['du_opt'])))
+        assert np.max(np.abs(sol['du_opt'].full() - solo['du_opt'])) <= RTOL * max(scale, 1e-3), k
+        assert abs(float(sol['J']) - solo['J']) <= RTOL * abs(solo['J']), k
+        up = sol['u_pred'].full().reshape(-1, 2)
+        assert (up >= np.asarray(bounds.get('ulb', [-np.inf] * 2)) - VIOL).all()
+        res = c.dynF(x0=x, du0=du, u0=u)
+        x = res['xkp1'].full(); u = res['ukp1'].full()
+        r = orc.dynF(xo, uo, solo['du_opt'][:, 0]); xo, uo = r['xkp1'], r['ukp1']
+        w0 = c.warmStart(sol, ysp); w0o = orc.warmStart(solo, ysp)
+    assert n_constrained >= 3
+
+
+def test_log_variant_ss_bound_active():
+    """One weighted objective only: the stationary ss = sqrt(m/2) < 1, so ss >= 1 (log.py:390-392) is active."""
+    from oracle.ihmpc_log_oracle import OracleIHMPCLog
+    from sihmpc.ihmpccontroller_log import IHMPCController as LogController
+    s = sc.fopdt_system([[1.5]], [[6.0]], [[0]], 1.0)
+
+    def declare(cls):
+        c = cls(s, 6)
+        c.subObjComposed(y=[0], Q=1, sat=6.0)
+        return c
+    c = declare(LogController); orc = declare(OracleIHMPCLog)
+    x = np.zeros(s.nx); u = [0.0]
+    for ysp in ([0.3], [0.0]):
+        sol = c.mpc(x0=x, ySP=ysp, w0=[], u0=u, lam_w0=[], lam_g0=[], ViN_ant=[])
+        solo = orc.mpc(x, ysp, [], np.array(u), [], [], ViN_ant=[])
+        assert abs(solo['w_opt'][-1] - 1.0) <= 1e-9 and orc.last_kkt['lam_min'] >= -1e-9
+        assert abs(float(sol['w_opt'][-1]) - 1.0) <= 1e-7
+        assert np.max(np.abs(sol['du_opt'].full() - solo['du_opt'])) <= RTOL * max(np.max(np.abs(solo['du_opt'])), 1e-3)
+        assert abs(float(sol['J']) - solo['J']) <= RTOL * max(abs(solo['J']), 1e-3)

@@ -166,3 +166,29 @@ def test_log_oracle_stationarity_and_crosscheck(sys_):
     r = minimize(literal, v + 0.01 * rng.normal(size=21) * np.r_[np.ones(20) * 0.1, 1.0], method="BFGS",
                  options=dict(gtol=1e-9, maxiter=2000))
     assert r.fun >= f0 - 1e-9 and np.max(np.abs(r.x - v)) < 1e-4
+
+
+def test_log_oracle_constrained_optimum_is_kkt_certified():
+    """Log-variant oracle with explicit inequalities active (input box / move box / ss >= 1): the constrained
+    optimum carries its own certificate -- stationarity of the Lagrangian, multipliers of the right sign, primal
+    feasibility -- and is not worse than any feasible point tried around it."""
+    from oracle.ihmpc_log_oracle import OracleIHMPCLog
+    s = sc.distillation_system()
+
+    def declare(**b):
+        N = 10
+        c = OracleIHMPCLog(s, N, **b)
+        c.subObjComposed(y=[0], Q=1, sat=N * 0.5 ** 2); c.subObjComposed(y=[1], Q=1, sat=N * 2.0 ** 2)
+        c.subObj(du=[0], Q=1, sat=N * 0.3 ** 2); c.subObj(du=[1], Q=1, sat=N * 0.3 ** 2)
+        c.subObj(siN=[0], Q=1, addJ=False); c.subObj(siN=[1], Q=1, addJ=False)
+        return c
+    x0 = np.zeros(22); x0[0] = 96; x0[1] = 0.5
+    u0 = np.array([1.95, 1.71])
+    free = declare(ulb=[0, 0]).mpc(x0, [96.0, 1.0], [], u0, [], [], ViN_ant=[])
+    for b in (dict(ulb=[1.93, 1.60], uub=[2.2, 1.9]), dict(ulb=[0, 0], dulb=[-0.01, -0.01], duub=[0.01, 0.01])):
+        c = declare(**b)
+        sol = c.mpc(x0, [96.0, 1.0], [], u0, [], [], ViN_ant=[])
+        assert min(sol['info']['margins']) >= -1e-9
+        assert min(sol['info']['margins']) <= 1e-9                     # something is active
+        assert c.last_kkt['stationarity'] <= 1e-9 and c.last_kkt['lam_min'] >= -1e-10 and c.last_kkt['n_active'] > 0
+        assert sol['J'] >= free['J'] - 1e-12                           # constraining cannot improve the cost
