@@ -31,8 +31,19 @@ complex mode ``xi+ = f xi + c f du``, ``f = exp(p Ts)``): ``F`` gets the block
 ``[[Re f, -Im f], [Im f, Re f]]``, the input column ``(Re(c f), Im(c f))`` and ``Psi`` the weights
 ``(2, 0)``.  ``F`` is then block diagonal instead of diagonal; the controller only needs it in the
 Lyapunov equation of the terminal weight (``ihmpccontroller.py:338-339``), which is general.
+
+Repeated real poles: a pole r of multiplicity m contributes ``sum_k c_k t^k exp(r t)/k!``; its m states are
+``w_k(t) = sum_{q>=k} c_q t^(q-k) exp(r t)/(q-k)!`` (``w_0`` = the response term, ``Psi`` weight 1 on it only) and
+``F`` gets the upper-triangular block ``exp(r Ts) Ts^(q-k)/(q-k)!``.
+
+Dead times that are not a multiple of Ts: ``theta = (l + f) Ts``; a move first shows ``l + 1`` samples later, when
+``tau_e = (l + 1) Ts - theta`` has elapsed since the dead time ran out.  It enters the states when it is ``l`` samples
+old (``theta_ij := l`` in the formulas above) with every step-response term evaluated at ``tau_e`` instead of ``Ts``:
+``Bs = d0 + tau_e di``, ``Bd = dd exp(r tau_e)`` (``tau_e = Ts`` for whole multiples).
 """
 from __future__ import annotations
+
+import math
 
 import numpy as np
 from scipy import signal
@@ -57,10 +68,10 @@ class TransferFunction(signal.TransferFunction):
     def step_coefficients(self, pole_tol=1e-9):
         """Partial fractions of G(s)/s -> (d0, [(dd_a, r_a)...], di).
 
-        Supported pole sets: distinct stable poles, real (``(dd, r)`` floats) or complex-conjugate
-        pairs (``(c, p)`` complex, one entry per pair, Im p > 0), plus at most one pole at the origin
-        (integrating channel).  Repeated or unstable poles raise NotImplementedError
-        (SURVEY.md section 8(f) item 2 -- not needed by the named configurations).
+        Supported pole sets: stable poles, real -- distinct (``(dd, r)`` floats) or REPEATED
+        (``(('jordan', [c_0 .. c_{m-1}]), r)``: the terms c_k t^k e^{rt}/k! of the step response) -- or distinct
+        complex-conjugate pairs (``(c, p)`` complex, one entry per pair, Im p > 0), plus at most one pole at the
+        origin (integrating channel).  Unstable poles and repeated complex pairs raise NotImplementedError.
         """
         num = np.atleast_1d(np.asarray(self.num, dtype=float))
         den = np.atleast_1d(np.asarray(self.den, dtype=float))
@@ -75,19 +86,28 @@ class TransferFunction(signal.TransferFunction):
         stable = p[~zero]
         if np.any(np.real(stable) >= 0):
             raise NotImplementedError("unstable pole in channel")
-        if len(stable) > 1 and np.min(np.abs(np.subtract.outer(stable, stable))
-                                       + np.eye(len(stable)) * 1e9) <= pole_tol:
-            raise NotImplementedError("repeated poles are not supported")
-        # scipy.signal.residue orders repeated roots by ascending power: r/(s-p), r/(s-p)^2
+        # scipy.signal.residue orders repeated roots by ascending power: r/(s-p), r/(s-p)^2, ...
         rz = np.real(r[zero])
         d0 = float(rz[0]) if nzero >= 1 else 0.0
         di = float(rz[1]) if nzero == 2 else 0.0
         modes = []
-        for rr, pp in zip(r[~zero], stable):
-            if abs(pp.imag) <= pole_tol:
-                modes.append((float(np.real(rr)), float(np.real(pp))))
+        rs, ps = list(r[~zero]), list(stable)
+        rep_tol = 1e-6                              # residue() groups roots closer than its own tolerance (1e-3)
+        k = 0
+        while k < len(ps):
+            pp = ps[k]
+            mult = 1
+            while k + mult < len(ps) and abs(ps[k + mult] - pp) <= rep_tol * max(1.0, abs(pp)):
+                mult += 1
+            if mult > 1:
+                if abs(pp.imag) > pole_tol:
+                    raise NotImplementedError("repeated complex-conjugate poles are not supported")
+                modes.append((('jordan', [float(np.real(c)) for c in rs[k:k + mult]]), float(np.real(pp))))
+            elif abs(pp.imag) <= pole_tol:
+                modes.append((float(np.real(rs[k])), float(np.real(pp))))
             elif pp.imag > 0:                       # one entry per conjugate pair
-                modes.append((complex(rr), complex(pp)))
+                modes.append((complex(rs[k]), complex(pp)))
+            k += mult
         return d0, modes, di
 
 
@@ -112,18 +132,26 @@ class OPOM(object):
         coeffs = [[Hm[i, j].step_coefficients() for j in range(nu)] for i in range(ny)]
 
         def n_states(modes):
-            return sum(2 if isinstance(mm[1], complex) else 1 for mm in modes)
+            return sum(2 if isinstance(mm[1], complex) else (len(mm[0][1]) if isinstance(mm[0], tuple) else 1)
+                       for mm in modes)
         self.na = max(1, max(n_states(coeffs[i][j][1]) for i in range(ny) for j in range(nu)))
         na = self.na
         self.nd = ny * nu * na
 
+        # Dead time theta = (l + f) Ts, 0 <= f < 1: a move made at sample k first shows at sample k + l + 1, by
+        # then tau_e = (l + 1) Ts - theta in (0, Ts] has elapsed since the dead time ran out (tau_e = Ts for a
+        # dead time that is a multiple of Ts).  The move enters the states when it is l samples old, with the
+        # step-response terms evaluated at tau_e.
         theta = np.zeros((ny, nu), dtype=int)
+        self.tau_e = np.full((ny, nu), float(Ts))
         for i in range(ny):
             for j in range(nu):
                 th = Hm[i, j].delay / Ts
-                if abs(th - round(th)) > 1e-9:
-                    raise NotImplementedError("dead time must be an integer multiple of Ts")
-                theta[i, j] = int(round(th))
+                if th < -1e-12:
+                    raise ValueError("negative dead time")
+                l = int(np.floor(th + 1e-9))
+                theta[i, j] = l
+                self.tau_e[i, j] = (l + 1) * Ts - Hm[i, j].delay if abs(th - l) > 1e-9 else float(Ts)
         self.theta = theta
         self.theta_max = int(theta.max())
         self.nz = self.theta_max * nu
@@ -143,25 +171,39 @@ class OPOM(object):
                 self.D0[i, j] = d0
                 self.Di[i, j] = di
                 a = 0
+                te = self.tau_e[i, j]
                 for dd, r in modes:
                     idx = (i * nu + j) * na + a
                     if isinstance(r, complex):
                         f = np.exp(r * Ts)
                         self.F[idx:idx + 2, idx:idx + 2] = [[f.real, -f.imag], [f.imag, f.real]]
-                        g = dd * f
+                        g = dd * np.exp(r * te)
                         self._bd[idx], self._bd[idx + 1] = g.real, g.imag
                         self.Psi[i, idx] = 2.0
                         self.R[idx] = self.R[idx + 1] = r.real
                         a += 2
+                    elif isinstance(dd, tuple):
+                        # repeated real pole: states w_k(t) = sum_{q>=k} c_q t^(q-k) e^{rt}/(q-k)!  (w_0 = the
+                        # response term); over one sample w <- e^{r Ts} sum_n (Ts^n/n!) shift^n w
+                        c = dd[1]
+                        mlt = len(c)
+                        for k in range(mlt):
+                            for q in range(k, mlt):
+                                self.F[idx + k, idx + q] = np.exp(r * Ts) * Ts ** (q - k) / math.factorial(q - k)
+                                self._bd[idx + k] += c[q] * te ** (q - k) * np.exp(r * te) / math.factorial(q - k)
+                            self.R[idx + k] = r
+                        self.Dd[idx] = c[0]
+                        self.Psi[i, idx] = 1.0
+                        a += mlt
                     else:
                         f = np.exp(r * Ts)
                         self.Dd[idx] = dd
                         self.R[idx] = r
                         self.F[idx, idx] = f
-                        self._bd[idx] = dd * f
+                        self._bd[idx] = dd * np.exp(r * te)
                         self.Psi[i, idx] = 1.0
                         a += 1
-                # states of this channel that no mode uses keep F = 0, Psi = 1 (they stay at zero)
+                # states of this channel that no mode uses keep F = 0 (they stay at zero)
                 for a2 in range(a, na):
                     self.Psi[i, (i * nu + j) * na + a2] = 1.0
         self.N = np.zeros((self.nd, nu))
@@ -178,7 +220,7 @@ class OPOM(object):
         """(Bs_l, Bd_l, Bi_l): how a move that is ``l`` samples old enters xs, xd, xi."""
         ny, nu, na, Ts = self.ny, self.nu, self.na, self.Ts
         mask = (self.theta == l)
-        Bs = np.where(mask, self.D0 + Ts * self.Di, 0.0)
+        Bs = np.where(mask, self.D0 + self.tau_e * self.Di, 0.0)
         Bi = np.where(mask, self.Di, 0.0)
         Bd = np.zeros((self.nd, nu))
         for i in range(ny):

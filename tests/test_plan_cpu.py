@@ -60,6 +60,50 @@ def test_opom_complex_poles_match_continuous_step_responses():
             assert np.max(np.abs(y[:, i] - ref)) <= 1e-12
 
 
+def test_opom_repeated_poles_and_fractional_dead_times():
+    """OPOM generality: repeated real poles (Jordan block in F) and dead times that
+    are not a multiple of Ts (step-response terms evaluated at the fraction of the sample left after the dead time)
+    against the analytic step responses at the sample instants."""
+    from sihmpc_b200.opom import OPOM, TransferFunction
+    # double pole: K/(tau s + 1)^2 e^{-2s}
+    K, tau, th = 2.0, 5.0, 2.0
+    o = OPOM([[TransferFunction([K], [tau * tau, 2 * tau, 1.0], delay=th)]], 1.0)
+    assert o.na == 2 and o.nx == 2 + 2 + 2
+    t = np.maximum(np.arange(41) - th, 0)
+    assert np.max(np.abs(o.step_response(40)[:, 0] - K * (1 - np.exp(-t / tau) * (1 + t / tau)))) < 1e-13
+    # triple pole
+    den = np.polymul(np.polymul([3, 1], [3, 1]), [3, 1])
+    o = OPOM([[TransferFunction([1.0], den, delay=1.0)]], 1.0)
+    a = np.maximum(np.arange(41) - 1.0, 0) / 3
+    assert o.na == 3 and np.max(np.abs(o.step_response(40)[:, 0] - (1 - np.exp(-a) * (1 + a + a * a / 2)))) < 1e-13
+    # fractional dead time, first order: first visible sample is ceil(theta/Ts)
+    K, tau, th = 1.5, 4.0, 2.5
+    o = OPOM([[TransferFunction([K], [tau, 1.0], delay=th)]], 1.0)
+    t = np.arange(31) - th
+    ya = np.where(t > 0, K * (1 - np.exp(-np.maximum(t, 0) / tau)), 0.0)
+    assert o.theta_max == 2 and abs(o.tau_e[0, 0] - 0.5) < 1e-15
+    assert np.max(np.abs(o.step_response(30)[:, 0] - ya)) < 1e-13
+    # fractional dead time on an integrating channel, Ts = 0.5
+    o = OPOM([[TransferFunction([0.3], [2.0, 1.0, 0.0], delay=0.4)]], 0.5)
+    t = np.arange(31) * 0.5 - 0.4
+    tt = np.maximum(t, 0)
+    assert np.max(np.abs(o.step_response(30)[:, 0] - np.where(t > 0, 0.3 * (tt - 2.0 * (1 - np.exp(-tt / 2.0))), 0.0))) < 1e-12
+    # a 2x2 plant mixing both with plain channels compiles into a controller plan whose prediction is the oracle's
+    h = [[TransferFunction([12.8], [16.7, 1], delay=1), TransferFunction([-18.9], [21.0, 1], delay=3.3)],
+         [TransferFunction([6.6], np.polymul([10.9, 1], [10.9, 1]), delay=7), TransferFunction([-19.4], [14.4, 1], delay=3)]]
+    s = OPOM(h, 1.0)
+    assert s.nx == 2 * 2 + 2 * 2 * 2 + 7 * 2
+    c = sc.declare_distillation(IHMPCController, s)
+    orc = sc.declare_distillation(OracleIHMPC, s)
+    p = c.compile()
+    rng = np.random.default_rng(5)
+    x = rng.normal(size=s.nx) * 0.1; x[s.ny + s.nd:2 * s.ny + s.nd] = 0.0
+    dU = rng.normal(size=p.nv) * 0.05
+    xi = orc._xi(np.concatenate([dU, np.zeros(2 * s.ny)]), x, np.zeros(s.nu), np.zeros(s.ny))
+    ypred = np.concatenate([Yk @ xi for Yk in orc.Y_pred])
+    assert np.max(np.abs(p.Myx @ x + p.Myu @ dU - ypred)) < 1e-12
+
+
 def test_plan_with_complex_poles_reproduces_oracle_problem():
     """The compiled plan of a controller on the under-damped plant == the oracle's un-condensed problem."""
     from oracle.ihmpc_oracle import OracleIHMPC
