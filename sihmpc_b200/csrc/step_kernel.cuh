@@ -380,25 +380,38 @@ ihmpc_step_kernel(const DevPlan P_in, const sihmpc_io io, const long long batch,
             for (int r = lane; r < R; r += 32) cbuf2[r] = om[r] * e[r];
             __syncwarp();
             for (int c = lane; c < nv; c += 32) f[c] = 2.0 * strided_dot(P.E + c, nv, cbuf2, R, 0.0);
-            // Hessian, lower triangle
-            {
+            // Hessian, lower triangle (+ reg on the diagonal); returns the largest diagonal entry
+            auto build_hessian = [&](const double reg) {
+                double hmax = 0.0;
                 int i = 0, j = lane;
                 while (j >= nv) { j -= nv; ++i; }
                 const int nn = nv * nv;
                 for (int idx = lane; idx < nn; idx += 32) {
                     if (j <= i) {
                         double h = strided_dot(P.HJ + idx, nn, pw_hj, P.mh, P.Ht[idx]);
-                        if (i == j) h += 2.0 * omdu[i];
+                        if (i == j) { h += 2.0 * omdu[i] + reg; hmax = fmax(hmax, h); }
                         Ls[i * ld + j] = h;
                     }
                     j += 32;
                     while (j >= nv) { j -= nv; ++i; }
                 }
-            }
-            __syncwarp();
+                __syncwarp();
+                return warp_max(hmax);
+            };
+            const double hdiag = build_hessian(0.0);
 
             // ---------------- K2: factor and solve
-            if (warp_cholesky<NVR>(Ls, ld, nv, dinv, lane)) status |= SIHMPC_ST_NOTPD;
+            // A pivot <= 0 is flagged (SIHMPC_ST_NOTPD).  It happens without a positive move weight -- and, in FP64, in
+            // closed loops that diverge (plant-model mismatch: weights from 1e-9 to 1e6 in one Hessian, condition
+            // 1e15); rather than stepping on with NaN the flagged scenario is solved with a diagonal shift that
+            // grows until the factorisation goes through.
+            if (warp_cholesky<NVR>(Ls, ld, nv, dinv, lane)) {
+                status |= SIHMPC_ST_NOTPD;
+                for (double rel = 1e-12; rel <= 1.0; rel *= 100.0) {
+                    build_hessian(rel * fmax(hdiag, 1e-300));
+                    if (!warp_cholesky<NVR>(Ls, ld, nv, dinv, lane)) break;
+                }
+            }
             double acc[NVR];
             load_acc<NVR>(acc, f, nv, lane, -1.0);
             warp_trsv_lower<NVR>(Ls, ld, dinv, nv, acc, lane);
