@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SIHMPC_ABI_VERSION 1
+#define SIHMPC_ABI_VERSION 2
 
 /* error codes */
 #define SIHMPC_OK            0
@@ -106,6 +106,9 @@ typedef struct sihmpc_plan_desc {
     const double *D;                 /* [ny][nu]                                                 */
     const double *Phi;               /* [N*nx][nx]  X_pred = Phi x + Gam dU; NULL: sihmpc_predict */
     const double *Gam;               /* [N*nx][nv]  cannot return x_pred                          */
+    int32_t n_extra;                 /* terminal residual RANGES (rslb != rsub / rilb != riub, ihmpccontroller.py:441-449):
+                                        one decision variable per ranged residual after the N*nu moves; every `nv`
+                                        above is then N*nu + n_extra wide, the range itself is a dense row (Gc).  0: none */
 } sihmpc_plan_desc;
 
 /* Per-call I/O.  DEVICE pointers; [batch][feature] FP64 unless noted; NULL = not wanted. */

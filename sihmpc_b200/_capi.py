@@ -11,7 +11,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SIHMPC_B200_LIB") or os.path.join(HERE, "libsihmpc_b200.so")   # override: A/B builds only
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 F_ADVANCE, F_UPDATE_VIN, F_WEIGHTS_SAT2, F_WEIGHTS_SAT1 = 1, 2, 4, 8
 ST_MAXITER, ST_INFEASIBLE, ST_NOTPD, ST_ACTIVE_UNSUPPORTED = 1, 2, 4, 8
 NSTATS_EXTRA = 5
@@ -35,6 +35,7 @@ class PlanDesc(C.Structure):
         ("gc_vin", _ip), ("gc_q", _dp), ("vin_row", _ip), ("vin_q", _dp),
         ("pl_rowptr", _ip), ("pl_col", _ip), ("pl_val", _dp),
         ("C", _dp), ("D", _dp), ("Phi", _dp), ("Gam", _dp),
+        ("n_extra", C.c_int32),
     ]
 
 
@@ -152,5 +153,5 @@ def make_desc(plan):
         Gc=d(plan.Gc), Gcx=d(plan.Gcx), Gcy=d(plan.Gcy), gc0=d(plan.gc0), Lc=d(plan.Lc), Uc=d(plan.Uc),
         gc_vin=i(plan.gc_vin), gc_q=d(plan.gc_q), vin_row=i(plan.vin_row), vin_q=d(plan.vin_q),
         pl_rowptr=i(plan.pl_rowptr), pl_col=i(plan.pl_col), pl_val=d(plan.pl_val),
-        C=d(plan.C), D=d(plan.D), Phi=d(plan.Phi), Gam=d(plan.Gam))
+        C=d(plan.C), D=d(plan.D), Phi=d(plan.Phi), Gam=d(plan.Gam), n_extra=int(getattr(plan, 'n_extra', 0)))
     return desc, keep

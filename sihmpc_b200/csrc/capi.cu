@@ -126,7 +126,7 @@ int configure(sihmpc_plan *p) {
         p->scratch_in_smem = 1;
         p->smem_bytes += sbytes * wpb;
     }
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes));
+    CUDA_TRY(sih_raise_smem_limit(reinterpret_cast<const void *>(kern), p->smem_bytes));
     int occ = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpb * 32, p->smem_bytes));
     if (occ < 1) return fail(SIHMPC_E_INVALID, "step kernel cannot be resident (registers/shared memory)%s");
@@ -199,8 +199,9 @@ int sihmpc_plan_create(const sihmpc_plan_desc *d, sihmpc_plan **out) {
     if (d->nx < 1 || d->nu < 1 || d->ny < 1 || d->N < 1 || d->m < 1 || d->R < 1 || d->nd < 0 ||
         d->mh < 0 || d->ncd < 0 || d->n_vin < 0 || d->pl_nnz < 1)
         return fail(SIHMPC_E_INVALID, "bad dimension in plan descriptor%s");
-    const int nv = d->N * d->nu;
-    if (nv > 64) return fail(SIHMPC_E_INVALID, "N*nu > 64 is not supported by the step kernel%s");
+    if (d->n_extra < 0) return fail(SIHMPC_E_INVALID, "negative n_extra%s");
+    const int nv = d->N * d->nu + d->n_extra;
+    if (nv > 64) return fail(SIHMPC_E_INVALID, "N*nu + n_extra > 64 is not supported by the step kernel%s");
     if (d->R != d->N * d->ny + 2 * d->ny + d->nd) return fail(SIHMPC_E_INVALID, "R must be N*ny+2*ny+nd%s");
     int ndev = sihmpc_device_count();
     if (ndev < 1) return fail(SIHMPC_E_CUDA, "no CUDA device: this library has no CPU fallback%s");
@@ -219,11 +220,11 @@ int sihmpc_plan_create(const sihmpc_plan_desc *d, sihmpc_plan **out) {
 
     DevPlan &P = p->d;
     memset(&P, 0, sizeof P);
-    P.nx = d->nx; P.nu = d->nu; P.ny = d->ny; P.nd = d->nd; P.N = d->N; P.nv = nv; P.m = d->m;
+    P.nx = d->nx; P.nu = d->nu; P.ny = d->ny; P.nd = d->nd; P.N = d->N; P.nv = nv; P.nvm = d->N * d->nu; P.m = d->m;
     P.mh = d->mh; P.R = d->R; P.ncd = d->ncd; P.n_vin = d->n_vin; P.pl_nnz = d->pl_nnz;
     P.Ny = d->N * d->ny; P.o_sy = P.Ny; P.o_si = P.Ny + d->ny; P.o_t = P.Ny + 2 * d->ny;
     P.ld = nv | 1; P.Ts = d->Ts;
-    p->nw = nv + 2 * d->ny;
+    p->nw = d->N * d->nu + 2 * d->ny;
     P.has_box = any_finite(d->dulb, d->nu) || any_finite(d->duub, d->nu);
     P.has_cum = any_finite(d->ulb, d->nu) || any_finite(d->uub, d->nu);
     P.eval_term = 0;
@@ -624,7 +625,7 @@ int sihmpc_subobjectives(sihmpc_plan *plan, const double *x, const double *w, co
     const size_t per = (size_t)(P.nx + P.nv + P.ny + 2 * P.ny + P.R + P.nv + P.m + 8) * 8;
     const size_t smem = per * wpb;
     if (smem > 200 * 1024) return fail(SIHMPC_E_INVALID, "controller too large%s");
-    CUDA_TRY(cudaFuncSetAttribute(sih::subobjectives_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(sih_raise_smem_limit(reinterpret_cast<const void *>(sih::subobjectives_kernel), smem));
     long long blocks = (batch + wpb - 1) / wpb;
     if (blocks > plan->sm_count * 8) blocks = plan->sm_count * 8;
     sih::subobjectives_kernel<<<(int)blocks, wpb * 32, smem, static_cast<cudaStream_t>(stream)>>>(
@@ -661,10 +662,10 @@ static int log_launch(sihmpc_plan *plan, const sihmpc_io &io, const double *w0, 
     if (blocks > plan->sm_count * 4) blocks = plan->sm_count * 4;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (plan->d.nv + 1 <= 32) {
-        CUDA_TRY(cudaFuncSetAttribute(sih::ihmpc_log_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(sih_raise_smem_limit(reinterpret_cast<const void *>(sih::ihmpc_log_kernel<1>), smem));
         sih::ihmpc_log_kernel<1><<<(int)blocks, wpb * 32, smem, st>>>(plan->d, io, w0, w_warm, batch, n_steps, iters, 100);
     } else {
-        CUDA_TRY(cudaFuncSetAttribute(sih::ihmpc_log_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(sih_raise_smem_limit(reinterpret_cast<const void *>(sih::ihmpc_log_kernel<2>), smem));
         sih::ihmpc_log_kernel<2><<<(int)blocks, wpb * 32, smem, st>>>(plan->d, io, w0, w_warm, batch, n_steps, iters, 100);
     }
     CUDA_TRY(cudaGetLastError());

@@ -4,10 +4,14 @@
 // bank-conflict free once staged); the suffix T marks those copies.
 #pragma once
 #include <stdint.h>
+#include <cuda_runtime.h>
+#include <map>
+#include <mutex>
 #include "../../include/sihmpc_b200.h"
 
 struct DevPlan {
     int nx, nu, ny, nd, N, nv, m, mh, R, ncd, n_vin, pl_nnz;
+    int nvm;             // N*nu: the moves among the nv decision variables (nv - nvm = ranged terminal residuals)
     int Ny;              // N*ny
     int o_sy, o_si, o_t; // residual row offsets
     int has_box, has_cum;
@@ -76,4 +80,18 @@ __host__ __device__ inline WarpLayout make_layout(const DevPlan &P) {
 __host__ __device__ inline size_t scratch_doubles_per_warp(int nv) {
     size_t lds = (size_t)(nv | 1);
     return (size_t)nv * nv + 2 * (size_t)nv * lds + 3 * (size_t)nv + 8;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the KERNEL, not to a plan: two live plans served by the
+// same instantiation (the controller's hot plan and its evaluation plan, two shapes with the same tile-row count)
+// must not lower each other's limit -- it is only ever raised.
+inline cudaError_t sih_raise_smem_limit(const void *func, size_t bytes) {
+    static std::mutex mu;
+    static std::map<const void *, size_t> limit;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = limit.find(func);
+    if (it != limit.end() && it->second >= bytes) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) limit[func] = bytes;
+    return e;
 }

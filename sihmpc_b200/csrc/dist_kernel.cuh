@@ -692,7 +692,7 @@ constexpr int QUAD_WARPS = 4;
 constexpr int QUAD_MINB = SIH_QUAD_MINB;
 
 inline int quad_match_shape(const DevPlan &P) {
-    if (P.nx == 22 && P.nu == 2 && P.ny == 2 && P.nd == 4 && P.N == 10 && P.m == 4 && P.ncd == 0) return 0;
+    if (P.nx == 22 && P.nu == 2 && P.ny == 2 && P.nd == 4 && P.N == 10 && P.m == 4 && P.ncd == 0 && P.nv == P.nvm) return 0;
     return -1;
 }
 
@@ -845,7 +845,7 @@ inline cudaError_t quad_configure(const sihmpc_plan_desc *d, const DevPlan &P, Q
     if (e != cudaSuccess) return e;
     qp->smem_bytes = quad_smem_bytes<D>(qp->qc);
     auto kern = quad_step_kernel<D, QUAD_WARPS, QUAD_MINB>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qp->smem_bytes);
+    e = sih_raise_smem_limit(reinterpret_cast<const void *>(kern), qp->smem_bytes);
     if (e != cudaSuccess) return e;
     int occ = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, QUAD_WARPS * 32, qp->smem_bytes);

@@ -840,7 +840,8 @@ inline std::vector<int> mma_dead_variables(const DevPlan &P, const sihmpc_plan_d
 inline int mma_match_shape(const DevPlan &P, const sihmpc_plan_desc *d) {
     for (int i = 0; i < P.nx; ++i)
         if (d->pl_rowptr[i + 1] - d->pl_rowptr[i] > 4) return -1;      // ELL width of the fast path
-    if (P.nx == 22 && P.nu == 2 && P.ny == 2 && P.nd == 4 && P.N == 10 && P.m == 4 && P.ncd == 0 && P.mh <= 3) {
+    if (P.nx == 22 && P.nu == 2 && P.ny == 2 && P.nd == 4 && P.N == 10 && P.m == 4 && P.ncd == 0 && P.mh <= 3 &&
+        P.nv == P.nvm) {
         if (getenv("SIHMPC_NO_PRESOLVE")) return 0;
         return mma_dead_variables(P, d).size() >= 4 ? 1 : 0;
     }
@@ -1097,8 +1098,8 @@ inline cudaError_t mma_configure_shape(const sihmpc_plan_desc *d, const DevPlan 
     if (qp->smem_bytes > 227 * 1024) { qp->shape = -1; return cudaSuccess; }
     auto kern = mma_step_kernel<D, MMA_WARPS, MMA_MINB, 0>;
     auto kern_resume = mma_step_kernel<D, MMA_WARPS, MMA_MINB, 1>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qp->smem_bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern_resume, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qp->smem_bytes);
+    e = sih_raise_smem_limit(reinterpret_cast<const void *>(kern), qp->smem_bytes);
+    if (e == cudaSuccess) e = sih_raise_smem_limit(reinterpret_cast<const void *>(kern_resume), qp->smem_bytes);
     if (e != cudaSuccess) return e;
     int occ = 0, occ_r = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, MMA_WARPS * 32, qp->smem_bytes);

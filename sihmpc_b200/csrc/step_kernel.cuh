@@ -176,15 +176,15 @@ __device__ __forceinline__ void scan_check(double val, double lo, double hi, int
 __device__ RowScan scan_rows(const DevPlan &P, const double *v, const double *uu,
                              const double *glo, const double *ghi, int lane) {
     RowScan b; b.rel = 0.0; b.abs = 0.0; b.code = -1;
-    const int nv = P.nv, nu = P.nu;
+    const int nv = P.nv, nu = P.nu, nvm = P.nvm;
     if (P.has_box) {
-        for (int i = lane; i < nv; i += 32) {
+        for (int i = lane; i < nvm; i += 32) {
             const int j = i % nu;
             scan_check(v[i], P.dulb[j], P.duub[j], i, b);
         }
     }
     if (P.has_cum) {
-        for (int i = lane; i < nv; i += 32) {
+        for (int i = lane; i < nvm; i += 32) {
             const int j = i % nu;
             double val = 0.0;
             for (int c = j; c <= i; c += nu) val += v[c];
@@ -668,11 +668,11 @@ ihmpc_step_kernel(const DevPlan P_in, const sihmpc_io io, const long long batch,
                 // results of the step, before any in-place advance
                 if (io.du) for (int j = lane; j < nu; j += 32) io.du[s * nu + j] = v[j];
                 if (io.w_opt) {
-                    const int nw = nv + 2 * ny;
-                    for (int i = lane; i < nv; i += 32) io.w_opt[s * nw + i] = v[i];
+                    const int nvm = P.nvm, nw = nvm + 2 * ny;
+                    for (int i = lane; i < nvm; i += 32) io.w_opt[s * nw + i] = v[i];
                     for (int i = lane; i < ny; i += 32) {
-                        io.w_opt[s * nw + nv + i] = e[P.o_sy + i];
-                        io.w_opt[s * nw + nv + ny + i] = e[P.o_si + i];
+                        io.w_opt[s * nw + nvm + i] = e[P.o_sy + i];
+                        io.w_opt[s * nw + nvm + ny + i] = e[P.o_si + i];
                     }
                 }
                 if (lane == 0) {
@@ -724,7 +724,7 @@ ihmpc_step_kernel(const DevPlan P_in, const sihmpc_io io, const long long batch,
                 }
                 for (int i = lane; i < nx; i += 32) xin[i] = xnew[i];
                 // shifted plan (ihmpccontroller.py:538-541) into f
-                for (int i = lane; i < nv; i += 32) f[i] = (i + nu < nv) ? v[i + nu] : 0.0;
+                for (int i = lane; i < nv; i += 32) f[i] = (i + nu < P.nvm) ? v[i + nu] : 0.0;
                 __syncwarp();
                 if (io.flags & (SIHMPC_F_WEIGHTS_SAT2 | SIHMPC_F_WEIGHTS_SAT1)) {
                     eval_subobjectives(P, xin, f, ysp, sy, om, omdu, vn, lane);
@@ -792,7 +792,7 @@ __global__ void predict_kernel(const DevPlan P, const double *__restrict__ x, co
     const int lane = threadIdx.x & 31;
     const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    const int nx = P.nx, nv = P.nv, nu = P.nu, Nx = P.N * P.nx, Ny = P.Ny;
+    const int nx = P.nx, nv = P.nvm, nu = P.nu, Nx = P.N * P.nx, Ny = P.Ny;      // dU: the N*nu moves
     for (long long s = gw; s < batch; s += nwarps) {
         const double *xs = x + s * nx, *dv = dU + s * nv;
         if (x_pred)

@@ -639,8 +639,8 @@ tile_step_kernel(const DevPlan P, const TileCfg C, const sihmpc_io io, const lon
 #define SIH_TL_CAT(a, b) SIH_TL_CAT2(a, b)
 #ifdef SIH_TL_ONLY_NT
 cudaError_t SIH_TL_CAT(tile_set_smem_, SIH_TL_ONLY_NT)(size_t bytes) {
-    cudaError_t e = cudaFuncSetAttribute(tile_step_kernel<SIH_TL_ONLY_NT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    return e != cudaSuccess ? e : cudaFuncSetAttribute(tile_step_kernel<SIH_TL_ONLY_NT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    cudaError_t e = sih_raise_smem_limit(reinterpret_cast<const void *>(tile_step_kernel<SIH_TL_ONLY_NT, 0>), bytes);
+    return e != cudaSuccess ? e : sih_raise_smem_limit(reinterpret_cast<const void *>(tile_step_kernel<SIH_TL_ONLY_NT, 1>), bytes);
 }
 // mode 0: first pass (appends to `list`, counts in `counter`); mode 1: resume pass over `list` (n_list scenarios,
 // known on the device only: blocks beyond it leave at once), failures counted in `counter`
@@ -725,7 +725,7 @@ inline int tl_stride(int n) { int s = (n + 3) & ~3; while (s % 16 != 4) s += 4; 
 cudaError_t tile_configure(const sihmpc_plan_desc *d, const DevPlan &P, TilePlan *tp) {
     memset(tp, 0, sizeof *tp);
     const int nx = d->nx, nu = d->nu, ny = d->ny, nv = P.nv, m = d->m, R = d->R, Ny = P.Ny, N = d->N;
-    if (nv + 1 > 8 * TL_NTMAX || d->ncd > 0 || P.eval_term) return cudaSuccess;
+    if (nv + 1 > 8 * TL_NTMAX || d->ncd > 0 || P.eval_term || P.nv != P.nvm) return cudaSuccess;
     TileCfg &C = tp->cfg;
     C.NT = (nv + 1 + 7) / 8; C.NP = (nv + 3) / 4; C.Ib = nv / 8; C.rb = nv % 8;
     const int ntiles = C.NT * (C.NT + 1) / 2;

@@ -285,20 +285,19 @@ class IHMPCController(object):
     # ------------------------------------------------------------------ plan / device objects
     def _bounds(self):
         return dict(xlb=self.xlb, xub=self.xub, ulb=self.ulb, uub=self.uub, dulb=self.dulb, duub=self.duub,
-                    sylb=self.sylb, syub=self.syub, silb=self.silb, siub=self.siub)
+                    sylb=self.sylb, syub=self.syub, silb=self.silb, siub=self.siub,
+                    rslb=self.rslb, rilb=self.rilb)
 
     def compile(self):
         """Condense the declarations into the constant blocks of the device step (once)."""
         if not self._dirty and self._plan is not None:
             return self._plan
-        for lo, hi, nm in ((self.rslb, self.rsub, 'rs'), (self.rilb, self.riub, 'ri')):
-            if not np.array_equal(np.asarray(lo, float), np.asarray(hi, float)):
-                raise NotImplementedError("terminal residual ranges (%slb != %sub) are not supported yet" % (nm, nm))
         if not self.VJ:
             raise ValueError("no weighted sub-objective declared")
         self._plan = compile_plan(self.sys, self.N, [V.coeff for V in self.VJ], self._bounds(),
                                   Q_bar=self.Q_bar, vin=self._vin,
-                                  rs=np.asarray(self.rslb, float), ri=np.asarray(self.rilb, float))
+                                  rs=np.asarray(self.rslb, float), ri=np.asarray(self.rilb, float),
+                                  rs_hi=np.asarray(self.rsub, float), ri_hi=np.asarray(self.riub, float))
         self._eval_plan = None
         self._stepper = None
         self._eval_dp = None

@@ -80,6 +80,11 @@ class Plan:
     Gam: np.ndarray = field(default=None, repr=False)      # (N*nx, nv)
     Q_bar: np.ndarray = None
     row_slices: dict = None
+    # terminal residual RANGES (ctl.py:441-449 with lb != ub): one extra decision variable per ranged residual,
+    # appended after the N*nu moves (every block with a `nv` dimension is nv + n_extra wide); extra[k] =
+    # ('s'|'i', output index)
+    n_extra: int = 0
+    extra: tuple = ()
 
 
 def plant_csr(A, B, pattern=None):
@@ -112,7 +117,14 @@ def _psd_factor(Q):
     return V * np.sqrt(lam)[None, :]
 
 
-def compile_plan(sys, N, VJ, bounds, Q_bar=None, vin=(), rs=None, ri=None):
+def bounds_rs(kind, i, rs_hi, ri_hi, bounds):
+    """(lb, ub) of the ranged terminal residual (kind 's': res2 = xs(N)-ysp-syN, 'i': res1 = xi(N)-siN)."""
+    lo = np.asarray(bounds['rslb' if kind == 's' else 'rilb'], float).reshape(-1)[i]
+    hi = (rs_hi if kind == 's' else ri_hi)[i]
+    return float(lo), float(hi)
+
+
+def compile_plan(sys, N, VJ, bounds, Q_bar=None, vin=(), rs=None, ri=None, rs_hi=None, ri_hi=None):
     """Build the Plan.
 
     sys    : OPOM-like object (attributes A,B,C,D,Ts,nx,nu,ny,nd,nz).
@@ -120,14 +132,26 @@ def compile_plan(sys, N, VJ, bounds, Q_bar=None, vin=(), rs=None, ri=None):
     bounds : dict with the constructor's bound vectors (ctl.py:38-53).
     Q_bar  : terminal weight (nd x nd) or None when no terminal objective was set.
     vin    : list of (output index, q) for the siN contraction rows, slot order (ctl.py:265-269).
+    rs, ri : lower ends of the terminal residual bounds rslb, rilb (ctl.py:50-53); rs_hi, ri_hi the upper ends.
+             Where they coincide (the default, 0) the residual is an equality and syN / siN are eliminated:
+             syN = xs(N) - ysp - rs, siN = xi(N) - ri.  Where lb != ub the residual rho in [lb, ub] becomes a
+             decision variable of its own: syN = xs(N) - ysp - rho_s, siN = xi(N) - rho_i (ctl.py:441-449), appended
+             after the moves with its range as a dense row.
     """
     A = np.asarray(sys.A, float); B = np.asarray(sys.B, float)
     C = np.asarray(sys.C, float); D = np.asarray(sys.D, float)
     nx, nu, ny, nd = int(sys.nx), int(sys.nu), int(sys.ny), int(sys.nd)
     N = int(N); nv = N * nu; Ts = float(sys.Ts)
     s0, d0, i0 = 0, ny, ny + nd
-    rs = np.zeros(ny) if rs is None else np.asarray(rs, float)
-    ri = np.zeros(ny) if ri is None else np.asarray(ri, float)
+    rs = np.zeros(ny) if rs is None else np.asarray(rs, float).copy()
+    ri = np.zeros(ny) if ri is None else np.asarray(ri, float).copy()
+    rs_hi = rs.copy() if rs_hi is None else np.asarray(rs_hi, float)
+    ri_hi = ri.copy() if ri_hi is None else np.asarray(ri_hi, float)
+    extra = [('s', i) for i in range(ny) if rs_hi[i] != rs[i]] + [('i', i) for i in range(ny) if ri_hi[i] != ri[i]]
+    n_extra = len(extra)
+    for kind, i in extra:                    # a ranged residual carries no constant offset: it is the variable
+        (rs if kind == 's' else ri)[i] = 0.0
+    nvm = nv                                 # moves
 
     # closed-form prediction matrices  X_pred[k] = A^{k+1} x + sum_{j<=k} A^{k-j} B dU_j
     Apow = [np.eye(nx)]
@@ -170,6 +194,18 @@ def compile_plan(sys, N, VJ, bounds, Q_bar=None, vin=(), rs=None, ri=None):
         Lbar = _psd_factor(np.asarray(Q_bar, float))
         E[o_t:o_t + nd] = Lbar.T @ xdu
         Px[o_t:o_t + nd] = Lbar.T @ xdx
+    if n_extra:
+        # widen every move-indexed block by the residual variables: r_y += rho_s + tau rho_i, syN -= rho_s, siN -= rho_i
+        nv = nvm + n_extra
+        Ex = np.zeros((R, n_extra))
+        for c, (kind, i) in enumerate(extra):
+            for k in range(N):
+                Ex[k * ny + i, c] = 1.0 if kind == 's' else tau[k]
+            Ex[(o_sy if kind == 's' else o_si) + i, c] = -1.0
+        E = np.hstack([E, Ex])
+        Myu = np.hstack([Myu, np.zeros((N * ny, n_extra))])
+        Mi1u = np.hstack([Mi1u, np.zeros((ny, n_extra))])
+        Gam = np.hstack([Gam, np.zeros((N * nx, n_extra))])
 
     m = len(VJ)
     Wrow = np.zeros((R, m)); w0row = np.zeros(R); Wdu = np.zeros((nv, m))
@@ -182,7 +218,7 @@ def compile_plan(sys, N, VJ, bounds, Q_bar=None, vin=(), rs=None, ri=None):
             Wrow[o_si + ind, i] = V.csi[ind]
         for k in range(N):
             for j in range(nu):
-                Wdu[k * nu + j, i] = V.cdu[j]
+                Wdu[k * nu + j, i] = V.cdu[j]                # (rows of the residual variables stay zero)
     if Q_bar is not None:
         w0row[o_t:o_t + nd] = 1.0
 
@@ -216,6 +252,10 @@ def compile_plan(sys, N, VJ, bounds, Q_bar=None, vin=(), rs=None, ri=None):
         vin_row.append(o_si + ind); vin_q.append(float(q))
         if q > 0:
             rows.append((E[o_si + ind], Px[o_si + ind], Py[o_si + ind], e0[o_si + ind], -INF, INF, slot, float(q)))
+    for c, (kind, i) in enumerate(extra):                       # lb <= rho <= ub
+        unit = np.zeros(nv); unit[nvm + c] = 1.0
+        lo_, hi_ = (bounds_rs(kind, i, rs_hi, ri_hi, bounds))
+        rows.append((unit, np.zeros(nx), np.zeros(ny), 0.0, lo_, hi_, -1, 0.0))
     # rows whose normal vanishes cannot be influenced by dU: vacuous or infeasible whatever
     # the solver does (non-integrating plants: xi(N) = xi(0)); they are not sent to the device.
     rows = [r for r in rows if np.linalg.norm(r[0]) > 1e-13 * max(1.0, np.linalg.norm(r[1]))]
@@ -231,7 +271,8 @@ def compile_plan(sys, N, VJ, bounds, Q_bar=None, vin=(), rs=None, ri=None):
 
     rowptr, col, val, _ = plant_csr(A, B)
 
-    return Plan(nx=nx, nu=nu, ny=ny, nd=nd, N=N, nv=nv, m=m, mh=len(hj_index), R=R, ncd=ncd,
+    return Plan(n_extra=n_extra, extra=tuple(extra),
+                nx=nx, nu=nu, ny=ny, nd=nd, N=N, nv=nvm, m=m, mh=len(hj_index), R=R, ncd=ncd,
                 n_vin=len(vin), Ts=Ts, E=E, Px=Px, Py=Py, e0=e0, Wrow=Wrow, w0row=w0row, Wdu=Wdu,
                 HJ=HJ, hj_index=np.array(hj_index, dtype=np.int32), Ht=Ht,
                 Myx=Myx, Myu=Myu, Mi1x=Mi1x, Mi1u=Mi1u, tau=tau,
@@ -263,7 +304,8 @@ def assemble_qp(plan: Plan, x, u, ysp, pesos, vinant=None):
     c = float(om @ (e * e))
     nv, nu, N = plan.nv, plan.nu, plan.N
     T = np.kron(np.tril(np.ones((N, N))), np.eye(nu))
-    G = [np.eye(nv), T]
+    pad = np.zeros((nv, getattr(plan, 'n_extra', 0)))        # residual variables: no move / input rows
+    G = [np.hstack([np.eye(nv), pad]), np.hstack([T, pad])]
     lo = [np.tile(plan.dulb, N), np.tile(plan.ulb - u, N)]
     hi = [np.tile(plan.duub, N), np.tile(plan.uub - u, N)]
     if plan.ncd:

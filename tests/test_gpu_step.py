@@ -598,3 +598,40 @@ def test_log_variant_ss_bound_active():
         assert abs(float(sol['w_opt'][-1]) - 1.0) <= 1e-7
         assert np.max(np.abs(sol['du_opt'].full() - solo['du_opt'])) <= RTOL * max(np.max(np.abs(solo['du_opt'])), 1e-3)
         assert abs(float(sol['J']) - solo['J']) <= RTOL * max(abs(solo['J']), 1e-3)
+
+
+@pytest.mark.parametrize("ranges", [dict(rslb=[-0.1, -0.05], rsub=[0.1, 0.05]),
+                                    dict(rslb=[-0.02, 0.0], rsub=[0.02, 0.0], ulb=[1.9, 1.6])])
+def test_terminal_residual_ranges_match_oracle(ranges):
+    """Terminal residual RANGES (rslb != rsub, ihmpccontroller.py:441-449): single steps through the drop-in mpc()
+    and a batched closed loop, general kernel with the ranged residuals as extra decision variables, vs the oracle's
+    un-condensed problem."""
+    sys_ = sc.distillation_system()
+    c = sc.declare_distillation(IHMPCController, sys_, **ranges)
+    orc = sc.declare_distillation(OracleIHMPC, sys_, **ranges)
+    rng = np.random.default_rng(2)
+    for t in range(4):
+        x = np.append([96, 0.5], np.zeros(20)) + rng.normal(size=22) * 0.05
+        x[6:8] = 0
+        u = [1.95, 1.71]; ysp = np.array([96, 1.0]) + rng.normal(size=2) * 0.3
+        pesos = np.array([0.1, 0.4, 4.4, 4.4]) * (1 + rng.random(4))
+        sol = c.mpc(x0=x, ySP=ysp, w0=[], u0=u, pesos=pesos, ViN_ant=[np.inf, np.inf])
+        solo = orc.mpc(x, ysp, [], np.array(u), pesos, ViN_ant=[np.inf, np.inf])
+        w = sol['w_opt'].full().reshape(-1)
+        assert w.size == 24
+        assert np.max(np.abs(w - solo['w_opt'])) <= RTOL * np.max(np.abs(solo['w_opt'])), t
+        assert abs(float(sol['J']) - solo['J']) <= RTOL * max(abs(solo['J']), 1e-6), t
+    B, T = 16, 40
+    scen = sc.distillation_scenarios(B)
+    scen["seg_start"][:, 1] = 3; scen["seg_start"][:, 2] = 20
+    eng = c.engine(B)
+    assert eng.dp.kernel_name() == "ihmpc_step_kernel"
+    eng.set_state(scen["x0"], scen["u0"])
+    eng.set_schedule(scen["ysp_seq"], scen["seg_start"])
+    tr = eng.run(T, record=True)
+    du = tr["du"].cpu().numpy()
+    assert (eng.stats[:, 5].cpu().numpy() == 0).all()
+    scen2 = {k: v for k, v in scen.items() if k not in ("dist_step", "dist")}
+    for idx in (0, 7):
+        ref = oracle_closed_loop(sc.declare_distillation, sys_, scen2, idx, T, bounds=ranges)
+        assert np.max(np.abs(du[:, idx] - ref["du"])) <= RTOL * np.max(np.abs(ref["du"])), idx

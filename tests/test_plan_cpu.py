@@ -169,6 +169,36 @@ def test_plan_reproduces_oracle_problem(bounds):
         assert info["n_active"] == sol["info"]["n_active"]
 
 
+@pytest.mark.parametrize("ranges", [dict(rslb=[-0.1, -0.05], rsub=[0.1, 0.05]),
+                                    dict(rslb=[-0.02, 0.0], rsub=[0.02, 0.0], ulb=[1.9, 1.6]),
+                                    dict(rslb=[0.05, -0.2], rsub=[0.05, 0.3])])
+def test_plan_with_terminal_residual_ranges_reproduces_oracle_problem(ranges):
+    """Terminal residual RANGES (rslb != rsub, ctl.py:441-449): the ranged residual becomes a decision variable
+    after the moves (Plan.n_extra); the condensed QP must have the optimum of the oracle's un-condensed problem,
+    with syN = xs(N) - ysp - rho."""
+    s = sc.distillation_system()
+    c = sc.declare_distillation(IHMPCController, s, **ranges)
+    orc = sc.declare_distillation(OracleIHMPC, s, **ranges)
+    plan = c.compile()
+    n_ranged = int(np.sum(np.asarray(ranges["rslb"]) != np.asarray(ranges["rsub"])))
+    assert plan.n_extra == n_ranged and plan.E.shape[1] == plan.nv + n_ranged and plan.nv == 20
+    rng = np.random.default_rng(1)
+    for t in range(5):
+        x = np.append([96, 0.5], np.zeros(20)) + rng.normal(size=22) * 0.05
+        x[6:8] = 0
+        u = np.array([1.95, 1.71]); ysp = np.array([96, 1.0]) + rng.normal(size=2) * 0.3
+        pesos = np.array([0.1, 0.4, 4.4, 4.4]) * (1 + rng.random(4))
+        sol = orc.mpc(x, ysp, [], u, pesos, ViN_ant=[np.inf, np.inf])
+        H, f, c0, G, lo, hi, *_ = assemble_qp(plan, x, u, ysp, pesos, [np.inf, np.inf])
+        v, lam, info = solve_qp_exact(H, f, G, lo, hi)
+        J = c0 + f @ v + 0.5 * v @ H @ v
+        assert np.max(np.abs(v[:20] - sol["w_opt"][:20])) < 1e-9
+        assert abs(J - sol["J"]) < 1e-9 * max(1.0, abs(sol["J"]))
+        res2 = sol["g"][-len(orc.V) - 2:-len(orc.V)] if "g" in sol else None
+        rho = v[20:]
+        assert (rho >= np.asarray(ranges["rslb"])[np.asarray(ranges["rslb"]) != np.asarray(ranges["rsub"])] - 1e-9).all()
+
+
 def test_plan_mimo10_shapes_and_parity():
     s = sc.mimo10_system()
     assert (s.nx, s.nd, s.theta_max) == (160, 100, 4)
@@ -211,11 +241,6 @@ def test_dm_behaves_like_casadi_dm():
 
 def test_unsupported_declarations_fail_loudly():
     s = sc.distillation_system()
-    c = IHMPCController(s, 10, rslb=[-0.1, -0.1], rsub=[0.1, 0.1])
-    c.subObjComposed(y=[0], Q=1, sat=10.0)
-    c.subObj(du=[0], Q=1, sat=1.0); c.subObj(du=[1], Q=1, sat=1.0)
-    with pytest.raises(NotImplementedError):
-        c.compile()
     c2 = IHMPCController(s, 10)
     with pytest.raises(NotImplementedError):
         c2.subObj(siN=[0, 1], Q=np.eye(2), addJ=False)
