@@ -71,7 +71,8 @@ class TransferFunction(signal.TransferFunction):
         Supported pole sets: stable poles, real -- distinct (``(dd, r)`` floats) or REPEATED
         (``(('jordan', [c_0 .. c_{m-1}]), r)``: the terms c_k t^k e^{rt}/k! of the step response) -- or distinct
         complex-conjugate pairs (``(c, p)`` complex, one entry per pair, Im p > 0), plus at most one pole at the
-        origin (integrating channel).  Unstable poles and repeated complex pairs raise NotImplementedError.
+        origin (integrating channel); repeated complex pairs as ``(('cjordan', [c_k complex]), p)``.  Unstable
+        poles raise NotImplementedError.
         """
         num = np.atleast_1d(np.asarray(self.num, dtype=float))
         den = np.atleast_1d(np.asarray(self.den, dtype=float))
@@ -101,8 +102,10 @@ class TransferFunction(signal.TransferFunction):
                 mult += 1
             if mult > 1:
                 if abs(pp.imag) > pole_tol:
-                    raise NotImplementedError("repeated complex-conjugate poles are not supported")
-                modes.append((('jordan', [float(np.real(c)) for c in rs[k:k + mult]]), float(np.real(pp))))
+                    if pp.imag > 0:                 # one entry per conjugate pair; complex coefficients
+                        modes.append((('cjordan', [complex(c) for c in rs[k:k + mult]]), complex(pp)))
+                else:
+                    modes.append((('jordan', [float(np.real(c)) for c in rs[k:k + mult]]), float(np.real(pp))))
             elif abs(pp.imag) <= pole_tol:
                 modes.append((float(np.real(rs[k])), float(np.real(pp))))
             elif pp.imag > 0:                       # one entry per conjugate pair
@@ -132,7 +135,7 @@ class OPOM(object):
         coeffs = [[Hm[i, j].step_coefficients() for j in range(nu)] for i in range(ny)]
 
         def n_states(modes):
-            return sum(2 if isinstance(mm[1], complex) else (len(mm[0][1]) if isinstance(mm[0], tuple) else 1)
+            return sum((2 if isinstance(mm[1], complex) else 1) * (len(mm[0][1]) if isinstance(mm[0], tuple) else 1)
                        for mm in modes)
         self.na = max(1, max(n_states(coeffs[i][j][1]) for i in range(ny) for j in range(nu)))
         na = self.na
@@ -174,7 +177,22 @@ class OPOM(object):
                 te = self.tau_e[i, j]
                 for dd, r in modes:
                     idx = (i * nu + j) * na + a
-                    if isinstance(r, complex):
+                    if isinstance(r, complex) and isinstance(dd, tuple):
+                        # repeated complex pair: the complex Jordan states of the real case, each as (Re, Im)
+                        c = dd[1]
+                        mlt = len(c)
+                        for k in range(mlt):
+                            bk = 0.0 + 0.0j
+                            for q in range(k, mlt):
+                                fkq = np.exp(r * Ts) * Ts ** (q - k) / math.factorial(q - k)
+                                a0, b0 = idx + 2 * k, idx + 2 * q
+                                self.F[a0:a0 + 2, b0:b0 + 2] = [[fkq.real, -fkq.imag], [fkq.imag, fkq.real]]
+                                bk += c[q] * te ** (q - k) * np.exp(r * te) / math.factorial(q - k)
+                            self._bd[idx + 2 * k], self._bd[idx + 2 * k + 1] = bk.real, bk.imag
+                            self.R[idx + 2 * k] = self.R[idx + 2 * k + 1] = r.real
+                        self.Psi[i, idx] = 2.0
+                        a += 2 * mlt
+                    elif isinstance(r, complex):
                         f = np.exp(r * Ts)
                         self.F[idx:idx + 2, idx:idx + 2] = [[f.real, -f.imag], [f.imag, f.real]]
                         g = dd * np.exp(r * te)

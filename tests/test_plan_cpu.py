@@ -88,6 +88,16 @@ def test_opom_repeated_poles_and_fractional_dead_times():
     t = np.arange(31) * 0.5 - 0.4
     tt = np.maximum(t, 0)
     assert np.max(np.abs(o.step_response(30)[:, 0] - np.where(t > 0, 0.3 * (tt - 2.0 * (1 - np.exp(-tt / 2.0))), 0.0))) < 1e-12
+    # repeated complex-conjugate pair (each complex Jordan state as Re/Im), integer and fractional dead times
+    import scipy.signal as ss
+    den = np.polymul([1, 0.4, 1.0], [1, 0.4, 1.0])
+    T = np.linspace(0, 40, 400001)
+    _, yy = ss.step(ss.TransferFunction([1.0], den), T=T)
+    for delay in (0.0, 2.0, 1.5):
+        o = OPOM([[TransferFunction([1.0], den, delay=delay)]], 0.5)
+        t = np.arange(61) * 0.5 - delay
+        assert o.na == 4
+        assert np.max(np.abs(o.step_response(60)[:, 0] - np.where(t > 0, np.interp(np.maximum(t, 0), T, yy), 0.0))) < 1e-9
     # a 2x2 plant mixing both with plain channels compiles into a controller plan whose prediction is the oracle's
     h = [[TransferFunction([12.8], [16.7, 1], delay=1), TransferFunction([-18.9], [21.0, 1], delay=3.3)],
          [TransferFunction([6.6], np.polymul([10.9, 1], [10.9, 1]), delay=7), TransferFunction([-19.4], [14.4, 1], delay=3)]]
