@@ -359,6 +359,16 @@ def main():
     ms_kernel = ev[0].elapsed_time(ev[1])
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     n_launch = (K + spl - 1) // spl
+    # kernels of OURS per sihmpc_step call: a fast path with bounds runs first pass + resume pass + general kernel
+    # (the last two leave at once when nothing was listed); without bounds, or on the general kernel alone, one
+    kname = eng.dp.kernel_name()
+    has_bounds = bool(np.isfinite(plan.ulb).any() or np.isfinite(plan.uub).any() or np.isfinite(plan.dulb).any()
+                      or np.isfinite(plan.duub).any())
+    if kname in ("mma_step_kernel", "tile_step_kernel") and has_bounds:
+        kernels_per_launch, kernels_desc = 3, "%s first pass, %s resume pass, ihmpc_step_kernel" % (kname, kname)
+    else:
+        kernels_per_launch, kernels_desc = 1, kname
+    counters = eng.dp.counters()
     t = torch.tensor([ms_total, ms_kernel], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -457,7 +467,11 @@ def main():
                        "l2": "flushed (512 MiB write) before the timed region; per-scenario state is read once "
                              "and written once per launch, everything else stays on chip",
                        "includes": "final on-device statistics reduction" + (" + NCCL all-reduce" if world > 1 else "")},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": n_launch + 1, "roofline": roofline,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": n_launch * kernels_per_launch + 1,
+            "gpu_launches_detail": "%d sihmpc_step call(s) x %d kernels (%s) + 1 stats_reduce_kernel"
+                                   % (n_launch, kernels_per_launch, kernels_desc),
+            "handed_over_to_general_kernel": counters[0], "constrained_steps_resolved_in_fast_path": counters[1],
+            "roofline": roofline,
             "cpu_baseline": cpu, "latency_batch1": lat, "status_or": status_or, "flagged_scenarios": flagged,
             "fp64_peak_tflops_measured": fp64_peak / 1e12}
     _emit(line)
