@@ -35,7 +35,7 @@
 namespace sih {
 
 struct MmaConst {            // offsets in doubles into the packed block
-    int be, bw, w0c, bf, br, bh, bomdu, by, byp, bvn, tau, gamma, bounds, vinq, ell_val, total_d;
+    int be, bw, w0c, bf, br, bh, bomdu, by, byp, bvn, tau, gamma, inv_gamma, bounds, vinq, ell_val, total_d;
     int ell_col, ell_csr, hj_idx, vin_row, vlive, vdead, total_i;
     int ell_w;
     // in-kernel active set on simple bounds (mma_active_set): gradient / Hessian / difference maps in the space
@@ -554,15 +554,16 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
 #pragma unroll
             for (int sl = 0; sl < SV; ++sl) bv[vlog[sl]] = fr[sl];
             __syncwarp();
-            // ---------------- feasibility of the unconstrained optimum
+            // ---------------- feasibility of the unconstrained optimum: viol = max over rows of (violation - 1e-10 (1 + |bound|)),
+            // a bound is violated when viol > 0 (the relative test of the general kernel without its divisions)
             double viol = 0.0, viol_abs = 0.0;
             if (P.has_box) {
 #pragma unroll
                 for (int sl = 0; sl < SV; ++sl) {
                     const int j = vlog[sl] % NU;
                     const double lo = cst[Q.bounds + j], hi = cst[Q.bounds + NU + j];
-                    if (lo > -SIH_INF) { const double a = lo - fr[sl]; viol_abs = fmax(viol_abs, a); viol = fmax(viol, a / (1.0 + fabs(lo))); }
-                    if (hi < SIH_INF) { const double a = fr[sl] - hi; viol_abs = fmax(viol_abs, a); viol = fmax(viol, a / (1.0 + fabs(hi))); }
+                    if (lo > -SIH_INF) { const double a = lo - fr[sl]; viol_abs = fmax(viol_abs, a); viol = fmax(viol, fma(-1e-10, 1.0 + fabs(lo), a)); }
+                    if (hi < SIH_INF) { const double a = fr[sl] - hi; viol_abs = fmax(viol_abs, a); viol = fmax(viol, fma(-1e-10, 1.0 + fabs(hi), a)); }
                 }
             }
             if (P.has_cum) {
@@ -572,8 +573,8 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
                     double cs = 0.0, cmin = SIH_INF, cmax = -SIH_INF;
 #pragma unroll
                     for (int k = 0; k < D::N; ++k) { cs += bv[k * NU + j]; cmin = fmin(cmin, cs); cmax = fmax(cmax, cs); }
-                    if (lo > -SIH_INF) { const double a = lo - cmin; viol_abs = fmax(viol_abs, a); viol = fmax(viol, a / (1.0 + fabs(lo))); }
-                    if (hi < SIH_INF) { const double a = cmax - hi; viol_abs = fmax(viol_abs, a); viol = fmax(viol, a / (1.0 + fabs(hi))); }
+                    if (lo > -SIH_INF) { const double a = lo - cmin; viol_abs = fmax(viol_abs, a); viol = fmax(viol, fma(-1e-10, 1.0 + fabs(lo), a)); }
+                    if (hi < SIH_INF) { const double a = cmax - hi; viol_abs = fmax(viol_abs, a); viol = fmax(viol, fma(-1e-10, 1.0 + fabs(hi), a)); }
                 }
             }
             viol = quad_max(viol);
@@ -581,7 +582,7 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
             int nact = 0;
             if constexpr (AS) {
                 if (Q.cspace >= 0) {           // bound violated: active set on the register-resident problem
-                    const bool need = alive && !notpd && viol > 1e-10;
+                    const bool need = alive && !notpd && viol > 0.0;
                     if (__any_sync(0xffffffffu, need)) {
                         const bool ok = mma_active_set<D>(cst, cint, Q, er, om, apes, pes, uu, vlog, mlo, mhi, need, fr,
                                                           lane, g, mh);
@@ -599,7 +600,7 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
                     }
                 }
             }
-            if (alive && (viol > 1e-10 || notpd)) {
+            if (alive && (viol > 0.0 || notpd)) {
                 alive = false;             // hand over from this step on (MODE 0: resume pass; else: general kernel)
                 mlo = mhi = 0u;
                 if (g == 0) {
@@ -760,18 +761,18 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
                 if (io.flags & SIHMPC_F_WEIGHTS_SAT2) {
                     double smax = -SIH_INF;
 #pragma unroll
-                    for (int i = 0; i < M; ++i) smax = fmax(smax, vn[i] / cst[Q.gamma + i]);
+                    for (int i = 0; i < M; ++i) smax = fmax(smax, vn[i] * cst[Q.inv_gamma + i]);
 #pragma unroll
                     for (int i = 0; i < M; ++i) {
                         const double g0 = cst[Q.gamma + i];
                         const double g1 = fmax(g0, g0 * smax + 1e-6);
-                        pes[i] = io.alfa * pes[i] + (1.0 - io.alfa) * (1.0 / (g1 - vn[i]));
+                        pes[i] = io.alfa * pes[i] + (1.0 - io.alfa) * fast_rcp(g1 - vn[i]);     // g1 - vn >= 1e-6 > 0
                     }
                 } else {
 #pragma unroll
                     for (int i = 0; i < M; ++i) {
                         const double g0 = cst[Q.gamma + i];
-                        pes[i] = 1.0 / (g0 - fmin(fmax(vn[i], 0.0), 0.99 * g0));
+                        pes[i] = fast_rcp(g0 - fmin(fmax(vn[i], 0.0), 0.99 * g0));
                     }
                 }
             }
@@ -875,6 +876,7 @@ inline void mma_build_constants(const sihmpc_plan_desc *d, const DevPlan &P, Mma
     qc.bvn = take(D::TM * (2 * D::TQ + SV) * 32);
     qc.tau = take(D::TY * 8);
     qc.gamma = take(M);
+    qc.inv_gamma = take(M);
     qc.bounds = take(4 * NU);
     qc.vinq = take(d->n_vin > 0 ? d->n_vin : 1);
     const int W = D::WELL;
@@ -1035,7 +1037,7 @@ inline void mma_build_constants(const sihmpc_plan_desc *d, const DevPlan &P, Mma
     for (int T = 0; T < D::TY; ++T)
         for (int g = 0; g < 4; ++g)
             for (int h = 0; h < 2; ++h) { int r = 8 * T + 2 * g + h; if (r < NYP) buf[qc.tau + (T * 4 + g) * 2 + h] = d->tau[r / NY]; }
-    for (int i = 0; i < M; ++i) buf[qc.gamma + i] = d->gamma[i];
+    for (int i = 0; i < M; ++i) { buf[qc.gamma + i] = d->gamma[i]; buf[qc.inv_gamma + i] = 1.0 / d->gamma[i]; }
     for (int j = 0; j < NU; ++j) {
         buf[qc.bounds + j] = d->dulb[j]; buf[qc.bounds + NU + j] = d->duub[j];
         buf[qc.bounds + 2 * NU + j] = d->ulb[j]; buf[qc.bounds + 3 * NU + j] = d->uub[j];

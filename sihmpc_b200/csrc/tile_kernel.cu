@@ -32,7 +32,6 @@
 #include <stdlib.h>
 #include "devplan.h"
 #include <math.h>
-#include <stdio.h>
 #include "tile_api.h"
 
 #define SIH_FULL 0xffffffffu
