@@ -437,13 +437,15 @@ tile_step_kernel(const DevPlan P, const TileCfg C, const sihmpc_io io, const lon
             const int notpd = tile_factor<NT>(Hw, omduw, nv, C.rb, lane, yw);
             tbs_panel<NT, 2 * NT - 1>(Hw, nv, lane, yw, zw);
             for (int i = lane; i < nv; i += 32) svw[nx + i] = zw[i];
+            // viol = max over rows of (violation - 1e-10 (1 + |bound|)): a bound is violated when viol > 0 (the relative
+            // test of the general kernel without its divisions)
             double viol = 0.0, viol_abs = 0.0;
             if (P.has_box)
                 for (int i = lane; i < nv; i += 32) {
                     const int j = i % nu;
                     const double lo = P.dulb[j], hi = P.duub[j], val = zw[i];
-                    if (lo > -SIH_INF) { const double a = lo - val; viol_abs = fmax(viol_abs, a); viol = fmax(viol, a / (1.0 + fabs(lo))); }
-                    if (hi < SIH_INF) { const double a = val - hi; viol_abs = fmax(viol_abs, a); viol = fmax(viol, a / (1.0 + fabs(hi))); }
+                    if (lo > -SIH_INF) { const double a = lo - val; viol_abs = fmax(viol_abs, a); viol = fmax(viol, fma(-1e-10, 1.0 + fabs(lo), a)); }
+                    if (hi < SIH_INF) { const double a = val - hi; viol_abs = fmax(viol_abs, a); viol = fmax(viol, fma(-1e-10, 1.0 + fabs(hi), a)); }
                 }
             if (P.has_cum)
                 for (int i = lane; i < nv; i += 32) {
@@ -451,8 +453,8 @@ tile_step_kernel(const DevPlan P, const TileCfg C, const sihmpc_io io, const lon
                     double val = 0.0;
                     for (int c = j; c <= i; c += nu) val += zw[c];
                     const double lo = P.ulb[j] - uw[j], hi = P.uub[j] - uw[j];
-                    if (lo > -SIH_INF) { const double a = lo - val; viol_abs = fmax(viol_abs, a); viol = fmax(viol, a / (1.0 + fabs(lo))); }
-                    if (hi < SIH_INF) { const double a = val - hi; viol_abs = fmax(viol_abs, a); viol = fmax(viol, a / (1.0 + fabs(hi))); }
+                    if (lo > -SIH_INF) { const double a = lo - val; viol_abs = fmax(viol_abs, a); viol = fmax(viol, fma(-1e-10, 1.0 + fabs(lo), a)); }
+                    if (hi < SIH_INF) { const double a = val - hi; viol_abs = fmax(viol_abs, a); viol = fmax(viol, fma(-1e-10, 1.0 + fabs(hi), a)); }
                 }
             viol = warp_max(viol);
             viol_abs = warp_max(viol_abs);
@@ -462,7 +464,7 @@ tile_step_kernel(const DevPlan P, const TileCfg C, const sihmpc_io io, const lon
 #include "tile_active_set.inc"
                 }
             }
-            if (alive && (viol > 1e-10 || notpd)) {
+            if (alive && (viol > 0.0 || notpd)) {
                 alive = false;                            // hand over from this step on (MODE 0: resume pass; else general kernel)
                 mlo = mhi = 0ull;
                 if (lane == 0) {
