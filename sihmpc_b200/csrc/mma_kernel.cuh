@@ -68,6 +68,7 @@ struct MmaDims {
     static constexpr int KP = (M + 3) / 4;             // k-tiles of pesos
     static constexpr int KH = 1;                       // k-tile [1 ; pesos of <= 3 dense Hessian blocks]
     static constexpr int KD = (NU + 3) / 4;            // k-tiles of du
+    static constexpr int KE = (3 * NY + 3) / 4;        // k-tiles of [ysp ; syN ; siN] (shifted-plan residuals)
     static constexpr int KHC = 2;                      // k-tiles [1 ; pesos of dense blocks ; pesos of move weights] (bound space)
     static constexpr int HPAIRS = SV * (SV + 1);
     static constexpr int BX = 8 * TX, BV = NVL;
@@ -722,33 +723,28 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
             }
             // ---------------- sub-objective values at the new state, weight update
             if (io.flags & (SIHMPC_F_WEIGHTS_SAT2 | SIHMPC_F_WEIGHTS_SAT1)) {
-                double yp[TY][2];
+                // residual stack of the shifted plan in ONE product: rows k*ny+i = Y'_k,i - ysp_i - syN_i - tau_k siN_i, then
+                // syN and siN themselves -- the set-point and the slacks ride along as two more k-tiles (their
+                // coefficients -1, -tau_k, 1 sit in the constant block) instead of a dozen selects per row
+                double yq[TQ][2];
 #pragma unroll
-                for (int T = 0; T < TY; ++T) yp[T][0] = yp[T][1] = 0.0;
+                for (int T = 0; T < TQ; ++T) yq[T][0] = yq[T][1] = 0.0;
                 {
-                    double ax[KX + SV];
+                    double ax[KX + SV + D::KE];
 #pragma unroll
                     for (int T = 0; T < TX; ++T) { ax[2 * T] = xr[T][0]; ax[2 * T + 1] = xr[T][1]; }
 #pragma unroll
                     for (int sl = 0; sl < SV; ++sl) ax[KX + sl] = fr[sl];     // shift folded into the constants
-                    mma_block<TY, KX + SV>(cst + Q.byp, ax, yp, lane);
+#pragma unroll
+                    for (int t = 0; t < D::KE; ++t) {                         // [ysp ; syN ; siN(next)], element 4t+g
+                        const int e = 4 * t + g;
+                        ax[KX + SV + t] = (e < NY) ? sel<NY>(ysp, e) : ((e < 3 * NY) ? sel<3 * NY>(syv, e < 2 * NY ? e - NY : e) : 0.0);
+                    }
+                    mma_block<TQ, KX + SV + D::KE>(cst + Q.byp, ax, yq, lane);
                 }
                 double asq[2 * TQ + SV];
 #pragma unroll
-                for (int T = 0; T < TQ; ++T)
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int r = 8 * T + 2 * g + h;
-                        double v;
-                        if (r < NYP) {
-                            const int i = r % NY;
-                            v = (T < TY ? yp[T < TY ? T : 0][h] : 0.0) - sel<NY>(ysp, i) - sel<3 * NY>(syv, i)
-                                - cst[Q.tau + ((T < TY ? T : 0) * 4 + g) * 2 + h] * sel<3 * NY>(syv, 2 * NY + i);
-                        } else if (r < NYP + NY) v = sel<3 * NY>(syv, r - NYP);
-                        else if (r < NYP + 2 * NY) v = sel<3 * NY>(syv, 2 * NY + (r - NYP - NY));
-                        else v = 0.0;
-                        asq[2 * T + h] = v * v;
-                    }
+                for (int T = 0; T < TQ; ++T) { asq[2 * T] = yq[T][0] * yq[T][0]; asq[2 * T + 1] = yq[T][1] * yq[T][1]; }
 #pragma unroll
                 for (int sl = 0; sl < SV; ++sl) asq[2 * TQ + sl] = fr[sl] * fr[sl];
                 double vc[TM][2];
@@ -872,7 +868,7 @@ inline void mma_build_constants(const sihmpc_plan_desc *d, const DevPlan &P, Mma
     qc.bh = take(D::HPAIRS * D::KH * 32);
     qc.bomdu = take(D::TV * D::KP * 32);
     qc.by = take(D::TC * (D::KX + D::KD) * 32);
-    qc.byp = take(D::TY * (D::KX + SV) * 32);
+    qc.byp = take(D::TQ * (D::KX + SV + D::KE) * 32);
     qc.bvn = take(D::TM * (2 * D::TQ + SV) * 32);
     qc.tau = take(D::TY * 8);
     qc.gamma = take(M);
@@ -943,12 +939,25 @@ inline void mma_build_constants(const sihmpc_plan_desc *d, const DevPlan &P, Mma
              [&](int t, int k) { if (t < D::KX) { int c = 8 * (t / 2) + 2 * k + (t % 2); return c < NX ? c : -1; }
                                  int e = 4 * (t - D::KX) + k; return e < NU ? NX + e : -1; },
              [&](int r, int c) { return c < NX ? d->C[(size_t)r * NX + c] : d->D[(size_t)r * NU + (c - NX)]; });
-    // Y' = Myx x+ + Myu shift(dU): column v of the shifted map is Myu[:, v - NU]
-    mma_pack(buf, qc.byp, D::TY, D::KX + SV, crow(NYP),
+    // residual stack of the shifted plan: rows r < NYP: Y' - ysp - syN - tau siN with Y' = Myx x+ + Myu shift(dU)
+    // (column v of the shifted map is Myu[:, v - NU]); rows NYP..: syN, siN.  Inputs: x+, dU (slots), [ysp ; syN ; siN]
+    mma_pack(buf, qc.byp, D::TQ, D::KX + SV + D::KE, crow(NYP + 2 * NY),
              [&](int t, int k) { if (t < D::KX) { int c = 8 * (t / 2) + 2 * k + (t % 2); return c < NX ? c : -1; }
-                                 return NX + live[D::var_of(t - D::KX, k)]; },
-             [&](int r, int c) { if (c < NX) return d->Myx[(size_t)r * NX + c];
-                                 int v = c - NX; return v >= NU ? d->Myu[(size_t)r * NVL + (v - NU)] : 0.0; });
+                                 if (t < D::KX + SV) return NX + live[D::var_of(t - D::KX, k)];
+                                 int e = 4 * (t - D::KX - SV) + k; return e < 3 * NY ? 5000 + e : -1; },
+             [&](int r, int c) {
+                 if (c >= 5000) {
+                     const int e = c - 5000;
+                     if (r < NYP) {
+                         const int i = r % NY, kk = r / NY;
+                         if (e < 2 * NY) return (e % NY == i) ? -1.0 : 0.0;          // - ysp_i , - syN_i
+                         return (e - 2 * NY == i) ? -d->tau[kk] : 0.0;             // - tau_k siN_i
+                     }
+                     return (e == NY + (r - NYP)) ? 1.0 : 0.0;                      // rows syN_i, siN_i
+                 }
+                 if (r >= NYP) return 0.0;
+                 if (c < NX) return d->Myx[(size_t)r * NX + c];
+                 int v = c - NX; return v >= NU ? d->Myu[(size_t)r * NVL + (v - NU)] : 0.0; });
     // V_i = sum_r Wrow[r][i] sq_r + sum_v Wdu[v-NU][i] dU_v^2
     mma_pack(buf, qc.bvn, D::TM, 2 * D::TQ + SV, crow(M),
              [&](int t, int k) { if (t < 2 * D::TQ) { int r = 8 * (t / 2) + 2 * k + (t % 2); return r < NYP + 2 * NY ? r : -1; }
