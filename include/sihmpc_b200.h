@@ -10,7 +10,13 @@
  * are CUDA device memory owned by the caller on the plan's device.  Per-scenario arrays are
  * [batch][feature] (scenario-major).  Every call returns 0 on success or a negative
  * SIHMPC_E_* code, never throws, never synchronises the stream unless stated, and never
- * allocates after plan creation (the caller supplies the workspace).  A plan is bound to the
+ * allocates after plan creation: the caller supplies the workspace (sihmpc_workspace_bytes /
+ * sihmpc_host_staging_bytes for the batch it steps), which also holds the hand-over lists and
+ * counters of the fast kernels; copy streams, events and the pinned pack buffer of the host-buffer
+ * entry point are created by sihmpc_plan_create.  (sihmpc_fp64_peak, a measurement helper, is the
+ * exception.)  Environment overrides (SIHMPC_FAST, SIHMPC_NO_FAST, SIHMPC_BOUNCE, SIHMPC_NO_ZEROCOPY,
+ * SIHMPC_ZEROCOPY_MAX, SIHMPC_HOST_CHUNKS: A/B measurements only) are read once, by
+ * sihmpc_plan_create.  A plan is bound to the
  * device that was current at creation and is not thread-safe; distinct plans may be used from
  * distinct threads.  There is no CPU fallback: without a CUDA device every compute entry point
  * fails with SIHMPC_E_CUDA.
@@ -180,7 +186,11 @@ int sihmpc_step(sihmpc_plan *plan, const sihmpc_io *io, int64_t batch, int32_t n
 /* Same step for callers whose state lives in HOST memory (the reference's calling convention:
  * numpy in, numpy out).  Copies x,u,pesos,vinant,ysp host->device, runs one step, copies
  * du,J,w_opt,status (and the advanced state when SIHMPC_F_ADVANCE) device->host, then
- * synchronises `stream`.  io holds HOST pointers here; staging buffers come from `workspace`.  */
+ * synchronises `stream`.  io holds HOST pointers here; staging buffers come from `workspace`.
+ * When every buffer is page-locked (cudaHostAlloc / cudaHostRegister, mapped) the kernel reads and
+ * writes the caller's arrays in place over PCIe (zero-copy); the device aliases are asked of the
+ * driver on every call, so buffers may be freed, unregistered or re-registered BETWEEN calls, but
+ * must stay valid and pinned for the duration of a call.                                          */
 int sihmpc_step_host(sihmpc_plan *plan, const sihmpc_io *host_io, int64_t batch,
                      void *workspace, size_t workspace_bytes, void *stream);
 size_t sihmpc_host_staging_bytes(const sihmpc_plan *plan, int64_t batch);
@@ -193,7 +203,7 @@ int sihmpc_predict(sihmpc_plan *plan, const double *x, const double *u, const do
 /* replaces: fObj.F(x0,u0,var,ysp) for every weighted sub-objective (ihmpccontroller.py:124-126,
  * 598-599, 628): V [batch][m] evaluated at explicit w = [dU ; syN ; siN].                       */
 int sihmpc_subobjectives(sihmpc_plan *plan, const double *x, const double *w, const double *ysp,
-                         int64_t batch, double *V, void *stream);
+                         int64_t batch, double *V, void *stream);      /* n_extra > 0: SIHMPC_E_INVALID */
 
 /* replaces: IHMPCController.mpc of the LOG-BARRIER variant (sihmpc/ihmpccontroller_log.py:552-563 and the
  * NLP of :349-461): minimise Vt + ss^2 - sum_i log(ss*gamma_i - V_i) over (dU, ss) by damped Newton.

@@ -309,7 +309,7 @@ class OracleIHMPCLog(OracleIHMPC):
         xN = np.asarray(sol['x_pred']).reshape(-1)[-nx:]
         Xknext = self.sys.A @ xN
         siNnext = Xknext[self.nxs + self.nxd:self.nxs + self.nxd + self.nxi]
-        syNnext = w0[-2 * ny - 1:-ny - 1]
+        syNnext = w0[-2 * ny:-ny]          # log.py:543 verbatim: on the ss-extended vector this is [syN[1:], siN[0]]
         return np.concatenate([dustart, syNnext, siNnext, [1.0]])       # log.py:548
 
     def satWeights(self, x, u, w0, ysp):                          # log.py:566-574

@@ -63,11 +63,18 @@ struct sihmpc_plan {
     size_t h_stage_bytes = 0;
     // host copies needed by the host-buffer entry point
     int nw;
-    // zero-copy path: pinned host pointers seen so far and their device aliases
-    void *pinned_host[16];
-    void *pinned_dev[16];
-    int n_pinned = 0;
+    // environment overrides (A/B measurements only), read ONCE at plan creation
+    int env_bounce = 0;            // SIHMPC_BOUNCE: bounce rounds of the tile path
+    int env_no_zerocopy = 0;       // SIHMPC_NO_ZEROCOPY
+    long long env_zc_max = 1LL << 40;   // SIHMPC_ZEROCOPY_MAX
+    int env_chunks = 0;            // SIHMPC_HOST_CHUNKS (0: default)
+    int env_grid = 0;              // SIHMPC_QUAD_GRID (debug: force many rounds)
 };
+
+// packed-upload path of sihmpc_step_host: largest batch served from the plan's pinned pack buffer
+#define SIH_PACK_MAX 512
+
+extern "C" { static size_t staging_layout(const sihmpc_plan *p, int64_t batch, size_t off[12]); }
 
 namespace {
 
@@ -152,6 +159,24 @@ int launch_step(sihmpc_plan *p, const sihmpc_io &io, long long batch, int n_step
     return 0;
 }
 
+// Hand-over block of the fast paths (counters, start_step[], list[], list2[], warm masks): it lives in the CALLER's
+// workspace right after the general kernel's active-set scratch, so nothing is allocated after plan creation.
+size_t general_scratch_bytes(const sihmpc_plan *p) {
+    return ((size_t)p->max_grid * p->wpb * scratch_doubles_per_warp(p->d.nv) * sizeof(double) + 255) & ~(size_t)255;
+}
+size_t handover_bytes(int64_t batch) {
+    const size_t ints = ((size_t)sih::TL_CTR + 3 * (size_t)batch + 3) & ~(size_t)3;
+    return ints * sizeof(int) + 2 * (size_t)batch * sizeof(unsigned long long) + 256;
+}
+void bind_handover(sihmpc_plan *p, char *base, int64_t batch) {
+    int *ctr = reinterpret_cast<int *>(base);
+    const size_t ints = ((size_t)sih::TL_CTR + 3 * (size_t)batch + 3) & ~(size_t)3;
+    unsigned long long *warm = reinterpret_cast<unsigned long long *>(base + ints * sizeof(int));
+    sih::tile_bind(&p->tile, ctr, warm, batch);
+    sih::mma_bind(&p->mma, ctr, batch);
+    sih::quad_bind(&p->quad, ctr, batch);
+}
+
 int check_io(const sihmpc_plan *p, const sihmpc_io *io, int n_steps) {
     if (!io->x || !io->u || !io->pesos) return fail(SIHMPC_E_INVALID, "io.x, io.u and io.pesos are required%s");
     if (!io->ysp && !(io->ysp_seq && io->seg_start && io->n_seg > 0))
@@ -203,6 +228,17 @@ int sihmpc_plan_create(const sihmpc_plan_desc *d, sihmpc_plan **out) {
     const int nv = d->N * d->nu + d->n_extra;
     if (nv > 64) return fail(SIHMPC_E_INVALID, "N*nu + n_extra > 64 is not supported by the step kernel%s");
     if (d->R != d->N * d->ny + 2 * d->ny + d->nd) return fail(SIHMPC_E_INVALID, "R must be N*ny+2*ny+nd%s");
+    {   // every block a kernel or the shape matching below dereferences must be there BEFORE anything reads it
+        const void *req[] = {d->E, d->Px, d->Py, d->e0, d->Wrow, d->w0row, d->Wdu, d->Ht, d->Myx, d->Myu, d->Mi1x, d->Mi1u,
+                             d->tau, d->gamma, d->dulb, d->duub, d->ulb, d->uub, d->pl_rowptr, d->pl_col, d->pl_val, d->C, d->D};
+        for (const void *q : req)
+            if (!q) return fail(SIHMPC_E_INVALID, "plan descriptor has a NULL block%s");
+        if (d->mh > 0 && (!d->HJ || !d->hj_index)) return fail(SIHMPC_E_INVALID, "plan descriptor: mh > 0 needs HJ and hj_index%s");
+        if (d->ncd > 0 && (!d->Gc || !d->Gcx || !d->Gcy || !d->gc0 || !d->Lc || !d->Uc || !d->gc_vin || !d->gc_q))
+            return fail(SIHMPC_E_INVALID, "plan descriptor: ncd > 0 needs the dense-row blocks%s");
+        if (d->n_vin > 0 && (!d->vin_row || !d->vin_q)) return fail(SIHMPC_E_INVALID, "plan descriptor: n_vin > 0 needs vin_row and vin_q%s");
+        if ((d->Phi == nullptr) != (d->Gam == nullptr)) return fail(SIHMPC_E_INVALID, "plan descriptor: Phi and Gam come together%s");
+    }
     int ndev = sihmpc_device_count();
     if (ndev < 1) return fail(SIHMPC_E_CUDA, "no CUDA device: this library has no CPU fallback%s");
 
@@ -301,15 +337,35 @@ int sihmpc_plan_create(const sihmpc_plan_desc *d, sihmpc_plan **out) {
         if (ff && !strcmp(ff, "quad")) p->use_fast = 1;
         if (ff && !strcmp(ff, "tile")) p->use_fast = 3;
         if (nf && nf[0] == '1') p->use_fast = 0;
+        p->env_bounce = getenv("SIHMPC_BOUNCE") ? 1 : 0;
+        p->env_no_zerocopy = getenv("SIHMPC_NO_ZEROCOPY") ? 1 : 0;
+        if (const char *zv = getenv("SIHMPC_ZEROCOPY_MAX")) p->env_zc_max = atoll(zv);
+        if (const char *cv = getenv("SIHMPC_HOST_CHUNKS")) { const int v = atoi(cv); if (v >= 1 && v <= 64) p->env_chunks = v; }
+        if (const char *gv = getenv("SIHMPC_QUAD_GRID")) { const int v = atoi(gv); if (v > 0) p->env_grid = v; }
+        p->mma.grid_cap = p->env_grid; p->quad.grid_cap = p->env_grid;
+    }
+    {   // host-buffer entry point: copy streams, events and the pinned pack buffer exist from here on
+        const int nchunk_max = p->env_chunks > 4 ? p->env_chunks : 4;
+        auto cu = [&](cudaError_t e, const char *what) { return e == cudaSuccess ? 0 : fail(SIHMPC_E_CUDA, "%s failed at plan creation", what); };
+        if (cu(cudaStreamCreateWithFlags(&p->s_h2d, cudaStreamNonBlocking), "cudaStreamCreate")) return bail(SIHMPC_E_CUDA);
+        if (cu(cudaStreamCreateWithFlags(&p->s_d2h, cudaStreamNonBlocking), "cudaStreamCreate")) return bail(SIHMPC_E_CUDA);
+        for (int i = 0; i < 2 * nchunk_max + 2; ++i) {
+            cudaEvent_t ev;
+            if (cu(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "cudaEventCreate")) return bail(SIHMPC_E_CUDA);
+            p->events.push_back(ev);
+        }
+        size_t off[12];
+        p->h_stage_bytes = staging_layout(p, SIH_PACK_MAX, off);
+        if (cu(cudaHostAlloc(&p->h_stage, p->h_stage_bytes, cudaHostAllocDefault), "cudaHostAlloc")) return bail(SIHMPC_E_CUDA);
     }
     *out = p;
     return 0;
 }
 
 size_t sihmpc_workspace_bytes(const sihmpc_plan *plan, int64_t batch) {
-    (void)batch;
     if (!plan) return 0;
-    return (size_t)plan->max_grid * plan->wpb * scratch_doubles_per_warp(plan->d.nv) * sizeof(double) + 256;
+    if (batch < 0) batch = 0;
+    return general_scratch_bytes(plan) + handover_bytes(batch) + 256;
 }
 
 const char *sihmpc_plan_kernel(const sihmpc_plan *plan) {
@@ -360,12 +416,12 @@ int sihmpc_step(sihmpc_plan *plan, const sihmpc_io *io, int64_t batch, int32_t n
         return fail(SIHMPC_E_WORKSPACE, "workspace smaller than sihmpc_workspace_bytes()%s");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     double *scratch = reinterpret_cast<double *>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    bind_handover(plan, reinterpret_cast<char *>(scratch) + general_scratch_bytes(plan), batch);
     int *start_step = nullptr;
     const int *n_handover = nullptr;
     const bool want_tile = plan->tile.ok && (plan->use_fast == 3 || (plan->use_fast == 2 && plan->mma.shape < 0));
     if (want_tile) {
-        cudaError_t e = sih::tile_ensure_capacity(&plan->tile, batch);
-        if (e == cudaSuccess) e = sih::tile_reset(plan->tile, batch, st);
+        cudaError_t e = sih::tile_reset(plan->tile, batch, st);
         if (e == cudaSuccess) e = sih::tile_launch(plan->tile, plan->d, *io, batch, n_steps, plan->sm_count, st);
         if (e != cudaSuccess) return fail(SIHMPC_E_CUDA, "tile fast-path launch failed: %s", cudaGetErrorString(e));
         if (!(plan->d.has_box || plan->d.has_cum)) return 0;      // nothing can be handed over
@@ -380,7 +436,7 @@ int sihmpc_step(sihmpc_plan *plan, const sihmpc_io *io, int64_t batch, int32_t n
             // Measured on the 10x10 workload (65536 x 200): three rounds resolve 23155 constrained scenario-steps
             // instead of 2437 and leave 1316 instead of 1871 scenarios to the final pass, but every round is two more
             // latency-bound launches and the launch got slower (791 vs 745 ms): opt-in (SIHMPC_BOUNCE=1).
-            const int rounds = getenv("SIHMPC_BOUNCE") ? sih::TL_BOUNCES : 0;
+            const int rounds = plan->env_bounce ? sih::TL_BOUNCES : 0;
             for (int r = 0; r < rounds; ++r) {
                 int *nb = sih::tile_bounce_counter(plan->tile, r);
                 rc = (plan->nvr == 1) ? launch_step<1>(plan, *io, batch, n_steps, scratch, st, start_step, n_handover, plan->tile.list2, nb,
@@ -395,15 +451,14 @@ int sihmpc_step(sihmpc_plan *plan, const sihmpc_io *io, int64_t batch, int32_t n
             plan->tile.last_final = n_handover;
         }
     } else if (plan->use_fast == 2 && plan->mma.shape >= 0) {
-        cudaError_t e = sih::mma_ensure_capacity(&plan->mma, batch);
-        if (e == cudaSuccess) e = sih::mma_reset(plan->mma, batch, st);
+        cudaError_t e = sih::mma_reset(plan->mma, batch, st);
         if (e == cudaSuccess) e = sih::mma_launch(plan->mma, plan->d, *io, batch, n_steps, plan->sm_count, st);
         if (e != cudaSuccess) return fail(SIHMPC_E_CUDA, "tensor fast-path launch failed: %s", cudaGetErrorString(e));
         if (!(plan->d.has_box || plan->d.has_cum)) return 0;      // nothing can be handed over
         start_step = plan->mma.start_step;
         n_handover = sih::mma_resumes(plan->mma, batch, n_steps) ? plan->mma.n_fail : plan->mma.n_handover;
     } else if (plan->use_fast == 1 && sih::quad_supported(plan->quad, *io)) {
-        cudaError_t e = sih::quad_ensure_capacity(&plan->quad, batch);
+        cudaError_t e = cudaSuccess;
         if (e == cudaSuccess) e = cudaMemsetAsync(plan->quad.n_handover, 0x7f, (size_t)(batch + 1) * sizeof(int), st);
         if (e == cudaSuccess) e = sih::quad_launch(plan->quad, plan->d, *io, batch, n_steps, plan->sm_count, st);
         if (e != cudaSuccess) return fail(SIHMPC_E_CUDA, "fast-path launch failed: %s", cudaGetErrorString(e));
@@ -483,9 +538,7 @@ int sihmpc_step_host(sihmpc_plan *plan, const sihmpc_io *h, int64_t batch, void 
     const size_t bx = (size_t)P.nx * 8, bu = (size_t)P.nu * 8, bp = (size_t)P.m * 8, bv = (size_t)P.n_vin * 8,
                  by = (size_t)P.ny * 8, bw = (size_t)plan->nw * 8;
 
-    long long zc_max = 1LL << 40;
-    if (const char *zv = getenv("SIHMPC_ZEROCOPY_MAX")) zc_max = atoll(zv);
-    if (batch <= zc_max) {
+    if (batch <= plan->env_zc_max && !plan->env_no_zerocopy && h->du && h->J && h->status && h->n_active) {
         // ---- every buffer pinned (cudaHostAlloc / cudaHostRegister): ZERO-COPY.  The kernel reads the caller's
         // arrays over PCIe through their device aliases and writes the results straight back: no staging
         // copies, no memcpy launches -- a step is one kernel plus one synchronise (batch 64: 39 us instead of
@@ -498,19 +551,14 @@ int sihmpc_step_host(sihmpc_plan *plan, const sihmpc_io *h, int64_t batch, void 
             for (int i = 0; i < 10 && all; ++i) {
                 dp[i] = nullptr;
                 if (!hp[i]) continue;
-                int hit = -1;
-                for (int k = 0; k < plan->n_pinned; ++k)
-                    if (plan->pinned_host[k] == hp[i]) { hit = k; break; }
-                if (hit >= 0) { dp[i] = plan->pinned_dev[hit]; continue; }
+                // asked of the driver on EVERY call: an address can be unpinned, freed and reused between two calls, so a
+                // device alias remembered from an earlier call may no longer be valid (a stale one is a device fault)
                 cudaPointerAttributes at;
                 if (cudaPointerGetAttributes(&at, hp[i]) != cudaSuccess) { cudaGetLastError(); all = false; break; }
                 if (at.type != cudaMemoryTypeHost || !at.devicePointer) { all = false; break; }
                 dp[i] = at.devicePointer;
-                if (plan->n_pinned < 16) {
-                    plan->pinned_host[plan->n_pinned] = hp[i]; plan->pinned_dev[plan->n_pinned] = dp[i]; ++plan->n_pinned;
-                }
             }
-            if (all && !getenv("SIHMPC_NO_ZEROCOPY") && h->du && h->J && h->status && h->n_active) {
+            if (all) {
                 sihmpc_io z = d;
                 z.x = static_cast<double *>(dp[0]); z.u = static_cast<double *>(dp[1]); z.pesos = static_cast<double *>(dp[2]);
                 z.vinant = static_cast<double *>(dp[3]); z.ysp = static_cast<double *>(dp[4]);
@@ -523,14 +571,8 @@ int sihmpc_step_host(sihmpc_plan *plan, const sihmpc_io *h, int64_t batch, void 
             }
         }
     }
-    if (batch <= 512) {
-        // ---- small batch (latency path): pack on the host, ONE upload, ONE download
-        if (plan->h_stage_bytes < stage_bytes) {
-            if (plan->h_stage) cudaFreeHost(plan->h_stage);
-            plan->h_stage = nullptr; plan->h_stage_bytes = 0;
-            CUDA_TRY(cudaHostAlloc(&plan->h_stage, stage_bytes, cudaHostAllocDefault));
-            plan->h_stage_bytes = stage_bytes;
-        }
+    if (batch <= SIH_PACK_MAX && stage_bytes <= plan->h_stage_bytes) {
+        // ---- small batch (latency path): pack on the host (pinned buffer of the plan), ONE upload, ONE download
         char *hs = static_cast<char *>(plan->h_stage);
         memcpy(hs + off[0], h->x, batch * bx); memcpy(hs + off[1], h->u, batch * bu);
         memcpy(hs + off[2], h->pesos, batch * bp); memcpy(hs + off[4], h->ysp, batch * by);
@@ -553,14 +595,7 @@ int sihmpc_step_host(sihmpc_plan *plan, const sihmpc_io *h, int64_t batch, void 
     // ---- large batch (throughput path): chunks pipelined over an upload stream, the caller's
     // stream (all kernels, in order: they share the plan's hand-over buffers) and a download stream
     int nchunk = batch >= 4096 ? 4 : 2;
-    if (const char *cv = getenv("SIHMPC_HOST_CHUNKS")) { const int v = atoi(cv); if (v >= 1 && v <= 64) nchunk = v; }
-    if (!plan->s_h2d) CUDA_TRY(cudaStreamCreateWithFlags(&plan->s_h2d, cudaStreamNonBlocking));
-    if (!plan->s_d2h) CUDA_TRY(cudaStreamCreateWithFlags(&plan->s_d2h, cudaStreamNonBlocking));
-    while ((int)plan->events.size() < 2 * nchunk + 2) {
-        cudaEvent_t e;
-        CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        plan->events.push_back(e);
-    }
+    if (plan->env_chunks) nchunk = plan->env_chunks;
     cudaEvent_t ev_start = plan->events[2 * nchunk], ev_done = plan->events[2 * nchunk + 1];
     CUDA_TRY(cudaEventRecord(ev_start, st));                 // uploads start after prior work of the caller's stream
     CUDA_TRY(cudaStreamWaitEvent(plan->s_h2d, ev_start, 0));
@@ -621,6 +656,9 @@ int sihmpc_subobjectives(sihmpc_plan *plan, const double *x, const double *w, co
     if (!plan || !x || !w || !ysp || !V) return fail(SIHMPC_E_INVALID, "NULL argument%s");
     if (batch <= 0) return batch == 0 ? 0 : fail(SIHMPC_E_INVALID, "negative batch%s");
     const DevPlan &P = plan->d;
+    // w is [N*nu ; syN ; siN] (sol['w_opt']): a plan with ranged terminal residuals carries them as extra decision
+    // variables, so syN/siN are no longer functions of that vector alone -- evaluate through a plan without ranges
+    if (P.nv != P.nvm) return fail(SIHMPC_E_INVALID, "sihmpc_subobjectives: plan has ranged terminal residuals (n_extra > 0)%s");
     const int wpb = 4;
     const size_t per = (size_t)(P.nx + P.nv + P.ny + 2 * P.ny + P.R + P.nv + P.m + 8) * 8;
     const size_t smem = per * wpb;

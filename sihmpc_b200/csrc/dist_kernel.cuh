@@ -680,6 +680,7 @@ struct QuadPlan {
     int *start_step;           // device [capacity]
     int *n_handover;           // device
     long long capacity;
+    int grid_cap;              // debug: upper limit of the grid (0: none)
     int blocks_per_sm;
     size_t smem_bytes;
 };
@@ -855,13 +856,9 @@ inline cudaError_t quad_configure(const sihmpc_plan_desc *d, const DevPlan &P, Q
     return cudaSuccess;
 }
 
-inline cudaError_t quad_ensure_capacity(QuadPlan *qp, long long batch) {
-    if (qp->capacity >= batch) return cudaSuccess;
-    if (qp->n_handover) cudaFree(qp->n_handover);      // one buffer: [counter | start_step[batch]]
-    qp->n_handover = nullptr; qp->start_step = nullptr; qp->capacity = 0;
-    cudaError_t e = cudaMalloc(&qp->n_handover, (size_t)(batch + 1) * sizeof(int));
-    if (e == cudaSuccess) { qp->start_step = qp->n_handover + 1; qp->capacity = batch; }
-    return e;
+// [counter | start_step[batch]] in the caller's workspace (capi.cu: bind_handover)
+inline void quad_bind(QuadPlan *qp, int *ctr, long long batch) {
+    qp->n_handover = ctr; qp->start_step = ctr + 1; qp->capacity = batch;
 }
 
 inline bool quad_supported(const QuadPlan &qp, const sihmpc_io &) { return qp.shape >= 0; }
@@ -873,7 +870,7 @@ inline cudaError_t quad_launch(const QuadPlan &qp, const DevPlan &P, const sihmp
     long long need = (batch + per_block - 1) / per_block;
     const long long cap = (long long)sm_count * qp.blocks_per_sm;
     int grid = (int)(need < cap ? need : cap);
-    if (const char *gv = getenv("SIHMPC_QUAD_GRID")) { int gg = atoi(gv); if (gg > 0 && gg < grid) grid = gg; }  // debug: force many rounds
+    if (qp.grid_cap > 0 && qp.grid_cap < grid) grid = qp.grid_cap;      // debug: force many rounds
     // start_step[] = n_steps (nothing to hand over), counter = 0
     quad_step_kernel<D, QUAD_WARPS, QUAD_MINB><<<grid, QUAD_WARPS * 32, qp.smem_bytes, st>>>(
         P, qp.qc, qp.qbuf, io, batch, n_steps, qp.start_step, qp.n_handover);
@@ -882,7 +879,6 @@ inline cudaError_t quad_launch(const QuadPlan &qp, const DevPlan &P, const sihmp
 
 inline void quad_destroy(QuadPlan *qp) {
     if (qp->qbuf) cudaFree(qp->qbuf);
-    if (qp->n_handover) cudaFree(qp->n_handover);
     memset(qp, 0, sizeof *qp);
     qp->shape = -1;
 }

@@ -789,7 +789,8 @@ struct MmaPlan {
     int shape;
     MmaConst qc;
     double *qbuf;
-    int *ctr;                // one device buffer: [n_handover | n_fail | n_inkernel | pad | start_step[cap] | list[cap]]
+    int *ctr;                // in the caller's workspace (mma_bind): [n_handover | n_fail | n_inkernel | pad | start_step[cap] | list[cap]]
+    int grid_cap;            // debug: upper limit of the grid (0: none)
     int *start_step;
     int *n_handover;         // scenarios the first pass appended to `list` (counter baseline 0x7f7f7f7f)
     int *n_fail;             // scenarios the resume pass could not resolve either: left to the general kernel
@@ -1129,16 +1130,10 @@ inline cudaError_t mma_configure(const sihmpc_plan_desc *d, const DevPlan &P, Mm
     return qp->shape == 1 ? mma_configure_shape<DistillationMma16>(d, P, qp) : mma_configure_shape<DistillationMma>(d, P, qp);
 }
 
-inline cudaError_t mma_ensure_capacity(MmaPlan *qp, long long batch) {
-    if (qp->capacity >= batch) return cudaSuccess;
-    if (qp->ctr) cudaFree(qp->ctr);
-    qp->ctr = qp->n_handover = qp->n_fail = qp->n_inkernel = qp->start_step = qp->list = nullptr; qp->capacity = 0;
-    cudaError_t e = cudaMalloc(&qp->ctr, (size_t)(4 + 2 * batch) * sizeof(int));
-    if (e == cudaSuccess) {
-        qp->n_handover = qp->ctr; qp->n_fail = qp->ctr + 1; qp->n_inkernel = qp->ctr + 2;
-        qp->start_step = qp->ctr + 4; qp->list = qp->ctr + 4 + batch; qp->capacity = batch;
-    }
-    return e;
+// the hand-over block lives in the caller's workspace (capi.cu: bind_handover): nothing is allocated at step time
+inline void mma_bind(MmaPlan *qp, int *ctr, long long batch) {
+    qp->ctr = ctr; qp->n_handover = ctr; qp->n_fail = ctr + 1; qp->n_inkernel = ctr + 2;
+    qp->start_step = ctr + 4; qp->list = ctr + 4 + batch; qp->capacity = batch;
 }
 
 // counters and start_step back to "nothing handed over" (every counter counts up from the baseline 0x7f7f7f7f)
@@ -1170,14 +1165,13 @@ inline cudaError_t mma_launch(MmaPlan &qp, const DevPlan &P, const sihmpc_io &io
     long long need = (batch + per_block - 1) / per_block;
     const long long cap = (long long)sm_count * qp.blocks_per_sm;
     int grid = (int)(need < cap ? need : cap);
-    if (const char *gv = getenv("SIHMPC_QUAD_GRID")) { int gg = atoi(gv); if (gg > 0 && gg < grid) grid = gg; }
+    if (qp.grid_cap > 0 && qp.grid_cap < grid) grid = qp.grid_cap;      // debug override (SIHMPC_QUAD_GRID, read at plan creation)
     return qp.shape == 1 ? mma_launch_shape<DistillationMma16>(qp, P, io, batch, n_steps, grid, st)
                          : mma_launch_shape<DistillationMma>(qp, P, io, batch, n_steps, grid, st);
 }
 
 inline void mma_destroy(MmaPlan *qp) {
     if (qp->qbuf) cudaFree(qp->qbuf);
-    if (qp->ctr) cudaFree(qp->ctr);
     memset(qp, 0, sizeof *qp);
     qp->shape = -1;
 }

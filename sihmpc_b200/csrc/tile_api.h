@@ -35,7 +35,7 @@ struct TilePlan {
     TileCfg cfg;
     int *ibuf;               // device: ptr | kt | hmap
     double *dbuf;            // device: stored tiles
-    int *ctr;                // one device buffer: [n_handover | n_fail | n_inkernel | pad | (n_bounce, n_fail2) x TL_BOUNCES | start_step[cap] | list[cap] | list2[cap]]
+    int *ctr;                // in the caller's workspace (tile_bind): [n_handover | n_fail | n_inkernel | pad | (n_bounce, n_fail2) x TL_BOUNCES | start_step[cap] | list[cap] | list2[cap]]
     int *start_step;
     int *n_handover;         // scenarios the first pass appended to `list` (counter baseline 0x7f7f7f7f)
     int *n_fail;             // scenarios the resume pass could not resolve: left to the general kernel
@@ -50,7 +50,7 @@ struct TilePlan {
 };
 
 cudaError_t tile_configure(const sihmpc_plan_desc *d, const DevPlan &P, TilePlan *tp);
-cudaError_t tile_ensure_capacity(TilePlan *tp, long long batch);
+void tile_bind(TilePlan *tp, int *ctr, unsigned long long *warm, long long batch);
 cudaError_t tile_reset(const TilePlan &tp, long long batch, cudaStream_t st);
 // the resume pass is one more launch: only worth it when the call carries enough work (not the single-step host API)
 inline bool tile_resumes(const TilePlan &tp, long long batch, int n_steps) { return tp.cfg.cspace >= 0 && (n_steps > 1 || batch >= 4096); }

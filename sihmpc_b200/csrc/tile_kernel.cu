@@ -901,20 +901,12 @@ cudaError_t tile_configure(const sihmpc_plan_desc *d, const DevPlan &P, TilePlan
     return cudaSuccess;
 }
 
-cudaError_t tile_ensure_capacity(TilePlan *tp, long long batch) {
-    if (tp->capacity >= batch) return cudaSuccess;
-    if (tp->ctr) cudaFree(tp->ctr);
-    if (tp->warm_mask) cudaFree(tp->warm_mask);
-    tp->ctr = tp->n_handover = tp->n_fail = tp->n_inkernel = tp->start_step = tp->list = tp->list2 = nullptr;
-    tp->warm_mask = nullptr; tp->capacity = 0;
-    cudaError_t e = cudaMalloc(&tp->ctr, (size_t)(TL_CTR + 3 * batch) * sizeof(int));
-    if (e == cudaSuccess) e = cudaMalloc(&tp->warm_mask, (size_t)2 * batch * sizeof(unsigned long long));
-    if (e == cudaSuccess) {
-        tp->n_handover = tp->ctr; tp->n_fail = tp->ctr + 1; tp->n_inkernel = tp->ctr + 2;
-        tp->start_step = tp->ctr + TL_CTR; tp->list = tp->ctr + TL_CTR + batch; tp->list2 = tp->ctr + TL_CTR + 2 * batch;
-        tp->capacity = batch;
-    }
-    return e;
+// the hand-over block lives in the caller's workspace (capi.cu: bind_handover): nothing is allocated at step time
+void tile_bind(TilePlan *tp, int *ctr, unsigned long long *warm, long long batch) {
+    tp->ctr = ctr; tp->warm_mask = warm;
+    tp->n_handover = ctr; tp->n_fail = ctr + 1; tp->n_inkernel = ctr + 2;
+    tp->start_step = ctr + TL_CTR; tp->list = ctr + TL_CTR + batch; tp->list2 = ctr + TL_CTR + 2 * batch;
+    tp->capacity = batch;
 }
 
 // counters and start_step back to "nothing handed over" (every counter counts up from the baseline 0x7f7f7f7f)
@@ -967,8 +959,6 @@ cudaError_t tile_launch_bounced(const TilePlan &tp, const DevPlan &P, const sihm
 void tile_destroy(TilePlan *tp) {
     if (tp->ibuf) cudaFree(tp->ibuf);
     if (tp->dbuf) cudaFree(tp->dbuf);
-    if (tp->ctr) cudaFree(tp->ctr);
-    if (tp->warm_mask) cudaFree(tp->warm_mask);
     memset(tp, 0, sizeof *tp);
 }
 #endif  // SIH_TL_ONLY_NT

@@ -19,7 +19,7 @@ import ctypes as C
 import numpy as np
 
 from .opom import OPOM
-from .plan import SubObjective, compile_plan, terminal_weight
+from .plan import SubObjective, compile_plan, fixed_row_violation, terminal_weight
 
 __all__ = ["IHMPCController", "DM"]
 
@@ -399,6 +399,8 @@ class IHMPCController(object):
         w = hs.w_opt.numpy()[0].copy()
         J = float(hs.J.numpy()[0])
         self.status = int(hs.status.numpy()[0])
+        if self._plan.fixed_rows and fixed_row_violation(self._plan, x, ysp, vin if len(vin) else None) > 1e-8:
+            self.status |= _capi.ST_INFEASIBLE            # a bound the moves cannot influence is violated at x0
         self.n_active = int(hs.n_active.numpy()[0])
         x_pred, y_pred, u_pred = self._predict(x, u, w[:N * nu])
         vals = self._eval_all(x, w, ysp)

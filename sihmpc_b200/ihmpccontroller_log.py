@@ -181,7 +181,11 @@ class IHMPCController(_Weighted):
         res = self.dynF(x0=xN, u0=np.zeros(nu), du0=np.zeros(nu))
         Xknext = res['xkp1'].full().reshape(-1)
         siNnext = Xknext[self.nxs + self.nxd:self.nxs + self.nxd + self.nxi]
-        syNnext = w0[-2 * ny - 1:-ny - 1]
+        # log.py:543 slices w0[-2*ny:-ny] on the vector that ends with ss, i.e. [syN[1:], siN[0]] -- kept as the
+        # reference has it (the value only seeds the next solve and the satWeights diagnostic of
+        # example_distillation_log.py:131; the optimum does not depend on it).  The device loop (sihmpc_log_loop)
+        # seeds its Newton iteration with the unshifted syN instead: same optimum, DESIGN.md "parity notes".
+        syNnext = w0[-2 * ny:-ny]
         return np.concatenate([dustart, syNnext, siNnext, [1.0]])                # log.py:548
 
     def satWeights(self, x, u, w0, ysp):                       # log.py:566-574

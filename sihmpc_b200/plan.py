@@ -85,6 +85,9 @@ class Plan:
     # ('s'|'i', output index)
     n_extra: int = 0
     extra: tuple = ()
+    # inequality rows the moves cannot influence (zero normal): not sent to the device, kept here so that the caller
+    # can still see them violated -- fixed_rows[k] = (Gcx, Gcy, gc0, lo, hi, vin_slot, q); see fixed_row_violation()
+    fixed_rows: tuple = ()
 
 
 def plant_csr(A, B, pattern=None):
@@ -258,7 +261,15 @@ def compile_plan(sys, N, VJ, bounds, Q_bar=None, vin=(), rs=None, ri=None, rs_hi
         rows.append((unit, np.zeros(nx), np.zeros(ny), 0.0, lo_, hi_, -1, 0.0))
     # rows whose normal vanishes cannot be influenced by dU: vacuous or infeasible whatever
     # the solver does (non-integrating plants: xi(N) = xi(0)); they are not sent to the device.
-    rows = [r for r in rows if np.linalg.norm(r[0]) > 1e-13 * max(1.0, np.linalg.norm(r[1]))]
+    keep = [np.linalg.norm(r[0]) > 1e-13 * max(1.0, np.linalg.norm(r[1])) for r in rows]
+    fixed_rows = tuple((r[1], r[2], r[3], r[4], r[5], r[6], r[7]) for r, k in zip(rows, keep)
+                       if not k and (np.isfinite(r[4]) or np.isfinite(r[5]) or r[6] >= 0))
+    if any(np.isfinite(fr[3]) or np.isfinite(fr[4]) for fr in fixed_rows):
+        import warnings
+        warnings.warn("%d bounded row(s) do not depend on the moves (e.g. silb/siub or xlb/xub on a state the inputs "
+                      "cannot reach): they are checked on the host (SIHMPC_ST_INFEASIBLE), not enforced by the solver"
+                      % sum(1 for fr in fixed_rows if np.isfinite(fr[3]) or np.isfinite(fr[4])), stacklevel=2)
+    rows = [r for r, k in zip(rows, keep) if k]
     ncd = len(rows)
     Gc = np.array([r[0] for r in rows]).reshape(ncd, nv)
     Gcx = np.array([r[1] for r in rows]).reshape(ncd, nx)
@@ -271,7 +282,7 @@ def compile_plan(sys, N, VJ, bounds, Q_bar=None, vin=(), rs=None, ri=None, rs_hi
 
     rowptr, col, val, _ = plant_csr(A, B)
 
-    return Plan(n_extra=n_extra, extra=tuple(extra),
+    return Plan(n_extra=n_extra, extra=tuple(extra), fixed_rows=fixed_rows,
                 nx=nx, nu=nu, ny=ny, nd=nd, N=N, nv=nvm, m=m, mh=len(hj_index), R=R, ncd=ncd,
                 n_vin=len(vin), Ts=Ts, E=E, Px=Px, Py=Py, e0=e0, Wrow=Wrow, w0row=w0row, Wdu=Wdu,
                 HJ=HJ, hj_index=np.array(hj_index, dtype=np.int32), Ht=Ht,
@@ -285,6 +296,22 @@ def compile_plan(sys, N, VJ, bounds, Q_bar=None, vin=(), rs=None, ri=None, rs_hi
                 A=A, B=B, C=C, D=D, Phi=Phi, Gam=Gam, Q_bar=Q_bar,
                 row_slices={'y': (0, N * ny), 'syN': (o_sy, o_sy + ny), 'siN': (o_si, o_si + ny),
                             'term': (o_t, o_t + nd)})
+
+
+def fixed_row_violation(plan: Plan, x, ysp, vinant=None) -> float:
+    """Largest violation of the rows the moves cannot influence (Plan.fixed_rows) at state x: the reference's IPOPT
+    would report such a problem infeasible (ctl.py:414-418,405-412 with a state or slack the inputs cannot reach);
+    here the step itself ignores them and the caller raises SIHMPC_ST_INFEASIBLE when this is > 1e-8."""
+    x = np.asarray(x, float).reshape(-1); ysp = np.asarray(ysp, float).reshape(-1)
+    worst = 0.0
+    for gx, gy, g0, lo, hi, slot, q in plan.fixed_rows:
+        v = float(gx @ x + gy @ ysp + g0)
+        if slot >= 0:
+            vin = np.inf if vinant is None else float(np.asarray(vinant, float).reshape(-1)[slot])
+            b = np.sqrt(max(vin, 0.0) / q) if np.isfinite(vin) and q > 0 else np.inf
+            lo, hi = -b, b
+        worst = max(worst, lo - v, v - hi)
+    return worst
 
 
 # ---------------------------------------------------------------------------------------

@@ -254,3 +254,19 @@ def test_unsupported_declarations_fail_loudly():
     c2 = IHMPCController(s, 10)
     with pytest.raises(NotImplementedError):
         c2.subObj(siN=[0, 1], Q=np.eye(2), addJ=False)
+
+
+def test_rows_the_moves_cannot_influence_are_recorded_and_checked():
+    """silb/siub on a plant without an integrating mode: xi(N) = xi(0) whatever the moves, the rows have a zero
+    normal.  They are not sent to the device, but the plan keeps them and reports their violation (the reference's
+    IPOPT would call the problem infeasible; ihmpccontroller.py:405-412)."""
+    from sihmpc_b200.plan import fixed_row_violation
+    s = sc.distillation_system()
+    c = sc.declare_distillation(IHMPCController, s, ulb=[0, 0], silb=[-1.0, -1.0], siub=[1.0, 1.0])
+    with pytest.warns(UserWarning, match="do not depend on the moves"):
+        p = c.compile()
+    assert p.ncd == 0 and len(p.fixed_rows) >= 2
+    x = np.zeros(s.nx); x[0], x[1] = 96.0, 0.5
+    assert fixed_row_violation(p, x, [96.0, 0.5]) <= 0.0
+    x[s.ny + s.nd] = 2.5                                   # xi_0 outside [-1, 1]
+    assert abs(fixed_row_violation(p, x, [96.0, 0.5]) - 1.5) < 1e-12
