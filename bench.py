@@ -2,17 +2,25 @@
 # -*- coding: utf-8 -*-
 """bench.py -- IHMPC closed-loop scenario-steps/s on N B200s (BASELINE.json metric).
 
-    python bench.py --gpus 1 --steps 200 --warmup 10
+    python bench.py --gpus 1 --steps 20 --warmup 5
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
     python bench.py --impl reference --steps 20 --warmup 3      # CPU arm (oracle port)
 
 A "step" is ONE control step (QP build + solve + first-move plant update + warm start + weight
-update) of EVERY scenario of the batch.  Workload (config.workload): the 2x2 distillation
+update) of EVERY scenario of the batch.  Headline workload (config.workload): the 2x2 distillation
 controller of example_distillation.py on the plant-model-mismatch Monte-Carlo scenario set
-(BASELINE.json configs[4], 1M scenarios over 8 GPUs = 131072 scenarios per GPU, weak scaling:
-at N=8 the run IS configs[4] including the final NCCL statistics reduction).  Other workloads:
---workload distillation4096 (configs[2]) and --workload mimo10 (configs[3]).
+(BASELINE.json configs[4], 1M scenarios over 8 GPUs = 131072 scenarios per GPU, weak scaling: at
+N=8 the run IS configs[4] including the NCCL statistics exchange).  The same line carries, under
+"configs", the other named workloads measured in the same run the same way: configs[2]
+(distillation4096), configs[3] (mimo10, 65536 scenarios per GPU) and configs[1] (the log-barrier
+controller: batch 4096 throughput and batch-1 p50 latency through sihmpc_log_loop).
+
+Timed region = EXACTLY K control steps of the window [k0, k0+K) of the 200-step closed loop (k0 chosen
+so that the window holds steps where bounds bind; k0 = 0 when K >= 200) + the on-device statistics
+reduction (+ the NCCL exchange when N > 1), on CUDA events, max over ranks.  It is repeated
+`--repeats` times from the same snapshot of the scenario state (L2 flushed before each); `value` is
+the MEDIAN repetition, min/max are reported next to it.
 
 Prints ONE JSON line on rank 0 (see DESIGN.md "Measurement" for every field).
 """
@@ -34,33 +42,35 @@ if ROOT not in sys.path:
 
 METRIC = "ihmpc_closed_loop_steps_per_sec"
 UNIT = "scenario-steps/s"
+LOOP_STEPS = 200                      # length of the closed loops of SURVEY.md section 8(d)
 
 
 # ----------------------------------------------------------------------------- workloads
-def build_workload(name, batch, first, n_total_steps):
+def build_workload(name, batch, first):
     from sihmpc_b200 import scenarios as sc
     from sihmpc_b200.ihmpccontroller import IHMPCController
     if name == "distillation_mismatch_mc":
         sys_ = sc.distillation_system()
         ctrl = sc.declare_distillation(IHMPCController, sys_)
         scen = sc.mismatch_scenarios(batch, first=first)
-        declare = sc.declare_distillation
     elif name == "distillation4096":
         sys_ = sc.distillation_system()
         ctrl = sc.declare_distillation(IHMPCController, sys_)
         scen = sc.distillation_scenarios(batch, first=first)
-        declare = sc.declare_distillation
     elif name == "mimo10":
         sys_ = sc.mimo10_system()
         ctrl = sc.declare_mimo10(IHMPCController, sys_)
         scen = sc.mimo10_scenarios(batch, sys_, first=first)
-        declare = sc.declare_mimo10
     else:
         raise SystemExit("unknown workload " + name)
-    return sys_, ctrl, scen, declare
+    return sys_, ctrl, scen
 
 
 DEFAULT_BATCH = {"distillation_mismatch_mc": 131072, "distillation4096": 4096, "mimo10": 65536}
+# first step of the timed window when K < 200: mismatch Monte-Carlo -- scenarios sit on u >= 0 from k ~ 120 on;
+# distillation4096 -- the set-point change at k = 11; mimo10 -- the second set-point change at k = 101, after which
+# ~3 % of the scenarios sit on the |u| <= 5 box (the large active-set transients)
+WINDOW_K0 = {"distillation_mismatch_mc": 115, "distillation4096": 5, "mimo10": 100}
 
 
 def algorithmic_flops(plan):
@@ -242,6 +252,203 @@ def cpu_arm(workload, per_core, n_steps, warm, cores=None):
                 p50_us=float(np.percentile(lat, 50) * 1e6), p99_us=float(np.percentile(lat, 99) * 1e6))
 
 
+# ----------------------------------------------------------------------------- GPU measurement
+class Ctx:
+    """Rank layout, device and the shared L2-flush buffer."""
+
+    def __init__(self, rank, world, local_rank, dev, torch, dist):
+        self.rank, self.world, self.local_rank, self.dev, self.torch, self.dist = rank, world, local_rank, dev, torch, dist
+        self.flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier(device_ids=[self.local_rank])
+        self.torch.cuda.synchronize(self.dev)
+
+    def max_over_ranks(self, values):
+        t = self.torch.tensor(values, dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(v) for v in t.cpu()]
+
+    def sum_over_ranks(self, values):
+        t = self.torch.tensor(values, dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return [float(v) for v in t.cpu()]
+
+
+def measure_workload(cx, name, batch, K, W, spl, repeats, fp64_peak, sampler_factory=None):
+    """K control steps of `name` on every rank's shard, timed `repeats` times from the same snapshot.
+    Returns (record, engine pieces) -- record = value / ms / roofline / counters of this workload."""
+    torch = cx.torch
+    from sihmpc_b200.dist import reduce_moments
+    from sihmpc_b200.engine import BatchedEngine
+    sys_, ctrl, scen = build_workload(name, batch, first=cx.rank * batch)
+    plan = ctrl.compile()
+    eng = BatchedEngine(plan, batch, device=cx.dev)
+    eng.set_state(scen["x0"], scen["u0"])
+    eng.set_schedule(scen["ysp_seq"], scen["seg_start"])
+    if "dist_step" in scen:
+        eng.set_disturbance(scen["dist_step"], scen["dist"])
+    if "plant_val" in scen:
+        eng.set_plant_values(scen["plant_val"])
+    spl = spl or K
+    k0 = WINDOW_K0[name] if K + WINDOW_K0[name] <= LOOP_STEPS else 0
+    # ---- untimed: pre-roll to the first step of the window, snapshot, then W warm-up steps through the same
+    # kernels and the same collective as the timed region (first-use NCCL channel set-up is not billed to a step)
+    if k0 > 0:
+        eng.run(k0)
+    snap = eng.snapshot()
+    eng.run(W, steps_per_launch=min(spl, W))
+    reduce_moments(eng.reduce_stats())
+    eng.restore(snap)
+    eng.run(K, steps_per_launch=spl)                    # one full-shape launch as well (W may be < K)
+    reduce_moments(eng.reduce_stats())
+    torch.cuda.synchronize(cx.dev)
+    sampler = sampler_factory() if sampler_factory else None
+    ms_total, ms_kernel, agg = [], [], None
+    t_wall0 = time.time()
+    for _ in range(repeats):
+        eng.restore(snap)
+        cx.flush.fill_(1)                               # L2 flush (512 MiB write) before every repetition
+        cx.barrier()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
+        eng.run(K, steps_per_launch=spl)                # ---- timed: EXACTLY K control steps ...
+        ev[1].record()
+        agg = reduce_moments(eng.reduce_stats())        # ... + statistics reduction (+ ONE NCCL collective)
+        ev[2].record()
+        cx.barrier()
+        ms_total.append(ev[0].elapsed_time(ev[2]))
+        ms_kernel.append(ev[0].elapsed_time(ev[1]))
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    counters = eng.dp.counters()
+    tot = np.asarray(cx.max_over_ranks(ms_total))       # per repetition: the slowest rank
+    ker = np.asarray(cx.max_over_ranks(ms_kernel))
+    med = int(np.argsort(tot)[len(tot) // 2])
+    flagged = int(cx.sum_over_ranks([float((eng.stats[:, plan.ny + 3] != 0).sum().item())])[0])
+    handed, solved = [int(v) for v in cx.sum_over_ranks([float(counters[0]), float(counters[1])])]
+    n_launch = (K + spl - 1) // spl
+    kname = eng.dp.kernel_name()
+    has_bounds = bool(np.isfinite(plan.ulb).any() or np.isfinite(plan.uub).any() or np.isfinite(plan.dulb).any()
+                      or np.isfinite(plan.duub).any())
+    if kname in ("mma_step_kernel", "tile_step_kernel") and has_bounds:
+        kpl, kdesc = 3, "%s first pass, %s resume pass, ihmpc_step_kernel" % (kname, kname)
+    else:
+        kpl, kdesc = 1, kname
+    F_alg, B_alg = algorithmic_flops(plan), algorithmic_bytes(plan)
+    per_launch_s = float(np.median(ker)) * 1e-3 / n_launch
+    achieved = F_alg * batch * (K / n_launch) / per_launch_s / 1e12
+    rec = {
+        "workload": name, "value": cx.world * batch * K / (tot[med] * 1e-3), "unit": UNIT,
+        "value_min": cx.world * batch * K / (tot.max() * 1e-3), "value_max": cx.world * batch * K / (tot.min() * 1e-3),
+        "repeats": repeats, "ms_per_step": float(tot[med]) / K,
+        "ms_timed_region": {"median": float(tot[med]), "min": float(tot.min()), "max": float(tot.max())},
+        "scenarios_per_gpu": batch, "window": [k0, k0 + K], "steps_per_launch": spl,
+        "plant": "%dx%d" % (plan.ny, plan.nu), "nx": plan.nx, "N": plan.N, "nv": plan.nv,
+        "kernel": "sih::" + kname, "kernel_ms_per_launch": per_launch_s * 1e3, "launches": n_launch,
+        "gpu_launches": n_launch * kpl + 2,
+        "gpu_launches_detail": "%d sihmpc_step call(s) x %d kernels (%s) + stats_init_kernel + stats_reduce_kernel"
+                               % (n_launch, kpl, kdesc),
+        "handed_over_to_general_kernel": handed, "constrained_steps_resolved_in_fast_path": solved,
+        "flagged_scenarios": flagged, "status_or": int(agg[2, plan.ny + 3].item()),
+        "flop_per_scenario_step": F_alg, "achieved_tflops": achieved, "frac_of_fp64_peak": achieved / (fp64_peak / 1e12),
+        "hbm_gbs": B_alg * batch / per_launch_s / 1e9, "bytes_per_scenario_launch": B_alg,
+    }
+    return rec, dict(plan=plan, scen=scen, eng=eng, clocks=clocks, snap=snap)
+
+
+def measure_log_variant(cx, K, W, repeats):
+    """configs[1]: the log-barrier controller (example_distillation_log.py) through sihmpc_log_loop --
+    throughput at batch 4096 and p50 latency of one step at batch 1 (host call to synchronised result)."""
+    torch = cx.torch
+    from sihmpc_b200 import scenarios as sc
+    from sihmpc_b200.ihmpccontroller_log import IHMPCController as LogController
+    sys_ = sc.distillation_system()
+    c = sc.declare_distillation_log(LogController, sys_)
+    batch = 4096
+    scen = sc.distillation_scenarios(batch)
+    seg = scen["seg_start"].copy(); seg[:, 1] = 51; seg[:, 2] = 401          # example_distillation_log.py:90-94
+    eng = c.engine(batch)
+    eng.set_state(scen["x0"], scen["u0"])
+    eng.set_schedule(scen["ysp_seq"], seg)
+    k0 = 45                                              # window over the set-point change at k = 51
+    eng.run(k0)
+    snap = eng.snapshot()
+    eng.run(max(W, 1)); eng.restore(snap); eng.run(K)
+    torch.cuda.synchronize(cx.dev)
+    ms = []
+    for _ in range(repeats):
+        eng.restore(snap)
+        cx.flush.fill_(1)
+        torch.cuda.synchronize(cx.dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); eng.run(K); e1.record()
+        torch.cuda.synchronize(cx.dev)
+        ms.append(e0.elapsed_time(e1))
+    ms = np.asarray(ms)
+    iters = float(eng.iters.to(torch.float64).mean().item())
+    st_or = int(eng.status.max().item())
+    # batch 1, one step per call, host to host
+    e1_ = c.engine(1)
+    e1_.set_state(scen["x0"][:1], scen["u0"][:1])
+    e1_.set_schedule(scen["ysp_seq"][:1], seg[:1])
+    ts = []
+    for i in range(260):
+        a = time.perf_counter()
+        e1_.run(1)
+        torch.cuda.synchronize(cx.dev)
+        ts.append(time.perf_counter() - a)
+    ts = np.asarray(ts[60:]) * 1e6
+    return {"workload": "distillation_log (example_distillation_log.py controller, ihmpc_log_kernel via sihmpc_log_loop)",
+            "value": batch * K / (float(np.median(ms)) * 1e-3), "unit": UNIT,
+            "value_min": batch * K / (ms.max() * 1e-3), "value_max": batch * K / (ms.min() * 1e-3),
+            "scenarios": batch, "window": [k0, k0 + K], "repeats": repeats, "ms_per_step": float(np.median(ms)) / K,
+            "mean_newton_iterations_last_step": iters, "status_or": st_or, "kernel": "sih::ihmpc_log_kernel",
+            "latency_batch1": {"p50_us": float(np.percentile(ts, 50)), "p99_us": float(np.percentile(ts, 99)),
+                               "what": "one closed-loop step (mpc + plant + warmStart) at batch 1, device-resident state, "
+                                       "call to synchronised result"}}
+
+
+def measure_e2e(cx, plan, scen, batch, steps):
+    """The same metric through the host-buffer C-ABI call (sihmpc_step_host): pinned host state, the step's
+    inputs go up and its results come down EVERY step inside the timed region."""
+    torch = cx.torch
+    from sihmpc_b200 import _capi
+    from sihmpc_b200.engine import HostStepper
+    hs = HostStepper(plan, batch, device=cx.dev)
+    hs.x.copy_(torch.as_tensor(scen["x0"])); hs.u.copy_(torch.as_tensor(scen["u0"]))
+    ysp_np = scen["ysp_seq"][:, 1, :]
+    hs.ysp.copy_(torch.as_tensor(np.ascontiguousarray(ysp_np)))
+    fl = _capi.F_ADVANCE | _capi.F_UPDATE_VIN | _capi.F_WEIGHTS_SAT2
+    for _ in range(3):
+        hs.step(flags=fl, want_w_opt=False)
+    cx.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        hs.step(flags=fl, want_w_opt=False)            # synchronises the stream itself
+    cx.barrier()
+    dt = cx.max_over_ranks([time.perf_counter() - t0])[0]
+    e2e = {"value": cx.world * batch * steps / dt, "unit": UNIT,
+           "h2d_bytes_per_step": hs.h2d_bytes(), "d2h_bytes_per_step": hs.d2h_bytes(advance=True, want_w_opt=False),
+           "steps": steps, "api": "sihmpc_step_host (pinned host buffers; in: x,u,pesos,ViNant,ysp; out: du,J,status,ViNant + "
+                                  "advanced x,u,pesos; zero-copy: the step kernel reads and writes the pinned arrays over PCIe)"}
+    lat = None
+    if cx.rank == 0:
+        h1 = HostStepper(plan, 1, device=cx.dev)
+        h1.x.copy_(torch.as_tensor(scen["x0"][:1])); h1.u.copy_(torch.as_tensor(scen["u0"][:1]))
+        h1.ysp.copy_(torch.as_tensor(np.ascontiguousarray(ysp_np[:1])))
+        ts = []
+        for i in range(300):
+            a = time.perf_counter(); h1.step(flags=fl); ts.append(time.perf_counter() - a)
+        ts = np.asarray(ts[50:]) * 1e6
+        lat = {"p50_us": float(np.percentile(ts, 50)), "p99_us": float(np.percentile(ts, 99)),
+               "what": "one closed-loop step at batch 1 through sihmpc_step_host, host to host"}
+    return e2e, lat
+
+
 # ----------------------------------------------------------------------------- main
 def _emit(line):
     """The ONE JSON line goes to the real stdout; everything else a library prints to fd 1 (NCCL's
@@ -259,14 +466,16 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="distillation_mismatch_mc")
     ap.add_argument("--batch", type=int, default=0, help="scenarios per GPU (default: the named config's)")
     ap.add_argument("--steps-per-launch", type=int, default=0, help="control steps fused in one launch (0 = all)")
+    ap.add_argument("--repeats", type=int, default=7, help="repetitions of the timed region (median reported)")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the sub-records of the other named workloads")
     ap.add_argument("--cpu-per-core", type=int, default=48,
                     help="scenarios per host core in the CPU arm (48 x 200 steps ~ 10 s per core)")
     args = ap.parse_args()
@@ -300,132 +509,68 @@ def main():
         os.environ["NCCL_DEBUG"] = "WARN"        # keep stdout to the one JSON line
     import torch
     import torch.distributed as dist
-    from sihmpc_b200 import _capi
-    from sihmpc_b200.engine import BatchedEngine, HostStepper, fp64_peak_flops
+    from sihmpc_b200.dist import gather_stats
+    from sihmpc_b200.engine import fp64_peak_flops
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-
-    batch = args.batch or DEFAULT_BATCH[args.workload]
-    sys_, ctrl, scen, _ = build_workload(args.workload, batch, first=rank * batch, n_total_steps=K + W)
-    plan = ctrl.compile()
-    eng = BatchedEngine(plan, batch, device=dev)
-    eng.set_state(scen["x0"], scen["u0"])
-    eng.set_schedule(scen["ysp_seq"], scen["seg_start"])
-    if "dist_step" in scen:
-        eng.set_disturbance(scen["dist_step"], scen["dist"])
-    if "plant_val" in scen:
-        eng.set_plant_values(scen["plant_val"])
-    spl = args.steps_per_launch or K
+    cx = Ctx(rank, world, local_rank, dev, torch, dist)
 
     fp64_peak = fp64_peak_flops()                      # measured DFMA throughput of this GPU
-    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    batch = args.batch or DEFAULT_BATCH[args.workload]
 
-    def barrier():
-        if world > 1:
-            dist.barrier(device_ids=[local_rank])
-        torch.cuda.synchronize(dev)
-
-    # ---- warm-up: W control steps, untimed (same kernel, same launch shape as the timed region)
-    eng.run(W, steps_per_launch=min(spl, W))
-    eng.reduce_stats()
-    torch.cuda.synchronize(dev)
-    flush.fill_(1)                                     # L2 flush before the timed region
-    sampler = None
-    if rank == 0:
+    def sampler_factory():
+        if rank != 0:
+            return None
         try:
             uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
         except Exception:
             uuid = None
-        sampler = ClockSampler(local_rank, uuid)
-    barrier()
-    # ---- timed region: EXACTLY K control steps (+ the statistics reduction / NCCL exchange)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-    t_wall0 = time.time()
-    ev[0].record()
-    eng.run(K, steps_per_launch=spl)
-    ev[1].record()
-    agg = eng.reduce_stats()
-    if world > 1:
-        dist.all_reduce(agg[:2], op=dist.ReduceOp.SUM)
-        dist.all_reduce(agg[2], op=dist.ReduceOp.MAX)
-    ev[2].record()
-    barrier()
-    t_wall1 = time.time()
-    ms_total = ev[0].elapsed_time(ev[2])
-    ms_kernel = ev[0].elapsed_time(ev[1])
-    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
-    n_launch = (K + spl - 1) // spl
-    # kernels of OURS per sihmpc_step call: a fast path with bounds runs first pass + resume pass + general kernel
-    # (the last two leave at once when nothing was listed); without bounds, or on the general kernel alone, one
-    kname = eng.dp.kernel_name()
-    has_bounds = bool(np.isfinite(plan.ulb).any() or np.isfinite(plan.uub).any() or np.isfinite(plan.dulb).any()
-                      or np.isfinite(plan.duub).any())
-    if kname in ("mma_step_kernel", "tile_step_kernel") and has_bounds:
-        kernels_per_launch, kernels_desc = 3, "%s first pass, %s resume pass, ihmpc_step_kernel" % (kname, kname)
-    else:
-        kernels_per_launch, kernels_desc = 1, kname
-    counters = eng.dp.counters()
-    t = torch.tensor([ms_total, ms_kernel], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_kernel = float(t[0]), float(t[1])
-    status_or = int(agg[2, plan.ny + 3].item())
-    # scenarios whose loop raised a status bit (e.g. an unstable mismatched plant: 1 of the 1M of configs[4])
-    flagged = (eng.stats[:, plan.ny + 3] != 0).sum().to(torch.float64).reshape(1)
-    if world > 1:
-        dist.all_reduce(flagged, op=dist.ReduceOp.SUM)
-    flagged = int(flagged.item())
-    value = world * batch * K / (ms_total * 1e-3)
+        return ClockSampler(local_rank, uuid)
 
-    # ---- end-to-end through the host-buffer C-ABI call (pinned host state, H2D + D2H every step)
-    e2e = None
-    lat = None
-    if True:
-        hs = HostStepper(plan, batch, device=dev)
-        hs.x.copy_(torch.as_tensor(scen["x0"])); hs.u.copy_(torch.as_tensor(scen["u0"]))
-        ysp_np = scen["ysp_seq"][:, 1, :]
-        hs.ysp.copy_(torch.as_tensor(np.ascontiguousarray(ysp_np)))
-        fl = _capi.F_ADVANCE | _capi.F_UPDATE_VIN | _capi.F_WEIGHTS_SAT2
-        for _ in range(3):
-            hs.step(flags=fl, want_w_opt=False)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            hs.step(flags=fl, want_w_opt=False)        # synchronises the stream itself
-        barrier()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * batch * args.e2e_steps / float(tt[0]), "unit": UNIT,
-               "h2d_bytes_per_step": hs.h2d_bytes(), "d2h_bytes_per_step": hs.d2h_bytes(advance=True, want_w_opt=False),
-               "steps": args.e2e_steps, "api": "sihmpc_step_host (pinned host buffers; in: x,u,pesos,ViNant,ysp; out: du,J,status,ViNant + advanced x,u,pesos; "
-                      "zero-copy: the step kernel reads and writes the pinned arrays over PCIe)"}
+    main_rec, m = measure_workload(cx, args.workload, batch, K, W, args.steps_per_launch, args.repeats, fp64_peak,
+                                   sampler_factory)
+    plan, scen, eng, clocks = m["plan"], m["scen"], m["eng"], m["clocks"]
+
+    # ---- the statistics GATHER of configs[4] (every scenario's block to every rank), once, timed on its own
+    gather_ms = None
+    if world > 1:
+        full = gather_stats(eng.stats, world * batch)          # warm
+        cx.barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(); full = gather_stats(eng.stats, world * batch); g1.record()
+        cx.barrier()
+        gather_ms = {"ms": cx.max_over_ranks([g0.elapsed_time(g1)])[0], "bytes_total": int(full.numel() * 8),
+                     "what": "NCCL all-gather of the per-scenario statistics block [scenarios][ny+5] FP64 to every rank "
+                             "(sihmpc_b200.dist.gather_stats), max over ranks"}
+        del full
+
+    e2e, lat = measure_e2e(cx, plan, scen, batch, args.e2e_steps)
+    del eng, m
+    torch.cuda.empty_cache()
+
+    # ---- the other named workloads, same method, same run
+    configs = {}
+    if not args.no_configs:
+        for name in ("distillation4096", "mimo10"):
+            if name == args.workload:
+                continue
+            rec, mm = measure_workload(cx, name, DEFAULT_BATCH[name], K, W, 0, max(3, args.repeats // 2), fp64_peak)
+            configs[name] = rec
+            del mm
+            torch.cuda.empty_cache()
         if rank == 0:
-            h1 = HostStepper(plan, 1, device=dev)
-            h1.x.copy_(torch.as_tensor(scen["x0"][:1])); h1.u.copy_(torch.as_tensor(scen["u0"][:1]))
-            h1.ysp.copy_(torch.as_tensor(np.ascontiguousarray(ysp_np[:1])))
-            ts = []
-            for i in range(300):
-                a = time.perf_counter(); h1.step(flags=fl); ts.append(time.perf_counter() - a)
-            ts = np.asarray(ts[50:]) * 1e6
-            lat = {"p50_us": float(np.percentile(ts, 50)), "p99_us": float(np.percentile(ts, 99)),
-                   "what": "one closed-loop step at batch 1 through sihmpc_step_host, host to host"}
+            configs["distillation_log"] = measure_log_variant(cx, K, W, max(3, args.repeats // 2))
+        cx.barrier()
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    F_alg = algorithmic_flops(plan)
-    B_alg = algorithmic_bytes(plan)
-    per_launch_s = ms_kernel * 1e-3 / n_launch
-    steps_per_launch_units = batch * (K / n_launch)
-    achieved_tflops = F_alg * steps_per_launch_units / per_launch_s / 1e12
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -437,18 +582,18 @@ def main():
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        ent = tj.get(eng.dp.kernel_name() + ":" + args.workload)
+        ent = tj.get(main_rec["kernel"].replace("sih::", "") + ":" + args.workload)
         if ent:
             traffic = float(ent["dram_bytes_per_scenario_launch"]) * batch
     except Exception:
         pass
-    roofline = {"bound": "fp64", "achieved": achieved_tflops, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
-                "frac": achieved_tflops / (fp64_peak / 1e12), "traffic": traffic,
+    roofline = {"bound": "fp64", "achieved": main_rec["achieved_tflops"], "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
+                "frac": main_rec["frac_of_fp64_peak"], "traffic": traffic,
                 "peak_source": "measured in this run (sihmpc_fp64_peak: dependent-free DFMA loop, all SMs)",
-                "flop_per_scenario_step": F_alg, "kernel": "sih::" + eng.dp.kernel_name(),
-                "kernel_ms_per_launch": per_launch_s * 1e3, "launches": n_launch,
-                "hbm": {"achieved": B_alg * batch / per_launch_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                        "bytes_per_scenario_launch": B_alg,
+                "flop_per_scenario_step": main_rec["flop_per_scenario_step"], "kernel": main_rec["kernel"],
+                "kernel_ms_per_launch": main_rec["kernel_ms_per_launch"], "launches": main_rec["launches"],
+                "hbm": {"achieved": main_rec["hbm_gbs"], "peak": hbm_peak, "unit": "GB/s",
+                        "bytes_per_scenario_launch": main_rec["bytes_per_scenario_launch"],
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
 
     cpu = None
@@ -459,21 +604,26 @@ def main():
                          % (r["cores"] * args.cpu_per_core, r["seconds"]),
                "p50_step_latency_us": r["p50_us"]}
 
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    line = {"metric": METRIC, "value": main_rec["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": main_rec["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "scenarios_per_gpu": batch, "plant": "%dx%d" % (plan.ny, plan.nu),
-                       "nx": plan.nx, "N": plan.N, "nv": plan.nv, "steps_per_launch": spl,
-                       "l2": "flushed (512 MiB write) before the timed region; per-scenario state is read once "
+            "config": {"workload": args.workload, "scenarios_per_gpu": batch, "plant": main_rec["plant"],
+                       "nx": plan.nx, "N": plan.N, "nv": plan.nv, "steps_per_launch": main_rec["steps_per_launch"],
+                       "window": "control steps [%d, %d) of the %d-step closed loop (pre-rolled untimed)"
+                                 % (main_rec["window"][0], main_rec["window"][1], LOOP_STEPS),
+                       "repeats": "%d repetitions from the same state snapshot; value = median" % args.repeats,
+                       "l2": "flushed (512 MiB write) before every repetition; per-scenario state is read once "
                              "and written once per launch, everything else stays on chip",
-                       "includes": "final on-device statistics reduction" + (" + NCCL all-reduce" if world > 1 else "")},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": n_launch * kernels_per_launch + 1,
-            "gpu_launches_detail": "%d sihmpc_step call(s) x %d kernels (%s) + 1 stats_reduce_kernel"
-                                   % (n_launch, kernels_per_launch, kernels_desc),
-            "handed_over_to_general_kernel": counters[0], "constrained_steps_resolved_in_fast_path": counters[1],
-            "roofline": roofline,
-            "cpu_baseline": cpu, "latency_batch1": lat, "status_or": status_or, "flagged_scenarios": flagged,
-            "fp64_peak_tflops_measured": fp64_peak / 1e12}
+                       "includes": "final on-device statistics reduction" + (" + one NCCL all-gather of the moments" if world > 1 else "")},
+            "value_min": main_rec["value_min"], "value_max": main_rec["value_max"],
+            "ms_timed_region": main_rec["ms_timed_region"],
+            "clocks": clocks, "e2e": e2e, "gpu_launches": main_rec["gpu_launches"],
+            "gpu_launches_detail": main_rec["gpu_launches_detail"],
+            "handed_over_to_general_kernel": main_rec["handed_over_to_general_kernel"],
+            "constrained_steps_resolved_in_fast_path": main_rec["constrained_steps_resolved_in_fast_path"],
+            "roofline": roofline, "cpu_baseline": cpu, "latency_batch1": lat, "status_or": main_rec["status_or"],
+            "flagged_scenarios": main_rec["flagged_scenarios"], "fp64_peak_tflops_measured": fp64_peak / 1e12,
+            "gather": gather_ms, "configs": configs}
     _emit(line)
     if world > 1:
         dist.destroy_process_group()

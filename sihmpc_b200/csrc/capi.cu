@@ -675,10 +675,8 @@ int sihmpc_subobjectives(sihmpc_plan *plan, const double *x, const double *w, co
 int sihmpc_stats_reduce(const double *stats, int64_t batch, int32_t nstat, double *out, void *stream) {
     if (!stats || !out || nstat < 1) return fail(SIHMPC_E_INVALID, "NULL argument%s");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    std::vector<double> init((size_t)3 * nstat, 0.0);
-    for (int c = 0; c < nstat; ++c) init[(size_t)2 * nstat + c] = -1e308;
-    CUDA_TRY(cudaMemcpyAsync(out, init.data(), init.size() * 8, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaStreamSynchronize(st));   // init[] is a stack-lifetime host buffer
+    sih::stats_init_kernel<<<1, 128, 0, st>>>(out, nstat);       // sums 0, max -1e308: no host buffer, no synchronise
+    CUDA_TRY(cudaGetLastError());
     if (batch <= 0) return 0;
     long long bx = (batch + 255) / 256;
     if (bx > 256) bx = 256;

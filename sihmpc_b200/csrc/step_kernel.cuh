@@ -843,6 +843,10 @@ __global__ void subobjectives_kernel(const DevPlan P, const double *__restrict__
     }
 }
 
+__global__ void stats_init_kernel(double *out, int nstat) {
+    for (int i = threadIdx.x; i < 3 * nstat; i += blockDim.x) out[i] = (i < 2 * nstat) ? 0.0 : -1e308;
+}
+
 // block-level reduction of the stats block: out[0][c] += sum, out[1][c] += sum sq, out[2][c] = max
 __global__ void stats_reduce_kernel(const double *__restrict__ stats, long long batch, int nstat,
                                     double *out) {

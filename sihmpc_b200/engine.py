@@ -197,9 +197,20 @@ class BatchedEngine:
                 done += n
         return traj_all
 
+    # ---- repeatable windows (bench.py: the same K steps timed several times) ------------------
+    def snapshot(self):
+        """Copy of everything a step advances (x, u, weights, ViN_ant, statistics, step index)."""
+        return dict(x=self.x.clone(), u=self.u.clone(), pesos=self.pesos.clone(), vinant=self.vinant.clone(),
+                    stats=self.stats.clone(), k=self.k)
+
+    def restore(self, snap):
+        self.x.copy_(snap["x"]); self.u.copy_(snap["u"]); self.pesos.copy_(snap["pesos"])
+        self.vinant.copy_(snap["vinant"]); self.stats.copy_(snap["stats"])
+        self.k = int(snap["k"])
+
     def reduce_stats(self):
         """[3][nstat] = (sum, sum of squares, max) over the scenarios of this device."""
-        out = torch.zeros(3, self.nstat, dtype=torch.float64, device=self.device)
+        out = torch.empty(3, self.nstat, dtype=torch.float64, device=self.device)
         st = torch.cuda.current_stream(self.device).cuda_stream
         with torch.cuda.device(self.device):
             _capi.check(self.dp.lib.sihmpc_stats_reduce(C.c_void_p(self.stats.data_ptr()), self.batch, self.nstat,
@@ -246,6 +257,14 @@ class LogBatchedEngine:
     set_schedule = BatchedEngine.set_schedule
     set_disturbance = BatchedEngine.set_disturbance
     set_plant_values = BatchedEngine.set_plant_values
+
+    def snapshot(self):
+        return dict(x=self.x.clone(), u=self.u.clone(), w_warm=self.w_warm.clone(), stats=self.stats.clone(), k=self.k)
+
+    def restore(self, snap):
+        self.x.copy_(snap["x"]); self.u.copy_(snap["u"]); self.w_warm.copy_(snap["w_warm"])
+        self.stats.copy_(snap["stats"])
+        self.k = int(snap["k"])
 
     def run(self, n_steps: int, steps_per_launch: Optional[int] = None, record: bool = False):
         spl = n_steps if steps_per_launch is None else int(steps_per_launch)

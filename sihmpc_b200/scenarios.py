@@ -66,6 +66,22 @@ def declare_distillation(ctrl_cls, sys=None, N=10, **bounds):
     return c
 
 
+def declare_distillation_log(ctrl_cls, sys=None, N=10, **bounds):
+    """The log-barrier controller of example_distillation_log.py:43-61 (`c.init_Qt` is referenced there without
+    being called, so Qt stays eye(ny))."""
+    sys = distillation_system() if sys is None else sys
+    if not bounds:
+        bounds = dict(ulb=[0, 0])
+    c = ctrl_cls(sys, N, **bounds)
+    c.subObjComposed(y=[0], Q=1, sat=N * 0.5 ** 2)
+    c.subObjComposed(y=[1], Q=1, sat=N * 2.0 ** 2)
+    c.subObj(du=[0], Q=1, sat=N * 0.3 ** 2)
+    c.subObj(du=[1], Q=1, sat=N * 0.3 ** 2)
+    c.subObj(siN=[0], Q=1, addJ=False)
+    c.subObj(siN=[1], Q=1, addJ=False)
+    return c
+
+
 def declare_mimo10(ctrl_cls, sys=None, N=5, **bounds):
     """Config 4 controller: one composed y per output, one du per input, siN rows, terminal cost."""
     sys = mimo10_system() if sys is None else sys
