@@ -245,3 +245,57 @@ def test_tile_single_step_solve(monkeypatch):
         assert (np.isfinite(a) == fin).all()
         assert np.max(np.abs(a[fin] - b[fin])) <= 1e-9 * max(1.0, np.max(np.abs(b[fin])))
     assert np.array_equal(outs[0][4], x)                           # no advance: the state is untouched
+
+
+def test_tile_mimo10_box5_setpoint_transients_resolved_in_kernel(monkeypatch):
+    """configs[3] as benchmarked: |u| <= 5, set-point changes at k = 11 and k = 101.  The scenarios below are the ones
+    of the 65536 draw whose inputs saturate after the second change (large changes of the active set from one step to
+    the next: up to 34 of 50 bounds active, the unconstrained optimum violates up to 48).  The in-kernel active set
+    (primal-dual rounds + primal fall-back, tile_active_set.inc) must resolve EVERY such step -- nothing handed over.
+    Parity is checked PER STEP FROM THE SAME STATE: once inputs saturate the closed loop amplifies a 1e-13 perturbation
+    of the set-point to 3e-7 in the moves (the oracle against itself), so trajectories can only be compared to
+    ~1e-5; the solve of each step from the state the device was in is compared at the north-star tolerance."""
+    from oracle.ihmpc_oracle import OracleIHMPC
+    from tests.util import schedule_fn
+    monkeypatch.delenv("SIHMPC_NO_FAST", raising=False)
+    monkeypatch.setenv("SIHMPC_FAST", "tile")
+    sys_ = sc.mimo10_system()
+    hard = [14, 39, 135, 195, 252, 259, 316, 351]
+    full = sc.mimo10_scenarios(max(hard) + 1, sys_)
+    scen = {k: (v[hard] if isinstance(v, np.ndarray) else v) for k, v in full.items()}
+    B, T, ny, nu = len(hard), 130, sys_.ny, sys_.nu
+    c = sc.declare_mimo10(IHMPCController, sys_)                                  # default bounds: |u| <= 5
+    eng = c.engine(B)
+    assert eng.dp.kernel_name() == "tile_step_kernel"
+    eng.set_state(scen["x0"], scen["u0"]); eng.set_schedule(scen["ysp_seq"], scen["seg_start"])
+    eng.set_disturbance(scen["dist_step"], scen["dist"])
+    eng.run(100)                                                                  # one launch up to the second change
+    states, moves, costs, nact, handed, solved = [], [], [], [], 0, 0
+    for k in range(100, T, 2):                      # then two steps per launch (the resume pass needs n_steps > 1),
+        states.append((eng.x.cpu().numpy().copy(), eng.u.cpu().numpy().copy(), eng.pesos.cpu().numpy().copy()))
+        tr = eng.run(2, record=True)                # keeping the state in front of every launch
+        moves.append(tr["du"][0].cpu().numpy().copy()); costs.append(tr["J"][0].cpu().numpy().copy())
+        umax = np.abs(states[-1][1] + moves[-1]).max(axis=1)
+        nact.append((umax > 5.0 - 1e-9).astype(int))                               # first step of the pair sits on the box
+        h, s_ = eng.dp.counters(); handed += h; solved += s_
+    st = eng.stats.cpu().numpy()
+    assert handed == 0 and solved >= 20, (handed, solved)
+    assert (st[:, ny + 3] == 0).all() and st[:, ny + 1].max() <= 1e-8            # status clean, largest violation seen
+    nact = np.array(nact)
+    assert nact.sum() >= 8
+    orc = sc.declare_mimo10(OracleIHMPC, sys_)
+    checked = 0
+    for col in range(4):
+        f = schedule_fn(scen["ysp_seq"][col], scen["seg_start"][col])
+        ks = [int(k) for k in np.nonzero(nact[:, col] > 0)[0]]
+        ks = ks[:6] + ks[-2:]                                                     # the transient and the saturated tail
+        for k in ks:
+            x, u, pes = (a[col] for a in states[k])
+            sol = orc.mpc(x0=x, ySP=f(100 + 2 * k), w0=[], u0=u, pesos=pes)
+            dref = np.asarray(sol["du_opt"])                                       # nu x N
+            assert sol["info"]["n_active"] > 0
+            assert np.max(np.abs(moves[k][col] - dref[:, 0])) <= RTOL * np.max(np.abs(dref)), (col, k)
+            assert abs(costs[k][col] - float(sol["J"])) <= RTOL * abs(float(sol["J"])), (col, k)
+            checked += 1
+    assert checked >= 12
+    monkeypatch.delenv("SIHMPC_FAST", raising=False)
