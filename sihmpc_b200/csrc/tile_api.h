@@ -12,8 +12,8 @@ constexpr int TL_CTR = 4 + 2 * TL_BOUNCES + (2 * TL_BOUNCES) % 4;      // counte
 constexpr int TL_KHMAX = 6;          // k-tiles of the Hessian product: 1 + max(hj_index) + 1 <= 24
 
 struct TileCfg {
-    const int *ptr;                  // per matrix: segment range [ptr[T], ptr[T+1]) of output tile T
-    const int *seg;                  // segments (runs of consecutive k-tiles): {4*k_first, n_tiles, first stored tile}
+    const int *ptr;                  // per matrix: stored tiles [ptr[T], ptr[T+1]) of output tile T (a multiple of four)
+    const int *kof;                  // first k (A offset in doubles) of every stored tile
     const int *hrows;                // Hessian product: real rows (0..8) of packed tile t
     const double *B;                 // stored tiles, 32 doubles each, B-fragment order
     const double *BH;                // Hessian constants, dense: [tile][row][k-tile][32]

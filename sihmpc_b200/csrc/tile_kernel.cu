@@ -70,45 +70,38 @@ __device__ __forceinline__ double fast_rsqrt(const double d) {
 
 __host__ __device__ __forceinline__ int tl_tid(int I, int J) { return (I * (I + 1)) / 2 + J; }
 
-// accumulators of output tile T of one tile-CSR matrix; in_q = in + q*S + g (A-fragment base of this lane).
-// A row is a short list of RUNS of consecutive k-tiles: inside a run the A address and the B address
-// advance by constants, the next four B tiles are fetched while the current four multiply.
+// accumulators of output tile T of one tile-ELL matrix; in_q = in + q*S + g (A-fragment base of this lane).
+// A row is the list of its non-zero 8x4 tiles: kof[t] = first k of stored tile t (the A address), the tile itself in
+// B-fragment order (one coalesced 256-byte load per MMA).  The host pads every list to a multiple of four with zero
+// tiles, so the loop is one body of four MMAs on four independent accumulator pairs, no remainder, no run
+// bookkeeping; the B tiles and A offsets of the next group are fetched while this one multiplies.
 __device__ __forceinline__ void tile_row(const TileCfg &C, const int poff, const int T, const double *in_q,
                                          const int lane, double &r0, double &r1) {
-    const int s0 = __ldg(C.ptr + poff + T), s1 = __ldg(C.ptr + poff + T + 1);
-    double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
-    for (int sgi = s0; sgi < s1; ++sgi) {
-        const int koff = __ldg(C.seg + 3 * sgi), n = __ldg(C.seg + 3 * sgi + 1), bi = __ldg(C.seg + 3 * sgi + 2);
-        const double *Bp = C.B + (size_t)bi * 32 + lane;
-        const double *ap = in_q + koff;
-        int t = 0;
-        double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
-        if (n >= 4) { b0 = __ldg(Bp); b1 = __ldg(Bp + 32); b2 = __ldg(Bp + 64); b3 = __ldg(Bp + 96); }
-        for (; t + 4 <= n; t += 4) {
-            const bool more = (t + 8 <= n);
+    const int t0 = __ldg(C.ptr + poff + T), n = __ldg(C.ptr + poff + T + 1) - t0;
+    double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0;
+    if (n > 0) {
+        const double *Bp = C.B + (size_t)t0 * 32 + lane;
+        const int4 *kp = reinterpret_cast<const int4 *>(C.kof + t0);          // lists start on multiples of four
+        int4 ko = __ldg(kp);
+        double b0 = __ldg(Bp), b1 = __ldg(Bp + 32), b2 = __ldg(Bp + 64), b3 = __ldg(Bp + 96);
+        for (int t = 4; ; t += 4) {
+            const bool more = t < n;
+            int4 nk = ko;
             double n0 = 0.0, n1 = 0.0, n2 = 0.0, n3 = 0.0;
             if (more) {
-                n0 = __ldg(Bp + (t + 4) * 32); n1 = __ldg(Bp + (t + 5) * 32);
-                n2 = __ldg(Bp + (t + 6) * 32); n3 = __ldg(Bp + (t + 7) * 32);
+                nk = __ldg(kp + (t >> 2));
+                n0 = __ldg(Bp + t * 32); n1 = __ldg(Bp + t * 32 + 32); n2 = __ldg(Bp + t * 32 + 64); n3 = __ldg(Bp + t * 32 + 96);
             }
-            const double a0 = ap[4 * t], a1 = ap[4 * t + 4], a2 = ap[4 * t + 8], a3 = ap[4 * t + 12];
+            const double a0 = in_q[ko.x], a1 = in_q[ko.y], a2 = in_q[ko.z], a3 = in_q[ko.w];
             dmma884(c0, c1, a0, b0);
             dmma884(d0, d1, a1, b1);
-            dmma884(c0, c1, a2, b2);
-            dmma884(d0, d1, a3, b3);
-            b0 = n0; b1 = n1; b2 = n2; b3 = n3;
-        }
-        if (t < n) {
-            const int rem = n - t;                       // 1..3
-            const double e0 = __ldg(Bp + t * 32);
-            const double e1 = (rem > 1) ? __ldg(Bp + (t + 1) * 32) : 0.0;
-            const double e2 = (rem > 2) ? __ldg(Bp + (t + 2) * 32) : 0.0;
-            dmma884(c0, c1, ap[4 * t], e0);
-            if (rem > 1) dmma884(d0, d1, ap[4 * t + 4], e1);
-            if (rem > 2) dmma884(c0, c1, ap[4 * t + 8], e2);
+            dmma884(e0, e1, a2, b2);
+            dmma884(f0, f1, a3, b3);
+            if (!more) break;
+            ko = nk; b0 = n0; b1 = n1; b2 = n2; b3 = n3;
         }
     }
-    r0 = c0 + d0; r1 = c1 + d1;
+    r0 = (c0 + d0) + (e0 + f0); r1 = (c1 + d1) + (e1 + f1);
 }
 
 __device__ __forceinline__ double tl_rsqrt(const double d) { return fast_rsqrt(d); }
@@ -277,30 +270,46 @@ __device__ __forceinline__ void tbs_panel(const double *A, const int nv, const i
 
 // Hessian product: packed lower tiles of  sum_k a_k X_k  for the eight scenarios of the CTA (k-space [1 ; pesos]),
 // BHm = the blocks in B-fragment order (du space: Ht, HJ_a; bound space: S^T (Ht | HJ_a + 2 diag Wdu_a) S)
-__device__ __forceinline__ void tile_hessian(const TileCfg &C, const double *__restrict__ BHm, const int KHm,
-                                             const double *pes, double *Hs, const int w, const int lane) {
+template <int KH>
+__device__ __forceinline__ void tile_hessian_k(const TileCfg &C, const double *__restrict__ BHm,
+                                               const double *pes, double *Hs, const int w, const int lane) {
     const int q = lane >> 2, g = lane & 3;
     for (int u = w; u < 2 * C.ntile; u += TL_WARPS) {
         const int tid = u >> 1, r0 = (u & 1) * 4;
         const int nrow = __ldg(C.hrows + tid);
-        double a[TL_KHMAX];
+        if (r0 >= nrow) continue;
+        // every row of a tile is stored (rows >= nrow hold zeros), so all 4 KH loads go out before the first MMA
+        const double *Bp = BHm + ((size_t)(tid * 8 + r0) * KH) * 32 + lane;
+        double b[4][KH], a[KH];
 #pragma unroll
-        for (int t = 0; t < TL_KHMAX; ++t) a[t] = (t < KHm) ? pes[q * C.S_p + 4 * t + g] : 0.0;
-        const double *Bp = BHm + ((size_t)(tid * 8 + r0) * KHm) * 32 + lane;
+        for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+            for (int t = 0; t < KH; ++t) b[rr][t] = __ldg(Bp + (rr * KH + t) * 32);
+#pragma unroll
+        for (int t = 0; t < KH; ++t) a[t] = pes[q * C.S_p + 4 * t + g];
         double h[4][2];
 #pragma unroll
         for (int rr = 0; rr < 4; ++rr) {
             h[rr][0] = h[rr][1] = 0.0;
-            if (r0 + rr < nrow) {
 #pragma unroll
-                for (int t = 0; t < TL_KHMAX; ++t)
-                    if (t < KHm) dmma884(h[rr][0], h[rr][1], a[t], __ldg(Bp + (rr * KHm + t) * 32));
-            }
+            for (int t = 0; t < KH; ++t) dmma884(h[rr][0], h[rr][1], a[t], b[rr][t]);
         }
 #pragma unroll
         for (int rr = 0; rr < 4; ++rr)
             if (r0 + rr < nrow)
                 *reinterpret_cast<double2 *>(Hs + (size_t)q * C.HS + tid * 64 + (r0 + rr) * 8 + 2 * g) = make_double2(h[rr][0], h[rr][1]);
+    }
+}
+
+__device__ __forceinline__ void tile_hessian(const TileCfg &C, const double *__restrict__ BHm, const int KHm,
+                                             const double *pes, double *Hs, const int w, const int lane) {
+    switch (KHm) {                                     // uniform; k-tiles of [1 ; pesos] that carry Hessian blocks
+        case 1: tile_hessian_k<1>(C, BHm, pes, Hs, w, lane); break;
+        case 2: tile_hessian_k<2>(C, BHm, pes, Hs, w, lane); break;
+        case 3: tile_hessian_k<3>(C, BHm, pes, Hs, w, lane); break;
+        case 4: tile_hessian_k<4>(C, BHm, pes, Hs, w, lane); break;
+        case 5: tile_hessian_k<5>(C, BHm, pes, Hs, w, lane); break;
+        default: tile_hessian_k<TL_KHMAX>(C, BHm, pes, Hs, w, lane); break;
     }
 }
 
@@ -587,7 +596,7 @@ tile_step_kernel(const DevPlan P, const TileCfg C, const sihmpc_io io, const lon
                     for (int h = 0; h < 2; ++h) {
                         const int r = 8 * T + 2 * g + h;
                         if (r < Ny) {
-                            const int i = r % ny, k = r / ny;
+                            const int i = r / P.N, k = r - i * P.N;      // output-major rows (tile_configure)
                             const double *eq = eb + q * C.S_r;
                             const double v_ = (h ? y1 : y0) - sv[q * C.S_sv + o_ysp + i] - eq[P.o_sy + i] - P.tau[k] * eq[R + i];
                             sq[q * C.S_q + r] = v_ * v_;
@@ -665,33 +674,26 @@ SIH_TL_DECL(1) SIH_TL_DECL(2) SIH_TL_DECL(3) SIH_TL_DECL(4) SIH_TL_DECL(5) SIH_T
 #undef SIH_TL_DECL
 
 struct TileBuilder {
-    std::vector<int> ptr, seg, hmap;
+    std::vector<int> ptr, kof;
     std::vector<double> B;
     int n_stored = 0;
-    // one output tile: fill(t, tile[32]) writes k-tile t in B-fragment order and returns true if non-zero.
-    // Non-zero k-tiles are grouped into runs; a gap of one zero tile is bridged (a zero MMA is cheaper
-    // than a new run).
+    // one output tile: fill(t, tile[32]) writes k-tile t in B-fragment order and returns true if non-zero.  The
+    // non-zero k-tiles are stored in order with their A offsets, the list padded to a multiple of four with zero
+    // tiles (offset 0: the scenario's own first entries times zero).
     void row(int KT, const std::function<bool(int, double *)> &fill) {
-        ptr.push_back((int)seg.size() / 3);
-        std::vector<double> tiles((size_t)KT * 32);
-        std::vector<char> nz(KT, 0);
-        for (int t = 0; t < KT; ++t) nz[t] = fill(t, tiles.data() + (size_t)t * 32) ? 1 : 0;
-        int t = 0;
-        while (t < KT) {
-            if (!nz[t]) { ++t; continue; }
-            int e = t;                                   // extend the run [t, e]
-            while (true) {
-                if (e + 1 < KT && nz[e + 1]) { ++e; continue; }
-                if (e + 2 < KT && nz[e + 2]) { e += 2; continue; }
-                break;
-            }
-            seg.push_back(4 * t); seg.push_back(e - t + 1); seg.push_back(n_stored);
-            B.insert(B.end(), tiles.begin() + (size_t)t * 32, tiles.begin() + (size_t)(e + 1) * 32);
-            n_stored += e - t + 1;
-            t = e + 1;
+        ptr.push_back(n_stored);
+        std::vector<double> tile(32);
+        int cnt = 0;
+        for (int t = 0; t < KT; ++t) {
+            if (!fill(t, tile.data())) continue;
+            kof.push_back(4 * t);
+            B.insert(B.end(), tile.begin(), tile.end());
+            ++cnt;
         }
+        for (; cnt % 4; ++cnt) { kof.push_back(0); B.insert(B.end(), 32, 0.0); }
+        n_stored += cnt;
     }
-    void close() { ptr.push_back((int)seg.size() / 3); }
+    void close() { ptr.push_back(n_stored); }
     // a matrix with nT output tiles; M(r,c) over rows [0, 8 nT) and k-space [0, nc); returns the ptr offset
     int add(int nT, int nc, const std::function<double(int, int)> &M) {
         const int off = (int)ptr.size();
@@ -749,23 +751,26 @@ cudaError_t tile_configure(const sihmpc_plan_desc *d, const DevPlan &P, TilePlan
 
     TileBuilder tb;
     const int o_v = nx, o_ysp = nx + nv, o_one = nx + nv + ny;
+    // residual rows of the prediction in OUTPUT-major order inside this kernel (row i*N + k <- plan row k*ny + i): an
+    // 8-row tile then spans two outputs instead of eight, and a row only touches the modes of its own output
+    auto yr = [&](int r) { return r < Ny ? (r % N) * ny + (r / N) : r; };
     // e = [Px | Py | e0][x ; ysp ; 1], rows R.. = Mi1x x
     C.me = tb.add(C.n_r, K_sv, [&](int r, int c) -> double {
         if (r >= RE) return 0.0;
-        if (c < nx) return r < R ? d->Px[(size_t)r * nx + c] : d->Mi1x[(size_t)(r - R) * nx + c];
-        if (c >= o_ysp && c < o_one) return r < R ? d->Py[(size_t)r * ny + (c - o_ysp)] : 0.0;
-        if (c == o_one) return r < R ? d->e0[r] : 0.0;
+        if (c < nx) return r < R ? d->Px[(size_t)yr(r) * nx + c] : d->Mi1x[(size_t)(r - R) * nx + c];
+        if (c >= o_ysp && c < o_one) return r < R ? d->Py[(size_t)yr(r) * ny + (c - o_ysp)] : 0.0;
+        if (c == o_one) return r < R ? d->e0[yr(r)] : 0.0;
         return 0.0; });
     // omega = [w0row | Wrow][1 ; pesos]
     C.mw = tb.add(C.n_r, m + 1, [&](int r, int c) -> double {
         if (r >= R) return 0.0;
-        return c == 0 ? d->w0row[r] : d->Wrow[(size_t)r * m + (c - 1)]; });
+        return c == 0 ? d->w0row[yr(r)] : d->Wrow[(size_t)yr(r) * m + (c - 1)]; });
     // omega_du = Wdu pesos
     C.mdu = tb.add(C.n_v, m + 1, [&](int r, int c) -> double {
         return (r < nv && c >= 1) ? d->Wdu[(size_t)r * m + (c - 1)] : 0.0; });
     // b = -2 E^T t
     C.mf = tb.add(C.n_f, R, [&](int r, int c) -> double {
-        return r < nv ? -2.0 * d->E[(size_t)c * nv + r] : 0.0; });
+        return r < nv ? -2.0 * d->E[(size_t)yr(c) * nv + r] : 0.0; });
     // Hessian tiles (lower), k-space [1 ; pesos]: Ht at k = 0, HJ_a at k = 1 + hj_index[a]  (dense k-tiles)
     std::vector<double> BH;
     std::vector<int> hrows;
@@ -844,7 +849,7 @@ cudaError_t tile_configure(const sihmpc_plan_desc *d, const DevPlan &P, TilePlan
     // r += [E ; Mi1u] dU
     C.mr = tb.add(C.n_r, K_sv, [&](int r, int c) -> double {
         if (r >= RE || c < o_v || c >= o_v + nv) return 0.0;
-        return r < R ? d->E[(size_t)r * nv + (c - o_v)] : d->Mi1u[(size_t)(r - R) * nv + (c - o_v)]; });
+        return r < R ? d->E[(size_t)yr(r) * nv + (c - o_v)] : d->Mi1u[(size_t)(r - R) * nv + (c - o_v)]; });
     // y = [C | D][x+ ; du]
     C.my = tb.add(C.n_y, K_sv, [&](int r, int c) -> double {
         if (r >= ny) return 0.0;
@@ -854,13 +859,13 @@ cudaError_t tile_configure(const sihmpc_plan_desc *d, const DevPlan &P, TilePlan
     // Y' = Myx x+ + Myu shift(dU)
     C.myp = tb.add(C.n_yp, K_sv, [&](int r, int c) -> double {
         if (r >= Ny) return 0.0;
-        if (c < nx) return d->Myx[(size_t)r * nx + c];
+        if (c < nx) return d->Myx[(size_t)yr(r) * nx + c];
         const int v = c - o_v;
-        return (v >= nu && v < nv) ? d->Myu[(size_t)r * nv + (v - nu)] : 0.0; });
+        return (v >= nu && v < nv) ? d->Myu[(size_t)yr(r) * nv + (v - nu)] : 0.0; });
     // V_i = sum_r Wrow[r][i] sq_r + sum_v Wdu[v-nu][i] dU_v^2
     C.mvn = tb.add(C.n_m, nsq + nv, [&](int i, int c) -> double {
         if (i >= m) return 0.0;
-        if (c < nsq) return d->Wrow[(size_t)c * m + i];
+        if (c < nsq) return d->Wrow[(size_t)yr(c) * m + i];
         const int v = c - nsq;
         return v >= nu ? d->Wdu[(size_t)(v - nu) * m + i] : 0.0; });
     // x+ = [A | B][x ; du]  (shared plant; per-scenario plant values use the CSR path)
@@ -869,13 +874,12 @@ cudaError_t tile_configure(const sihmpc_plan_desc *d, const DevPlan &P, TilePlan
         for (int pp = d->pl_rowptr[r]; pp < d->pl_rowptr[r + 1]; ++pp)
             if (d->pl_col[pp] == c) return d->pl_val[pp];
         return 0.0; });
-    (void)N;
 
-    const size_t np = tb.ptr.size(), nk = tb.seg.size(), nh = hrows.size();
-    std::vector<int> ib(np + nk + nh);
-    memcpy(ib.data(), tb.ptr.data(), np * sizeof(int));
-    memcpy(ib.data() + np, tb.seg.data(), nk * sizeof(int));
-    memcpy(ib.data() + np + nk, hrows.data(), nh * sizeof(int));
+    const size_t nk = tb.kof.size(), np = tb.ptr.size(), nh = hrows.size();      // kof first: 16-byte aligned int4 loads
+    std::vector<int> ib(nk + np + nh);
+    memcpy(ib.data(), tb.kof.data(), nk * sizeof(int));
+    memcpy(ib.data() + nk, tb.ptr.data(), np * sizeof(int));
+    memcpy(ib.data() + nk + np, hrows.data(), nh * sizeof(int));
     cudaError_t e = cudaMalloc(&tp->ibuf, ib.size() * sizeof(int));
     if (e != cudaSuccess) return e;
     e = cudaMemcpy(tp->ibuf, ib.data(), ib.size() * sizeof(int), cudaMemcpyHostToDevice);
@@ -892,7 +896,7 @@ cudaError_t tile_configure(const sihmpc_plan_desc *d, const DevPlan &P, TilePlan
         e = cudaMemcpy(tp->dbuf + nB + nBH, BHc.data(), BHc.size() * sizeof(double), cudaMemcpyHostToDevice);
         if (e != cudaSuccess) return e;
     }
-    C.ptr = tp->ibuf; C.seg = tp->ibuf + np; C.hrows = tp->ibuf + np + nk; C.B = tp->dbuf; C.BH = tp->dbuf + nB;
+    C.kof = tp->ibuf; C.ptr = tp->ibuf + nk; C.hrows = tp->ibuf + nk + np; C.B = tp->dbuf; C.BH = tp->dbuf + nB;
     C.BHc = tp->dbuf + nB + nBH;
     tp->n_tiles = tb.n_stored;
     e = tile_set_smem(C.NT, tp->smem_bytes);

@@ -113,11 +113,28 @@ def terminal_weight(sys, Qt):
 
 
 def _psd_factor(Q):
-    """Lbar with Q = Lbar Lbar^T for a symmetric PSD matrix (eigen form; Q_bar may be singular)."""
+    """Lbar with Q = Lbar Lbar^T for a symmetric PSD matrix (eigen form; Q_bar may be singular).
+    Q_bar of an OPOM model is block diagonal (one block per output: F is (block) diagonal and Psi^T Qt Psi couples
+    only the modes of one output), so the factor is taken block by block and its columns -- the terminal residual
+    rows -- stay local to one output's modes: the tile-CSR products of the device skip the zero tiles (an eigen
+    factor of the whole matrix orders the columns by eigenvalue and scatters every 8-row tile over all outputs)."""
+    from scipy.sparse.csgraph import connected_components
     Q = 0.5 * (Q + Q.T)
-    lam, V = np.linalg.eigh(Q)
-    lam = np.where(lam > 0, lam, 0.0)
-    return V * np.sqrt(lam)[None, :]
+    n = Q.shape[0]
+    if n == 0:
+        return np.zeros((0, 0))
+    scale = np.max(np.abs(Q))
+    ncomp, lab = connected_components(np.abs(Q) > 1e-14 * scale, directed=False) if scale > 0 else (1, np.zeros(n, int))
+    L = np.zeros((n, n))
+    col = 0
+    for comp in sorted(range(ncomp), key=lambda k: int(np.nonzero(lab == k)[0][0])):
+        idx = np.nonzero(lab == comp)[0]
+        lam, V = np.linalg.eigh(Q[np.ix_(idx, idx)])
+        order = np.argsort(-lam)
+        lam = np.where(lam[order] > 0, lam[order], 0.0)
+        L[np.ix_(idx, np.arange(col, col + idx.size))] = V[:, order] * np.sqrt(lam)[None, :]
+        col += idx.size
+    return L
 
 
 def bounds_rs(kind, i, rs_hi, ri_hi, bounds):
