@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SIHMPC_ABI_VERSION 2
+#define SIHMPC_ABI_VERSION 3
 
 /* error codes */
 #define SIHMPC_OK            0
@@ -151,6 +151,13 @@ typedef struct sihmpc_io {
     int32_t flags;
     int32_t k0;                      /* absolute index of the first step of this call            */
     double alfa;                     /* satWeights2 blending (ihmpccontroller.py:634)            */
+    /* multipliers of the inequality rows at the optimum of the LAST step (sol['lam_w'], sol['lam_g'] of
+       ihmpccontroller.py:525-529 are assembled from them), casadi's sign convention: > 0 upper bound active,
+       < 0 lower bound active, 0 inactive.  Rows: [0,nv) move box dulb <= dU_i <= duub (-> lam_w), [nv,2nv)
+       input box ulb <= u + cumsum(dU) <= uub, row nv + k*nu + j = U_pred[k][j] (-> lam_g), [2nv,2nv+ncd) dense
+       rows in the order of sihmpc_plan_desc.Gc.  NULL: not wanted.  When set, scenarios with active bounds are
+       solved by the dual active-set kernel (the resume passes of the fast kernels do not report multipliers). */
+    double *lam;                     /* [batch][2*nv + ncd]                                      */
 } sihmpc_io;
 
 /* -- lifecycle ------------------------------------------------------------------------------ */

@@ -11,7 +11,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SIHMPC_B200_LIB") or os.path.join(HERE, "libsihmpc_b200.so")   # override: A/B builds only
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 F_ADVANCE, F_UPDATE_VIN, F_WEIGHTS_SAT2, F_WEIGHTS_SAT1 = 1, 2, 4, 8
 ST_MAXITER, ST_INFEASIBLE, ST_NOTPD, ST_ACTIVE_UNSUPPORTED = 1, 2, 4, 8
 NSTATS_EXTRA = 5
@@ -50,6 +50,7 @@ class IO(C.Structure):
         ("status", C.c_void_p), ("n_active", C.c_void_p),
         ("stats", C.c_void_p), ("traj_du", C.c_void_p), ("traj_J", C.c_void_p), ("traj_y", C.c_void_p),
         ("flags", C.c_int32), ("k0", C.c_int32), ("alfa", C.c_double),
+        ("lam", C.c_void_p),
     ]
 
 

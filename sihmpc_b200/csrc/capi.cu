@@ -417,17 +417,19 @@ int sihmpc_step(sihmpc_plan *plan, const sihmpc_io *io, int64_t batch, int32_t n
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     double *scratch = reinterpret_cast<double *>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     bind_handover(plan, reinterpret_cast<char *>(scratch) + general_scratch_bytes(plan), batch);
+    const bool want_lam = io->lam != nullptr;     // multipliers: the dual active-set kernel reports them, no resume pass
+    if (want_lam) CUDA_TRY(cudaMemsetAsync(io->lam, 0, (size_t)batch * (2 * plan->d.nv + plan->d.ncd) * sizeof(double), st));
     int *start_step = nullptr;
     const int *n_handover = nullptr;
     const bool want_tile = plan->tile.ok && (plan->use_fast == 3 || (plan->use_fast == 2 && plan->mma.shape < 0));
     if (want_tile) {
         cudaError_t e = sih::tile_reset(plan->tile, batch, st);
-        if (e == cudaSuccess) e = sih::tile_launch(plan->tile, plan->d, *io, batch, n_steps, plan->sm_count, st);
+        if (e == cudaSuccess) e = sih::tile_launch(plan->tile, plan->d, *io, batch, n_steps, plan->sm_count, st, !want_lam);
         if (e != cudaSuccess) return fail(SIHMPC_E_CUDA, "tile fast-path launch failed: %s", cudaGetErrorString(e));
         if (!(plan->d.has_box || plan->d.has_cum)) return 0;      // nothing can be handed over
         start_step = plan->tile.start_step;
         n_handover = plan->tile.n_handover;
-        if (sih::tile_resumes(plan->tile, batch, n_steps)) {
+        if (!want_lam && sih::tile_resumes(plan->tile, batch, n_steps)) {
             // What the resume pass gave up on (large changes of the active set right after a set-point change): the
             // general kernel solves ONE step of those scenarios and sends them back with the active set it found, the
             // tile kernel resumes them from there -- TL_BOUNCES rounds, every launch of a round leaves at once when its
@@ -452,11 +454,11 @@ int sihmpc_step(sihmpc_plan *plan, const sihmpc_io *io, int64_t batch, int32_t n
         }
     } else if (plan->use_fast == 2 && plan->mma.shape >= 0) {
         cudaError_t e = sih::mma_reset(plan->mma, batch, st);
-        if (e == cudaSuccess) e = sih::mma_launch(plan->mma, plan->d, *io, batch, n_steps, plan->sm_count, st);
+        if (e == cudaSuccess) e = sih::mma_launch(plan->mma, plan->d, *io, batch, n_steps, plan->sm_count, st, !want_lam);
         if (e != cudaSuccess) return fail(SIHMPC_E_CUDA, "tensor fast-path launch failed: %s", cudaGetErrorString(e));
         if (!(plan->d.has_box || plan->d.has_cum)) return 0;      // nothing can be handed over
         start_step = plan->mma.start_step;
-        n_handover = sih::mma_resumes(plan->mma, batch, n_steps) ? plan->mma.n_fail : plan->mma.n_handover;
+        n_handover = (!want_lam && sih::mma_resumes(plan->mma, batch, n_steps)) ? plan->mma.n_fail : plan->mma.n_handover;
     } else if (plan->use_fast == 1 && sih::quad_supported(plan->quad, *io)) {
         cudaError_t e = cudaSuccess;
         if (e == cudaSuccess) e = cudaMemsetAsync(plan->quad.n_handover, 0x7f, (size_t)(batch + 1) * sizeof(int), st);
@@ -485,6 +487,7 @@ static size_t staging_layout(const sihmpc_plan *p, int64_t batch, size_t off[12]
     off[7] = take((size_t)batch * p->nw * 8);                      // w_opt
     off[8] = take((size_t)batch * 4);                              // status
     off[9] = take((size_t)batch * 4);                              // n_active
+    off[10] = take((size_t)batch * (2 * P.nv + P.ncd) * 8);        // lam
     return o;
 }
 
@@ -503,6 +506,7 @@ static sihmpc_io slice_io(const sihmpc_io &d, const DevPlan &P, int nw, long lon
     r.du = d.du + lo * P.nu; r.J = d.J + lo;
     if (d.w_opt) r.w_opt = d.w_opt + lo * nw;
     r.status = d.status + lo; r.n_active = d.n_active + lo;
+    if (d.lam) r.lam = d.lam + lo * (2 * P.nv + P.ncd);
     return r;
 }
 
@@ -532,11 +536,12 @@ int sihmpc_step_host(sihmpc_plan *plan, const sihmpc_io *h, int64_t batch, void 
     d.w_opt = h->w_opt ? reinterpret_cast<double *>(base + off[7]) : nullptr;
     d.status = reinterpret_cast<int32_t *>(base + off[8]);
     d.n_active = reinterpret_cast<int32_t *>(base + off[9]);
+    d.lam = h->lam ? reinterpret_cast<double *>(base + off[10]) : nullptr;
     d.ysp_seq = nullptr; d.seg_start = nullptr; d.n_seg = 0;
     d.dist_step = nullptr; d.dist = nullptr; d.plant_val = nullptr;
     d.stats = nullptr; d.traj_du = nullptr; d.traj_J = nullptr; d.traj_y = nullptr;
     const size_t bx = (size_t)P.nx * 8, bu = (size_t)P.nu * 8, bp = (size_t)P.m * 8, bv = (size_t)P.n_vin * 8,
-                 by = (size_t)P.ny * 8, bw = (size_t)plan->nw * 8;
+                 by = (size_t)P.ny * 8, bw = (size_t)plan->nw * 8, bl = (size_t)(2 * P.nv + P.ncd) * 8;
 
     if (batch <= plan->env_zc_max && !plan->env_no_zerocopy && h->du && h->J && h->status && h->n_active) {
         // ---- every buffer pinned (cudaHostAlloc / cudaHostRegister): ZERO-COPY.  The kernel reads the caller's
@@ -544,11 +549,11 @@ int sihmpc_step_host(sihmpc_plan *plan, const sihmpc_io *h, int64_t batch, void 
         // copies, no memcpy launches -- a step is one kernel plus one synchronise (batch 64: 39 us instead of
         // 52 us; 131072 scenarios: 1.13 ms instead of 1.24 ms with the chunked DMA pipeline below).
         {
-            void *hp[10] = {h->x, h->u, h->pesos, want_vin ? h->vinant : nullptr, const_cast<double *>(h->ysp),
-                            h->du, h->J, h->w_opt, h->status, h->n_active};
-            void *dp[10];
+            void *hp[11] = {h->x, h->u, h->pesos, want_vin ? h->vinant : nullptr, const_cast<double *>(h->ysp),
+                            h->du, h->J, h->w_opt, h->status, h->n_active, h->lam};
+            void *dp[11];
             bool all = true;
-            for (int i = 0; i < 10 && all; ++i) {
+            for (int i = 0; i < 11 && all; ++i) {
                 dp[i] = nullptr;
                 if (!hp[i]) continue;
                 // asked of the driver on EVERY call: an address can be unpinned, freed and reused between two calls, so a
@@ -564,6 +569,7 @@ int sihmpc_step_host(sihmpc_plan *plan, const sihmpc_io *h, int64_t batch, void 
                 z.vinant = static_cast<double *>(dp[3]); z.ysp = static_cast<double *>(dp[4]);
                 z.du = static_cast<double *>(dp[5]); z.J = static_cast<double *>(dp[6]); z.w_opt = static_cast<double *>(dp[7]);
                 z.status = static_cast<int32_t *>(dp[8]); z.n_active = static_cast<int32_t *>(dp[9]);
+                z.lam = static_cast<double *>(dp[10]);
                 int rc = sihmpc_step(plan, &z, batch, 1, workspace, wsb, stream);
                 if (rc) return rc;
                 CUDA_TRY(cudaStreamSynchronize(st));
@@ -587,6 +593,7 @@ int sihmpc_step_host(sihmpc_plan *plan, const sihmpc_io *h, int64_t batch, void 
         if (h->w_opt) memcpy(h->w_opt, hs + off[7], batch * bw);
         if (h->status) memcpy(h->status, hs + off[8], batch * 4);
         if (h->n_active) memcpy(h->n_active, hs + off[9], batch * 4);
+        if (h->lam) memcpy(h->lam, hs + off[10], batch * bl);
         if (want_vin && (h->flags & SIHMPC_F_UPDATE_VIN)) memcpy(h->vinant, hs + off[3], batch * bv);
         if (adv) { memcpy(h->x, hs + off[0], batch * bx); memcpy(h->u, hs + off[1], batch * bu); memcpy(h->pesos, hs + off[2], batch * bp); }
         return 0;
@@ -623,6 +630,7 @@ int sihmpc_step_host(sihmpc_plan *plan, const sihmpc_io *h, int64_t batch, void 
         if (h->w_opt) CUDA_TRY(cudaMemcpyAsync(h->w_opt + lo * plan->nw, d.w_opt + lo * plan->nw, n * bw, cudaMemcpyDeviceToHost, sd));
         if (h->status) CUDA_TRY(cudaMemcpyAsync(h->status + lo, d.status + lo, n * 4, cudaMemcpyDeviceToHost, sd));
         if (h->n_active) CUDA_TRY(cudaMemcpyAsync(h->n_active + lo, d.n_active + lo, n * 4, cudaMemcpyDeviceToHost, sd));
+        if (h->lam) CUDA_TRY(cudaMemcpyAsync(h->lam + lo * (2 * P.nv + P.ncd), d.lam + lo * (2 * P.nv + P.ncd), n * bl, cudaMemcpyDeviceToHost, sd));
         if (want_vin && (h->flags & SIHMPC_F_UPDATE_VIN))
             CUDA_TRY(cudaMemcpyAsync(h->vinant + lo * P.n_vin, d.vinant + lo * P.n_vin, n * bv, cudaMemcpyDeviceToHost, sd));
         if (adv) {

@@ -1146,12 +1146,12 @@ inline bool mma_resumes(const MmaPlan &qp, long long batch, int n_steps) { retur
 
 template <typename D>
 inline cudaError_t mma_launch_shape(MmaPlan &qp, const DevPlan &P, const sihmpc_io &io, long long batch,
-                                    int n_steps, int grid, cudaStream_t st) {
+                                    int n_steps, int grid, cudaStream_t st, bool allow_resume) {
     mma_step_kernel<D, MMA_WARPS, MMA_MINB, 0><<<grid, MMA_WARPS * 32, qp.smem_bytes, st>>>(
         P, qp.qc, qp.qbuf, io, batch, n_steps, qp.start_step, qp.n_handover, qp.n_inkernel, qp.list, nullptr);
     cudaError_t e = cudaGetLastError();
     qp.last_resumed = 0;
-    if (e != cudaSuccess || !mma_resumes(qp, batch, n_steps)) return e;
+    if (e != cudaSuccess || !allow_resume || !mma_resumes(qp, batch, n_steps)) return e;
     qp.last_resumed = 1;
     // resume pass over the listed scenarios (their number is only known on the device: blocks beyond it leave at once)
     mma_step_kernel<D, MMA_WARPS, MMA_MINB, 1><<<grid, MMA_WARPS * 32, qp.smem_bytes, st>>>(
@@ -1160,14 +1160,14 @@ inline cudaError_t mma_launch_shape(MmaPlan &qp, const DevPlan &P, const sihmpc_
 }
 
 inline cudaError_t mma_launch(MmaPlan &qp, const DevPlan &P, const sihmpc_io &io, long long batch,
-                              int n_steps, int sm_count, cudaStream_t st) {
+                              int n_steps, int sm_count, cudaStream_t st, bool allow_resume = true) {
     const long long per_block = MMA_WARPS * 8;
     long long need = (batch + per_block - 1) / per_block;
     const long long cap = (long long)sm_count * qp.blocks_per_sm;
     int grid = (int)(need < cap ? need : cap);
     if (qp.grid_cap > 0 && qp.grid_cap < grid) grid = qp.grid_cap;      // debug override (SIHMPC_QUAD_GRID, read at plan creation)
-    return qp.shape == 1 ? mma_launch_shape<DistillationMma16>(qp, P, io, batch, n_steps, grid, st)
-                         : mma_launch_shape<DistillationMma>(qp, P, io, batch, n_steps, grid, st);
+    return qp.shape == 1 ? mma_launch_shape<DistillationMma16>(qp, P, io, batch, n_steps, grid, st, allow_resume)
+                         : mma_launch_shape<DistillationMma>(qp, P, io, batch, n_steps, grid, st, allow_resume);
 }
 
 inline void mma_destroy(MmaPlan *qp) {

@@ -680,6 +680,16 @@ ihmpc_step_kernel(const DevPlan P_in, const sihmpc_io io, const long long batch,
                     if (io.status) io.status[s] = status;
                     if (io.n_active) io.n_active[s] = q;
                 }
+                if (io.lam) {
+                    // multipliers of the active rows (lam >= 0 for n.v >= b), casadi's sign: + upper, - lower
+                    const long long nl = 2 * (long long)nv + P.ncd;
+                    for (int i = lane; i < nl; i += 32) io.lam[s * nl + i] = 0.0;
+                    __syncwarp();
+                    for (int a = lane; a < q; a += 32) {
+                        const int code = act[a];
+                        io.lam[s * nl + (code >> 1)] = (code & 1) ? lam[a] : -lam[a];
+                    }
+                }
             }
             if (io.traj_du) for (int j = lane; j < nu; j += 32) io.traj_du[((long long)step * batch + s) * nu + j] = v[j];
             if (io.traj_J && lane == 0) io.traj_J[(long long)step * batch + s] = Jval;

@@ -55,7 +55,7 @@ cudaError_t tile_reset(const TilePlan &tp, long long batch, cudaStream_t st);
 // the resume pass is one more launch: only worth it when the call carries enough work (not the single-step host API)
 inline bool tile_resumes(const TilePlan &tp, long long batch, int n_steps) { return tp.cfg.cspace >= 0 && (n_steps > 1 || batch >= 4096); }
 cudaError_t tile_launch(TilePlan &tp, const DevPlan &P, const sihmpc_io &io, long long batch, int n_steps,
-                        int sm_count, cudaStream_t st);
+                        int sm_count, cudaStream_t st, bool allow_resume = true);
 inline int *tile_bounce_counter(const TilePlan &tp, int round) { return tp.ctr + 4 + 2 * round; }
 inline int *tile_fail_counter(const TilePlan &tp, int round) { return tp.ctr + 4 + 2 * round + 1; }
 cudaError_t tile_launch_bounced(const TilePlan &tp, const DevPlan &P, const sihmpc_io &io, long long batch, int n_steps,

@@ -943,11 +943,11 @@ static cudaError_t tile_dispatch(const TilePlan &tp, const DevPlan &P, const sih
 // more launch) the resume pass over the scenarios it listed; what that cannot resolve is counted in n_fail with
 // start_step set
 cudaError_t tile_launch(TilePlan &tp, const DevPlan &P, const sihmpc_io &io, long long batch,
-                               int n_steps, int sm_count, cudaStream_t st) {
+                               int n_steps, int sm_count, cudaStream_t st, bool allow_resume) {
     const int grid = tile_grid(tp, batch, sm_count);
     tp.last_resumed = 0;
     cudaError_t e = tile_dispatch(tp, P, io, batch, n_steps, grid, 0, tp.list, nullptr, tp.n_handover, nullptr, st);
-    if (e != cudaSuccess || !tile_resumes(tp, batch, n_steps) || !(P.has_box || P.has_cum)) return e;
+    if (e != cudaSuccess || !allow_resume || !tile_resumes(tp, batch, n_steps) || !(P.has_box || P.has_cum)) return e;
     tp.last_resumed = 1;
     return tile_dispatch(tp, P, io, batch, n_steps, grid, 1, tp.list, tp.n_handover, tp.n_fail, nullptr, st);
 }

@@ -326,6 +326,7 @@ class HostStepper:
         self.w_opt = torch.zeros(B, p.nv + 2 * p.ny, **pin)
         self.status = torch.zeros(B, dtype=torch.int32, pin_memory=True)
         self.n_active = torch.zeros(B, dtype=torch.int32, pin_memory=True)
+        self.lam = torch.zeros(B, 2 * (p.nv + getattr(p, "n_extra", 0)) + p.ncd, **pin)   # multipliers per inequality row
         self.ws, self.ws_bytes = self.dp.workspace(B, host=True)
 
     def h2d_bytes(self):
@@ -339,7 +340,7 @@ class HostStepper:
             b += self.batch * 8 * (p.nx + p.nu + p.m)
         return b
 
-    def step(self, flags=_capi.F_UPDATE_VIN, alfa=0.0, want_w_opt=True):
+    def step(self, flags=_capi.F_UPDATE_VIN, alfa=0.0, want_w_opt=True, want_lam=False):
         io = _capi.IO()
         io.x, io.u, io.pesos = self.x.data_ptr(), self.u.data_ptr(), self.pesos.data_ptr()
         io.vinant = self.vinant.data_ptr() if self.plan.n_vin > 0 else None
@@ -347,6 +348,7 @@ class HostStepper:
         io.du, io.J = self.du.data_ptr(), self.J.data_ptr()
         io.w_opt = self.w_opt.data_ptr() if want_w_opt else None
         io.status, io.n_active = self.status.data_ptr(), self.n_active.data_ptr()
+        io.lam = self.lam.data_ptr() if want_lam else None
         io.flags = flags
         io.alfa = alfa
         st = torch.cuda.current_stream(self.dp.device).cuda_stream

@@ -395,7 +395,7 @@ class IHMPCController(object):
         hs.pesos.numpy()[0] = pesos
         if len(vin):
             hs.vinant.numpy()[0, :len(vin)] = vin
-        hs.step(flags=_capi.F_UPDATE_VIN)
+        hs.step(flags=_capi.F_UPDATE_VIN, want_lam=True)
         w = hs.w_opt.numpy()[0].copy()
         J = float(hs.J.numpy()[0])
         self.status = int(hs.status.numpy()[0])
@@ -408,12 +408,13 @@ class IHMPCController(object):
         res1 = XN[self.nxs + self.nxd:self.nxs + self.nxd + self.nxi] - w[N * nu + ny:]
         res2 = XN[:self.nxs] - ysp - w[N * nu:N * nu + ny]
         gvec = np.concatenate([x_pred, u_pred, res1, res2, vals])
+        lam_w, lam_g = self._duals(hs.lam.numpy()[0], x, ysp, w, pesos, vin)
         sol = {
             'J': DM(J),
             'du_opt': DM(w[:N * nu].reshape(N, nu).T),        # nu x N (ctl.py:510-515)
             'w_opt': DM(w),
-            'lam_w': DM(np.zeros(w.size)),                    # duals are not reported (SURVEY 8c traps)
-            'lam_g': DM(np.zeros(gvec.size)),
+            'lam_w': DM(lam_w),                               # ctl.py:525-529, casadi's sign convention
+            'lam_g': DM(lam_g),
             'g': DM(gvec),
             'x_pred': DM(x_pred), 'y_pred': DM(y_pred), 'u_pred': DM(u_pred),
         }
@@ -429,6 +430,60 @@ class IHMPCController(object):
         for i in range(len(self.VJ)):
             self.VJ[i].peso_hist.append(pesos[i])
         return sol
+
+    def _duals(self, lam_rows, x, ysp, w, pesos, vin):
+        """sol['lam_w'] (nw) and sol['lam_g'] (dim_g = N nx + N nu + 2 ny + len(V), the g layout of ctl.py:414-456)
+        from the device multipliers of the inequality rows (sihmpc_io.lam), casadi's sign convention (> 0: upper
+        bound active, < 0: lower).  The multipliers of the terminal residual rows res1 / res2 (equalities by
+        default, ctl.py:441-449) follow from stationarity in siN / syN:  grad_w J + J_g^T lam_g + lam_w = 0.
+        Rows 0 <= V_i <= inf are vacuous (multiplier 0; where V_i = 0 the reference's IPOPT returns noise, SURVEY
+        8c); a contraction row V_siN <= ViN_ant is enforced as |siN| <= sqrt(ViN_ant/q), its multiplier mu maps to
+        lam = mu / (2 q |siN|)."""
+        p = self._plan
+        N, nu, ny, nx = self.N, self.nu, self.ny, self.nx
+        nvm, nv = N * nu, p.nv + p.n_extra
+        lam_w = np.zeros(nvm + 2 * ny)
+        lam_g = np.zeros(N * nx + N * nu + 2 * ny + len(self.V))
+        lam_w[:nvm] = lam_rows[:nvm]                                            # move box
+        lam_g[N * nx:N * nx + nvm] = lam_rows[nv:nv + nvm]                      # U_pred rows, k-major like the reference
+        o_res1, o_res2, o_V = N * nx + nvm, N * nx + nvm + ny, N * nx + nvm + 2 * ny
+        dense = lam_rows[2 * nv:2 * nv + p.ncd]
+        syN, siN = w[nvm:nvm + ny], w[nvm + ny:nvm + 2 * ny]
+        lam_rho = {}
+        for r, kind in enumerate(p.row_kind):
+            if kind[0] == 'x':
+                lam_g[kind[1] * nx + kind[2]] = dense[r]
+            elif kind[0] == 'sy':
+                lam_w[nvm + kind[1]] = dense[r]
+            elif kind[0] == 'si':
+                lam_w[nvm + ny + kind[1]] = dense[r]
+            elif kind[0] == 'rho':
+                lam_rho[kind[1]] = dense[r]
+            elif kind[0] == 'vin':
+                slot = kind[1]
+                V = next(V for V in self.V if V.coeff.vin_slot == slot)
+                ind, q = self._vin[slot]
+                if dense[r] != 0.0 and abs(siN[ind]) > 0:
+                    lam_g[o_V + self.V.index(V)] = abs(dense[r]) / (2.0 * q * abs(siN[ind]))
+        # stationarity in the slacks: d J / d syN_i - lam_res2_i + lam_w[syN_i] = 0, and the same for siN with res1 and
+        # the contraction row (d V_siN / d siN_i = 2 q siN_i)
+        om = p.Wrow @ pesos + p.w0row
+        Y = (p.Myx @ x + p.Myu[:, :nvm] @ w[:nvm]).reshape(N, ny)
+        r_y = Y - ysp[None, :] - syN[None, :] - p.tau[:, None] * siN[None, :]   # ctl.py:174
+        om_y = om[:N * ny].reshape(N, ny)
+        a, b = p.row_slices['syN']; om_sy = om[a:b]
+        a, b = p.row_slices['siN']; om_si = om[a:b]
+        dJ_sy = -2.0 * np.sum(om_y * r_y, axis=0) + 2.0 * om_sy * syN
+        dJ_si = -2.0 * np.sum(om_y * r_y * p.tau[:, None], axis=0) + 2.0 * om_si * siN
+        lam_res2 = dJ_sy + lam_w[nvm:nvm + ny]
+        lam_res1 = dJ_si + lam_w[nvm + ny:]
+        for slot, (ind, q) in enumerate(self._vin):
+            V = next((V for V in self.V if V.coeff.vin_slot == slot), None)
+            if V is not None:
+                lam_res1[ind] += 2.0 * q * siN[ind] * lam_g[o_V + self.V.index(V)]
+        lam_g[o_res1:o_res1 + ny] = lam_res1
+        lam_g[o_res2:o_res2 + ny] = lam_res2
+        return lam_w, lam_g
 
     def warmStart(self, sol, ysp):                            # ctl.py:534-564
         w0 = np.asarray(sol['w_opt']).reshape(-1)

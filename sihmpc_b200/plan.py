@@ -88,6 +88,10 @@ class Plan:
     # inequality rows the moves cannot influence (zero normal): not sent to the device, kept here so that the caller
     # can still see them violated -- fixed_rows[k] = (Gcx, Gcy, gc0, lo, hi, vin_slot, q); see fixed_row_violation()
     fixed_rows: tuple = ()
+    # origin of every dense row (same order as Gc): ('x', k, c) state box on X_pred[k][c], ('sy', i) / ('si', i) slack
+    # boxes, ('vin', slot) siN contraction, ('rho', c) range of a ranged terminal residual -- used to scatter the
+    # device multipliers into sol['lam_w'] / sol['lam_g'] (ihmpccontroller.py:525-529)
+    row_kind: tuple = ()
 
 
 def plant_csr(A, B, pattern=None):
@@ -257,25 +261,31 @@ def compile_plan(sys, N, VJ, bounds, Q_bar=None, vin=(), rs=None, ri=None, rs_hi
     silb = g('silb', np.full(ny, -INF)); siub = g('siub', np.full(ny, INF))
 
     rows = []   # (Gc, Gcx, Gcy, g0, lo, hi, vin_slot, q)
+    kinds = []
     for k in range(N):
         for c in range(nx):
             if np.isfinite(xlb[c]) or np.isfinite(xub[c]):
                 rows.append((Gam[k * nx + c], Phi[k * nx + c], np.zeros(ny), 0.0, xlb[c], xub[c], -1, 0.0))
+                kinds.append(('x', k, c))
     for i in range(ny):
         if np.isfinite(sylb[i]) or np.isfinite(syub[i]):
             rows.append((E[o_sy + i], Px[o_sy + i], Py[o_sy + i], e0[o_sy + i], sylb[i], syub[i], -1, 0.0))
+            kinds.append(('sy', i))
     for i in range(ny):
         if np.isfinite(silb[i]) or np.isfinite(siub[i]):
             rows.append((E[o_si + i], Px[o_si + i], Py[o_si + i], e0[o_si + i], silb[i], siub[i], -1, 0.0))
+            kinds.append(('si', i))
     vin_row = []; vin_q = []
     for slot, (ind, q) in enumerate(vin):
         vin_row.append(o_si + ind); vin_q.append(float(q))
         if q > 0:
             rows.append((E[o_si + ind], Px[o_si + ind], Py[o_si + ind], e0[o_si + ind], -INF, INF, slot, float(q)))
+            kinds.append(('vin', slot))
     for c, (kind, i) in enumerate(extra):                       # lb <= rho <= ub
         unit = np.zeros(nv); unit[nvm + c] = 1.0
         lo_, hi_ = (bounds_rs(kind, i, rs_hi, ri_hi, bounds))
         rows.append((unit, np.zeros(nx), np.zeros(ny), 0.0, lo_, hi_, -1, 0.0))
+        kinds.append(('rho', c))
     # rows whose normal vanishes cannot be influenced by dU: vacuous or infeasible whatever
     # the solver does (non-integrating plants: xi(N) = xi(0)); they are not sent to the device.
     keep = [np.linalg.norm(r[0]) > 1e-13 * max(1.0, np.linalg.norm(r[1])) for r in rows]
@@ -287,6 +297,7 @@ def compile_plan(sys, N, VJ, bounds, Q_bar=None, vin=(), rs=None, ri=None, rs_hi
                       "cannot reach): they are checked on the host (SIHMPC_ST_INFEASIBLE), not enforced by the solver"
                       % sum(1 for fr in fixed_rows if np.isfinite(fr[3]) or np.isfinite(fr[4])), stacklevel=2)
     rows = [r for r, k in zip(rows, keep) if k]
+    kinds = [kd for kd, k in zip(kinds, keep) if k]
     ncd = len(rows)
     Gc = np.array([r[0] for r in rows]).reshape(ncd, nv)
     Gcx = np.array([r[1] for r in rows]).reshape(ncd, nx)
@@ -299,7 +310,7 @@ def compile_plan(sys, N, VJ, bounds, Q_bar=None, vin=(), rs=None, ri=None, rs_hi
 
     rowptr, col, val, _ = plant_csr(A, B)
 
-    return Plan(n_extra=n_extra, extra=tuple(extra), fixed_rows=fixed_rows,
+    return Plan(n_extra=n_extra, extra=tuple(extra), fixed_rows=fixed_rows, row_kind=tuple(kinds),
                 nx=nx, nu=nu, ny=ny, nd=nd, N=N, nv=nvm, m=m, mh=len(hj_index), R=R, ncd=ncd,
                 n_vin=len(vin), Ts=Ts, E=E, Px=Px, Py=Py, e0=e0, Wrow=Wrow, w0row=w0row, Wdu=Wdu,
                 HJ=HJ, hj_index=np.array(hj_index, dtype=np.int32), Ht=Ht,

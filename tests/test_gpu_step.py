@@ -215,6 +215,53 @@ def test_dropin_example_loop_matches_oracle():
     assert np.allclose([V.v_hist[-1] for V in c.V], [V.v_hist[-1] for V in orc.V], atol=1e-9)
 
 
+def test_duals_match_oracle_on_the_example_loop():
+    """sol['lam_w'] / sol['lam_g'] (ihmpccontroller.py:525-529; consumed as IPOPT warm start by
+    example_distillation_log.py:101-103) on the reference's driver loop with an input box AND a move box that bind:
+    multipliers of the move box (lam_w), of the U_pred rows and of the terminal residual equalities res1 / res2
+    (lam_g) against the oracle's KKT multipliers of the un-reduced (w, g) problem, casadi's sign convention.
+    Compared where the active set is not degenerate (every active multiplier well away from zero)."""
+    sys_ = sc.distillation_system()
+    bounds = dict(ulb=[1.80, 1.62], uub=[2.02, 1.78], dulb=[-0.03, -0.03], duub=[0.03, 0.03])
+    c = sc.declare_distillation(IHMPCController, sys_, **bounds)
+    orc = sc.declare_distillation(OracleIHMPC, sys_, **bounds)
+    N, nu, ny, nx = c.N, c.nu, c.ny, c.nx
+    nw = N * nu + 2 * ny
+    ng = N * nx + N * nu + 2 * ny
+    u = np.array([1.95, 1.71]); x = np.append([96, 0.5], np.zeros(nx - 2)); ysp = [96, 0.5]
+    w0 = []; pesos = []
+    compared = active_w = active_g = 0
+    for k in range(40):
+        if k > 5:
+            ysp = [96.6, 0.2]
+        if k > 22:
+            ysp = [95.2, 1.1]
+        # ViN_ant = inf: with the contraction bound at 0 (siN = 0 on this non-integrating plant) the rows res1 and
+        # V_siN <= 0 share a normal and their multipliers are not unique (LICQ fails; the oracle's least squares
+        # splits them evenly, IPOPT returns whatever it ends on)
+        vin = [np.inf, np.inf]
+        sol = c.mpc(x0=x, ySP=ysp, w0=w0, u0=u, pesos=pesos, ViN_ant=vin)
+        solo = orc.mpc(x0=x, ySP=ysp, w0=[], u0=u, pesos=pesos, ViN_ant=vin)   # same state in: per-step parity
+        lam_o = solo['lam_rows']
+        lam_w, lam_g = sol['lam_w'].full().reshape(-1), sol['lam_g'].full().reshape(-1)
+        assert lam_w.size == nw and lam_g.size == ng + len(c.V)           # dim_g of ctl.py:414-456
+        assert np.allclose(sol['w_opt'].full().reshape(-1), solo['w_opt'], atol=1e-8)
+        act = np.abs(lam_o[:nw + N * nx + N * nu])
+        if not np.any((act > 0) & (act < 1e-7 * max(1.0, act.max()))):    # non-degenerate active set
+            scale = max(1.0, np.max(np.abs(lam_o)))
+            assert np.max(np.abs(lam_w - lam_o[:nw])) <= 1e-6 * scale, k
+            assert np.max(np.abs(lam_g[:ng] - lam_o[nw:nw + ng])) <= 1e-6 * scale, k
+            compared += 1
+            active_w += int(np.count_nonzero(lam_w)); active_g += int(np.count_nonzero(lam_g[N * nx:N * nx + N * nu]))
+        assert np.all(lam_g[ng:] == 0.0)                                   # vacuous rows 0 <= V_i
+        du = c.du
+        res = c.dynF(x0=x, u0=u, du0=du)
+        x = res['xkp1'].full().reshape(-1); u = res['ukp1'].full().reshape(-1)
+        w0 = c.warmStart(sol, ysp)
+        pesos, _ = c.satWeights2(x, u, w0, ysp)
+    assert compared >= 30 and active_w > 10 and active_g > 10, (compared, active_w, active_g)
+
+
 def test_fast_path_handover_many_rounds(monkeypatch):
     """Quad fast path with a tiny grid (many scenarios per quad, one after the other) on a bound
     set that makes a good share of the scenarios hand over to the exact active-set kernel mid-loop:
