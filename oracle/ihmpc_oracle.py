@@ -270,6 +270,7 @@ class OracleIHMPC:
             c += p * r0 @ V.W @ r0
 
         rows, lo, hi = [], [], []
+        self._ellipsoids = []            # (Rw, r0, W, vmax) of every multi-index siN row with a finite limit
         # bounds on w (ctl.py:399-412)
         lbw = np.concatenate([np.tile(self.dulb, self.N), self.sylb, self.silb])
         ubw = np.concatenate([np.tile(self.duub, self.N), self.syub, self.siub])
@@ -295,7 +296,15 @@ class OracleIHMPC:
                 vmax = ViN_ant[V.ViN_slot]
                 if np.isfinite(vmax):
                     if V.R.shape[0] != 1:
-                        raise NotImplementedError("multi-index siN ellipsoid (QCQP) not supported")
+                        # sum_j q_j siN_j^2 <= ViN_ant (ctl.py:246-247,266): ONE convex quadratic row.  With the limit
+                        # at 0 it pins every siN_j (linear rows); otherwise it is kept aside for mpc()'s outer search
+                        Rw, r0 = split(V.R)
+                        if vmax <= 0.0:
+                            Gw_rows.append(Rw); r0_rows.append(r0)
+                            lo_rows.append(np.zeros(Rw.shape[0])); hi_rows.append(np.zeros(Rw.shape[0]))
+                        else:
+                            self._ellipsoids.append((Rw, r0, V.W, float(vmax)))
+                        continue
                     q = float(V.W[0, 0])
                     if q > 0:
                         bound = np.sqrt(max(vmax, 0.0) / q)
@@ -335,6 +344,8 @@ class OracleIHMPC:
 
         H, f, c, G, lo, hi = self._problem(x0, u0, ySP, pesos, ViN_ant)
         w, lam_rows, info = solve_qp_exact(H, f, G, lo, hi)
+        if self._ellipsoids:
+            w, lam_rows, info = self._solve_with_ellipsoid(H, f, G, lo, hi, w, lam_rows, info)
         nw, N, nu, ny = self.nw, self.N, self.nu, self.ny
         xi = self._xi(w, x0, u0, ySP)
         J = c + f @ w + 0.5 * w @ H @ w
@@ -361,6 +372,43 @@ class OracleIHMPC:
         for i, V in enumerate(self.VJ):
             V.peso_hist.append(pesos[i])
         return sol
+
+    def _solve_with_ellipsoid(self, H, f, G, lo, hi, w, lam_rows, info):
+        """The QP plus ONE convex quadratic row  V_e(w) = (Rw w + r0)' W (Rw w + r0) <= vmax  (multi-index siN,
+        ctl.py:243-271).  KKT: grad J + lam_e grad V_e + G' lam = 0, lam_e >= 0, lam_e (V_e - vmax) = 0.  For fixed
+        lam_e the rest is the strictly convex QP of J + lam_e V_e, whose V_e decreases monotonically in lam_e:
+        bracket, then Brent on phi(lam_e) = V_e - vmax down to rounding, keeping the feasible end."""
+        from scipy.optimize import brentq
+        if len(self._ellipsoids) > 1:
+            raise NotImplementedError("more than one multi-index siN row with a finite limit")
+        Rw, r0, W, vmax = self._ellipsoids[0]
+        He, fe = 2.0 * Rw.T @ W @ Rw, 2.0 * Rw.T @ W @ r0
+
+        def val(wv):
+            r = Rw @ wv + r0
+            return float(r @ W @ r)
+
+        if val(w) <= vmax * (1.0 + 1e-12):
+            info = dict(info, lam_ellipsoid=0.0)
+            return w, lam_rows, info
+        cache = {}
+
+        def phi(lam):
+            ww, ll, ii = solve_qp_exact(H + lam * He, f + lam * fe, G, lo, hi)
+            cache[lam] = (ww, ll, ii)
+            return val(ww) - vmax
+
+        hi_l = 1.0
+        while phi(hi_l) > 0.0:
+            hi_l *= 8.0
+            if hi_l > 1e16:
+                raise RuntimeError("ellipsoid row cannot be met (infeasible)")
+        lo_l = 0.0 if hi_l == 1.0 else hi_l / 8.0
+        lam = brentq(phi, lo_l, hi_l, xtol=1e-300, rtol=8.9e-16, maxiter=200)
+        feas = [l for l in cache if val(cache[l][0]) <= vmax * (1.0 + 1e-12)]
+        lam = min(feas, key=lambda l: abs(l - lam))              # the feasible end of the last bracket
+        ww, ll, ii = cache[lam]
+        return ww, ll, dict(ii, lam_ellipsoid=float(lam))
 
     def warmStart(self, sol, ysp):                               # ctl.py:534-564
         w0 = np.asarray(sol['w_opt']).reshape(-1)

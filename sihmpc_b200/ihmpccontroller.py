@@ -177,7 +177,9 @@ class IHMPCController(object):
         self.j_hist = []
         self.Qt = None
         self.Q_bar = None
-        self._vin = []              # (output index, q) per contraction slot
+        self._vin = []              # (output index, q) per contraction slot of the PLAN (dense row |siN| <= sqrt(ViN/q))
+        self._vin_of = []           # per entry of self.ViNant: ('row', plan slot) or ('ell', index into self._ell)
+        self._ell = []              # multi-index siN rows (ellipsoids): dict(V, inds, q, slots = plan slots of its box)
         self._dirty = True
         self._plan = None
         self._eval_plan = None
@@ -222,13 +224,25 @@ class IHMPCController(object):
             self.Pesos.append(V.weight)
             self.VJ.append(V)
         if kind == 'siN':                                     # contraction (ctl.py:265-269)
-            if len(inds) != 1:
-                raise NotImplementedError("siN sub-objective over several outputs (QCQP) is not supported")
             V.lim(0, 'ViN_ant_' + str(inds))
             co.vin_slot = len(self.ViNant)
             self.ViN_ant.append('ViN_ant_' + str(inds))
             self.ViNant.append(np.inf)
-            self._vin.append((int(inds[0]), float(qd[0])))
+            if len(inds) == 1:
+                self._vin_of.append(('row', len(self._vin)))
+                self._vin.append((int(inds[0]), float(qd[0])))
+            else:
+                # sum_j q_j siN_j^2 <= ViN_ant over several outputs (ctl.py:246-247,266): ONE convex quadratic row.
+                # It enters the plan as one more weighted sub-objective whose weight is the row's MULTIPLIER (found by
+                # mpc() in an outer search, every trial a device QP solve), plus its box |siN_j| <= sqrt(ViN_ant/q_j)
+                # as ordinary contraction rows (implied by the ellipsoid; exact when ViN_ant = 0)
+                slots = []
+                for j, ind in enumerate(inds):
+                    if qd[j] > 0:
+                        slots.append(len(self._vin))
+                        self._vin.append((int(ind), float(qd[j])))
+                self._vin_of.append(('ell', len(self._ell)))
+                self._ell.append(dict(V=V, inds=[int(i) for i in inds], q=[float(v) for v in qd[:len(inds)]], slots=slots))
         self._dirty = True
         return V
 
@@ -294,7 +308,12 @@ class IHMPCController(object):
             return self._plan
         if not self.VJ:
             raise ValueError("no weighted sub-objective declared")
-        self._plan = compile_plan(self.sys, self.N, [V.coeff for V in self.VJ], self._bounds(),
+        cos = [V.coeff for V in self.VJ]
+        for e in self._ell:                                   # multiplier slots of the ellipsoid rows: weights m.. of the plan
+            c0 = e['V'].coeff
+            cos.append(SubObjective(name='lam_' + c0.name, cy=np.zeros(self.ny), csy=np.zeros(self.ny),
+                                    csi=c0.csi.copy(), cdu=np.zeros(self.nu)))
+        self._plan = compile_plan(self.sys, self.N, cos, self._bounds(),
                                   Q_bar=self.Q_bar, vin=self._vin,
                                   rs=np.asarray(self.rslb, float), ri=np.asarray(self.rilb, float),
                                   rs_hi=np.asarray(self.rsub, float), ri_hi=np.asarray(self.riub, float))
@@ -324,6 +343,9 @@ class IHMPCController(object):
 
     def engine(self, batch, **kw):
         from .engine import BatchedEngine
+        if self._ell:
+            raise NotImplementedError("a siN sub-objective over several outputs (quadratic row) is solved by mpc()'s outer "
+                                      "multiplier search; the batched closed-loop engine does not carry it")
         return BatchedEngine(self.compile(), batch, **kw)
 
     def _get_stepper(self):
@@ -388,18 +410,34 @@ class IHMPCController(object):
             pesos = self.init_pesos()
         pesos = _vec(pesos, l, "pesos")
         x = _vec(x0, nx, "x0"); u = _vec(u0, nu, "u0"); ysp = _vec(ySP, ny, "ySP")
+        # limits of the plan's contraction rows: a single-index siN row takes its own ViN_ant, the box of an
+        # ellipsoid takes the ellipsoid's
+        pvin = np.full(len(self._vin), np.inf)
+        for i, (kind, k) in enumerate(self._vin_of):
+            for slot in ([k] if kind == 'row' else self._ell[k]['slots']):
+                pvin[slot] = vin[i]
+        pes_ext = np.concatenate([pesos, np.zeros(len(self._ell))])
 
-        hs.x.numpy()[0] = x
-        hs.u.numpy()[0] = u
-        hs.ysp.numpy()[0] = ysp
-        hs.pesos.numpy()[0] = pesos
-        if len(vin):
-            hs.vinant.numpy()[0, :len(vin)] = vin
-        hs.step(flags=_capi.F_UPDATE_VIN, want_lam=True)
-        w = hs.w_opt.numpy()[0].copy()
+        def solve(pes):
+            hs.x.numpy()[0] = x
+            hs.u.numpy()[0] = u
+            hs.ysp.numpy()[0] = ysp
+            hs.pesos.numpy()[0] = pes
+            if len(pvin):
+                hs.vinant.numpy()[0, :len(pvin)] = pvin
+            hs.step(flags=_capi.F_UPDATE_VIN, want_lam=True)
+            return hs.w_opt.numpy()[0].copy()
+
+        w = solve(pes_ext)
+        for k, e in enumerate(self._ell):
+            rho = vin[[i for i, (kd, kk) in enumerate(self._vin_of) if kd == 'ell' and kk == k][0]]
+            w = self._ellipsoid_search(e, l + k, rho, pes_ext, solve, w)
         J = float(hs.J.numpy()[0])
+        for k, e in enumerate(self._ell):                     # sol['J'] is the cost, without the multiplier term
+            si = w[N * nu + ny:][e['inds']]
+            J -= pes_ext[l + k] * float(np.dot(e['q'], si * si))
         self.status = int(hs.status.numpy()[0])
-        if self._plan.fixed_rows and fixed_row_violation(self._plan, x, ysp, vin if len(vin) else None) > 1e-8:
+        if self._plan.fixed_rows and fixed_row_violation(self._plan, x, ysp, pvin if len(pvin) else None) > 1e-8:
             self.status |= _capi.ST_INFEASIBLE            # a bound the moves cannot influence is violated at x0
         self.n_active = int(hs.n_active.numpy()[0])
         x_pred, y_pred, u_pred = self._predict(x, u, w[:N * nu])
@@ -408,7 +446,7 @@ class IHMPCController(object):
         res1 = XN[self.nxs + self.nxd:self.nxs + self.nxd + self.nxi] - w[N * nu + ny:]
         res2 = XN[:self.nxs] - ysp - w[N * nu:N * nu + ny]
         gvec = np.concatenate([x_pred, u_pred, res1, res2, vals])
-        lam_w, lam_g = self._duals(hs.lam.numpy()[0], x, ysp, w, pesos, vin)
+        lam_w, lam_g = self._duals(hs.lam.numpy()[0], x, ysp, w, pes_ext, pvin)
         sol = {
             'J': DM(J),
             'du_opt': DM(w[:N * nu].reshape(N, nu).T),        # nu x N (ctl.py:510-515)
@@ -418,10 +456,14 @@ class IHMPCController(object):
             'g': DM(gvec),
             'x_pred': DM(x_pred), 'y_pred': DM(y_pred), 'u_pred': DM(u_pred),
         }
-        if len(vin):                                          # ctl.py:581-584
-            newv = hs.vinant.numpy()[0, :len(vin)]
-            for i in range(len(vin)):
-                self.ViNant[i] = float(newv[i])
+        if len(vin):                                          # ctl.py:581-584: ViNant[i] = F_ViN[i](warm start)
+            newv = hs.vinant.numpy()[0, :len(pvin)]           # q siN_next^2 per plan slot, from the device
+            for i, (kind, k) in enumerate(self._vin_of):
+                if kind == 'row':
+                    self.ViNant[i] = float(newv[k])
+                else:
+                    e = self._ell[k]
+                    self.ViNant[i] = float(sum(newv[slot] for slot in e['slots']))
         self.du = sol['du_opt'][:, 0].full()                  # ctl.py:595
         self.j_value = J
         self.j_hist.append(self.j_value)
@@ -450,6 +492,7 @@ class IHMPCController(object):
         dense = lam_rows[2 * nv:2 * nv + p.ncd]
         syN, siN = w[nvm:nvm + ny], w[nvm + ny:nvm + 2 * ny]
         lam_rho = {}
+        vin_terms = []                                          # (output, d row / d siN * multiplier) of contraction rows
         for r, kind in enumerate(p.row_kind):
             if kind[0] == 'x':
                 lam_g[kind[1] * nx + kind[2]] = dense[r]
@@ -461,10 +504,14 @@ class IHMPCController(object):
                 lam_rho[kind[1]] = dense[r]
             elif kind[0] == 'vin':
                 slot = kind[1]
-                V = next(V for V in self.V if V.coeff.vin_slot == slot)
+                owner = next((i for i, (kd, k) in enumerate(self._vin_of) if kd == 'row' and k == slot), None)
                 ind, q = self._vin[slot]
-                if dense[r] != 0.0 and abs(siN[ind]) > 0:
+                if owner is not None and dense[r] != 0.0 and abs(siN[ind]) > 0:
+                    V = next(V for V in self.V if V.coeff.vin_slot == owner)
                     lam_g[o_V + self.V.index(V)] = abs(dense[r]) / (2.0 * q * abs(siN[ind]))
+                    vin_terms.append((ind, 2.0 * q * siN[ind] * lam_g[o_V + self.V.index(V)]))
+                elif owner is None:
+                    vin_terms.append((ind, dense[r]))           # box row of an ellipsoid: d siN_ind / d siN_ind = 1
         # stationarity in the slacks: d J / d syN_i - lam_res2_i + lam_w[syN_i] = 0, and the same for siN with res1 and
         # the contraction row (d V_siN / d siN_i = 2 q siN_i)
         om = p.Wrow @ pesos + p.w0row
@@ -476,14 +523,50 @@ class IHMPCController(object):
         dJ_sy = -2.0 * np.sum(om_y * r_y, axis=0) + 2.0 * om_sy * syN
         dJ_si = -2.0 * np.sum(om_y * r_y * p.tau[:, None], axis=0) + 2.0 * om_si * siN
         lam_res2 = dJ_sy + lam_w[nvm:nvm + ny]
-        lam_res1 = dJ_si + lam_w[nvm + ny:]
-        for slot, (ind, q) in enumerate(self._vin):
-            V = next((V for V in self.V if V.coeff.vin_slot == slot), None)
-            if V is not None:
-                lam_res1[ind] += 2.0 * q * siN[ind] * lam_g[o_V + self.V.index(V)]
+        lam_res1 = dJ_si + lam_w[nvm + ny:]                   # (om carries the ellipsoid multipliers: pesos m..)
+        for ind, t in vin_terms:
+            lam_res1[ind] += t
+        for k, e in enumerate(self._ell):
+            lam_g[o_V + self.V.index(e['V'])] = pesos[len(self.VJ) + k]
         lam_g[o_res1:o_res1 + ny] = lam_res1
         lam_g[o_res2:o_res2 + ny] = lam_res2
         return lam_w, lam_g
+
+    def _ellipsoid_search(self, e, slot, rho, pes_ext, solve, w):
+        """Multiplier of the quadratic row  V_e(w) = sum_j q_j siN_j^2 <= rho  (ctl.py:243-271): for a fixed
+        multiplier the problem is the QP of J + lam V_e (one device solve), V_e falls monotonically in lam; bracket,
+        then Brent on V_e - rho to rounding, keeping the feasible end of the last bracket.  KKT of the QCQP:
+        grad J + lam grad V_e + (rows) = 0, lam >= 0, lam (V_e - rho) = 0."""
+        from scipy.optimize import brentq
+        nvm, ny = self.N * self.nu, self.ny
+        q, inds = np.asarray(e['q']), e['inds']
+
+        def val(wv):
+            si = wv[nvm + ny:nvm + 2 * ny][inds]
+            return float(np.dot(q, si * si))
+
+        if not np.isfinite(rho) or val(w) <= rho * (1.0 + 1e-12):
+            return w
+        if rho <= 0.0:
+            return w            # the box rows already pin every siN_j at 0
+        seen = {}
+
+        def phi(lam):
+            pes_ext[slot] = lam
+            seen[lam] = solve(pes_ext)
+            return val(seen[lam]) - rho
+
+        hi = 1.0
+        while phi(hi) > 0.0:
+            hi *= 8.0
+            if hi > 1e16:
+                raise RuntimeError("the siN ellipsoid row cannot be met")
+        lo = 0.0 if hi == 1.0 else hi / 8.0
+        lam = brentq(phi, lo, hi, xtol=1e-300, rtol=8.9e-16, maxiter=200)
+        feas = [l for l in seen if val(seen[l]) <= rho * (1.0 + 1e-12)]
+        lam = min(feas, key=lambda l: abs(l - lam))
+        pes_ext[slot] = lam
+        return solve(pes_ext)          # leaves J, status, multipliers of THIS solve in the stepper's buffers
 
     def warmStart(self, sol, ysp):                            # ctl.py:534-564
         w0 = np.asarray(sol['w_opt']).reshape(-1)

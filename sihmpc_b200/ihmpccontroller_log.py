@@ -94,6 +94,8 @@ class IHMPCController(_Weighted):
         for lo, hi, nm in ((self.rslb, self.rsub, 'rs'), (self.rilb, self.riub, 'ri')):
             if not np.array_equal(np.asarray(lo, float), np.asarray(hi, float)):
                 raise NotImplementedError("terminal residual ranges (%slb != %sub) are not supported yet" % (nm, nm))
+        if self._ell:
+            raise NotImplementedError("siN sub-objective over several outputs (quadratic row) in the log variant")
         if not self.VJ:
             raise ValueError("no log sub-objective declared")
         self._plan = compile_plan(self.sys, self.N, [V.coeff for V in self.VJ], self._bounds(),

@@ -262,6 +262,47 @@ def test_duals_match_oracle_on_the_example_loop():
     assert compared >= 30 and active_w > 10 and active_g > 10, (compared, active_w, active_g)
 
 
+def test_multi_index_siN_ellipsoid_matches_oracle():
+    """subObj(siN=[0, 1], Q=diag(1, 2), addJ=False): ONE quadratic row q0 siN0^2 + q1 siN1^2 <= ViN_ant
+    (ihmpccontroller.py:243-271) on a 2x2 plant whose channels integrate.  mpc() finds the row's multiplier by an outer
+    search whose every trial is a device QP solve; moves, cost, the contracted limit and the multiplier against the
+    oracle (same state in), the row itself to 1e-8."""
+    from tests.util import integrating_2x2, declare_ellipsoid
+    s = integrating_2x2()
+    c = declare_ellipsoid(IHMPCController, s)
+    orc = declare_ellipsoid(OracleIHMPC, s)
+    N, nu, ny = c.N, c.nu, c.ny
+    x = np.zeros(s.nx); u = np.zeros(2); w0 = []; pesos = []
+    active = 0
+    for k in range(30):
+        ysp = [1.0, -0.5] if k < 15 else [0.2, 0.4]
+        vin = list(c.ViNant)
+        orc.ViNant = list(vin)
+        sol = c.mpc(x0=x, ySP=ysp, w0=w0, u0=u, pesos=pesos)
+        solo = orc.mpc(x0=x, ySP=ysp, w0=[], u0=u, pesos=pesos)
+        w = sol['w_opt'].full().reshape(-1)
+        scale = max(np.max(np.abs(solo['w_opt'][:N * nu])), 1e-9)
+        assert np.max(np.abs(w[:N * nu] - solo['w_opt'][:N * nu])) <= RTOL * scale, k
+        assert abs(float(sol['J']) - solo['J']) <= RTOL * max(abs(solo['J']), 1e-9), k
+        si = w[N * nu + ny:]
+        Ve = 1.0 * si[0] ** 2 + 2.0 * si[1] ** 2
+        assert Ve <= vin[0] * (1 + 1e-8) + 1e-300
+        lam_e = solo['info'].get('lam_ellipsoid', 0.0)
+        if lam_e > 0:
+            active += 1
+            mine = float(sol['lam_g'].full().reshape(-1)[N * s.nx + N * nu + 2 * ny + c.V.index(c._ell[0]['V'])])
+            assert abs(mine - lam_e) <= 1e-5 * lam_e, (k, mine, lam_e)
+        assert abs(c.ViNant[0] - orc.ViNant[0]) <= 1e-6 * max(orc.ViNant[0], 1e-12), k
+        du = c.du
+        res = c.dynF(x0=x, u0=u, du0=du)
+        x = res['xkp1'].full().reshape(-1); u = res['ukp1'].full().reshape(-1)
+        w0 = c.warmStart(sol, ysp)
+        pesos, _ = c.satWeights2(x, u, w0, ysp)
+    assert active >= 3
+    with pytest.raises(NotImplementedError):
+        c.engine(8)
+
+
 def test_fast_path_handover_many_rounds(monkeypatch):
     """Quad fast path with a tiny grid (many scenarios per quad, one after the other) on a bound
     set that makes a good share of the scenarios hand over to the exact active-set kernel mid-loop:

@@ -192,3 +192,52 @@ def test_log_oracle_constrained_optimum_is_kkt_certified():
         assert min(sol['info']['margins']) <= 1e-9                     # something is active
         assert c.last_kkt['stationarity'] <= 1e-9 and c.last_kkt['lam_min'] >= -1e-10 and c.last_kkt['n_active'] > 0
         assert sol['J'] >= free['J'] - 1e-12                           # constraining cannot improve the cost
+
+
+def test_multi_index_siN_ellipsoid_row():
+    """siN=[0,1]: ONE quadratic row q0 siN0^2 + q1 siN1^2 <= ViN_ant (ihmpccontroller.py:243-271) on a plant whose
+    channels integrate.  The outer multiplier search lands on the boundary when the row is active, the limit
+    contracts along the loop, and an independent SLSQP solve of the un-reduced problem WITH the quadratic
+    constraint agrees."""
+    from tests.util import integrating_2x2, declare_ellipsoid
+    s = integrating_2x2()
+    c = declare_ellipsoid(OracleIHMPC, s)
+    assert len(c.ViNant) == 1 and c.V[[V.name for V in c.V].index('VsiN_[0, 1]')].R.shape[0] == 2
+    x = np.zeros(s.nx); u = np.zeros(2); w0 = []; pesos = []
+    vin_hist, active, checked = [], 0, 0
+    for k in range(30):
+        ysp = [1.0, -0.5] if k < 15 else [0.2, 0.4]
+        vin = list(c.ViNant)
+        sol = c.mpc(x0=x, ySP=ysp, w0=w0, u0=u, pesos=pesos)
+        Ve = c.F(c.F_ViN[0], x, u, sol["w_opt"], ysp)
+        assert Ve <= vin[0] * (1 + 1e-10) + 1e-300
+        lam_e = sol["info"].get("lam_ellipsoid", 0.0)
+        if lam_e > 0:
+            active += 1
+            assert abs(Ve - vin[0]) <= 1e-9 * vin[0]                     # on the boundary
+            if checked < 4:
+                H, f, c0, G, lo, hi = c._problem(x, u, np.asarray(ysp, float), np.asarray(pesos if len(pesos) else c.init_pesos(), float), vin)
+                Rw, r0, W, vmax = c._ellipsoids[0]
+                cons = [{"type": "ineq", "fun": lambda w: vmax - (Rw @ w + r0) @ W @ (Rw @ w + r0),
+                         "jac": lambda w: -2.0 * Rw.T @ W @ (Rw @ w + r0)}]
+                for i in range(G.shape[0]):
+                    if np.isfinite(lo[i]) and lo[i] == hi[i]:
+                        cons.append({"type": "eq", "fun": lambda w, i=i: G[i] @ w - lo[i], "jac": lambda w, i=i: G[i]})
+                    else:
+                        if np.isfinite(lo[i]):
+                            cons.append({"type": "ineq", "fun": lambda w, i=i: G[i] @ w - lo[i], "jac": lambda w, i=i: G[i]})
+                        if np.isfinite(hi[i]):
+                            cons.append({"type": "ineq", "fun": lambda w, i=i: hi[i] - G[i] @ w, "jac": lambda w, i=i: -G[i]})
+                r = minimize(lambda w: 0.5 * w @ H @ w + f @ w + c0, sol["w_opt"] * 0.9, jac=lambda w: H @ w + f,
+                             constraints=cons, method="SLSQP", options=dict(ftol=1e-15, maxiter=800))
+                if r.success:
+                    assert abs(r.fun - sol["J_quad"]) < 1e-7 * max(1.0, abs(sol["J_quad"]))
+                    assert np.max(np.abs(r.x - sol["w_opt"])) < 5e-5
+                    checked += 1
+        vin_hist.append(c.ViNant[0])
+        r_ = c.dynF(x, u, c.du)
+        x, u = r_['xkp1'], r_['ukp1']
+        w0 = c.warmStart(sol, ysp)
+        pesos, _ = c.satWeights2(x, u, w0, ysp)
+    assert active >= 3 and checked >= 2, (active, checked)
+    assert np.isfinite(vin_hist).all() and vin_hist[-1] < 1e-2 * max(vin_hist)     # the limit dies out with the loop

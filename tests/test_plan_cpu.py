@@ -251,9 +251,11 @@ def test_dm_behaves_like_casadi_dm():
 
 def test_unsupported_declarations_fail_loudly():
     s = sc.distillation_system()
-    c2 = IHMPCController(s, 10)
+    c2 = sc.declare_distillation(IHMPCController, s)
+    c2.subObj(siN=[0, 1], Q=np.eye(2), addJ=False)          # accepted: mpc() carries the quadratic row ...
+    assert c2._ell and c2.compile().m == len(c2.VJ) + 1      # ... as one more weight of the plan (its multiplier)
     with pytest.raises(NotImplementedError):
-        c2.subObj(siN=[0, 1], Q=np.eye(2), addJ=False)
+        c2.engine(4)                                         # ... the batched closed-loop engine does not
 
 
 def test_rows_the_moves_cannot_influence_are_recorded_and_checked():

@@ -32,3 +32,25 @@ def oracle_closed_loop(declare, sys, scen, idx, n_steps, bounds=None, plant=None
     return closed_loop(c, scen["x0"][idx], scen["u0"][idx],
                        schedule_fn(scen["ysp_seq"][idx], scen["seg_start"][idx]), n_steps,
                        plant=plant, disturbance=dist)
+
+
+def integrating_2x2():
+    """2x2 plant whose four channels all integrate (K / (s (tau s + 1)) with dead times): siN != 0 on both outputs,
+    so a siN sub-objective over BOTH outputs is a genuine ellipsoid row (ihmpccontroller.py:243-271)."""
+    from sihmpc_b200.opom import OPOM, TransferFunction
+    h = [[TransferFunction([1.0], [5.0, 1.0, 0.0], delay=1), TransferFunction([0.3], [4.0, 1.0, 0.0], delay=0)],
+         [TransferFunction([0.2], [6.0, 1.0, 0.0], delay=0), TransferFunction([1.5], [3.0, 1.0, 0.0], delay=2)]]
+    return OPOM(h, 1.0)
+
+
+def declare_ellipsoid(cls, s, N=6, **bounds):
+    if not bounds:
+        bounds = dict(dulb=[-0.4, -0.4], duub=[0.4, 0.4])
+    c = cls(s, N, **bounds)
+    c.subObjComposed(y=[0], Q=1, sat=N * 1.0 ** 2)
+    c.subObjComposed(y=[1], Q=1, sat=N * 1.0 ** 2)
+    c.subObj(du=[0], Q=1, sat=N * 0.3 ** 2)
+    c.subObj(du=[1], Q=1, sat=N * 0.3 ** 2)
+    c.subObj(siN=[0, 1], Q=np.diag([1.0, 2.0]), addJ=False)      # sum_j q_j siN_j^2 <= ViN_ant
+    c.set_terminal_objective()
+    return c
