@@ -13,8 +13,13 @@ OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libsihmpc_b200.so")
 # (source, extra defines, object, dependencies): the tile kernels are instantiated one tile-row count per unit
 _TILE_DEPS = ["tile_kernel.cu", "tile_active_set.inc", "tile_api.h", "devplan.h", "../../include/sihmpc_b200.h"]
+_MMA_DEPS = ["mma_units.cu", "mma_kernel.cuh", "mma_api.h", "dist_kernel.cuh", "step_kernel.cuh", "devplan.h",
+             "../../include/sihmpc_b200.h"]
+MMA_SHAPES = [(n, x) for n in (6, 8, 10, 12) for x in (16, 24, 32)]       # (horizon, state capacity) of the tensor fast path
 UNITS = [("capi.cu", [], "capi.o", None), ("tile_kernel.cu", [], "tile_host.o", _TILE_DEPS)] + [
-    ("tile_kernel.cu", ["-DSIH_TL_ONLY_NT=%d" % k], "tile_nt%d.o" % k, _TILE_DEPS) for k in range(1, 9)]
+    ("tile_kernel.cu", ["-DSIH_TL_ONLY_NT=%d" % k], "tile_nt%d.o" % k, _TILE_DEPS) for k in range(1, 9)] + [
+    ("mma_units.cu", [], "mma_host.o", _MMA_DEPS)] + [
+    ("mma_units.cu", ["-DSIH_MMA_N=%d" % n, "-DSIH_MMA_NXP=%d" % x], "mma_%d_%d.o" % (n, x), _MMA_DEPS) for n, x in MMA_SHAPES]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 
@@ -45,20 +50,31 @@ def build(force: bool = False, verbose: bool = False, extra=()) -> str:
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
     os.makedirs(OBJ, exist_ok=True)
-    procs, objs = [], []
+    jobs, objs = [], []
     for src, defs, oname, deps in UNITS:
         obj = os.path.join(OBJ, oname)
         objs.append(obj)
         if not force and not extra and not _stale(obj, deps):
             continue
         cmd = [nvcc] + NVCC_FLAGS + list(extra) + defs + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, os.path.join(CSRC, src)]
-        procs.append((oname, subprocess.Popen(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
-    for u, pr in procs:
+        jobs.append((oname, cmd))
+    width = max(1, (os.cpu_count() or 4))
+    running = []
+
+    def reap(pr_entry):
+        u, pr = pr_entry
         out, err = pr.communicate()
         if pr.returncode != 0:
             raise RuntimeError("nvcc failed on %s:\n%s%s" % (u, out, err))
         if verbose:
             sys.stderr.write(err)
+
+    for oname, cmd in jobs:
+        if len(running) >= width:
+            reap(running.pop(0))
+        running.append((oname, subprocess.Popen(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
+    for entry in running:
+        reap(entry)
     r = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs,
                        cwd=CSRC, capture_output=True, text=True)
     if r.returncode != 0:

@@ -12,7 +12,7 @@
 #include "devplan.h"
 #include "step_kernel.cuh"
 #include "dist_kernel.cuh"
-#include "mma_kernel.cuh"
+#include "mma_api.h"
 #include "tile_api.h"
 #include "log_kernel.cuh"
 

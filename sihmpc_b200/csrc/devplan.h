@@ -9,6 +9,11 @@
 #include <mutex>
 #include "../../include/sihmpc_b200.h"
 
+#ifndef SIH_FULL
+#define SIH_FULL 0xffffffffu
+#define SIH_INF (__longlong_as_double(0x7ff0000000000000LL))
+#endif
+
 struct DevPlan {
     int nx, nu, ny, nd, N, nv, m, mh, R, ncd, n_vin, pl_nnz;
     int nvm;             // N*nu: the moves among the nv decision variables (nv - nvm = ranged terminal residuals)

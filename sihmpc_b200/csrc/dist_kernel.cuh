@@ -672,6 +672,7 @@ quad_step_kernel(const DevPlan P, const QuadConst Q, const double *__restrict__ 
     }
 }
 
+#ifndef SIH_NO_QUAD_HOST   // (the tensor fast path includes this file for the factorisation helpers only)
 // ---- host side: shape table, packing, launch ---------------------------------------------------
 struct QuadPlan {
     int shape;                 // index into the instantiation table, -1 = none
@@ -882,5 +883,7 @@ inline void quad_destroy(QuadPlan *qp) {
     memset(qp, 0, sizeof *qp);
     qp->shape = -1;
 }
+
+#endif  // SIH_NO_QUAD_HOST
 
 }  // namespace sih

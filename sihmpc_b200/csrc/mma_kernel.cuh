@@ -31,18 +31,9 @@
 #include <stdlib.h>
 #include "devplan.h"
 #include "dist_kernel.cuh"
+#include "mma_api.h"
 
 namespace sih {
-
-struct MmaConst {            // offsets in doubles into the packed block
-    int be, bw, w0c, bf, br, bh, bomdu, by, byp, bvn, tau, gamma, inv_gamma, bounds, vinq, ell_val, total_d;
-    int ell_col, ell_csr, hj_idx, vin_row, vlive, vdead, total_i;
-    int ell_w;
-    // in-kernel active set on simple bounds (mma_active_set): gradient / Hessian / difference maps in the space
-    // where the bounds are simple (cspace 1: cumulative moves c = cumsum(dU), input box; 0: dU itself, move box;
-    // -1: not available, a violated bound hands the scenario over)
-    int bfc, bhc, bdp, bdpt, du_idx, n_du, cspace;
-};
 
 // NVE_: number of QP variables that are actually eliminated.  Moves whose dead time pushes their whole
 // effect past the horizon have a zero column in E, Ht, HJ: their optimum is exactly 0 (presolve on the
@@ -348,7 +339,8 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
         n_work = (long long)(*n_list) - 0x7f7f7f7f;
         if ((long long)blockIdx.x * WARPS * 8 >= n_work) return;
     }
-    constexpr int NX = D::NX, NU = D::NU, NY = D::NY, M = D::M, NV = D::NV, NYP = D::NYP, R = D::R;
+    constexpr int NU = D::NU, NY = D::NY, M = D::M, NV = D::NV, NYP = D::NYP, R = D::R;
+    const int nxr = P.nx;                     // states of THIS model (<= D::NX = 8 TX: the compiled capacity)
     constexpr int SV = D::SV, TX = D::TX, TR = D::TR, TV = D::TV, TY = D::TY, TQ = D::TQ, TC = D::TC, TM = D::TM;
     constexpr int KX = D::KX, KA = D::KA, KP = D::KP, KH = D::KH, KD = D::KD;
     constexpr int BS = D::BS;
@@ -421,7 +413,7 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int r = 8 * T + 2 * g + h;
-                xr[T][h] = (r < NX) ? io.x[sc * NX + r] : 0.0;
+                xr[T][h] = (r < nxr) ? io.x[sc * nxr + r] : 0.0;
             }
         double uu[NU], pes[M], ise[2];
         double st_du2 = 0.0, st_viol = 0.0, st_J = 0.0;
@@ -444,7 +436,7 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
 #pragma unroll
             for (int T = 0; T < TX; ++T)
 #pragma unroll
-                for (int h = 0; h < 2; ++h) { const int r = 8 * T + 2 * g + h; if (r < NX) io.x[s * NX + r] = xr[T][h]; }
+                for (int h = 0; h < 2; ++h) { const int r = 8 * T + 2 * g + h; if (r < nxr) io.x[s * nxr + r] = xr[T][h]; }
             if (g == 0) {
 #pragma unroll
                 for (int j = 0; j < NU; ++j) io.u[s * NU + j] = uu[j];
@@ -785,25 +777,6 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
 }
 
 // ---- host side ----------------------------------------------------------------------------------
-struct MmaPlan {
-    int shape;
-    MmaConst qc;
-    double *qbuf;
-    int *ctr;                // in the caller's workspace (mma_bind): [n_handover | n_fail | n_inkernel | pad | start_step[cap] | list[cap]]
-    int grid_cap;            // debug: upper limit of the grid (0: none)
-    int *start_step;
-    int *n_handover;         // scenarios the first pass appended to `list` (counter baseline 0x7f7f7f7f)
-    int *n_fail;             // scenarios the resume pass could not resolve either: left to the general kernel
-    int *n_inkernel;         // scenario-steps of the last launch whose active bounds were resolved by mma_active_set
-    int *list;
-    int last_resumed;        // the last launch ran the resume pass (sihmpc_plan_counters)
-    long long capacity;
-    int blocks_per_sm;
-    size_t smem_bytes;
-};
-
-using DistillationMma = MmaDims<22, 2, 2, 4, 10, 4>;
-using DistillationMma16 = MmaDims<22, 2, 2, 4, 10, 4, 16>;     // four presolved moves (Wood & Berry dead times)
 #ifndef SIH_MMA_WARPS
 #define SIH_MMA_WARPS 4
 #endif
@@ -834,23 +807,12 @@ inline std::vector<int> mma_dead_variables(const DevPlan &P, const sihmpc_plan_d
     return dead;
 }
 
-// 0: all 20 variables live, 1: four presolved moves (16 live), -1: no MMA fast path
-inline int mma_match_shape(const DevPlan &P, const sihmpc_plan_desc *d) {
-    for (int i = 0; i < P.nx; ++i)
-        if (d->pl_rowptr[i + 1] - d->pl_rowptr[i] > 4) return -1;      // ELL width of the fast path
-    if (P.nx == 22 && P.nu == 2 && P.ny == 2 && P.nd == 4 && P.N == 10 && P.m == 4 && P.ncd == 0 && P.mh <= 3 &&
-        P.nv == P.nvm) {
-        if (getenv("SIHMPC_NO_PRESOLVE")) return 0;
-        return mma_dead_variables(P, d).size() >= 4 ? 1 : 0;
-    }
-    return -1;
-}
-
 template <typename D>
 inline void mma_build_constants(const sihmpc_plan_desc *d, const DevPlan &P, MmaConst &qc, std::vector<double> &buf,
                                 std::vector<int> &ibuf) {
-    constexpr int NX = D::NX, NU = D::NU, NY = D::NY, M = D::M, NV = D::NV, NVL = D::NVL, R = D::R, RE = D::RE, NYP = D::NYP;
+    constexpr int NU = D::NU, NY = D::NY, M = D::M, NV = D::NV, NVL = D::NVL, R = D::R, RE = D::RE, NYP = D::NYP;
     constexpr int SV = D::SV;
+    const int NX = d->nx;                     // states of this model (<= D::NX), stride of the descriptor's blocks
     // live[position] = logical variable; the last NVL-NV dead variables are presolved
     std::vector<int> live, deadv;
     {
@@ -1123,27 +1085,6 @@ inline cudaError_t mma_configure_shape(const sihmpc_plan_desc *d, const DevPlan 
     return cudaSuccess;
 }
 
-inline cudaError_t mma_configure(const sihmpc_plan_desc *d, const DevPlan &P, MmaPlan *qp) {
-    memset(qp, 0, sizeof *qp);
-    qp->shape = mma_match_shape(P, d);
-    if (qp->shape < 0) return cudaSuccess;
-    return qp->shape == 1 ? mma_configure_shape<DistillationMma16>(d, P, qp) : mma_configure_shape<DistillationMma>(d, P, qp);
-}
-
-// the hand-over block lives in the caller's workspace (capi.cu: bind_handover): nothing is allocated at step time
-inline void mma_bind(MmaPlan *qp, int *ctr, long long batch) {
-    qp->ctr = ctr; qp->n_handover = ctr; qp->n_fail = ctr + 1; qp->n_inkernel = ctr + 2;
-    qp->start_step = ctr + 4; qp->list = ctr + 4 + batch; qp->capacity = batch;
-}
-
-// counters and start_step back to "nothing handed over" (every counter counts up from the baseline 0x7f7f7f7f)
-inline cudaError_t mma_reset(const MmaPlan &qp, long long batch, cudaStream_t st) {
-    return cudaMemsetAsync(qp.ctr, 0x7f, (size_t)(4 + batch) * sizeof(int), st);
-}
-
-// the resume pass is one more launch: only worth it when the call carries enough work (not the single-step host API)
-inline bool mma_resumes(const MmaPlan &qp, long long batch, int n_steps) { return qp.qc.cspace >= 0 && (n_steps > 1 || batch >= 4096); }
-
 template <typename D>
 inline cudaError_t mma_launch_shape(MmaPlan &qp, const DevPlan &P, const sihmpc_io &io, long long batch,
                                     int n_steps, int grid, cudaStream_t st, bool allow_resume) {
@@ -1157,23 +1098,6 @@ inline cudaError_t mma_launch_shape(MmaPlan &qp, const DevPlan &P, const sihmpc_
     mma_step_kernel<D, MMA_WARPS, MMA_MINB, 1><<<grid, MMA_WARPS * 32, qp.smem_bytes, st>>>(
         P, qp.qc, qp.qbuf, io, batch, n_steps, qp.start_step, qp.n_fail, qp.n_inkernel, qp.list, qp.n_handover);
     return cudaGetLastError();
-}
-
-inline cudaError_t mma_launch(MmaPlan &qp, const DevPlan &P, const sihmpc_io &io, long long batch,
-                              int n_steps, int sm_count, cudaStream_t st, bool allow_resume = true) {
-    const long long per_block = MMA_WARPS * 8;
-    long long need = (batch + per_block - 1) / per_block;
-    const long long cap = (long long)sm_count * qp.blocks_per_sm;
-    int grid = (int)(need < cap ? need : cap);
-    if (qp.grid_cap > 0 && qp.grid_cap < grid) grid = qp.grid_cap;      // debug override (SIHMPC_QUAD_GRID, read at plan creation)
-    return qp.shape == 1 ? mma_launch_shape<DistillationMma16>(qp, P, io, batch, n_steps, grid, st, allow_resume)
-                         : mma_launch_shape<DistillationMma>(qp, P, io, batch, n_steps, grid, st, allow_resume);
-}
-
-inline void mma_destroy(MmaPlan *qp) {
-    if (qp->qbuf) cudaFree(qp->qbuf);
-    memset(qp, 0, sizeof *qp);
-    qp->shape = -1;
 }
 
 }  // namespace sih

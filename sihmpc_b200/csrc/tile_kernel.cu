@@ -34,8 +34,6 @@
 #include <math.h>
 #include "tile_api.h"
 
-#define SIH_FULL 0xffffffffu
-#define SIH_INF (__longlong_as_double(0x7ff0000000000000LL))
 
 namespace sih {
 

@@ -303,6 +303,56 @@ def test_multi_index_siN_ellipsoid_matches_oracle():
         c.engine(8)
 
 
+@pytest.mark.parametrize("theta,N", [([[2, 1], [3, 2]], 10),      # nx = 14: other dead times, same horizon
+                                     ([[1, 3], [7, 3]], 8),       # Wood & Berry with N = 8 (N*nu = 16)
+                                     ([[1, 0], [0, 1]], 6),       # nx = 10, N*nu = 12
+                                     ([[5, 9], [10, 6]], 12)])    # nx = 28, N*nu = 24
+def test_tensor_fast_path_shape_family(theta, N, monkeypatch):
+    """The tensor fast path (mma_step_kernel) is compiled for a family of 2x2 shapes -- any dead times (nx <= 32),
+    horizons 6, 8, 10, 12 -- not for the benchmark's one: each member must be SERVED by it, resolve bounds that bind
+    in its own resume pass, and match the general kernel and the oracle."""
+    monkeypatch.delenv("SIHMPC_NO_FAST", raising=False); monkeypatch.delenv("SIHMPC_FAST", raising=False)
+    wb = sc.WOOD_BERRY
+    sys_ = sc.fopdt_system(wb["K"], wb["tau"], theta, 1.0)
+    bounds = dict(ulb=[1.80, 1.62], uub=[2.02, 1.78])
+    declare = lambda cls, s, **b: sc.declare_distillation(cls, s, N=N, **(b or bounds))
+    B, T = 96, 60
+    rng = np.random.default_rng(5)
+    a = rng.uniform(-1, 1, size=(B, 2)) * np.array([0.8, 0.4])
+    x0 = np.zeros((B, sys_.nx)); x0[:, 0] = 96.0; x0[:, 1] = 0.5
+    scen = dict(x0=x0, u0=np.tile([1.95, 1.71], (B, 1)),
+                ysp_seq=np.stack([np.tile([96.0, 0.5], (B, 1)), np.array([96.0, 0.5]) + a], axis=1),
+                seg_start=np.tile(np.array([0, 4], dtype=np.int32), (B, 1)))
+
+    def run(no_fast):
+        if no_fast:
+            monkeypatch.setenv("SIHMPC_NO_FAST", "1")
+        else:
+            monkeypatch.delenv("SIHMPC_NO_FAST", raising=False)
+        c = declare(IHMPCController, sys_)
+        eng = c.engine(B)
+        eng.set_state(scen["x0"], scen["u0"]); eng.set_schedule(scen["ysp_seq"], scen["seg_start"])
+        tr = eng.run(T, record=True)
+        return eng, tr["du"].cpu().numpy(), tr["J"].cpu().numpy()
+
+    eng, du, J = run(False)
+    assert eng.dp.kernel_name() == "mma_step_kernel"
+    handed, solved = eng.dp.counters()
+    st = eng.stats.cpu().numpy()
+    assert (st[:, 2 + 3] == 0).all() and handed == 0
+    engg, dug, Jg = run(True)
+    monkeypatch.delenv("SIHMPC_NO_FAST", raising=False)
+    assert engg.dp.kernel_name() == "ihmpc_step_kernel"
+    n_constrained = int((engg.stats.cpu().numpy()[:, 2 + 4] > 0).sum())
+    assert n_constrained > 0 and solved > 0, (n_constrained, solved)
+    assert np.max(np.abs(du - dug)) <= 1e-7 * max(1.0, np.max(np.abs(dug)))
+    worst = int(np.argmax(engg.stats.cpu().numpy()[:, 2 + 4]))
+    for idx in (0, worst, B - 1):
+        ref = oracle_closed_loop(declare, sys_, scen, idx, T, bounds=bounds)
+        assert np.max(np.abs(du[:, idx] - ref["du"])) <= RTOL * np.max(np.abs(ref["du"])), idx
+        assert np.max(np.abs(J[:, idx] - ref["J"]) / np.maximum(np.abs(ref["J"]), 1e-9)) <= RTOL, idx
+
+
 def test_fast_path_handover_many_rounds(monkeypatch):
     """Quad fast path with a tiny grid (many scenarios per quad, one after the other) on a bound
     set that makes a good share of the scenarios hand over to the exact active-set kernel mid-loop:
