@@ -412,12 +412,52 @@ def measure_log_variant(cx, K, W, repeats):
                                        "call to synchronised result"}}
 
 
-def measure_e2e(cx, plan, scen, batch, steps):
-    """The same metric through the host-buffer C-ABI call (sihmpc_step_host): pinned host state, the step's
-    inputs go up and its results come down EVERY step inside the timed region."""
+def measure_e2e(cx, plan, scen, eng, snap, batch, steps):
+    """The same metric end to end through the C-ABI calls a host application makes, host<->device copies inside the
+    timed region, every step:
+      * e2e        -- sihmpc_resident_step: the plant lives with the caller; measured state + set-point go up from
+                      pinned host memory, move + cost + status come down, the controller's own state (u, weights,
+                      ViN_ant, warm start) stays on the device.  The measurements fed in are the states of the SAME
+                      closed loop (recorded beforehand, untimed, with the batched engine), so every solve is the one of
+                      the timed device run;
+      * full_state -- sihmpc_step_host: the whole scenario state both ways every step (the reference's numpy-in /
+                      numpy-out convention)."""
     torch = cx.torch
     from sihmpc_b200 import _capi
-    from sihmpc_b200.engine import HostStepper
+    from sihmpc_b200.engine import HostStepper, ResidentStepper
+    # ---- record the measured states of the window, one step per launch (untimed)
+    eng.restore(snap)
+    k0 = eng.k
+    xs = torch.empty(steps, batch, plan.nx, dtype=torch.float64, pin_memory=True)
+    ys = torch.empty(steps, batch, plan.ny, dtype=torch.float64, pin_memory=True)
+    seq, start = scen["ysp_seq"], scen["seg_start"]
+    u_k0 = eng.u.cpu().numpy().copy(); pes_k0 = eng.pesos.cpu().numpy().copy()
+    for i in range(steps):
+        xs[i].copy_(eng.x)
+        seg = (start <= k0 + i).sum(axis=1) - 1
+        ys[i].copy_(torch.as_tensor(np.ascontiguousarray(seq[np.arange(batch), seg])))
+        eng.run(1)
+    # the resident controller starts from u and the weights of step k0 (the loop has been running for k0 steps)
+    rs_pes = torch.as_tensor(pes_k0)
+    rs = ResidentStepper(plan, batch, u_k0)
+    _set_resident_weights(rs, rs_pes)
+    for i in range(min(3, steps)):                         # warm-up (untimed), then start over from step k0
+        rs.step_from(xs[i], ys[i])
+    del rs
+    rs = ResidentStepper(plan, batch, u_k0)
+    _set_resident_weights(rs, rs_pes)
+    cx.barrier()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        rs.step_from(xs[i], ys[i])                          # synchronises the stream itself
+    cx.barrier()
+    dt = cx.max_over_ranks([time.perf_counter() - t0])[0]
+    e2e = {"value": cx.world * batch * steps / dt, "unit": UNIT,
+           "h2d_bytes_per_step": rs.h2d_bytes(), "d2h_bytes_per_step": rs.d2h_bytes(), "steps": steps,
+           "api": "sihmpc_resident_step (controller-resident: measured x and ysp up from pinned host memory, du + J + status "
+                  "down, every step; u, weights, ViN_ant and the warm start stay on the device; chunked cudaMemcpyAsync "
+                  "pipeline over three streams).  Measurements = the recorded states of the same closed loop"}
+    # ---- the full-state host path
     hs = HostStepper(plan, batch, device=cx.dev)
     hs.x.copy_(torch.as_tensor(scen["x0"])); hs.u.copy_(torch.as_tensor(scen["u0"]))
     ysp_np = scen["ysp_seq"][:, 1, :]
@@ -428,13 +468,12 @@ def measure_e2e(cx, plan, scen, batch, steps):
     cx.barrier()
     t0 = time.perf_counter()
     for _ in range(steps):
-        hs.step(flags=fl, want_w_opt=False)            # synchronises the stream itself
+        hs.step(flags=fl, want_w_opt=False)
     cx.barrier()
     dt = cx.max_over_ranks([time.perf_counter() - t0])[0]
-    e2e = {"value": cx.world * batch * steps / dt, "unit": UNIT,
-           "h2d_bytes_per_step": hs.h2d_bytes(), "d2h_bytes_per_step": hs.d2h_bytes(advance=True, want_w_opt=False),
-           "steps": steps, "api": "sihmpc_step_host (pinned host buffers; in: x,u,pesos,ViNant,ysp; out: du,J,status,ViNant + "
-                                  "advanced x,u,pesos; zero-copy: the step kernel reads and writes the pinned arrays over PCIe)"}
+    e2e["full_state"] = {"value": cx.world * batch * steps / dt, "unit": UNIT, "h2d_bytes_per_step": hs.h2d_bytes(),
+                         "d2h_bytes_per_step": hs.d2h_bytes(advance=True, want_w_opt=False),
+                         "api": "sihmpc_step_host (x,u,pesos,ViNant,ysp up; du,J,status + advanced x,u,pesos down; zero-copy)"}
     lat = None
     if cx.rank == 0:
         h1 = HostStepper(plan, 1, device=cx.dev)
@@ -444,9 +483,28 @@ def measure_e2e(cx, plan, scen, batch, steps):
         for i in range(300):
             a = time.perf_counter(); h1.step(flags=fl); ts.append(time.perf_counter() - a)
         ts = np.asarray(ts[50:]) * 1e6
+        r1 = ResidentStepper(plan, 1, scen["u0"][:1])
+        x1 = torch.as_tensor(scen["x0"][:1]).pin_memory(); y1 = torch.as_tensor(np.ascontiguousarray(ysp_np[:1])).pin_memory()
+        tr_ = []
+        for i in range(300):
+            a = time.perf_counter(); r1.step_from(x1, y1); tr_.append(time.perf_counter() - a)
+        tr_ = np.asarray(tr_[50:]) * 1e6
         lat = {"p50_us": float(np.percentile(ts, 50)), "p99_us": float(np.percentile(ts, 99)),
-               "what": "one closed-loop step at batch 1 through sihmpc_step_host, host to host"}
+               "what": "one closed-loop step at batch 1 through sihmpc_step_host, host to host",
+               "resident_p50_us": float(np.percentile(tr_, 50)), "resident_p99_us": float(np.percentile(tr_, 99))}
     return e2e, lat
+
+
+def _set_resident_weights(rs, pes):
+    """Weights of a loop that is already running: written into the resident state (the C ABI initialises every scenario
+    with the same initial weights; a bench window that starts at step k0 carries per-scenario ones)."""
+    import ctypes as C
+    from sihmpc_b200 import _capi
+    lib = rs.dp.lib
+    off = C.c_size_t(0)
+    _capi.check(lib.sihmpc_resident_weights_offset(rs.dp.handle, rs.batch, C.byref(off)), "sihmpc_resident_weights_offset")
+    view = rs.state[off.value:off.value + pes.numel() * 8].view(rs.x.dtype).reshape(pes.shape)
+    view.copy_(pes.to(rs.state.device))
 
 
 # ----------------------------------------------------------------------------- main
@@ -548,7 +606,7 @@ def main():
                              "(sihmpc_b200.dist.gather_stats), max over ranks"}
         del full
 
-    e2e, lat = measure_e2e(cx, plan, scen, batch, args.e2e_steps)
+    e2e, lat = measure_e2e(cx, plan, scen, eng, m["snap"], batch, min(args.e2e_steps, K))
     del eng, m
     torch.cuda.empty_cache()
 

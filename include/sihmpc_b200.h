@@ -202,6 +202,35 @@ int sihmpc_step_host(sihmpc_plan *plan, const sihmpc_io *host_io, int64_t batch,
                      void *workspace, size_t workspace_bytes, void *stream);
 size_t sihmpc_host_staging_bytes(const sihmpc_plan *plan, int64_t batch);
 
+/* -- controller-resident stepping ------------------------------------------------------------- */
+/* The driver loop of example_distillation.py:81-113 with the PLANT on the caller's side (a real process, or the
+ * caller's own simulator): every call takes the measured state and the set-point of this control step from HOST
+ * memory and returns the move and the cost to HOST memory; everything the controller carries from one step to the
+ * next -- u (ihmpccontroller.py:108), the weights, ViN_ant, the warm start of the last solve -- stays on the device.
+ * One call =  satWeights2 at the measured state with the previous warm start (ihmpccontroller.py:619-636; skipped on
+ * the first call)  ->  mpc (:567-604)  ->  u += du, warmStart (:534-564).  Per scenario-step (nx + ny) doubles go
+ * up and (nu + 1) doubles + a status word come down, instead of the whole state both ways through sihmpc_step_host.
+ * Uploads, the kernels and downloads of consecutive chunks of the batch overlap (three streams).  One resident batch
+ * per plan.  `state` is caller-owned DEVICE memory of sihmpc_resident_bytes(); the call synchronises `stream`.    */
+typedef struct sihmpc_resident_io {
+    const double *x;                 /* HOST [batch][nx]  measured state x0 of this step                 */
+    const double *ysp;               /* HOST [batch][ny]  set-point of this step                          */
+    double *du;                      /* HOST [batch][nu]  first move (out)                                */
+    double *J;                       /* HOST [batch]      cost (out)                                      */
+    int32_t *status;                 /* HOST [batch]      SIHMPC_ST_* (out) or NULL                       */
+    int32_t flags;                   /* SIHMPC_F_WEIGHTS_SAT2 | SIHMPC_F_WEIGHTS_SAT1 | SIHMPC_F_UPDATE_VIN */
+    double alfa;                     /* satWeights2 blending                                               */
+} sihmpc_resident_io;
+size_t sihmpc_resident_bytes(const sihmpc_plan *plan, int64_t batch);
+/* u0 HOST [batch][nu]; pesos0 HOST [m] initial weights of every scenario (init_pesos, ihmpccontroller.py:87-91) */
+int sihmpc_resident_init(sihmpc_plan *plan, void *state, size_t state_bytes, int64_t batch,
+                         const double *u0, const double *pesos0, void *stream);
+int sihmpc_resident_step(sihmpc_plan *plan, void *state, size_t state_bytes, const sihmpc_resident_io *io,
+                         int64_t batch, void *stream);
+/* byte offset of the weights [batch][m] inside a 256-byte aligned `state` (a loop that is already running hands its
+ * per-scenario weights over with one cudaMemcpy there after sihmpc_resident_init)                                  */
+int sihmpc_resident_weights_offset(const sihmpc_plan *plan, int64_t batch, size_t *offset);
+
 /* replaces: the `pred` Function of _OptimProbl (ihmpccontroller.py:466-472,523):
  * x_pred [batch][N*nx], y_pred [batch][N*ny], u_pred [batch][N*nu] from (x, u, dU). NULL skips. */
 int sihmpc_predict(sihmpc_plan *plan, const double *x, const double *u, const double *dU,

@@ -54,11 +54,17 @@ class IO(C.Structure):
     ]
 
 
+class ResidentIO(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("ysp", C.c_void_p), ("du", C.c_void_p), ("J", C.c_void_p), ("status", C.c_void_p),
+                ("flags", C.c_int32), ("alfa", C.c_double)]
+
+
 EXPORTS = [
     "sihmpc_abi_version", "sihmpc_last_error", "sihmpc_device_count", "sihmpc_plan_create",
     "sihmpc_plan_destroy", "sihmpc_workspace_bytes", "sihmpc_step", "sihmpc_step_host",
     "sihmpc_host_staging_bytes", "sihmpc_predict", "sihmpc_subobjectives", "sihmpc_stats_reduce",
     "sihmpc_fp64_peak", "sihmpc_log_step", "sihmpc_log_loop", "sihmpc_plan_kernel", "sihmpc_plan_counters",
+    "sihmpc_resident_bytes", "sihmpc_resident_init", "sihmpc_resident_step", "sihmpc_resident_weights_offset",
 ]
 
 _lib = None
@@ -110,6 +116,14 @@ def load():
     lib.sihmpc_plan_kernel.restype = C.c_char_p
     lib.sihmpc_plan_counters.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_void_p]
     lib.sihmpc_plan_counters.restype = C.c_int
+    lib.sihmpc_resident_bytes.argtypes = [C.c_void_p, C.c_int64]
+    lib.sihmpc_resident_bytes.restype = C.c_size_t
+    lib.sihmpc_resident_init.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.sihmpc_resident_init.restype = C.c_int
+    lib.sihmpc_resident_step.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(ResidentIO), C.c_int64, C.c_void_p]
+    lib.sihmpc_resident_step.restype = C.c_int
+    lib.sihmpc_resident_weights_offset.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_size_t)]
+    lib.sihmpc_resident_weights_offset.restype = C.c_int
     lib.sihmpc_fp64_peak.argtypes = [C.POINTER(C.c_double)]
     lib.sihmpc_fp64_peak.restype = C.c_int
     if lib.sihmpc_abi_version() != ABI_VERSION:

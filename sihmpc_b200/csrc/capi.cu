@@ -69,6 +69,8 @@ struct sihmpc_plan {
     long long env_zc_max = 1LL << 40;   // SIHMPC_ZEROCOPY_MAX
     int env_chunks = 0;            // SIHMPC_HOST_CHUNKS (0: default)
     int env_grid = 0;              // SIHMPC_QUAD_GRID (debug: force many rounds)
+    long long resident_steps = -1; // controller-resident batch: steps taken since sihmpc_resident_init (-1: none)
+    long long resident_batch = 0;
 };
 
 // packed-upload path of sihmpc_step_host: largest batch served from the plan's pinned pack buffer
@@ -642,6 +644,148 @@ int sihmpc_step_host(sihmpc_plan *plan, const sihmpc_io *h, int64_t batch, void 
     CUDA_TRY(cudaEventRecord(ev_done, plan->s_d2h));
     CUDA_TRY(cudaStreamWaitEvent(st, ev_done, 0));
     CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ---- controller-resident stepping --------------------------------------------------------
+struct ResidentLayout { size_t u, pesos, vinant, wstart, ysp_prev, x, ysp, du, J, w_opt, status, n_active, ws, total; };
+
+static ResidentLayout resident_layout(const sihmpc_plan *p, int64_t batch) {
+    const DevPlan &P = p->d;
+    ResidentLayout L;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~(size_t)255; return r; };
+    const size_t B = (size_t)batch;
+    L.u = take(B * P.nu * 8); L.pesos = take(B * P.m * 8); L.vinant = take(B * (P.n_vin > 0 ? P.n_vin : 1) * 8);
+    L.wstart = take(B * p->nw * 8); L.ysp_prev = take(B * P.ny * 8);
+    L.x = take(B * P.nx * 8); L.ysp = take(B * P.ny * 8); L.du = take(B * P.nu * 8); L.J = take(B * 8);
+    L.w_opt = take(B * p->nw * 8); L.status = take(B * 4); L.n_active = take(B * 4);
+    L.ws = take(sihmpc_workspace_bytes(p, batch));
+    L.total = o + 256;
+    return L;
+}
+
+size_t sihmpc_resident_bytes(const sihmpc_plan *plan, int64_t batch) {
+    if (!plan || batch <= 0) return 0;
+    return resident_layout(plan, batch).total;
+}
+
+int sihmpc_resident_weights_offset(const sihmpc_plan *plan, int64_t batch, size_t *offset) {
+    if (!plan || !offset || batch <= 0) return fail(SIHMPC_E_INVALID, "NULL argument%s");
+    *offset = resident_layout(plan, batch).pesos;
+    return 0;
+}
+
+int sihmpc_resident_init(sihmpc_plan *plan, void *state, size_t state_bytes, int64_t batch, const double *u0,
+                         const double *pesos0, void *stream) {
+    if (!plan || !state || !u0 || !pesos0) return fail(SIHMPC_E_INVALID, "NULL argument%s");
+    if (batch <= 0) return fail(SIHMPC_E_INVALID, "batch must be positive%s");
+    if (plan->d.nv != plan->d.nvm) return fail(SIHMPC_E_INVALID, "resident stepping: ranged terminal residuals are not carried%s");
+    const ResidentLayout L = resident_layout(plan, batch);
+    if (state_bytes < L.total) return fail(SIHMPC_E_WORKSPACE, "state smaller than sihmpc_resident_bytes()%s");
+    const DevPlan &P = plan->d;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    char *base = reinterpret_cast<char *>(((uintptr_t)state + 255) & ~(uintptr_t)255);
+    CUDA_TRY(cudaMemcpyAsync(base + L.u, u0, (size_t)batch * P.nu * 8, cudaMemcpyHostToDevice, st));
+    std::vector<double> pes((size_t)batch * P.m), vin((size_t)batch * (P.n_vin > 0 ? P.n_vin : 1), 1.0 / 0.0);
+    for (int64_t b = 0; b < batch; ++b)
+        for (int i = 0; i < P.m; ++i) pes[(size_t)b * P.m + i] = pesos0[i];
+    CUDA_TRY(cudaMemcpyAsync(base + L.pesos, pes.data(), pes.size() * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(base + L.vinant, vin.data(), vin.size() * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(base + L.wstart, 0, (size_t)batch * plan->nw * 8, st));
+    CUDA_TRY(cudaMemsetAsync(base + L.ysp_prev, 0, (size_t)batch * P.ny * 8, st));
+    CUDA_TRY(cudaStreamSynchronize(st));           // pes / vin are stack-lifetime host buffers
+    plan->resident_steps = 0;
+    plan->resident_batch = batch;
+    return 0;
+}
+
+int sihmpc_resident_step(sihmpc_plan *plan, void *state, size_t state_bytes, const sihmpc_resident_io *h,
+                         int64_t batch, void *stream) {
+    if (!plan || !state || !h) return fail(SIHMPC_E_INVALID, "NULL argument%s");
+    if (!h->x || !h->ysp || !h->du || !h->J) return fail(SIHMPC_E_INVALID, "resident io needs x, ysp, du, J%s");
+    if (plan->resident_steps < 0 || plan->resident_batch != batch)
+        return fail(SIHMPC_E_INVALID, "sihmpc_resident_init has not been called for this batch%s");
+    const ResidentLayout L = resident_layout(plan, batch);
+    if (state_bytes < L.total) return fail(SIHMPC_E_WORKSPACE, "state smaller than sihmpc_resident_bytes()%s");
+    const DevPlan &P = plan->d;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    char *base = reinterpret_cast<char *>(((uintptr_t)state + 255) & ~(uintptr_t)255);
+    auto D = [&](size_t off) { return reinterpret_cast<double *>(base + off); };
+    sihmpc_io d;
+    memset(&d, 0, sizeof d);
+    d.x = D(L.x); d.u = D(L.u); d.pesos = D(L.pesos); d.vinant = P.n_vin > 0 ? D(L.vinant) : nullptr;
+    d.ysp = D(L.ysp); d.du = D(L.du); d.J = D(L.J); d.w_opt = D(L.w_opt);
+    d.status = reinterpret_cast<int32_t *>(base + L.status); d.n_active = reinterpret_cast<int32_t *>(base + L.n_active);
+    d.flags = h->flags & SIHMPC_F_UPDATE_VIN;      // the solve only: plant, warm start and weights are the caller's / ours below
+    d.alfa = h->alfa;
+    const bool first = plan->resident_steps == 0;
+    const int wflags = h->flags & (SIHMPC_F_WEIGHTS_SAT2 | SIHMPC_F_WEIGHTS_SAT1);
+    const size_t per_w = (size_t)(P.nx + P.nv + P.ny + 2 * P.ny + P.R + P.nv + P.m + 8) * 8;
+    const int wpb = 4;
+    if (per_w * wpb > 200 * 1024) return fail(SIHMPC_E_INVALID, "controller too large%s");
+    // constants of the weight update staged in shared memory when they are small (not with terminal rows in a
+    // weighted sub-objective: those read Px / E as well)
+    const size_t cst_w = (size_t)(P.nx * P.Ny + P.nv * P.Ny + (P.Ny + 2 * P.ny) * P.m + P.nv * P.m + P.N + P.m) * 8;
+    const int stage_w = (!P.eval_term && cst_w <= 48 * 1024) ? 1 : 0;
+    const size_t smem_w = per_w * wpb + (stage_w ? cst_w : 0);
+    CUDA_TRY(sih_raise_smem_limit(reinterpret_cast<const void *>(sih::resident_weights_kernel), smem_w));
+
+    int nchunk = batch >= 16384 ? 4 : 1;
+    if (plan->env_chunks) nchunk = plan->env_chunks;
+    if (2 * nchunk + 2 > (int)plan->events.size()) nchunk = ((int)plan->events.size() - 2) / 2;
+    cudaEvent_t ev_start = plan->events[2 * nchunk], ev_done = plan->events[2 * nchunk + 1];
+    CUDA_TRY(cudaEventRecord(ev_start, st));
+    CUDA_TRY(cudaStreamWaitEvent(plan->s_h2d, ev_start, 0));
+    CUDA_TRY(cudaStreamWaitEvent(plan->s_d2h, ev_start, 0));
+    const long long per = (batch + nchunk - 1) / nchunk;
+    const size_t wsb = sihmpc_workspace_bytes(plan, batch);
+    for (int c = 0; c < nchunk; ++c) {
+        const long long lo = (long long)c * per, hi = (lo + per < batch) ? lo + per : batch;
+        if (lo >= hi) break;
+        const long long n = hi - lo;
+        CUDA_TRY(cudaMemcpyAsync(D(L.x) + lo * P.nx, h->x + lo * P.nx, (size_t)n * P.nx * 8, cudaMemcpyHostToDevice, plan->s_h2d));
+        CUDA_TRY(cudaMemcpyAsync(D(L.ysp) + lo * P.ny, h->ysp + lo * P.ny, (size_t)n * P.ny * 8, cudaMemcpyHostToDevice, plan->s_h2d));
+        CUDA_TRY(cudaEventRecord(plan->events[2 * c], plan->s_h2d));
+        CUDA_TRY(cudaStreamWaitEvent(st, plan->events[2 * c], 0));
+        const bool in_kernel_weights = plan->use_fast == 2 && plan->mma.shape >= 0;      // MODE 3 of the tensor fast path
+        plan->mma.res_active = 0;
+        if (in_kernel_weights) {
+            plan->mma.res_active = 1;
+            plan->mma.res_flags = first ? 0 : wflags;
+            plan->mma.res_wstart = D(L.wstart) + lo * plan->nw;
+            plan->mma.res_ysp_prev = D(L.ysp_prev) + lo * P.ny;
+        } else if (!first && wflags) {
+            long long blocks = (n + wpb - 1) / wpb;
+            if (blocks > plan->sm_count * 8) blocks = plan->sm_count * 8;
+            sih::resident_weights_kernel<<<(int)blocks, wpb * 32, smem_w, st>>>(
+                P, D(L.x) + lo * P.nx, D(L.wstart) + lo * plan->nw, D(L.ysp_prev) + lo * P.ny, D(L.pesos) + lo * P.m, n, wflags,
+                h->alfa, stage_w);
+            CUDA_TRY(cudaGetLastError());
+        }
+        sihmpc_io dc = slice_io(d, P, plan->nw, lo);
+        int rc = sihmpc_step(plan, &dc, (int64_t)n, 1, base + L.ws, wsb, stream);
+        plan->mma.res_active = 0;
+        if (rc) return rc;
+        {
+            long long blocks = (n + 127) / 128;
+            if (blocks > plan->sm_count * 16) blocks = plan->sm_count * 16;
+            sih::resident_advance_kernel<<<(int)blocks, 128, 0, st>>>(
+                P, D(L.x) + lo * P.nx, D(L.w_opt) + lo * plan->nw, D(L.ysp) + lo * P.ny, D(L.u) + lo * P.nu,
+                D(L.wstart) + lo * plan->nw, D(L.ysp_prev) + lo * P.ny, n);
+            CUDA_TRY(cudaGetLastError());
+        }
+        CUDA_TRY(cudaEventRecord(plan->events[2 * c + 1], st));
+        CUDA_TRY(cudaStreamWaitEvent(plan->s_d2h, plan->events[2 * c + 1], 0));
+        CUDA_TRY(cudaMemcpyAsync(h->du + lo * P.nu, D(L.du) + lo * P.nu, (size_t)n * P.nu * 8, cudaMemcpyDeviceToHost, plan->s_d2h));
+        CUDA_TRY(cudaMemcpyAsync(h->J + lo, D(L.J) + lo, (size_t)n * 8, cudaMemcpyDeviceToHost, plan->s_d2h));
+        if (h->status)
+            CUDA_TRY(cudaMemcpyAsync(h->status + lo, reinterpret_cast<int32_t *>(base + L.status) + lo, (size_t)n * 4, cudaMemcpyDeviceToHost, plan->s_d2h));
+    }
+    CUDA_TRY(cudaEventRecord(ev_done, plan->s_d2h));
+    CUDA_TRY(cudaStreamWaitEvent(st, ev_done, 0));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    ++plan->resident_steps;
     return 0;
 }
 

@@ -32,6 +32,9 @@ struct MmaPlan {
     long long capacity;
     int blocks_per_sm;
     size_t smem_bytes;
+    // controller-resident stepping (sihmpc_resident_step): set for the launches of one call, first pass = MODE 3
+    int res_active, res_flags;                 // weight rule to apply before the solve (0: first call, none)
+    const double *res_wstart, *res_ysp_prev;   // warm start of the previous solve, the set-point it was made for
 };
 
 

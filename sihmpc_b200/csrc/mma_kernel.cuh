@@ -321,23 +321,93 @@ __device__ __forceinline__ bool mma_active_set(const double *__restrict__ cst, c
     return ok;
 }
 
+// Sub-objective values of the shifted plan at the state xr and the satisficing weights from them
+// (satWeights2 / satWeights, ihmpccontroller.py:619-636,607-617).  fr: the moves of the last solve in factorisation
+// slots (UNshifted: the shift is folded into the constants), syv = [syN ; siN ; siN_next], ysp the set-point that
+// solve was made for.
+template <typename D>
+__device__ __forceinline__ void mma_weight_update(const double *__restrict__ cst, const MmaConst &Q,
+                                                  const double (&xr)[D::TX][2], const double (&fr)[D::SV],
+                                                  const double (&ysp)[D::NY], const double (&syv)[3 * D::NY],
+                                                  double (&pes)[D::M], const int flags, const double alfa,
+                                                  const int lane, const int g) {
+    constexpr int NY = D::NY, M = D::M, SV = D::SV, TX = D::TX, TQ = D::TQ, TM = D::TM, KX = D::KX;
+    // residual stack of the shifted plan in ONE product: rows k*ny+i = Y'_k,i - ysp_i - syN_i - tau_k siN_i, then
+    // syN and siN themselves -- the set-point and the slacks ride along as two more k-tiles (their
+    // coefficients -1, -tau_k, 1 sit in the constant block) instead of a dozen selects per row
+    double yq[TQ][2];
+#pragma unroll
+    for (int T = 0; T < TQ; ++T) yq[T][0] = yq[T][1] = 0.0;
+    {
+        double ax[KX + SV + D::KE];
+#pragma unroll
+        for (int T = 0; T < TX; ++T) { ax[2 * T] = xr[T][0]; ax[2 * T + 1] = xr[T][1]; }
+#pragma unroll
+        for (int sl = 0; sl < SV; ++sl) ax[KX + sl] = fr[sl];     // shift folded into the constants
+#pragma unroll
+        for (int t = 0; t < D::KE; ++t) {                         // [ysp ; syN ; siN(next)], element 4t+g
+            const int e = 4 * t + g;
+            ax[KX + SV + t] = (e < NY) ? sel<NY>(ysp, e) : ((e < 3 * NY) ? sel<3 * NY>(syv, e < 2 * NY ? e - NY : e) : 0.0);
+        }
+        mma_block<TQ, KX + SV + D::KE>(cst + Q.byp, ax, yq, lane);
+    }
+    double asq[2 * TQ + SV];
+#pragma unroll
+    for (int T = 0; T < TQ; ++T) { asq[2 * T] = yq[T][0] * yq[T][0]; asq[2 * T + 1] = yq[T][1] * yq[T][1]; }
+#pragma unroll
+    for (int sl = 0; sl < SV; ++sl) asq[2 * TQ + sl] = fr[sl] * fr[sl];
+    double vc[TM][2];
+#pragma unroll
+    for (int T = 0; T < TM; ++T) vc[T][0] = vc[T][1] = 0.0;
+    mma_block<TM, 2 * TQ + SV>(cst + Q.bvn, asq, vc, lane);
+    double vn[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) vn[i] = quad_bcast(vc[i / 8][i % 2], (i % 8) / 2);
+    if (flags & SIHMPC_F_WEIGHTS_SAT2) {
+        double smax = -SIH_INF;
+#pragma unroll
+        for (int i = 0; i < M; ++i) smax = fmax(smax, vn[i] * cst[Q.inv_gamma + i]);
+#pragma unroll
+        for (int i = 0; i < M; ++i) {
+            const double g0 = cst[Q.gamma + i];
+            const double g1 = fmax(g0, g0 * smax + 1e-6);
+            pes[i] = alfa * pes[i] + (1.0 - alfa) * fast_rcp(g1 - vn[i]);     // g1 - vn >= 1e-6 > 0
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < M; ++i) {
+            const double g0 = cst[Q.gamma + i];
+            pes[i] = fast_rcp(g0 - fmin(fmax(vn[i], 0.0), 0.99 * g0));
+        }
+    }
+}
+
 // MODE 0: first pass.  Unconstrained optimum + bound check; a scenario that violates a bound is appended to `list`
 //         and leaves the kernel (the active set inlined here cost the hot loop 20 %: register pressure).
 // MODE 1: resume pass over the scenarios of `list` (n_list = their counter), each from its own start_step, with the
 //         in-kernel active set (mma_active_set); eight listed scenarios per warp, every quad on its own step index.
 //         What it cannot resolve is flagged in start_step / n_handover for the general kernel (third pass).
 // MODE 2: first pass with the active set inline (workloads where most scenarios sit on bounds).
+// MODE 3: first pass of CONTROLLER-RESIDENT stepping (sihmpc_resident_step, one step per launch, no plant): the
+//         weights are brought up to date FIRST, at the measured state with the plan of the previous solve
+//         (res_wstart / io.w_opt / res_ysp_prev), then the step is MODE 0.
 template <typename D, int WARPS, int MINB, int MODE>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qbuf, const sihmpc_io io,
                 const long long batch, const int n_steps, int *__restrict__ start_step,
                 int *__restrict__ n_handover, int *__restrict__ n_inkernel, int *__restrict__ list,
-                const int *__restrict__ n_list) {
-    constexpr bool AS = (MODE != 0), RESUME = (MODE == 1);
+                const int *__restrict__ n_list, const double *__restrict__ res_wstart = nullptr,
+                const double *__restrict__ res_ysp_prev = nullptr, const int res_flags = 0) {
+    constexpr bool AS = (MODE == 1 || MODE == 2), RESUME = (MODE == 1), RESIDENT = (MODE == 3);
     long long n_work = batch;
+    // resume pass over a SHORT list: one listed scenario per warp instead of eight -- the quads of a warp iterate in
+    // lockstep, so a warp of eight constrained scenarios pays the rounds of the slowest one at every step; alone in
+    // its warp a scenario pays its own (the pass is a latency tail of a few dozen scenarios, not throughput)
+    bool spread = false;
     if constexpr (RESUME) {
         n_work = (long long)(*n_list) - 0x7f7f7f7f;
-        if ((long long)blockIdx.x * WARPS * 8 >= n_work) return;
+        spread = n_work <= (long long)gridDim.x * WARPS;
+        if ((long long)blockIdx.x * WARPS * (spread ? 1 : 8) >= n_work) return;
     }
     constexpr int NU = D::NU, NY = D::NY, M = D::M, NV = D::NV, NYP = D::NYP, R = D::R;
     const int nxr = P.nx;                     // states of THIS model (<= D::NX = 8 TX: the compiled capacity)
@@ -365,9 +435,10 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
     for (int sl = 0; sl < SV; ++sl) vlog[sl] = cint[Q.vlive + D::var_of(sl, g)];
     for (int e = g; e < D::NVL; e += 4) bv[e] = 0.0;      // presolved moves stay exactly zero
     __syncwarp();
-    const long long gq = ((long long)blockIdx.x * WARPS + wib) * 8 + q;
+    const long long gq = spread ? ((q == 0) ? (long long)blockIdx.x * WARPS + wib : n_work)
+                                : ((long long)blockIdx.x * WARPS + wib) * 8 + q;
     const long long nq = (long long)gridDim.x * WARPS * 8;
-    const long long rounds = (n_work + nq - 1) / nq;
+    const long long rounds = spread ? 1 : (n_work + nq - 1) / nq;
     const int nstat = NY + SIHMPC_NSTATS_EXTRA;
     const bool advance = (io.flags & SIHMPC_F_ADVANCE) != 0;
     const int mh = P.mh;
@@ -453,6 +524,23 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
             }
         };
 
+        if constexpr (RESIDENT) {
+            if (res_flags & (SIHMPC_F_WEIGHTS_SAT2 | SIHMPC_F_WEIGHTS_SAT1)) {
+                // previous solve of this scenario: moves (unshifted, io.w_opt of the last call), syN, siN_next, set-point
+                constexpr int nwl = D::NVL + 2 * NY;
+                double frp[SV], syp[3 * NY], yspp[NY];
+#pragma unroll
+                for (int sl = 0; sl < SV; ++sl) frp[sl] = io.w_opt[sc * nwl + vlog[sl]];
+#pragma unroll
+                for (int i = 0; i < NY; ++i) {
+                    syp[i] = io.w_opt[sc * nwl + D::NVL + i];
+                    syp[NY + i] = 0.0;
+                    syp[2 * NY + i] = res_wstart[sc * nwl + D::NVL + NY + i];
+                    yspp[i] = res_ysp_prev[sc * NY + i];
+                }
+                mma_weight_update<D>(cst, Q, xr, frp, yspp, syp, pes, res_flags, io.alfa, lane, g);
+            }
+        }
         for (int it = 0; it < n_iter; ++it) {
             const int step = st0 + it;
             if constexpr (RESUME) { if (step >= n_steps) alive = false; }
@@ -714,56 +802,8 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
                 st_du2 += du2; st_viol = fmax(st_viol, viol_abs); st_J = Jval;
             }
             // ---------------- sub-objective values at the new state, weight update
-            if (io.flags & (SIHMPC_F_WEIGHTS_SAT2 | SIHMPC_F_WEIGHTS_SAT1)) {
-                // residual stack of the shifted plan in ONE product: rows k*ny+i = Y'_k,i - ysp_i - syN_i - tau_k siN_i, then
-                // syN and siN themselves -- the set-point and the slacks ride along as two more k-tiles (their
-                // coefficients -1, -tau_k, 1 sit in the constant block) instead of a dozen selects per row
-                double yq[TQ][2];
-#pragma unroll
-                for (int T = 0; T < TQ; ++T) yq[T][0] = yq[T][1] = 0.0;
-                {
-                    double ax[KX + SV + D::KE];
-#pragma unroll
-                    for (int T = 0; T < TX; ++T) { ax[2 * T] = xr[T][0]; ax[2 * T + 1] = xr[T][1]; }
-#pragma unroll
-                    for (int sl = 0; sl < SV; ++sl) ax[KX + sl] = fr[sl];     // shift folded into the constants
-#pragma unroll
-                    for (int t = 0; t < D::KE; ++t) {                         // [ysp ; syN ; siN(next)], element 4t+g
-                        const int e = 4 * t + g;
-                        ax[KX + SV + t] = (e < NY) ? sel<NY>(ysp, e) : ((e < 3 * NY) ? sel<3 * NY>(syv, e < 2 * NY ? e - NY : e) : 0.0);
-                    }
-                    mma_block<TQ, KX + SV + D::KE>(cst + Q.byp, ax, yq, lane);
-                }
-                double asq[2 * TQ + SV];
-#pragma unroll
-                for (int T = 0; T < TQ; ++T) { asq[2 * T] = yq[T][0] * yq[T][0]; asq[2 * T + 1] = yq[T][1] * yq[T][1]; }
-#pragma unroll
-                for (int sl = 0; sl < SV; ++sl) asq[2 * TQ + sl] = fr[sl] * fr[sl];
-                double vc[TM][2];
-#pragma unroll
-                for (int T = 0; T < TM; ++T) vc[T][0] = vc[T][1] = 0.0;
-                mma_block<TM, 2 * TQ + SV>(cst + Q.bvn, asq, vc, lane);
-                double vn[M];
-#pragma unroll
-                for (int i = 0; i < M; ++i) vn[i] = quad_bcast(vc[i / 8][i % 2], (i % 8) / 2);
-                if (io.flags & SIHMPC_F_WEIGHTS_SAT2) {
-                    double smax = -SIH_INF;
-#pragma unroll
-                    for (int i = 0; i < M; ++i) smax = fmax(smax, vn[i] * cst[Q.inv_gamma + i]);
-#pragma unroll
-                    for (int i = 0; i < M; ++i) {
-                        const double g0 = cst[Q.gamma + i];
-                        const double g1 = fmax(g0, g0 * smax + 1e-6);
-                        pes[i] = io.alfa * pes[i] + (1.0 - io.alfa) * fast_rcp(g1 - vn[i]);     // g1 - vn >= 1e-6 > 0
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < M; ++i) {
-                        const double g0 = cst[Q.gamma + i];
-                        pes[i] = fast_rcp(g0 - fmin(fmax(vn[i], 0.0), 0.99 * g0));
-                    }
-                }
-            }
+            if (io.flags & (SIHMPC_F_WEIGHTS_SAT2 | SIHMPC_F_WEIGHTS_SAT1))
+                mma_weight_update<D>(cst, Q, xr, fr, ysp, syv, pes, io.flags, io.alfa, lane, g);
             if constexpr (RESUME) {
                 if (alive && last_step) { write_state(); alive = false; }
             }
@@ -772,6 +812,12 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
         __syncwarp();
         if (!RESUME && alive && advance) {
             write_state();
+        }
+        if constexpr (RESIDENT) {          // no advance in this mode: the weights brought up to date above still go back
+            if (alive && !advance && g == 0) {
+#pragma unroll
+                for (int i = 0; i < M; ++i) io.pesos[s * M + i] = pes[i];
+            }
         }
     }
 }
@@ -1072,8 +1118,10 @@ inline cudaError_t mma_configure_shape(const sihmpc_plan_desc *d, const DevPlan 
     if (qp->smem_bytes > 227 * 1024) { qp->shape = -1; return cudaSuccess; }
     auto kern = mma_step_kernel<D, MMA_WARPS, MMA_MINB, 0>;
     auto kern_resume = mma_step_kernel<D, MMA_WARPS, MMA_MINB, 1>;
+    auto kern_resident = mma_step_kernel<D, MMA_WARPS, MMA_MINB, 3>;
     e = sih_raise_smem_limit(reinterpret_cast<const void *>(kern), qp->smem_bytes);
     if (e == cudaSuccess) e = sih_raise_smem_limit(reinterpret_cast<const void *>(kern_resume), qp->smem_bytes);
+    if (e == cudaSuccess) e = sih_raise_smem_limit(reinterpret_cast<const void *>(kern_resident), qp->smem_bytes);
     if (e != cudaSuccess) return e;
     int occ = 0, occ_r = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, MMA_WARPS * 32, qp->smem_bytes);
@@ -1088,8 +1136,14 @@ inline cudaError_t mma_configure_shape(const sihmpc_plan_desc *d, const DevPlan 
 template <typename D>
 inline cudaError_t mma_launch_shape(MmaPlan &qp, const DevPlan &P, const sihmpc_io &io, long long batch,
                                     int n_steps, int grid, cudaStream_t st, bool allow_resume) {
-    mma_step_kernel<D, MMA_WARPS, MMA_MINB, 0><<<grid, MMA_WARPS * 32, qp.smem_bytes, st>>>(
-        P, qp.qc, qp.qbuf, io, batch, n_steps, qp.start_step, qp.n_handover, qp.n_inkernel, qp.list, nullptr);
+    if (qp.res_active) {
+        mma_step_kernel<D, MMA_WARPS, MMA_MINB, 3><<<grid, MMA_WARPS * 32, qp.smem_bytes, st>>>(
+            P, qp.qc, qp.qbuf, io, batch, n_steps, qp.start_step, qp.n_handover, qp.n_inkernel, qp.list, nullptr,
+            qp.res_wstart, qp.res_ysp_prev, qp.res_flags);
+    } else {
+        mma_step_kernel<D, MMA_WARPS, MMA_MINB, 0><<<grid, MMA_WARPS * 32, qp.smem_bytes, st>>>(
+            P, qp.qc, qp.qbuf, io, batch, n_steps, qp.start_step, qp.n_handover, qp.n_inkernel, qp.list, nullptr);
+    }
     cudaError_t e = cudaGetLastError();
     qp.last_resumed = 0;
     if (e != cudaSuccess || !allow_resume || !mma_resumes(qp, batch, n_steps)) return e;

@@ -851,6 +851,84 @@ __global__ void subobjectives_kernel(const DevPlan P, const double *__restrict__
     }
 }
 
+// ---- controller-resident stepping (sihmpc_resident_step): the two halves of the driver-loop body that run around the
+// solve when the PLANT lives with the caller (example_distillation.py:98-113 with a real plant instead of dynF).
+// resident_weights_kernel: satWeights2 / satWeights (ihmpccontroller.py:619-636,607-617) at the MEASURED state with the
+// warm start of the previous solve and the set-point it was made for; one warp per scenario.
+__global__ void resident_weights_kernel(const DevPlan P_in, const double *__restrict__ x, const double *__restrict__ w_start,
+                                        const double *__restrict__ ysp_prev, double *__restrict__ pesos,
+                                        const long long batch, const int flags, const double alfa, const int stage) {
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const long long gw = (long long)blockIdx.x * wpb + wib, nwarps = (long long)gridDim.x * wpb;
+    DevPlan P = P_in;
+    const int nx = P.nx, nv = P.nv, ny = P.ny, m = P.m, nw = P.nvm + 2 * ny;
+    const int per = nx + nv + ny + 2 * ny + P.R + nv + m + 8;
+    double *cst = smem + (size_t)wpb * per;
+    if (stage) {
+        // the matrices every scenario multiplies with, once per block into shared memory (small controllers): the
+        // per-scenario loops are chains of dependent loads, from L2 they cost several times the arithmetic
+        const int nr = P.Ny + 2 * ny;
+        double *a = cst, *b = a + nx * P.Ny, *c = b + nv * P.Ny, *d_ = c + nr * m, *t = d_ + nv * m, *g_ = t + P.N;
+        for (int i = threadIdx.x; i < nx * P.Ny; i += blockDim.x) a[i] = P.MyxT[i];
+        for (int i = threadIdx.x; i < nv * P.Ny; i += blockDim.x) b[i] = P.MyuT[i];
+        for (int i = threadIdx.x; i < nr * m; i += blockDim.x) c[i] = P.Wrow[i];
+        for (int i = threadIdx.x; i < nv * m; i += blockDim.x) d_[i] = P.Wdu[i];
+        for (int i = threadIdx.x; i < P.N; i += blockDim.x) t[i] = P.tau[i];
+        for (int i = threadIdx.x; i < m; i += blockDim.x) g_[i] = P.gamma[i];
+        P.MyxT = a; P.MyuT = b; P.Wrow = c; P.Wdu = d_; P.tau = t; P.gamma = g_;
+        __syncthreads();
+    }
+    double *B = smem + (size_t)wib * per;
+    double *xs = B, *dv = xs + nx, *yv = dv + nv, *sy = yv + ny, *sq = sy + 2 * ny, *sqdu = sq + P.R, *vn = sqdu + nv;
+    for (long long s = gw; s < batch; s += nwarps) {
+        for (int i = lane; i < nx; i += 32) xs[i] = x[s * nx + i];
+        for (int i = lane; i < nv; i += 32) dv[i] = (i < P.nvm) ? w_start[s * nw + i] : 0.0;
+        for (int i = lane; i < 2 * ny; i += 32) sy[i] = w_start[s * nw + P.nvm + i];
+        for (int i = lane; i < ny; i += 32) yv[i] = ysp_prev[s * ny + i];
+        __syncwarp();
+        eval_subobjectives(P, xs, dv, yv, sy, sq, sqdu, vn, lane);
+        if (flags & SIHMPC_F_WEIGHTS_SAT2) {
+            double smax = -SIH_INF;
+            for (int i = lane; i < m; i += 32) smax = fmax(smax, vn[i] / P.gamma[i]);
+            smax = warp_max(smax);
+            for (int i = lane; i < m; i += 32) {
+                const double g0 = P.gamma[i];
+                const double g1 = fmax(g0, g0 * smax + 1e-6);
+                pesos[s * m + i] = alfa * pesos[s * m + i] + (1.0 - alfa) * (1.0 / (g1 - vn[i]));
+            }
+        } else if (flags & SIHMPC_F_WEIGHTS_SAT1) {
+            for (int i = lane; i < m; i += 32) {
+                const double g0 = P.gamma[i];
+                pesos[s * m + i] = 1.0 / (g0 - fmin(fmax(vn[i], 0.0), 0.99 * g0));
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// resident_advance_kernel: u += du (ihmpccontroller.py:108), warmStart (:534-564: shifted moves, syN kept,
+// siN_next = xi(N+1) with a zero move appended), the set-point the plan was made for; one thread per scenario.
+__global__ void resident_advance_kernel(const DevPlan P, const double *__restrict__ x, const double *__restrict__ w_opt,
+                                        const double *__restrict__ ysp, double *__restrict__ u,
+                                        double *__restrict__ w_start, double *__restrict__ ysp_prev, const long long batch) {
+    const int nx = P.nx, nu = P.nu, ny = P.ny, nvm = P.nvm, nw = nvm + 2 * ny;
+    for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < batch; s += (long long)gridDim.x * blockDim.x) {
+        const double *w = w_opt + s * nw;
+        double *ws = w_start + s * nw;
+        for (int i = 0; i < ny; ++i) {
+            double a = 0.0;
+            for (int j = 0; j < nx; ++j) a = fma(P.Mi1xT[(size_t)j * ny + i], x[s * nx + j], a);
+            for (int c = 0; c < nvm; ++c) a = fma(P.Mi1uT[(size_t)c * ny + i], w[c], a);
+            ws[nvm + ny + i] = a;
+            ws[nvm + i] = w[nvm + i];
+            ysp_prev[s * ny + i] = ysp[s * ny + i];
+        }
+        for (int j = 0; j < nu; ++j) u[s * nu + j] += w[j];
+        for (int i = 0; i < nvm; ++i) ws[i] = (i + nu < nvm) ? w[i + nu] : 0.0;
+    }
+}
+
 __global__ void stats_init_kernel(double *out, int nstat) {
     for (int i = threadIdx.x; i < 3 * nstat; i += blockDim.x) out[i] = (i < 2 * nstat) ? 0.0 : -1e308;
 }

@@ -358,6 +358,64 @@ class HostStepper:
                                                      C.c_void_p(st)), "sihmpc_step_host")
 
 
+class ResidentStepper:
+    """Controller-resident stepping (sihmpc_resident_step): the plant lives with the caller.  Every step the measured
+    state and the set-point go up from pinned host memory, the move and the cost come down; u, the weights, ViN_ant
+    and the warm start stay on the device.  Same arithmetic as the reference's driver loop
+    (/root/reference/example_distillation.py:81-113) with `dynF` replaced by the caller's plant."""
+
+    def __init__(self, plan: Plan, batch: int, u0, pesos0=None, device=None, weights: str = "sat2", alfa: float = 0.0):
+        self.dp = DevicePlan(plan, device)
+        self.plan = plan
+        self.batch = int(batch)
+        B, p = self.batch, plan
+        pin = dict(dtype=torch.float64, pin_memory=True)
+        self.x = torch.zeros(B, p.nx, **pin)
+        self.ysp = torch.zeros(B, p.ny, **pin)
+        self.du = torch.zeros(B, p.nu, **pin)
+        self.J = torch.zeros(B, **pin)
+        self.status = torch.zeros(B, dtype=torch.int32, pin_memory=True)
+        self.alfa = float(alfa)
+        self.flags = _capi.F_UPDATE_VIN | {"sat2": _capi.F_WEIGHTS_SAT2, "sat1": _capi.F_WEIGHTS_SAT1, "fixed": 0}[weights]
+        lib = self.dp.lib
+        self.nbytes = lib.sihmpc_resident_bytes(self.dp.handle, B)
+        self.state = torch.empty(self.nbytes, dtype=torch.uint8, device=self.dp.device)
+        u0 = np.ascontiguousarray(np.broadcast_to(np.asarray(u0, dtype=np.float64).reshape(-1, p.nu), (B, p.nu)))
+        pes = np.ascontiguousarray(np.asarray(p.peso0 if pesos0 is None else pesos0, dtype=np.float64).reshape(-1))
+        st = torch.cuda.current_stream(self.dp.device).cuda_stream
+        with torch.cuda.device(self.dp.device):
+            _capi.check(lib.sihmpc_resident_init(self.dp.handle, C.c_void_p(self.state.data_ptr()), self.nbytes, B,
+                                                 u0.ctypes.data_as(C.c_void_p), pes.ctypes.data_as(C.c_void_p),
+                                                 C.c_void_p(st)), "sihmpc_resident_init")
+
+    def h2d_bytes(self):
+        return self.batch * 8 * (self.plan.nx + self.plan.ny)
+
+    def d2h_bytes(self):
+        return self.batch * (8 * (self.plan.nu + 1) + 4)
+
+    def step(self, x=None, ysp=None):
+        """x [B][nx], ysp [B][ny] (tensors / arrays; None: whatever is in self.x / self.ysp).  Returns (du, J)
+        as views of the pinned result buffers."""
+        if x is not None:
+            self.x.copy_(torch.as_tensor(x).reshape(self.batch, -1))
+        if ysp is not None:
+            self.ysp.copy_(torch.as_tensor(ysp).reshape(self.batch, -1))
+        return self.step_from(self.x, self.ysp)
+
+    def step_from(self, x_pinned: torch.Tensor, ysp_pinned: torch.Tensor):
+        """The same with caller-owned pinned buffers (no host copy): [B][nx] and [B][ny] FP64."""
+        io = _capi.ResidentIO()
+        io.x, io.ysp = x_pinned.data_ptr(), ysp_pinned.data_ptr()
+        io.du, io.J, io.status = self.du.data_ptr(), self.J.data_ptr(), self.status.data_ptr()
+        io.flags, io.alfa = self.flags, self.alfa
+        st = torch.cuda.current_stream(self.dp.device).cuda_stream
+        with torch.cuda.device(self.dp.device):
+            _capi.check(self.dp.lib.sihmpc_resident_step(self.dp.handle, C.c_void_p(self.state.data_ptr()), self.nbytes,
+                                                         C.byref(io), self.batch, C.c_void_p(st)), "sihmpc_resident_step")
+        return self.du, self.J
+
+
 def fp64_peak_flops() -> float:
     """Measured DFMA throughput of the current device (FLOP/s)."""
     lib = _capi.load()

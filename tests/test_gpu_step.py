@@ -353,6 +353,47 @@ def test_tensor_fast_path_shape_family(theta, N, monkeypatch):
         assert np.max(np.abs(J[:, idx] - ref["J"]) / np.maximum(np.abs(ref["J"]), 1e-9)) <= RTOL, idx
 
 
+def test_resident_controller_stepping_matches_closed_loop():
+    """sihmpc_resident_step: the plant with the caller (here NumPy, one mismatched plant per scenario), measured state
+    and set-point up, move and cost down, u / weights / warm start resident on the device.  Same numbers as the
+    batched engine that simulates the same plants on the device, and as the oracle's driver loop."""
+    from sihmpc_b200.engine import ResidentStepper
+    sys_ = sc.distillation_system()
+    bounds = dict(ulb=[1.80, 1.62], uub=[2.02, 1.78])
+    c = sc.declare_distillation(IHMPCController, sys_, **bounds)
+    B, T = 128, 45
+    scen = sc.mismatch_scenarios(B)
+    scen["seg_start"][:, 1] = 5; scen["seg_start"][:, 2] = 25
+    plants = [sc.plant_matrices_from_values(sys_, scen["plant_val"][b]) for b in range(B)]
+    Ap = np.stack([p[0] for p in plants]); Bp = np.stack([p[1] for p in plants])
+    rs = ResidentStepper(c.compile(), B, scen["u0"])
+    x = scen["x0"].copy()
+    du_r, J_r = [], []
+    for k in range(T):
+        seg = (scen["seg_start"] <= k).sum(axis=1) - 1
+        ysp = scen["ysp_seq"][np.arange(B), seg]
+        du, J = rs.step(x, ysp)
+        du = du.numpy().copy(); du_r.append(du); J_r.append(J.numpy().copy())
+        x = np.einsum('bij,bj->bi', Ap, x) + np.einsum('bij,bj->bi', Bp, du)
+    du_r, J_r = np.array(du_r), np.array(J_r)
+    assert (rs.status.numpy() == 0).all()
+    eng = c.engine(B)
+    eng.set_state(scen["x0"], scen["u0"]); eng.set_schedule(scen["ysp_seq"], scen["seg_start"])
+    eng.set_plant_values(scen["plant_val"])
+    tr = eng.run(T, record=True)
+    du_e, J_e = tr["du"].cpu().numpy(), tr["J"].cpu().numpy()
+    assert int((eng.stats.cpu().numpy()[:, 2 + 1] >= 0).sum()) == B
+    assert np.max(np.abs(du_r - du_e)) <= 1e-9 * max(1.0, np.max(np.abs(du_e)))
+    assert np.max(np.abs(J_r - J_e) / np.maximum(np.abs(J_e), 1e-9)) <= 1e-7
+    on_bound = (np.abs(scen["u0"][None] + np.cumsum(du_r, axis=0) - np.array(bounds["ulb"])) < 1e-9) | \
+               (np.abs(scen["u0"][None] + np.cumsum(du_r, axis=0) - np.array(bounds["uub"])) < 1e-9)
+    worst = int(np.argmax(on_bound.sum(axis=(0, 2))))
+    assert on_bound[:, worst].sum() > 0
+    for idx in (0, worst):
+        ref = oracle_closed_loop(sc.declare_distillation, sys_, scen, idx, T, bounds=bounds, plant=plants[idx])
+        assert np.max(np.abs(du_r[:, idx] - ref["du"])) <= RTOL * np.max(np.abs(ref["du"])), idx
+
+
 def test_fast_path_handover_many_rounds(monkeypatch):
     """Quad fast path with a tiny grid (many scenarios per quad, one after the other) on a bound
     set that makes a good share of the scenarios hand over to the exact active-set kernel mid-loop:
