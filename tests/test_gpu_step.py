@@ -6,7 +6,7 @@ constraint violation <= 1e-8.
 import numpy as np
 import pytest
 
-from tests.util import RTOL, VIOL, oracle_closed_loop, schedule_fn
+from tests.util import RTOL, VIOL, assert_loop_close, oracle_closed_loop, schedule_fn
 from oracle.ihmpc_oracle import OracleIHMPC
 from sihmpc_b200 import scenarios as sc
 from sihmpc_b200.ihmpccontroller import IHMPCController
@@ -90,11 +90,10 @@ def test_closed_loop_parity_config3():
     tr = eng.run(T, record=True)
     du = tr["du"].cpu().numpy(); J = tr["J"].cpu().numpy(); y = tr["y"].cpu().numpy()
     assert (eng.stats[:, 2 + 3].cpu().numpy() == 0).all()          # status OR
-    for idx in [0, 1, 777, 4095]:
+    picks = [0, 1, 777, 4095] + [int(i) for i in np.random.default_rng(2026).choice(B, 60, replace=False)]
+    for idx in picks:                                              # 64 scenarios: moves and cost per step at 1e-6
         ref = oracle_closed_loop(sc.declare_distillation, sys_, scen, idx, T)
-        scale = np.max(np.abs(ref["du"]))
-        assert np.max(np.abs(du[:, idx] - ref["du"])) <= RTOL * scale, idx
-        assert np.max(np.abs(J[:, idx] - ref["J"]) / np.maximum(np.abs(ref["J"]), 1e-6)) <= 10 * RTOL, idx
+        assert_loop_close(du[:, idx], J[:, idx], ref, tag=idx)
         assert np.max(np.abs(y[:, idx] - ref["y"])) <= RTOL * 100.0
     # size-independent properties over the whole batch: outputs end on the last set-point
     yend = y[-1]
@@ -139,10 +138,11 @@ def test_closed_loop_constrained_parity():
     assert (st[:, 5] == 0).all()
     assert st[:, 3].max() <= VIOL                                   # max violation seen
     assert st[:, 6].max() > 0                                       # active-set iterations happened
-    for idx in [0, 5, 63]:
+    J = tr["J"].cpu().numpy()
+    for idx in range(0, 64, 4):
         ref = oracle_closed_loop(sc.declare_distillation, sys_, scen, idx, T, bounds=bounds)
         assert ref["n_active"].max() > 0
-        assert np.max(np.abs(du[:, idx] - ref["du"])) <= RTOL * np.max(np.abs(ref["du"])), idx
+        assert_loop_close(du[:, idx], J[:, idx], ref, tag=idx)
 
 
 def test_mismatch_closed_loop_parity():
@@ -156,11 +156,11 @@ def test_mismatch_closed_loop_parity():
     eng.set_schedule(scen["ysp_seq"], scen["seg_start"])
     eng.set_plant_values(scen["plant_val"])
     tr = eng.run(T, record=True)
-    du = tr["du"].cpu().numpy(); y = tr["y"].cpu().numpy()
-    for idx in [0, 17, 127]:
+    du = tr["du"].cpu().numpy(); y = tr["y"].cpu().numpy(); J = tr["J"].cpu().numpy()
+    for idx in [0, 17, 127] + [int(i) for i in np.random.default_rng(5).choice(B, 61, replace=False)]:
         plant = sc.plant_matrices_from_values(sys_, scen["plant_val"][idx])
         ref = oracle_closed_loop(sc.declare_distillation, sys_, scen, idx, T, plant=plant)
-        assert np.max(np.abs(du[:, idx] - ref["du"])) <= RTOL * np.max(np.abs(ref["du"])), idx
+        assert_loop_close(du[:, idx], J[:, idx], ref, tag=idx)
         assert np.max(np.abs(y[:, idx] - ref["y"])) <= RTOL * 100.0
 
 
@@ -178,10 +178,9 @@ def test_mimo10_parity():
     tr = eng.run(T, record=True)
     du = tr["du"].cpu().numpy(); J = tr["J"].cpu().numpy()
     assert (eng.stats[:, sys_.ny + 3].cpu().numpy() == 0).all()
-    for idx in [0, 63]:
+    for idx in [0, 21, 42, 63]:
         ref = oracle_closed_loop(sc.declare_mimo10, sys_, scen, idx, T)
-        assert np.max(np.abs(du[:, idx] - ref["du"])) <= RTOL * np.max(np.abs(ref["du"])), idx
-        assert np.max(np.abs(J[:, idx] - ref["J"]) / np.maximum(np.abs(ref["J"]), 1e-6)) <= 10 * RTOL
+        assert_loop_close(du[:, idx], J[:, idx], ref, tag=idx)
 
 
 def test_dropin_example_loop_matches_oracle():
@@ -392,6 +391,79 @@ def test_resident_controller_stepping_matches_closed_loop():
     for idx in (0, worst):
         ref = oracle_closed_loop(sc.declare_distillation, sys_, scen, idx, T, bounds=bounds, plant=plants[idx])
         assert np.max(np.abs(du_r[:, idx] - ref["du"])) <= RTOL * np.max(np.abs(ref["du"])), idx
+
+
+def _guarded(t, guard=512):
+    """The same tensor between two guard regions of NaN-pattern words; returns (view, whole storage)."""
+    import torch
+    flat = t.contiguous().reshape(-1)
+    if flat.dtype == torch.float64:
+        store = torch.full((flat.numel() + 2 * guard,), float("nan"), dtype=torch.float64, device=t.device)
+    else:
+        store = torch.full((flat.numel() + 2 * guard,), -1431655766, dtype=flat.dtype, device=t.device)
+    store[guard:guard + flat.numel()] = flat
+    return store[guard:guard + flat.numel()].view(t.shape), store
+
+
+def _guards_intact(store, n, guard=512):
+    import torch
+    g = torch.cat([store[:guard], store[guard + n:]])
+    if store.dtype == torch.float64:
+        return bool(torch.isnan(g).all().item())
+    return bool((g == -1431655766).all().item())
+
+
+@pytest.mark.parametrize("which", ["mma", "tile", "general", "mimo10", "log"])
+def test_no_kernel_writes_outside_its_buffers(which, monkeypatch):
+    """Stand-in for compute-sanitizer memcheck (closed on this pool, profiles/r02_sanitizer_unavailable.md): every
+    array a step call receives sits between guard regions; closed loops with active bounds, hand-over, resume pass and
+    an odd batch size must leave every guard word untouched."""
+    import torch
+    monkeypatch.delenv("SIHMPC_NO_FAST", raising=False); monkeypatch.delenv("SIHMPC_FAST", raising=False)
+    bounds = dict(ulb=[1.80, 1.62], uub=[2.02, 1.78])
+    if which == "mimo10":
+        sys_ = sc.mimo10_system()
+        c = sc.declare_mimo10(IHMPCController, sys_, ulb=[-0.4] * 10, uub=[0.4] * 10)
+        B = 37
+        scen = sc.mimo10_scenarios(B, sys_)
+    elif which == "log":
+        from sihmpc_b200.ihmpccontroller_log import IHMPCController as LogC
+        sys_ = sc.distillation_system()
+        c = sc.declare_distillation_log(LogC, sys_)
+        B = 37
+        scen = sc.distillation_scenarios(B)
+    else:
+        if which == "tile":
+            monkeypatch.setenv("SIHMPC_FAST", "tile")
+        if which == "general":
+            monkeypatch.setenv("SIHMPC_NO_FAST", "1")
+        sys_ = sc.distillation_system()
+        c = sc.declare_distillation(IHMPCController, sys_, **bounds)
+        B = 4099
+        scen = sc.distillation_scenarios(B)
+    scen["seg_start"][:, 1] = 3; scen["seg_start"][:, 2] = 12
+    eng = c.engine(B)
+    eng.set_state(scen["x0"], scen["u0"]); eng.set_schedule(scen["ysp_seq"], scen["seg_start"])
+    eng.set_disturbance(np.minimum(scen["dist_step"], 15), scen["dist"])
+    stores = {}
+    names = ["x", "u", "du", "J", "w_opt", "status", "stats", "ysp_seq", "seg_start", "dist", "dist_step"]
+    names += ["w_warm", "iters"] if which == "log" else ["pesos", "vinant", "n_active"]
+    for name in names:
+        view, store = _guarded(getattr(eng, name))
+        setattr(eng, name, view); stores[name] = (store, view.numel())
+    if which != "log":
+        ws, nb = eng.dp.workspace(B)
+        eng.dp._ws = torch.full((nb + 8192,), 0xAB, dtype=torch.uint8, device=ws.device)[4096:4096 + nb]
+        wstore = eng.dp._ws._base if eng.dp._ws._base is not None else None
+    tr = eng.run(20, steps_per_launch=7, record=True)
+    torch.cuda.synchronize()
+    assert np.isfinite(tr["du"].cpu().numpy()).all()
+    for name, (store, n) in stores.items():
+        assert _guards_intact(store, n), name
+    if which != "log" and wstore is not None:
+        w = wstore.cpu().numpy()
+        assert (w[:4096] == 0xAB).all() and (w[4096 + nb:] == 0xAB).all()
+    monkeypatch.delenv("SIHMPC_NO_FAST", raising=False); monkeypatch.delenv("SIHMPC_FAST", raising=False)
 
 
 def test_fast_path_handover_many_rounds(monkeypatch):

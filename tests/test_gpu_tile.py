@@ -5,7 +5,7 @@ and the NumPy oracle.  Tolerances: BASELINE.json (moves and cost 1e-6 relative, 
 import numpy as np
 import pytest
 
-from tests.util import RTOL, oracle_closed_loop
+from tests.util import RTOL, assert_loop_close, oracle_closed_loop
 from sihmpc_b200 import scenarios as sc
 from sihmpc_b200.ihmpccontroller import IHMPCController
 
@@ -92,9 +92,9 @@ def test_tile_equals_general_on_random_shapes(ny, nu, N, dmax, monkeypatch):
     assert (t["stats"][:, ny + 3] == 0).all() and (g["stats"][:, ny + 3] == 0).all()
     assert (t["stats"][:, ny + 4] == 0).all()            # nothing was handed over: the tile path did the work
     _close(t, g)
-    ref = oracle_closed_loop(declare, sys_, scen, 3, T)
-    assert np.max(np.abs(t["du"][:, 3] - ref["du"])) <= RTOL * np.max(np.abs(ref["du"]))
-    assert np.max(np.abs(t["J"][:, 3] - ref["J"]) / np.maximum(np.abs(ref["J"]), 1e-6)) <= 10 * RTOL
+    for idx in (3, 11, 20):
+        ref = oracle_closed_loop(declare, sys_, scen, idx, T)
+        assert_loop_close(t["du"][:, idx], t["J"][:, idx], ref, tag=idx)
 
 
 def test_tile_underdamped_plant_matches_oracle(monkeypatch):

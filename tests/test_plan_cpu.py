@@ -272,3 +272,33 @@ def test_rows_the_moves_cannot_influence_are_recorded_and_checked():
     assert fixed_row_violation(p, x, [96.0, 0.5]) <= 0.0
     x[s.ny + s.nd] = 2.5                                   # xi_0 outside [-1, 1]
     assert abs(fixed_row_violation(p, x, [96.0, 0.5]) - 1.5) < 1e-12
+
+
+def test_opom_markov_parameters_match_an_independent_discretisation():
+    """OPOM builder against code it shares NOTHING with: every channel discretised on its own by
+    scipy.signal.cont2discrete (zero-order hold) with an explicit delay line, stepped by scipy.signal.dlsim.  The
+    OPOM model is driven by MOVES, so its Markov parameters C A^(k-1) B (+ D at k = 0) are the plant's unit STEP
+    response; A, B, C, D of the product must reproduce it sample by sample -- first-order + dead time (Wood & Berry),
+    an integrating channel, an under-damped pair and a third-order channel."""
+    from scipy.signal import cont2discrete, dlsim
+    wn, z = 0.5, 0.3
+    chans = [[([12.8], [16.7, 1.0], 1), ([-18.9], [21.0, 1.0], 3)],
+             [([2.0], [3.0, 1.0, 0.0], 2), ([2.0 * wn * wn], list(np.polymul([1, 2 * z * wn, wn * wn], [4.0, 1.0])), 2)]]
+    for Ts in (1.0, 0.5):
+        h = [[TransferFunction(num, den, delay=d * Ts) for (num, den, d) in row] for row in chans]
+        s = OPOM(h, Ts)
+        n = 80
+        A, B, C, D = (np.asarray(getattr(s, k), float) for k in "ABCD")
+        markov = [D.copy()]
+        Ak = np.eye(s.nx)
+        for k in range(1, n + 1):
+            markov.append(C @ Ak @ B)
+            Ak = A @ Ak
+        markov = np.array(markov)                                   # [k][i][j]
+        for i, row in enumerate(chans):
+            for j, (num, den, d) in enumerate(row):
+                numd, dend, _ = cont2discrete((num, den), Ts, method="zoh")
+                _, ystep = dlsim((numd.reshape(-1), dend, Ts), np.ones(n + 1))
+                ref = np.concatenate([np.zeros(d), ystep.reshape(-1)])[:n + 1]      # delay line of d samples
+                scale = max(1.0, np.max(np.abs(ref)))
+                assert np.max(np.abs(markov[:, i, j] - ref)) <= 1e-9 * scale, (Ts, i, j)

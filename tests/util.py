@@ -14,6 +14,19 @@ def rel_err(a, b, floor=1e-9):
     return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor + 1e-3 * np.max(np.abs(b)))))
 
 
+def assert_loop_close(du, J, ref, rtol=RTOL, tag=None, move_floor=1e-3, cost_floor=1e-6):
+    """Closed-loop parity at the north-star tolerance, PER STEP: the moves of every step relative to the largest
+    move of THAT step (floored at move_floor x the largest move of the trajectory, so steps at rest are not compared
+    at rounding level), the cost of every step relative to itself (floored at cost_floor x the largest cost)."""
+    rd, rj = np.asarray(ref["du"]), np.asarray(ref["J"])
+    step_scale = np.maximum(np.max(np.abs(rd), axis=1), move_floor * np.max(np.abs(rd)))
+    err = np.max(np.abs(np.asarray(du) - rd), axis=1) / step_scale
+    assert np.max(err) <= rtol, (tag, "moves", int(np.argmax(err)), float(np.max(err)))
+    if J is not None:
+        ej = np.abs(np.asarray(J) - rj) / np.maximum(np.abs(rj), cost_floor * np.max(np.abs(rj)))
+        assert np.max(ej) <= rtol, (tag, "cost", int(np.argmax(ej)), float(np.max(ej)))
+
+
 def schedule_fn(seq, start):
     def f(k):
         seg = 0
