@@ -100,13 +100,20 @@ class OracleIHMPCLog(OracleIHMPC):
         for lo, hi in ((self.rslb, self.rsub), (self.rilb, self.riub)):
             if not np.array_equal(lo, hi):
                 raise NotImplementedError("terminal residual ranges")
-        # contraction rows with ViN_ant = 0 force siN = 0: must hold identically (non-integrating plant)
+        # contraction rows q siN^2 <= ViN_ant (log.py:245-270, row bounds :429-434): |siN| <= sqrt(ViN_ant / q) is linear
+        # in dU on an integrating plant; where siN cannot be moved (non-integrating: xi(N) = xi(0)) it must hold as is
+        self._extra_lin = []                                   # (row over dU, lo, hi)
         for V in self.V:
             if V.ViN_slot is not None and np.isfinite(ViN_ant[V.ViN_slot]):
+                if len(V.index) != 1:
+                    raise NotImplementedError("multi-index siN row in the log variant")
                 k = nv + ny + V.index[0]
                 bound = np.sqrt(max(ViN_ant[V.ViN_slot], 0.0) / float(V.W[0, 0]))
-                if np.linalg.norm(T[k]) > 1e-13 or abs(t0[k]) > bound + 1e-12:
-                    raise NotImplementedError("active siN contraction row in the log variant")
+                if np.linalg.norm(T[k]) <= 1e-13:
+                    if abs(t0[k]) > bound + 1e-12:
+                        raise RuntimeError("siN contraction row violated and out of reach of the moves")
+                else:
+                    self._extra_lin.append((T[k].copy(), -bound - t0[k], bound - t0[k]))
 
         def quad(V):
             Rw = V.R[:, :nwq] @ T
@@ -170,9 +177,14 @@ class OracleIHMPCLog(OracleIHMPC):
         dU, ss = v[:nv], v[nv]
         # explicit inequalities must be strictly inactive
         u_pred = np.asarray(u0)[None, :] + np.cumsum(dU.reshape(N, nu), axis=0)
-        margin = [ss - 1.0, float(np.min(d - 0.01)),
+        def margins(dU, ss, d, u_pred):
+            mg = [ss - 1.0, float(np.min(d - 0.01)),
                   float(np.min(u_pred - self.ulb)), float(np.min(self.uub - u_pred)),
                   float(np.min(dU.reshape(N, nu) - self.dulb)), float(np.min(self.duub - dU.reshape(N, nu)))]
+            for row, lo_, hi_ in self._extra_lin:
+                mg.append(float(min(row @ dU - lo_, hi_ - row @ dU)))
+            return mg
+        margin = margins(dU, ss, d, u_pred)
         if min(margin) <= 1e-9:
             # an explicit inequality of the NLP is active: solve the constrained problem with SciPy's trust-constr
             # (its own interior point / SQP machinery -- independent of the product's barrier continuation), from a
@@ -181,9 +193,7 @@ class OracleIHMPCLog(OracleIHMPC):
             Vt, Vi, d, gi, Hi, rt = evaluate(v)
             dU, ss = v[:nv], v[nv]
             u_pred = np.asarray(u0)[None, :] + np.cumsum(dU.reshape(N, nu), axis=0)
-            margin = [ss - 1.0, float(np.min(d - 0.01)),
-                      float(np.min(u_pred - self.ulb)), float(np.min(self.uub - u_pred)),
-                      float(np.min(dU.reshape(N, nu) - self.dulb)), float(np.min(self.duub - dU.reshape(N, nu)))]
+            margin = margins(dU, ss, d, u_pred)
             self.last_kkt = kkt
         w = np.concatenate([T @ dU + t0, [ss]])
         xi = self._xi(w, x0, u0, ySP)
@@ -218,9 +228,13 @@ class OracleIHMPCLog(OracleIHMPC):
             return g, H
         # linear rows: cumulative input box and move box
         Tc = np.kron(np.tril(np.ones((N, N))), np.eye(nu))
-        A = np.zeros((2 * nv, n)); A[:nv, :nv] = Tc; A[nv:, :nv] = np.eye(nv)
-        lo = np.concatenate([np.tile(self.ulb - u0, N), np.tile(self.dulb, N)])
-        hi = np.concatenate([np.tile(self.uub - u0, N), np.tile(self.duub, N)])
+        ne = len(getattr(self, '_extra_lin', []))
+        A = np.zeros((2 * nv + ne, n)); A[:nv, :nv] = Tc; A[nv:2 * nv, :nv] = np.eye(nv)
+        lo = np.concatenate([np.tile(self.ulb - u0, N), np.tile(self.dulb, N), np.zeros(ne)])
+        hi = np.concatenate([np.tile(self.uub - u0, N), np.tile(self.duub, N), np.zeros(ne)])
+        for k, (row, lo_, hi_) in enumerate(getattr(self, '_extra_lin', [])):       # siN contraction rows
+            A[2 * nv + k, :nv] = row; lo[2 * nv + k] = lo_; hi[2 * nv + k] = hi_
+        nrow = A.shape[0]
 
         def dfun(v):
             return evaluate(v)[2] - 0.01
@@ -247,7 +261,7 @@ class OracleIHMPCLog(OracleIHMPC):
         # polish: primal active-set Newton from there.  Rows: ('lin', k, +1/-1) of A v >= lo / <= hi, ('ss',), ('d', i).
         cs = A @ v
         active = []
-        for k in range(2 * nv):
+        for k in range(nrow):
             if np.isfinite(lo[k]) and cs[k] - lo[k] < 1e-7: active.append(('lin', k, 1.0))
             elif np.isfinite(hi[k]) and hi[k] - cs[k] < 1e-7: active.append(('lin', k, -1.0))
         if v[nv] - 1.0 < 1e-7: active.append(('ss', 0, 1.0))
@@ -270,7 +284,7 @@ class OracleIHMPCLog(OracleIHMPC):
             t, block = 1.0, None
             act_lin = {(k, sg) for kind, k, sg in active if kind == 'lin'}
             ds = A @ step
-            for k in range(2 * nv):
+            for k in range(nrow):
                 if np.isfinite(lo[k]) and (k, 1.0) not in act_lin and ds[k] < -1e-16:
                     tk = (lo[k] - cs[k]) / ds[k]
                     if tk < t: t, block = max(tk, 0.0), ('lin', k, 1.0)

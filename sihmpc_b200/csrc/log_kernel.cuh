@@ -26,7 +26,7 @@
 
 namespace sih {
 
-struct LogLayout { int H, dinv, x, xn, uu, ysp, e, r, v, g, p, gi, d, Vi, vt, s1, s2, b1, b2, total; };
+struct LogLayout { int H, dinv, x, xn, uu, ysp, e, r, v, g, p, gi, d, Vi, vt, s1, s2, b1, b2, glo, ghi, t1, t2, vw, total; };
 
 __host__ __device__ inline LogLayout make_log_layout(const DevPlan &P) {
     LogLayout w; int o = 0;
@@ -36,6 +36,9 @@ __host__ __device__ inline LogLayout make_log_layout(const DevPlan &P) {
     SIH_TAKE(r, P.R); SIH_TAKE(v, n); SIH_TAKE(g, n); SIH_TAKE(p, n); SIH_TAKE(gi, P.m * P.nv);
     SIH_TAKE(d, P.m); SIH_TAKE(Vi, P.m); SIH_TAKE(vt, n);
     SIH_TAKE(s1, n); SIH_TAKE(s2, n); SIH_TAKE(b1, n); SIH_TAKE(b2, n);
+    const int nc = P.ncd > 0 ? P.ncd : 1;           // dense rows: bounds on Gc dU, barrier coefficients
+    SIH_TAKE(glo, nc); SIH_TAKE(ghi, nc); SIH_TAKE(t1, nc); SIH_TAKE(t2, nc);
+    SIH_TAKE(vw, n);                                // the point this step started from (warm start / shifted plan)
 #undef SIH_TAKE
     w.total = o;
     return w;
@@ -75,10 +78,23 @@ __device__ __forceinline__ double log_relax(const double b, const double sgn) { 
 // barrier of the explicit inequalities at vv (d[] from log_eval at the same point):  -mu sum log c_j, inf outside.
 // With `deriv` the first/second derivative coefficients are left in shared memory: S1/S2[k*nu+j] = suffix sums
 // over the horizon of the input-box rows of input j, b1/b2 = move-box terms per variable.
+// Dense rows lo <= Gc dU <= hi (state / slack boxes, the siN contraction row |siN| <= sqrt(ViN_ant/q) of an
+// integrating plant, log.py:245-270,429-434): glo/ghi hold the bounds on Gc dU of THIS step, T1/T2 receive
+// mu (-1/s_lo + 1/s_hi) and mu (1/s_lo^2 + 1/s_hi^2) per row.
 __device__ double log_barrier(const DevPlan &P, const double *vv, const double *uu, const double *d, const double mu,
-                              const bool deriv, double *S1, double *S2, double *b1, double *b2, int lane) {
+                              const bool deriv, double *S1, double *S2, double *b1, double *b2, int lane,
+                              const double *glo = nullptr, const double *ghi = nullptr, double *T1 = nullptr,
+                              double *T2 = nullptr) {
     const int nv = P.nv, nu = P.nu, m = P.m, N = P.N;
     double acc = 0.0, bad = 0.0;
+    for (int r = lane; r < P.ncd; r += 32) {
+        double val = 0.0;
+        for (int c = 0; c < nv; ++c) val = fma(P.GcT[(size_t)c * P.ncd + r], vv[c], val);
+        double t1 = 0.0, t2 = 0.0;
+        if (glo[r] > -SIH_INF) { const double sl = val - log_relax(glo[r], -1.0); if (!(sl > 0.0)) bad = 1.0; else { acc -= log(sl); t1 -= 1.0 / sl; t2 += 1.0 / (sl * sl); } }
+        if (ghi[r] < SIH_INF) { const double sl = log_relax(ghi[r], 1.0) - val; if (!(sl > 0.0)) bad = 1.0; else { acc -= log(sl); t1 += 1.0 / sl; t2 += 1.0 / (sl * sl); } }
+        if (deriv) { T1[r] = mu * t1; T2[r] = mu * t2; }
+    }
     if (lane == 0) {
         const double s = vv[nv] - log_relax(1.0, -1.0);
         if (!(s > 0.0)) bad = 1.0; else acc -= log(s);
@@ -129,6 +145,8 @@ ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__
     double *r = W + lay.r, *v = W + lay.v, *g = W + lay.g, *gi = W + lay.gi, *d = W + lay.d, *Vi = W + lay.Vi;
     double *vt = W + lay.vt, *xn = W + lay.xn, *uu = W + lay.uu;
     double *S1 = W + lay.s1, *S2 = W + lay.s2, *b1 = W + lay.b1, *b2 = W + lay.b2;
+    double *glo = W + lay.glo, *ghi = W + lay.ghi, *T1 = W + lay.t1, *T2 = W + lay.t2, *vw = W + lay.vw;
+    const int ncd = P.ncd;
     const int nx = P.nx, nu = P.nu, ny = P.ny, nv = P.nv, m = P.m, R = P.R;
     const int n = nv + 1, ld = n | 1, nw = nv + 2 * ny + 1;
     const int nstat = ny + SIHMPC_NSTATS_EXTRA;
@@ -166,6 +184,21 @@ ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__
             for (int c = 0; c < ny; ++c) a = fma(P.PyT[(size_t)c * R + k], ys[c], a);
             e[k] = a;
         }
+        // dense rows: bounds on Gc dU for this state (contraction rows from ViN_ant: +inf = not yet set)
+        for (int rr = lane; rr < ncd; rr += 32) {
+            double off = P.gc0[rr];
+            for (int j = 0; j < nx; ++j) off = fma(P.GcxT[(size_t)j * ncd + rr], xs[j], off);
+            for (int c = 0; c < ny; ++c) off = fma(P.GcyT[(size_t)c * ncd + rr], ys[c], off);
+            double lo = P.Lc[rr], hi = P.Uc[rr];
+            const int slot = P.gc_vin[rr];
+            if (slot >= 0) {
+                const double vin = io.vinant ? io.vinant[s * P.n_vin + slot] : SIH_INF;
+                const double b = (vin < SIH_INF) ? sqrt(fmax(vin, 0.0) / P.gc_q[rr]) : SIH_INF;
+                lo = -b; hi = b;
+            }
+            glo[rr] = lo - off; ghi[rr] = hi - off;
+        }
+        for (int i = lane; i < nv; i += 32) vw[i] = v[i];
         __syncwarp();
         int st = 0, it = 0;
         double phi = log_eval(P, v, e, r, Vi, d, lane);
@@ -185,7 +218,7 @@ ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__
                                           return 1.0 / (di * di) + (mu > 0.0 ? mu / (si * si) : 0.0); };
         for (int itn = 1; itn <= lim; ++itn) {
             ++it;
-            if (mu > 0.0) log_barrier(P, v, uu, d, mu, true, S1, S2, b1, b2, lane);     // derivative coefficients at v
+            if (mu > 0.0) log_barrier(P, v, uu, d, mu, true, S1, S2, b1, b2, lane, glo, ghi, T1, T2);     // derivative coefficients at v
             // ---- gradients a_i = grad_dU V_i (rows of gi), lanes over variables
             for (int c = lane; c < nv; c += 32) {
                 for (int i = 0; i < m; ++i) {
@@ -197,7 +230,10 @@ ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__
                 for (int k = 0; k < R; ++k) a = fma(P.E[(size_t)k * nv + c], P.w0row[k] * r[k], a);
                 double gc = 2.0 * a;
                 for (int i = 0; i < m; ++i) gc += gi[i * nv + c] * w1f(i);
-                if (mu > 0.0) gc += S1[c] + b1[c];
+                if (mu > 0.0) {
+                    gc += S1[c] + b1[c];
+                    for (int rr = 0; rr < ncd; ++rr) gc = fma(T1[rr], P.GcT[(size_t)c * ncd + rr], gc);
+                }
                 g[c] = gc;
             }
             if (lane == 0) {
@@ -222,6 +258,8 @@ ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__
                     if (mu > 0.0) {
                         if ((a % nu) == (b % nu)) h += S2[a];          // a >= b: rows k >= k_a cover both moves
                         if (a == b) h += b2[a];
+                        for (int rr = 0; rr < ncd; ++rr)
+                            h = fma(T2[rr] * P.GcT[(size_t)a * ncd + rr], P.GcT[(size_t)b * ncd + rr], h);
                     }
                 } else if (b < nv) {
                     h = 0.0;
@@ -252,7 +290,7 @@ ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__
                 for (int t = 0; t < NVR; ++t) { const int i = lane + 32 * t; if (i < n) vt[i] = fma(t_, acc[t], v[i]); }
                 __syncwarp();
                 phin = log_eval(P, vt, e, r, Vi, d, lane);
-                if (mu > 0.0 && phin < SIH_INF) phin += log_barrier(P, vt, uu, d, mu, false, S1, S2, b1, b2, lane);
+                if (mu > 0.0 && phin < SIH_INF) phin += log_barrier(P, vt, uu, d, mu, false, S1, S2, b1, b2, lane, glo, ghi, T1, T2);
                 if (phin <= phi - 1e-4 * t_ * dec) { ok = true; break; }
                 t_ *= 0.5;
                 __syncwarp();
@@ -260,7 +298,7 @@ ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__
             if (!ok) {                     // rounding level: restore the state of v and stop
                 __syncwarp();
                 phi = log_eval(P, v, e, r, Vi, d, lane);
-                if (mu > 0.0) phi += log_barrier(P, v, uu, d, mu, false, S1, S2, b1, b2, lane);
+                if (mu > 0.0) phi += log_barrier(P, v, uu, d, mu, false, S1, S2, b1, b2, lane, glo, ghi, T1, T2);
                 break;
             }
             __syncwarp();
@@ -290,13 +328,60 @@ ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__
                     marg = fmin(marg, fmin(dv - P.dulb[j], P.duub[j] - dv));
                 }
             }
+            for (int rr = lane; rr < ncd; rr += 32) {
+                double val = 0.0;
+                for (int c = 0; c < nv; ++c) val = fma(P.GcT[(size_t)c * ncd + rr], v[c], val);
+                marg = fmin(marg, fmin(val - glo[rr], ghi[rr] - val));
+            }
             marg = -warp_max(-marg);
             if (!(marg > 1e-9)) {
-                // ---- interior point on the explicit inequalities (see the header): strictly feasible start = no moves,
-                // ss large enough for every barrier
+                // ---- interior point on the explicit inequalities (see the header): strictly feasible start = no moves
+                // (or, when a dense row excludes that, the warm start the caller passed: the shifted plan of the last
+                // step sits ON its contraction row, inside the relaxed one), ss large enough for every barrier
                 __syncwarp();
-                for (int i = lane; i < nv; i += 32) v[i] = 0.0;
+                double feas0 = SIH_INF;
+                for (int rr = lane; rr < ncd; rr += 32) feas0 = fmin(feas0, fmin(0.0 - log_relax(glo[rr], -1.0), log_relax(ghi[rr], 1.0) - 0.0));
+                feas0 = -warp_max(-feas0);
+                const bool zero_ok = !(feas0 <= 0.0);
+                for (int i = lane; i < nv; i += 32) v[i] = zero_ok ? 0.0 : vw[i];
                 if (lane == 0) v[nv] = 2.0;
+                __syncwarp();
+                if (!zero_ok && lane == 0) {
+                    // the shifted plan sits ON its contraction row (slack = the 1e-10 relaxation: a barrier curvature of
+                    // 1e19 that no factorisation survives): move it, by the least change, to the CENTRES of the bounded
+                    // dense rows --  v -= Gc_b^T (Gc_b Gc_b^T)^-1 (Gc_b v - centre)  over the (few) bounded rows b
+                    constexpr int MB = 8;
+                    int rows[MB], nb = 0;
+                    double G[MB][MB + 1];
+                    for (int rr = 0; rr < ncd && nb < MB; ++rr)
+                        if (glo[rr] > -SIH_INF || ghi[rr] < SIH_INF) rows[nb++] = rr;
+                    for (int a = 0; a < nb; ++a) {
+                        const int ra = rows[a];
+                        const double lo = glo[ra], hi = ghi[ra];
+                        const double centre = (lo > -SIH_INF && hi < SIH_INF) ? 0.5 * (lo + hi)
+                                            : (lo > -SIH_INF ? lo + fmax(1.0, fabs(lo)) : hi - fmax(1.0, fabs(hi)));
+                        double val = 0.0;
+                        for (int c = 0; c < nv; ++c) val = fma(P.GcT[(size_t)c * ncd + ra], v[c], val);
+                        G[a][nb] = val - centre;
+                        for (int b = 0; b < nb; ++b) {
+                            double acc = 0.0;
+                            for (int c = 0; c < nv; ++c) acc = fma(P.GcT[(size_t)c * ncd + ra], P.GcT[(size_t)c * ncd + rows[b]], acc);
+                            G[a][b] = acc;
+                        }
+                    }
+                    for (int a = 0; a < nb; ++a) {                 // Gauss-Jordan on the (SPD) Gram matrix
+                        const double piv = G[a][a];
+                        if (!(fabs(piv) > 1e-300)) continue;
+                        for (int b = a; b <= nb; ++b) G[a][b] /= piv;
+                        for (int r2 = 0; r2 < nb; ++r2)
+                            if (r2 != a) { const double f_ = G[r2][a]; for (int b = a; b <= nb; ++b) G[r2][b] = fma(-f_, G[a][b], G[r2][b]); }
+                    }
+                    for (int c = 0; c < nv; ++c) {
+                        double corr = 0.0;
+                        for (int a = 0; a < nb; ++a) corr = fma(P.GcT[(size_t)c * ncd + rows[a]], G[a][nb], corr);
+                        v[c] -= corr;
+                    }
+                }
                 __syncwarp();
                 log_eval(P, v, e, r, Vi, d, lane);
                 {
@@ -309,7 +394,7 @@ ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__
                 bool fail_ip = false;
                 for (double mu = 1e-1; mu >= 0.99e-14; mu *= 0.1) {
                     phi = log_eval(P, v, e, r, Vi, d, lane);
-                    const double bar = log_barrier(P, v, uu, d, mu, false, S1, S2, b1, b2, lane);
+                    const double bar = log_barrier(P, v, uu, d, mu, false, S1, S2, b1, b2, lane, glo, ghi, T1, T2);
                     if (!(phi < SIH_INF) || !(bar < SIH_INF)) { fail_ip = true; break; }
                     phi += bar;
                     newton(mu, 60);
@@ -335,6 +420,16 @@ ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__
                 if (status) status[s] = st;
                 if (iters_out) iters_out[s] = it;
             }
+        }
+        if ((io.flags & SIHMPC_F_UPDATE_VIN) && io.vinant) {          // ViNant = q siN_next^2 (log.py:558-561), every step:
+            for (int k = lane; k < P.n_vin; k += 32) {                // the next step's contraction row reads it
+                const int i = P.vin_row[k] - P.o_si;
+                double a = 0.0;
+                for (int j = 0; j < nx; ++j) a = fma(P.Mi1xT[(size_t)j * ny + i], xs[j], a);
+                for (int c = 0; c < nv; ++c) a = fma(P.Mi1uT[(size_t)c * ny + i], v[c], a);
+                io.vinant[s * P.n_vin + k] = P.vin_q[k] * a * a;
+            }
+            __syncwarp();
         }
         if (io.traj_du) for (int j = lane; j < nu; j += 32) io.traj_du[((long long)step * batch + s) * nu + j] = v[j];
         if (io.traj_J && lane == 0) io.traj_J[(long long)step * batch + s] = phi;

@@ -241,6 +241,7 @@ class LogBatchedEngine:
         self.w_opt = torch.zeros(B, self.nw, dtype=f64, device=dev)
         self.w_warm = torch.zeros(B, self.nw, dtype=f64, device=dev)
         self.w_warm[:, -1] = 1.0
+        self.vinant = torch.full((B, max(p.n_vin, 1)), float("inf"), dtype=f64, device=dev)   # contracting ViN_ant
         self.status = torch.zeros(B, dtype=torch.int32, device=dev)
         self.iters = torch.zeros(B, dtype=torch.int32, device=dev)
         self.stats = torch.zeros(B, self.nstat, dtype=f64, device=dev)
@@ -251,6 +252,7 @@ class LogBatchedEngine:
         self.x.copy_(torch.as_tensor(np.asarray(x, dtype=np.float64)).reshape(self.batch, -1))
         self.u.copy_(torch.as_tensor(np.asarray(u, dtype=np.float64)).reshape(self.batch, -1))
         self.w_warm.zero_(); self.w_warm[:, -1] = 1.0
+        self.vinant.fill_(float("inf"))
         self.k = 0
         self.stats.zero_()
 
@@ -259,11 +261,12 @@ class LogBatchedEngine:
     set_plant_values = BatchedEngine.set_plant_values
 
     def snapshot(self):
-        return dict(x=self.x.clone(), u=self.u.clone(), w_warm=self.w_warm.clone(), stats=self.stats.clone(), k=self.k)
+        return dict(x=self.x.clone(), u=self.u.clone(), w_warm=self.w_warm.clone(), stats=self.stats.clone(),
+                    vinant=self.vinant.clone(), k=self.k)
 
     def restore(self, snap):
         self.x.copy_(snap["x"]); self.u.copy_(snap["u"]); self.w_warm.copy_(snap["w_warm"])
-        self.stats.copy_(snap["stats"])
+        self.stats.copy_(snap["stats"]); self.vinant.copy_(snap["vinant"])
         self.k = int(snap["k"])
 
     def run(self, n_steps: int, steps_per_launch: Optional[int] = None, record: bool = False):
@@ -298,6 +301,9 @@ class LogBatchedEngine:
                     io.traj_J = traj_all["J"][done:done + n].data_ptr()
                     io.traj_y = traj_all["y"][done:done + n].data_ptr()
                 io.flags = _capi.F_ADVANCE
+                if self.plan.n_vin > 0:
+                    io.vinant = self.vinant.data_ptr()
+                    io.flags |= _capi.F_UPDATE_VIN
                 io.k0 = self.k
                 _capi.check(self.dp.lib.sihmpc_log_loop(self.dp.handle, C.byref(io), C.c_void_p(self.w_warm.data_ptr()),
                                                         self.batch, n, C.c_void_p(self.iters.data_ptr()), C.c_void_p(st)),

@@ -124,8 +124,6 @@ class IHMPCController(_Weighted):
         if ViN_ant is None:                                    # log.py:554-555
             ViN_ant = self.ViNant
         vin = _vec(ViN_ant, len(self.ViNant), "ViN_ant") if len(self.ViNant) else np.zeros(0)
-        if self._plan.ncd > 0 and np.any(np.isfinite(vin)):
-            raise NotImplementedError("siN contraction rows of an integrating plant in the log variant")
         x = _vec(x0, nx, "x0"); u = _vec(u0, nu, "u0"); ysp = _vec(ySP, ny, "ySP")
         w0a = np.asarray(w0, dtype=np.float64).reshape(-1)
         dev = dp.device
@@ -137,12 +135,18 @@ class IHMPCController(_Weighted):
         sd = torch.zeros(1, dtype=torch.int32, device=dev)
         itd = torch.zeros(1, dtype=torch.int32, device=dev)
         st = torch.cuda.current_stream(dev).cuda_stream
+        # one step of sihmpc_log_loop without SIHMPC_F_ADVANCE = mpc() with the contraction limits ViN_ant of this call
+        # (dense rows |siN| <= sqrt(ViN_ant/q) of an integrating plant, log.py:245-270,429-434)
+        io = _capi.IO()
+        io.x, io.u, io.ysp = xd.data_ptr(), ud.data_ptr(), yd.data_ptr()
+        vind = t(vin) if (len(vin) and self._plan.n_vin > 0) else None
+        io.vinant = vind.data_ptr() if vind is not None else None
+        io.w_opt, io.J, io.status = wo.data_ptr(), Jd.data_ptr(), sd.data_ptr()
+        io.flags = 0
         with torch.cuda.device(dev):
-            _capi.check(dp.lib.sihmpc_log_step(
-                dp.handle, C.c_void_p(xd.data_ptr()), C.c_void_p(ud.data_ptr()), C.c_void_p(yd.data_ptr()),
-                C.c_void_p(w0d.data_ptr()) if w0d is not None else None, 1, C.c_void_p(wo.data_ptr()),
-                C.c_void_p(Jd.data_ptr()), C.c_void_p(sd.data_ptr()), C.c_void_p(itd.data_ptr()), C.c_void_p(st)),
-                "sihmpc_log_step")
+            _capi.check(dp.lib.sihmpc_log_loop(
+                dp.handle, C.byref(io), C.c_void_p(w0d.data_ptr()) if w0d is not None else None, 1, 1,
+                C.c_void_p(itd.data_ptr()), C.c_void_p(st)), "sihmpc_log_loop")
         w = wo.cpu().numpy().reshape(-1)
         J = float(Jd.cpu().numpy()[0])
         self.status = int(sd.cpu().numpy()[0])

@@ -830,6 +830,50 @@ def test_log_variant_active_inequalities_match_oracle(bname, bounds):
     assert n_constrained >= 3
 
 
+def _declare_siso_log(cls, s, **bounds):
+    c = cls(s, 6, **(bounds or dict(dulb=[-0.5], duub=[0.5])))
+    c.subObjComposed(y=[0], Q=1, sat=6.0)
+    c.subObj(du=[0], Q=1, sat=1.0)
+    c.subObj(siN=[0], Q=1, addJ=False)
+    return c
+
+
+def test_log_variant_integrating_plant_contraction_row():
+    """Log-barrier variant on an INTEGRATING channel: siN != 0 and the contraction row q siN^2 <= ViN_ant
+    (ihmpccontroller_log.py:245-270, row bounds :429-434) with the limit contracting along the loop (ViN_ant=None ->
+    self.ViNant, log.py:554-561).  The row is a dense row |siN| <= sqrt(ViN_ant/q) of the kernel's interior-point
+    phase; moves, cost and the limit itself against the log oracle, same state in."""
+    from oracle.ihmpc_log_oracle import OracleIHMPCLog
+    from sihmpc.ihmpccontroller_log import IHMPCController as LogController
+    s = _siso_integrating()
+    c = _declare_siso_log(LogController, s)
+    orc = _declare_siso_log(OracleIHMPCLog, s)
+    assert c.compile().ncd == 1 and c.compile().n_vin == 1
+    x = np.zeros(s.nx); u = np.zeros(1); w0 = []
+    tight = 0
+    for k in range(40):
+        ysp = [1.0] if k < 20 else [0.3]
+        orc.ViNant = list(c.ViNant)
+        vin = c.ViNant[0]
+        sol = c.mpc(x0=x, ySP=ysp, w0=w0, u0=u, lam_w0=[], lam_g0=[])
+        solo = orc.mpc(x, ysp, w0, u, [], [])
+        assert c.status == 0, (k, c.status)
+        scale = max(np.max(np.abs(solo['du_opt'])), 1e-3)
+        assert np.max(np.abs(sol['du_opt'].full() - solo['du_opt'])) <= RTOL * scale, k
+        assert abs(float(sol['J']) - solo['J']) <= RTOL * max(abs(solo['J']), 1e-9), k
+        siN = float(sol['w_opt'].full().reshape(-1)[-2])
+        if np.isfinite(vin):
+            assert abs(siN) <= np.sqrt(vin) + VIOL, k              # the row itself, north-star violation bound
+            if abs(siN) >= np.sqrt(vin) * (1 - 1e-6):
+                tight += 1
+        assert abs(np.sqrt(c.ViNant[0]) - np.sqrt(orc.ViNant[0])) <= max(VIOL, 1e-6 * np.sqrt(orc.ViNant[0])), k
+        res = c.dynF(x0=x, du0=sol['du_opt'][:, 0].full(), u0=u)
+        x = res['xkp1'].full().reshape(-1); u = res['ukp1'].full().reshape(-1)
+        w0 = c.warmStart(sol, ysp)
+    assert abs(float((s.C @ x)[0]) - 0.3) < 0.1          # on its way to the last set-point (the pinned siN slows it)
+    assert tight >= 10         # the row binds on most steps once the limit has contracted
+
+
 def test_log_variant_ss_bound_active():
     """One weighted objective only: the stationary ss = sqrt(m/2) < 1, so ss >= 1 (log.py:390-392) is active."""
     from oracle.ihmpc_log_oracle import OracleIHMPCLog
