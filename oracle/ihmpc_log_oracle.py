@@ -314,7 +314,14 @@ class OracleIHMPCLog(OracleIHMPC):
                 break
         sg = np.array([a_[2] for a_ in active])
         lam_min = float(np.min(sg * lam)) if len(active) else 0.0       # >= 0: multipliers have the KKT sign
-        return v, dict(stationarity=stat, n_active=len(active), lam=lam, lam_min=lam_min)
+        # multipliers in casadi's convention (grad f + sum lam grad g = 0, > 0 at an upper bound): row kinds
+        # ('U', k) input box row k of U_pred, ('dU', k) move box, ('lin', k) extra linear row, ('ss',), ('d', i)
+        duals = {}
+        for (kind, k, sg_), la in zip(active, lam):
+            key = ('U', k) if (kind == 'lin' and k < nv) else (('dU', k - nv) if (kind == 'lin' and k < 2 * nv) else
+                  (('lin', k - 2 * nv) if kind == 'lin' else ((kind,) if kind == 'ss' else (kind, k))))
+            duals[key] = -float(la)
+        return v, dict(stationarity=stat, n_active=len(active), lam=lam, lam_min=lam_min, duals=duals)
 
     def warmStart(self, sol, ysp):                                # log.py:518-549
         w0 = np.asarray(sol['w_opt']).reshape(-1)

@@ -162,9 +162,10 @@ class IHMPCController(_Weighted):
         res2 = XN[:self.nxs] - ysp - w[nv:nv + ny]
         sat = np.array([w[-1] * V.gamma - vals[self.V.index(V)] for V in self.VJ])
         gvec = np.concatenate([x_pred, u_pred, res1, res2, vals, sat])           # log.py:394-440
+        lam_w, lam_g = self._log_duals(x, u, ysp, w, vals, vin, gvec.size)
         sol = {
             'J': DM(J), 'du_opt': DM(w[:nv].reshape(N, nu).T), 'w_opt': DM(w),
-            'lam_w': DM(np.zeros(w.size)), 'lam_g': DM(np.zeros(gvec.size)), 'g': DM(gvec),
+            'lam_w': DM(lam_w), 'lam_g': DM(lam_g), 'g': DM(gvec),
             'x_pred': DM(x_pred), 'y_pred': DM(y_pred), 'u_pred': DM(u_pred),
         }
         if len(self.ViNant):                                   # log.py:558-561
@@ -178,6 +179,90 @@ class IHMPCController(_Weighted):
         self.du = sol['du_opt'][:, 0].full()
         self.j_value = J
         return sol
+
+    def _log_duals(self, x, u, ysp, w, vals, vin, dim_g):
+        """sol['lam_w'] (nw + 1: moves, syN, siN, ss) and sol['lam_g'] (g layout of log.py:394-440: X_pred, U_pred, res1,
+        res2, the len(V) rows 0 <= V_i, the m rows ss gamma_i - V_i >= 0.01), casadi's sign convention, which the
+        reference feeds back as IPOPT's warm start (example_distillation_log.py:101-103).  The kernel is a primal
+        barrier method, so the multipliers are recovered on the host from the optimum it returns: the inequality rows
+        that sit on their bound (move box, U_pred rows, ss >= 1, the 0.01 rows, siN contraction) by least squares on
+        stationarity  grad phi + sum lam grad g = 0  in (dU, ss), the terminal-residual rows res1 / res2 from
+        stationarity in siN / syN like the weighted class (the weights being 1/d_i here)."""
+        p = self._plan
+        N, nu, ny, nx, m = self.N, self.nu, self.ny, self.nx, len(self.VJ)
+        nv = N * nu
+        dU, ss = w[:nv], w[-1]
+        Vi = np.array([vals[self.V.index(V)] for V in self.VJ])
+        gam = np.array([V.gamma for V in self.VJ], dtype=float)
+        d = ss * gam - Vi
+        inv = 1.0 / d
+        e = p.Px @ x + p.Py @ ysp + p.e0
+        r = p.E @ dU + e
+        om = p.Wrow @ inv + p.w0row
+        grad_V = [2.0 * p.E.T @ (p.Wrow[:, i] * r) + 2.0 * p.Wdu[:, i] * dU for i in range(m)]
+        g = np.zeros(nv + 1)
+        g[:nv] = 2.0 * p.E.T @ (om * r) + 2.0 * (p.Wdu @ inv) * dU
+        g[nv] = 2.0 * ss - float(gam @ inv)
+        rows, keys = [], []                                   # (normal over (dU, ss), key) of the rows on a bound
+        tol = 1e-7
+        Tc = np.kron(np.tril(np.ones((N, N))), np.eye(nu))
+        up = u[None, :] + np.cumsum(dU.reshape(N, nu), axis=0)
+        for k in range(nv):
+            j = k % nu
+            if abs(dU[k] - np.asarray(self.dulb, float)[j]) <= tol or abs(dU[k] - np.asarray(self.duub, float)[j]) <= tol:
+                n_ = np.zeros(nv + 1); n_[k] = 1.0; rows.append(n_); keys.append(('w', k))
+            uk = up[k // nu, j]
+            if abs(uk - np.asarray(self.ulb, float)[j]) <= tol or abs(uk - np.asarray(self.uub, float)[j]) <= tol:
+                n_ = np.zeros(nv + 1); n_[:nv] = Tc[k]; rows.append(n_); keys.append(('U', k))
+        if ss - 1.0 <= tol:
+            n_ = np.zeros(nv + 1); n_[nv] = 1.0; rows.append(n_); keys.append(('ss',))
+        for i in range(m):
+            if d[i] - 0.01 <= tol:
+                n_ = np.zeros(nv + 1); n_[:nv] = -grad_V[i]; n_[nv] = gam[i]; rows.append(n_); keys.append(('d', i))
+        siN = w[nv + ny:nv + 2 * ny]
+        for rr, kind in enumerate(p.row_kind):
+            if kind[0] == 'vin' and len(vin) and np.isfinite(vin[kind[1]]):
+                ind, q = self._vin[kind[1]]
+                if abs(abs(siN[ind]) - np.sqrt(max(vin[kind[1]], 0.0) / q)) <= tol:
+                    n_ = np.zeros(nv + 1); n_[:nv] = 2.0 * q * siN[ind] * p.Gc[rr][:nv]; rows.append(n_); keys.append(('vin', kind[1]))
+        lam = np.zeros(0)
+        if rows:
+            lam = np.linalg.lstsq(np.array(rows).T, -g, rcond=None)[0]
+        lam_w = np.zeros(nv + 2 * ny + 1)
+        lam_g = np.zeros(dim_g)
+        o_res1, o_res2, o_V, o_sat = N * nx + nv, N * nx + nv + ny, N * nx + nv + 2 * ny, N * nx + nv + 2 * ny + len(self.V)
+        extra_si = np.zeros(ny)
+        for key, la in zip(keys, lam):
+            if key[0] == 'w':
+                lam_w[key[1]] = la
+            elif key[0] == 'U':
+                lam_g[N * nx + key[1]] = la
+            elif key[0] == 'ss':
+                lam_w[-1] = la
+            elif key[0] == 'd':
+                lam_g[o_sat + key[1]] = la
+            elif key[0] == 'vin':
+                slot = key[1]
+                owner = [i for i, (kd, k) in enumerate(self._vin_of) if kd == 'row' and k == slot][0]
+                V = next(V for V in self.V if V.coeff.vin_slot == owner)
+                lam_g[o_V + self.V.index(V)] = la
+                ind, q = self._vin[slot]
+                extra_si[ind] += 2.0 * q * siN[ind] * la
+        # res2 / res1: stationarity in syN / siN with the weights 1/d_i plus the multipliers of the 0.01 rows
+        wts = inv.copy()
+        for key, la in zip(keys, lam):
+            if key[0] == 'd':
+                wts[key[1]] -= la                               # d/dsyN of lam (ss gamma - V_i) = -lam dV_i/dsyN
+        omr = p.Wrow @ wts + p.w0row
+        syN = w[nv:nv + ny]
+        Y = (p.Myx @ x + p.Myu[:, :nv] @ dU).reshape(N, ny)
+        r_y = Y - ysp[None, :] - syN[None, :] - p.tau[:, None] * siN[None, :]
+        om_y = omr[:N * ny].reshape(N, ny)
+        a, b = p.row_slices['syN']; om_sy = omr[a:b]
+        a, b = p.row_slices['siN']; om_si = omr[a:b]
+        lam_g[o_res2:o_res2 + ny] = -2.0 * np.sum(om_y * r_y, axis=0) + 2.0 * om_sy * syN
+        lam_g[o_res1:o_res1 + ny] = -2.0 * np.sum(om_y * r_y * p.tau[:, None], axis=0) + 2.0 * om_si * siN + extra_si
+        return lam_w, lam_g
 
     def warmStart(self, sol, ysp):                             # log.py:518-549
         w0 = np.asarray(sol['w_opt']).reshape(-1)

@@ -466,6 +466,55 @@ def test_no_kernel_writes_outside_its_buffers(which, monkeypatch):
     monkeypatch.delenv("SIHMPC_NO_FAST", raising=False); monkeypatch.delenv("SIHMPC_FAST", raising=False)
 
 
+def test_histories_of_a_scenario_subset_and_result_export(tmp_path):
+    """Per-step histories for a SUBSET of a big batch (sihmpc_b200.history.trace_subset) equal what the drop-in class
+    records scenario by scenario (j_hist, v_hist, peso_hist: ihmpccontroller.py:592-601) and what the batched engine
+    computes for those scenarios inside the full batch; the pickle has the reference's layout and file name
+    (example_distillation_log.py:263-269)."""
+    import pickle
+    from sihmpc_b200.history import trace_subset, export_results
+    sys_ = sc.distillation_system()
+    c = sc.declare_distillation(IHMPCController, sys_)
+    B, T = 512, 30
+    scen = sc.distillation_scenarios(B)
+    scen["seg_start"][:, 1] = 4; scen["seg_start"][:, 2] = 15
+    picks = [3, 200, 511]
+    h = trace_subset(c, scen, picks, T)
+    eng = c.engine(B)
+    eng.set_state(scen["x0"], scen["u0"]); eng.set_schedule(scen["ysp_seq"], scen["seg_start"])
+    eng.set_disturbance(scen["dist_step"], scen["dist"])
+    tr = eng.run(T, record=True)
+    du = tr["du"].cpu().numpy(); J = tr["J"].cpu().numpy(); y = tr["y"].cpu().numpy()
+    for a, idx in enumerate(picks):
+        assert np.max(np.abs(h["du"][a].T - du[:, idx])) <= 1e-12
+        assert np.max(np.abs(h["J"][a] - J[:, idx])) <= 1e-12 * max(1.0, np.max(np.abs(J[:, idx])))
+        assert np.max(np.abs(h["y"][a][:, 1:].T - y[:, idx])) <= 1e-10
+    # the drop-in class on scenario 200, step by step
+    idx = 200
+    cc = sc.declare_distillation(IHMPCController, sys_)
+    x = scen["x0"][idx].copy(); u = scen["u0"][idx].copy(); w0 = []; pesos = []
+    f = schedule_fn(scen["ysp_seq"][idx], scen["seg_start"][idx])
+    for k in range(T):
+        sol = cc.mpc(x0=x, ySP=f(k), w0=w0, u0=u, pesos=pesos)
+        res = cc.dynF(x0=x, u0=u, du0=cc.du)
+        x = res['xkp1'].full().reshape(-1); u = res['ukp1'].full().reshape(-1)
+        if k == int(scen["dist_step"][idx]):
+            x[:2] += scen["dist"][idx]
+        w0 = cc.warmStart(sol, f(k))
+        pesos, _ = cc.satWeights2(x, u, w0, f(k))
+    a = picks.index(idx)
+    assert np.allclose(h["J"][a], cc.j_hist, rtol=1e-9, atol=1e-14)
+    assert np.allclose(h["v"][a].T, np.array([V.v_hist for V in cc.V]).T, rtol=1e-8, atol=1e-12)
+    assert np.allclose(h["pesos"][a].T, np.array([V.peso_hist for V in cc.VJ]).T, rtol=1e-8)
+    path = export_results(c, h, a, path=str(tmp_path / "out.dat"))
+    tup = pickle.load(open(path, "rb"))
+    assert len(tup) == 8 and tup[0].shape == (2, T + 1) and tup[1].shape == (2, T) and tup[3].shape == (sys_.nx, T)
+    assert tup[4].shape == (len(c.V), T) and tup[5].shape == (len(c.VJ), T) and tup[6].shape == (T,)
+    import os
+    assert os.path.basename(export_results(c, h, a, path=None)).startswith("dist_10_[")
+    os.remove(export_results(c, h, a, path=None))
+
+
 def test_fast_path_handover_many_rounds(monkeypatch):
     """Quad fast path with a tiny grid (many scenarios per quad, one after the other) on a bound
     set that makes a good share of the scenarios hand over to the exact active-set kernel mid-loop:
@@ -816,6 +865,18 @@ def test_log_variant_active_inequalities_match_oracle(bname, bounds):
         if min(solo['info']['margins']) <= 1e-8:
             n_constrained += 1
             assert orc.last_kkt['stationarity'] <= 1e-8 and orc.last_kkt['lam_min'] >= -1e-9
+            # duals (log.py:489-513; fed back as IPOPT's warm start by example_distillation_log.py:101-103) against
+            # the oracle's KKT multipliers, casadi's sign convention
+            N_, nu_, nx_ = 10, 2, sys_.nx
+            lw = sol['lam_w'].full().reshape(-1); lg = sol['lam_g'].full().reshape(-1)
+            assert lw.size == N_ * nu_ + 4 + 1 and lg.size == 260
+            big = max(1.0, max(abs(v) for v in orc.last_kkt['duals'].values()))
+            for key, val in orc.last_kkt['duals'].items():
+                if abs(val) < 1e-6 * big:
+                    continue                                   # weakly active rows: the set is not unique
+                mine = lw[key[1]] if key[0] == 'dU' else (lg[N_ * nx_ + key[1]] if key[0] == 'U' else
+                       (lw[-1] if key[0] == 'ss' else lg[N_ * nx_ + N_ * nu_ + 4 + len(c.V) + key[1]]))
+                assert abs(mine - val) <= 1e-4 * big, (k, key, mine, val)
         assert c.status == 0
         du = sol['du_opt'][:, 0].full().reshape(-1)
         scale = max(scale, np.max(np.abs(solo['du_opt'])))
