@@ -21,7 +21,7 @@ struct MmaPlan {
     int N, nxp, nve;         // horizon, state capacity (multiple of 8) and live variables of the instantiation
     MmaConst qc;
     double *qbuf;
-    int *ctr;                // in the caller's workspace (mma_bind): [n_handover | n_fail | n_inkernel | pad | start_step[cap] | list[cap]]
+    int *ctr;                // in the caller's workspace (mma_bind): [n_handover | n_fail | n_inkernel | first-pass CTAs done | entries claimed | pad x3 | start_step[cap] | list[cap]]
     int grid_cap;            // debug: upper limit of the grid (0: none)
     int *start_step;
     int *n_handover;         // scenarios the first pass appended to `list` (counter baseline 0x7f7f7f7f)
@@ -35,6 +35,11 @@ struct MmaPlan {
     // controller-resident stepping (sihmpc_resident_step): set for the launches of one call, first pass = MODE 3
     int res_active, res_flags;                 // weight rule to apply before the solve (0: first call, none)
     const double *res_wstart, *res_ysp_prev;   // warm start of the previous solve, the set-point it was made for
+    // streaming resume (MODE 4): workers on an auxiliary stream consume the hand-over list while the first pass runs
+    cudaStream_t aux;
+    cudaEvent_t ev_fork, ev_join;
+    int stream_workers;      // CTAs of the worker launch (0: resume pass after the first pass, as in round 1)
+    int sm_count;
 };
 
 
@@ -48,11 +53,11 @@ void mma_destroy(MmaPlan *qp);
 // the hand-over block lives in the caller's workspace (capi.cu: bind_handover): nothing is allocated at step time
 inline void mma_bind(MmaPlan *qp, int *ctr, long long batch) {
     qp->ctr = ctr; qp->n_handover = ctr; qp->n_fail = ctr + 1; qp->n_inkernel = ctr + 2;
-    qp->start_step = ctr + 4; qp->list = ctr + 4 + batch; qp->capacity = batch;
+    qp->start_step = ctr + 8; qp->list = ctr + 8 + batch; qp->capacity = batch;
 }
 // counters and start_step back to "nothing handed over" (every counter counts up from the baseline 0x7f7f7f7f)
 inline cudaError_t mma_reset(const MmaPlan &qp, long long batch, cudaStream_t st) {
-    return cudaMemsetAsync(qp.ctr, 0x7f, (size_t)(4 + batch) * sizeof(int), st);
+    return cudaMemsetAsync(qp.ctr, 0x7f, (size_t)(8 + 2 * batch) * sizeof(int), st);      // counters, start_step[] AND list[] (entry = "not published")
 }
 // the resume pass is one more launch: only worth it when the call carries enough work (not the single-step host API)
 inline bool mma_resumes(const MmaPlan &qp, long long batch, int n_steps) { return qp.qc.cspace >= 0 && (n_steps > 1 || batch >= 4096); }

@@ -382,12 +382,22 @@ __device__ __forceinline__ void mma_weight_update(const double *__restrict__ cst
     }
 }
 
+// loads of per-scenario state that ANOTHER kernel may have written while this one runs (the streaming resume workers
+// read what the first pass hands over): around L1, which is not coherent across SMs
+template <bool CG>
+__device__ __forceinline__ double mma_gload(const double *p) { return CG ? __ldcg(p) : *p; }
+__device__ __forceinline__ int mma_vload(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
+
 // MODE 0: first pass.  Unconstrained optimum + bound check; a scenario that violates a bound is appended to `list`
 //         and leaves the kernel (the active set inlined here cost the hot loop 20 %: register pressure).
 // MODE 1: resume pass over the scenarios of `list` (n_list = their counter), each from its own start_step, with the
 //         in-kernel active set (mma_active_set); eight listed scenarios per warp, every quad on its own step index.
 //         What it cannot resolve is flagged in start_step / n_handover for the general kernel (third pass).
 // MODE 2: first pass with the active set inline (workloads where most scenarios sit on bounds).
+// MODE 4: STREAMING resume workers.  A handful of CTAs launched WITH the first pass (second stream): every warp claims
+//         the next entry of the hand-over list (atomic), waits until the first pass has published it (the entry is
+//         written after the scenario's state and a fence) or has finished, and steps that scenario like MODE 1 -- the
+//         resume pass is a latency chain of a few dozen scenarios, this overlaps all of it but the last entries.
 // MODE 3: first pass of CONTROLLER-RESIDENT stepping (sihmpc_resident_step, one step per launch, no plant): the
 //         weights are brought up to date FIRST, at the measured state with the plan of the previous solve
 //         (res_wstart / io.w_opt / res_ysp_prev), then the step is MODE 0.
@@ -397,18 +407,22 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
                 const long long batch, const int n_steps, int *__restrict__ start_step,
                 int *__restrict__ n_handover, int *__restrict__ n_inkernel, int *__restrict__ list,
                 const int *__restrict__ n_list, const double *__restrict__ res_wstart = nullptr,
-                const double *__restrict__ res_ysp_prev = nullptr, const int res_flags = 0) {
-    constexpr bool AS = (MODE == 1 || MODE == 2), RESUME = (MODE == 1), RESIDENT = (MODE == 3);
+                const double *__restrict__ res_ysp_prev = nullptr, const int res_flags = 0,
+                int *__restrict__ sync_ctr = nullptr, const int n_first_ctas = 0) {
+    // sync_ctr[0]: CTAs of the first pass that have finished, sync_ctr[1]: list entries claimed by the workers
+    constexpr bool STREAM = (MODE == 4);
+    constexpr bool AS = (MODE == 1 || MODE == 2 || MODE == 4), RESUME = (MODE == 1 || MODE == 4), RESIDENT = (MODE == 3);
     long long n_work = batch;
     // resume pass over a SHORT list: one listed scenario per warp instead of eight -- the quads of a warp iterate in
     // lockstep, so a warp of eight constrained scenarios pays the rounds of the slowest one at every step; alone in
     // its warp a scenario pays its own (the pass is a latency tail of a few dozen scenarios, not throughput)
     bool spread = false;
-    if constexpr (RESUME) {
+    if constexpr (RESUME && !STREAM) {
         n_work = (long long)(*n_list) - 0x7f7f7f7f;
         spread = n_work <= (long long)gridDim.x * WARPS;
         if ((long long)blockIdx.x * WARPS * (spread ? 1 : 8) >= n_work) return;
     }
+    if constexpr (STREAM) spread = true;
     constexpr int NU = D::NU, NY = D::NY, M = D::M, NV = D::NV, NYP = D::NYP, R = D::R;
     const int nxr = P.nx;                     // states of THIS model (<= D::NX = 8 TX: the compiled capacity)
     constexpr int SV = D::SV, TX = D::TX, TR = D::TR, TV = D::TV, TY = D::TY, TQ = D::TQ, TC = D::TC, TM = D::TM;
@@ -438,16 +452,47 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
     const long long gq = spread ? ((q == 0) ? (long long)blockIdx.x * WARPS + wib : n_work)
                                 : ((long long)blockIdx.x * WARPS + wib) * 8 + q;
     const long long nq = (long long)gridDim.x * WARPS * 8;
-    const long long rounds = spread ? 1 : (n_work + nq - 1) / nq;
+    const long long rounds = STREAM ? (1LL << 40) : (spread ? 1 : (n_work + nq - 1) / nq);
     const int nstat = NY + SIHMPC_NSTATS_EXTRA;
     const bool advance = (io.flags & SIHMPC_F_ADVANCE) != 0;
     const int mh = P.mh;
 
     for (long long rd = 0; rd < rounds; ++rd) {
         long long s = gq + rd * nq;
-        const bool valid = s < n_work;
+        bool valid = s < n_work;
         int st0 = 0, n_iter = n_steps;
-        if constexpr (RESUME) {
+        if constexpr (STREAM) {
+            // claim the next list entry; wait (lane 0 polls, around L1) until it is published or the first pass is over
+            int got = -1;
+            if (lane == 0) {
+                const int idx = atomicAdd(sync_ctr + 1, 1) - 0x7f7f7f7f;
+                unsigned long long t_start, t_now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+                for (;;) {                                                           // bounded (2 s): a lost worker only delays
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
+                    if (t_now - t_start > 2000000000ull) break;
+                    const int npub = mma_vload(n_list) - 0x7f7f7f7f;
+                    if (idx < npub) {
+                        const int e = mma_vload(list + idx);
+                        if (e != 0x7f7f7f7f) { got = e; break; }
+                    } else if (mma_vload(sync_ctr) - 0x7f7f7f7f >= n_first_ctas) {
+                        if (idx >= mma_vload(n_list) - 0x7f7f7f7f) break;             // nothing more will come
+                        continue;
+                    }
+                    __nanosleep(256);
+                }
+            }
+            got = __shfl_sync(0xffffffffu, got, 0);
+            if (got < 0) break;                                                        // uniform
+            __threadfence();
+            s = got;
+            valid = (q == 0);
+            st0 = valid ? mma_vload(start_step + s) : n_steps;
+            if (st0 < 0 || st0 > n_steps) st0 = n_steps;
+            n_iter = __reduce_max_sync(0xffffffffu, n_steps - st0);
+            __syncwarp();
+            if (valid && g == 0) start_step[s] = 0x7f7f7f7f;    // resolved here unless flagged again below
+        } else if constexpr (RESUME) {
             s = valid ? list[s] : 0;
             st0 = valid ? start_step[s] : n_steps;
             if (st0 < 0 || st0 > n_steps) st0 = n_steps;
@@ -484,22 +529,22 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int r = 8 * T + 2 * g + h;
-                xr[T][h] = (r < nxr) ? io.x[sc * nxr + r] : 0.0;
+                xr[T][h] = (r < nxr) ? mma_gload<STREAM>(io.x + sc * nxr + r) : 0.0;
             }
         double uu[NU], pes[M], ise[2];
         double st_du2 = 0.0, st_viol = 0.0, st_J = 0.0;
         int st_or = 0;
         unsigned mlo = 0u, mhi = 0u;         // warm start of the in-kernel active set (bound masks of the last step)
 #pragma unroll
-        for (int j = 0; j < NU; ++j) uu[j] = io.u[sc * NU + j];
+        for (int j = 0; j < NU; ++j) uu[j] = mma_gload<STREAM>(io.u + sc * NU + j);
 #pragma unroll
-        for (int i = 0; i < M; ++i) pes[i] = io.pesos[sc * M + i];
+        for (int i = 0; i < M; ++i) pes[i] = mma_gload<STREAM>(io.pesos + sc * M + i);
         ise[0] = ise[1] = 0.0;
         if (io.stats) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) ise[h] = (2 * g + h < NY) ? io.stats[sc * nstat + 2 * g + h] : 0.0;
-            st_du2 = io.stats[sc * nstat + NY]; st_viol = io.stats[sc * nstat + NY + 1];
-            st_J = io.stats[sc * nstat + NY + 2]; st_or = (int)io.stats[sc * nstat + NY + 3];
+            for (int h = 0; h < 2; ++h) ise[h] = (2 * g + h < NY) ? mma_gload<STREAM>(io.stats + sc * nstat + 2 * g + h) : 0.0;
+            st_du2 = mma_gload<STREAM>(io.stats + sc * nstat + NY); st_viol = mma_gload<STREAM>(io.stats + sc * nstat + NY + 1);
+            st_J = mma_gload<STREAM>(io.stats + sc * nstat + NY + 2); st_or = (int)mma_gload<STREAM>(io.stats + sc * nstat + NY + 3);
         }
 
         // state of an alive scenario back to global memory (end of the launch, or hand-over)
@@ -684,12 +729,17 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
             if (alive && (viol > 0.0 || notpd)) {
                 alive = false;             // hand over from this step on (MODE 0: resume pass; else: general kernel)
                 mlo = mhi = 0u;
+                // the state first, then (fence) the step it stopped at, then (fence) the list entry: a streaming worker
+                // that sees the entry sees everything behind it
+                write_state();
+                __threadfence();
+                __syncwarp(0xFu << (lane & ~3));            // THIS quad only: the branch is per quad (never a full-warp barrier here)
                 if (g == 0) {
                     start_step[s] = step;
+                    __threadfence();
                     const int slot = atomicAdd(n_handover, 1) - 0x7f7f7f7f;
-                    if constexpr (MODE == 0) list[slot] = (int)s;
+                    if constexpr (MODE == 0 || MODE == 3) atomicExch(list + slot, (int)s);
                 }
-                write_state();
             }
             // ---------------- K3: r = e + E dU, cost, slacks
             double syv[3 * NY];
@@ -818,6 +868,12 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
 #pragma unroll
                 for (int i = 0; i < M; ++i) io.pesos[s * M + i] = pes[i];
             }
+        }
+    }
+    if constexpr (MODE == 0) {
+        if (sync_ctr) {                    // this CTA of the first pass is done: the workers stop waiting once all are
+            __syncthreads();
+            if (threadIdx.x == 0) { __threadfence(); atomicAdd(sync_ctr, 1); }
         }
     }
 }
@@ -1119,9 +1175,11 @@ inline cudaError_t mma_configure_shape(const sihmpc_plan_desc *d, const DevPlan 
     auto kern = mma_step_kernel<D, MMA_WARPS, MMA_MINB, 0>;
     auto kern_resume = mma_step_kernel<D, MMA_WARPS, MMA_MINB, 1>;
     auto kern_resident = mma_step_kernel<D, MMA_WARPS, MMA_MINB, 3>;
+    auto kern_stream = mma_step_kernel<D, MMA_WARPS, MMA_MINB, 4>;
     e = sih_raise_smem_limit(reinterpret_cast<const void *>(kern), qp->smem_bytes);
     if (e == cudaSuccess) e = sih_raise_smem_limit(reinterpret_cast<const void *>(kern_resume), qp->smem_bytes);
     if (e == cudaSuccess) e = sih_raise_smem_limit(reinterpret_cast<const void *>(kern_resident), qp->smem_bytes);
+    if (e == cudaSuccess) e = sih_raise_smem_limit(reinterpret_cast<const void *>(kern_stream), qp->smem_bytes);
     if (e != cudaSuccess) return e;
     int occ = 0, occ_r = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, MMA_WARPS * 32, qp->smem_bytes);
@@ -1136,6 +1194,29 @@ inline cudaError_t mma_configure_shape(const sihmpc_plan_desc *d, const DevPlan 
 template <typename D>
 inline cudaError_t mma_launch_shape(MmaPlan &qp, const DevPlan &P, const sihmpc_io &io, long long batch,
                                     int n_steps, int grid, cudaStream_t st, bool allow_resume) {
+    const bool stream_resume = allow_resume && !qp.res_active && qp.aux && mma_resumes(qp, batch, n_steps) && qp.stream_workers > 0;
+    if (stream_resume) {
+        // workers on the auxiliary stream, concurrent with the first pass (which leaves them room when it fills the GPU)
+        const int nw = qp.stream_workers;
+        const int cap = qp.blocks_per_sm * qp.sm_count;
+        const int g1 = (grid + nw > cap) ? ((cap - nw > 1) ? cap - nw : 1) : grid;
+        cudaError_t e = cudaEventRecord(qp.ev_fork, st);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(qp.aux, qp.ev_fork, 0);
+        if (e != cudaSuccess) return e;
+        mma_step_kernel<D, MMA_WARPS, MMA_MINB, 4><<<nw, MMA_WARPS * 32, qp.smem_bytes, qp.aux>>>(
+            P, qp.qc, qp.qbuf, io, batch, n_steps, qp.start_step, qp.n_fail, qp.n_inkernel, qp.list, qp.n_handover,
+            nullptr, nullptr, 0, qp.ctr + 3, g1);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        mma_step_kernel<D, MMA_WARPS, MMA_MINB, 0><<<g1, MMA_WARPS * 32, qp.smem_bytes, st>>>(
+            P, qp.qc, qp.qbuf, io, batch, n_steps, qp.start_step, qp.n_handover, qp.n_inkernel, qp.list, nullptr,
+            nullptr, nullptr, 0, qp.ctr + 3, g1);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaEventRecord(qp.ev_join, qp.aux);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(st, qp.ev_join, 0);
+        qp.last_resumed = 1;
+        return e;
+    }
     if (qp.res_active) {
         mma_step_kernel<D, MMA_WARPS, MMA_MINB, 3><<<grid, MMA_WARPS * 32, qp.smem_bytes, st>>>(
             P, qp.qc, qp.qbuf, io, batch, n_steps, qp.start_step, qp.n_handover, qp.n_inkernel, qp.list, nullptr,

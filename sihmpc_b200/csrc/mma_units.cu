@@ -60,7 +60,21 @@ cudaError_t mma_configure(const sihmpc_plan_desc *d, const DevPlan &P, MmaPlan *
     const MmaPlan sel = *qp;
     cudaError_t e = mma_unit(sel, 0, d, P, *qp, nullptr, 0, 0, 0, nullptr, false);
     if (e != cudaSuccess) return e;
-    return cudaSuccess;              // (mma_configure_shape sets shape = -1 itself when the kernel cannot be resident)
+    if (qp->shape >= 0) {            // (mma_configure_shape sets shape = -1 itself when the kernel cannot be resident)
+        cudaDeviceProp prop;
+        int dev = 0;
+        e = cudaGetDevice(&dev);
+        if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, dev);
+        if (e != cudaSuccess) return e;
+        qp->sm_count = prop.multiProcessorCount;
+        qp->stream_workers = getenv("SIHMPC_NO_STREAM_RESUME") ? 0 : 2;
+        if (const char *wv = getenv("SIHMPC_STREAM_WORKERS")) { const int v = atoi(wv); if (v >= 0 && v <= 32) qp->stream_workers = v; }
+        e = cudaStreamCreateWithFlags(&qp->aux, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&qp->ev_fork, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&qp->ev_join, cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 cudaError_t mma_launch(MmaPlan &qp, const DevPlan &P, const sihmpc_io &io, long long batch, int n_steps, int sm_count,
@@ -76,6 +90,9 @@ cudaError_t mma_launch(MmaPlan &qp, const DevPlan &P, const sihmpc_io &io, long 
 
 void mma_destroy(MmaPlan *qp) {
     if (qp->qbuf) cudaFree(qp->qbuf);
+    if (qp->aux) cudaStreamDestroy(qp->aux);
+    if (qp->ev_fork) cudaEventDestroy(qp->ev_fork);
+    if (qp->ev_join) cudaEventDestroy(qp->ev_join);
     memset(qp, 0, sizeof *qp);
     qp->shape = -1;
 }
