@@ -515,6 +515,29 @@ def test_histories_of_a_scenario_subset_and_result_export(tmp_path):
     os.remove(export_results(c, h, a, path=None))
 
 
+def test_unstable_mismatch_scenario_is_flagged_not_nan():
+    """One scenario in 10^6 of the mismatch Monte-Carlo (global index 843890) is closed-loop UNSTABLE (gain and
+    time-constant mismatch; the oracle diverges on it too).  Its weights end up spanning 1e-9 ... 1e6 inside one
+    Hessian and a pivot comes out <= 0 in FP64: the step must be FLAGGED (SIHMPC_ST_NOTPD in the statistics) and
+    carried on with the shifted factorisation -- finite numbers, never NaN -- while its neighbours stay clean."""
+    from sihmpc_b200 import _capi
+    c = sc.declare_distillation(IHMPCController)
+    first, B, T = 843890 - 3, 8, 200
+    scen = sc.mismatch_scenarios(B, first=first)
+    eng = c.engine(B)
+    eng.set_state(scen["x0"], scen["u0"]); eng.set_schedule(scen["ysp_seq"], scen["seg_start"])
+    eng.set_plant_values(scen["plant_val"])
+    eng.run(T)
+    st = eng.stats.cpu().numpy(); x = eng.x.cpu().numpy()
+    assert np.isfinite(x).all() and np.isfinite(st).all()
+    flags = st[:, 2 + 3].astype(int)
+    assert np.abs(x[3]).max() > 1e2                     # the unstable one has run away ...
+    assert (np.abs(np.delete(x, 3, axis=0)) < 1e2 + 100).all()
+    assert (np.delete(flags, 3) == 0).all()             # ... its neighbours are clean
+    if flags[3]:
+        assert flags[3] & _capi.ST_NOTPD
+
+
 def test_fast_path_handover_many_rounds(monkeypatch):
     """Quad fast path with a tiny grid (many scenarios per quad, one after the other) on a bound
     set that makes a good share of the scenarios hand over to the exact active-set kernel mid-loop:
