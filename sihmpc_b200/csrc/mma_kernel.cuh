@@ -468,9 +468,9 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
                 const int idx = atomicAdd(sync_ctr + 1, 1) - 0x7f7f7f7f;
                 unsigned long long t_start, t_now;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
-                for (;;) {                                                           // bounded (2 s): a lost worker only delays
+                for (;;) {                                                           // bounded (0.5 s): a lost worker only delays
                     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
-                    if (t_now - t_start > 2000000000ull) break;
+                    if (t_now - t_start > 500000000ull) break;
                     const int npub = mma_vload(n_list) - 0x7f7f7f7f;
                     if (idx < npub) {
                         const int e = mma_vload(list + idx);
@@ -1215,7 +1215,13 @@ inline cudaError_t mma_launch_shape(MmaPlan &qp, const DevPlan &P, const sihmpc_
         if (e == cudaSuccess) e = cudaEventRecord(qp.ev_join, qp.aux);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(st, qp.ev_join, 0);
         qp.last_resumed = 1;
-        return e;
+        if (e != cudaSuccess) return e;
+        // sweep: the sequential resume pass over whatever the workers did not take (nothing, normally: resolved entries
+        // carry start_step = "done" and cost a state load).  It is what keeps the result right when the two kernels do
+        // NOT overlap -- a profiler or CUDA_LAUNCH_BLOCKING serialises them, the workers then give up after their bounded wait
+        mma_step_kernel<D, MMA_WARPS, MMA_MINB, 1><<<grid, MMA_WARPS * 32, qp.smem_bytes, st>>>(
+            P, qp.qc, qp.qbuf, io, batch, n_steps, qp.start_step, qp.n_fail, qp.n_inkernel, qp.list, qp.n_handover);
+        return cudaGetLastError();
     }
     if (qp.res_active) {
         mma_step_kernel<D, MMA_WARPS, MMA_MINB, 3><<<grid, MMA_WARPS * 32, qp.smem_bytes, st>>>(
