@@ -92,14 +92,21 @@ class OracleIHMPCLog(OracleIHMPC):
             self.nw = saved
         XN = self.X_pred[-1]
         XsN = XN[0:self.nxs]; XiN = XN[self.nxs + self.nxd:self.nxs + self.nxd + self.nxi]
-        # w(dU) = T dU + t0
-        T = np.zeros((nwq, nv)); t0 = np.zeros(nwq)
-        T[:nv] = np.eye(nv)
-        T[nv:nv + ny] = XsN[:, :nv]; t0[nv:nv + ny] = XsN @ xi0 - ySP - self.rslb
-        T[nv + ny:] = XiN[:, :nv]; t0[nv + ny:] = XiN @ xi0 - self.rilb
-        for lo, hi in ((self.rslb, self.rsub), (self.rilb, self.riub)):
-            if not np.array_equal(lo, hi):
-                raise NotImplementedError("terminal residual ranges")
+        # w(z) = T z + t0 with z = [dU ; rho]: a terminal residual held as an equality (rs/ri lb == ub, the default) is
+        # eliminated, syN = xs(N) - ysp - rs, siN = xi(N) - ri; a RANGED one (lb != ub, log.py:413-427) stays a decision
+        # variable rho in [lb, ub] after the moves: syN = xs(N) - ysp - rho_s, siN = xi(N) - rho_i
+        ext = [('s', i) for i in range(ny) if self.rslb[i] != self.rsub[i]] + \
+              [('i', i) for i in range(ny) if self.rilb[i] != self.riub[i]]
+        ne = len(ext)
+        nz = nv + ne
+        T = np.zeros((nwq, nz)); t0 = np.zeros(nwq)
+        T[:nv, :nv] = np.eye(nv)
+        T[nv:nv + ny, :nv] = XsN[:, :nv]; t0[nv:nv + ny] = XsN @ xi0 - ySP - self.rslb
+        T[nv + ny:, :nv] = XiN[:, :nv]; t0[nv + ny:] = XiN @ xi0 - self.rilb
+        for c_, (kind, i) in enumerate(ext):
+            row = nv + i if kind == 's' else nv + ny + i
+            T[row, nv + c_] = -1.0
+            t0[row] += self.rslb[i] if kind == 's' else self.rilb[i]     # no constant offset: rho is the variable
         # contraction rows q siN^2 <= ViN_ant (log.py:245-270, row bounds :429-434): |siN| <= sqrt(ViN_ant / q) is linear
         # in dU on an integrating plant; where siN cannot be moved (non-integrating: xi(N) = xi(0)) it must hold as is
         self._extra_lin = []                                   # (row over dU, lo, hi)
@@ -114,6 +121,10 @@ class OracleIHMPCLog(OracleIHMPC):
                         raise RuntimeError("siN contraction row violated and out of reach of the moves")
                 else:
                     self._extra_lin.append((T[k].copy(), -bound - t0[k], bound - t0[k]))
+        for c_, (kind, i) in enumerate(ext):                    # lb <= rho <= ub
+            row = np.zeros(nz); row[nv + c_] = 1.0
+            lo_, hi_ = (self.rslb[i], self.rsub[i]) if kind == 's' else (self.rilb[i], self.riub[i])
+            self._extra_lin.append((row, float(lo_), float(hi_)))
 
         def quad(V):
             Rw = V.R[:, :nwq] @ T
@@ -125,14 +136,14 @@ class OracleIHMPCLog(OracleIHMPC):
         m = len(terms)
 
         def evaluate(v):
-            dU, ss = v[:nv], v[nv]
-            rt = Rt @ dU + rt0
+            z, ss = v[:nz], v[nz]
+            rt = Rt @ z + rt0
             Vt = rt @ Wt @ rt
-            Vi = np.empty(m); gi = np.zeros((m, nv + 1)); Hi = []
+            Vi = np.empty(m); gi = np.zeros((m, nz + 1)); Hi = []
             for i, (Rw, r0, W) in enumerate(terms):
-                r = Rw @ dU + r0
+                r = Rw @ z + r0
                 Vi[i] = r @ W @ r
-                gi[i, :nv] = 2 * Rw.T @ W @ r
+                gi[i, :nz] = 2 * Rw.T @ W @ r
                 Hi.append(2 * Rw.T @ W @ Rw)
             d = ss * gam - Vi
             return Vt, Vi, d, gi, Hi, rt
@@ -141,26 +152,26 @@ class OracleIHMPCLog(OracleIHMPC):
             Vt, Vi, d, *_ = evaluate(v)
             if np.any(d <= 0):
                 return INF
-            return Vt + v[nv] ** 2 - np.sum(np.log(d))
+            return Vt + v[nz] ** 2 - np.sum(np.log(d))
 
         # start: warm start if given, else zeros with ss large enough
         w0 = np.asarray(w0, float).reshape(-1)
-        v = np.zeros(nv + 1)
+        v = np.zeros(nz + 1)
         if w0.size == nwq + 1:
-            v[:nv] = w0[:nv]; v[nv] = w0[-1]
+            v[:nv] = w0[:nv]; v[nz] = w0[-1]
         Vt, Vi, d, *_ = evaluate(v)
-        v[nv] = max(v[nv], 1.0, 1.1 * float(np.max(Vi / gam)) + 0.1)
+        v[nz] = max(v[nz], 1.0, 1.1 * float(np.max(Vi / gam)) + 0.1)
         iters = 0
         for iters in range(1, 200):
             Vt, Vi, d, gi, Hi, rt = evaluate(v)
-            g = np.zeros(nv + 1); H = np.zeros((nv + 1, nv + 1))
-            g[:nv] = 2 * Rt.T @ Wt @ rt
-            H[:nv, :nv] = 2 * Rt.T @ Wt @ Rt
-            g[nv] = 2 * v[nv]; H[nv, nv] = 2.0
+            g = np.zeros(nz + 1); H = np.zeros((nz + 1, nz + 1))
+            g[:nz] = 2 * Rt.T @ Wt @ rt
+            H[:nz, :nz] = 2 * Rt.T @ Wt @ Rt
+            g[nz] = 2 * v[nz]; H[nz, nz] = 2.0
             for i in range(m):
-                a = gi[i].copy(); a[nv] = -gam[i]               # grad of V_i - ss*gamma_i  (= -grad d_i)
+                a = gi[i].copy(); a[nz] = -gam[i]               # grad of V_i - ss*gamma_i  (= -grad d_i)
                 g += a / d[i]
-                H[:nv, :nv] += Hi[i] / d[i]
+                H[:nz, :nz] += Hi[i] / d[i]
                 H += np.outer(a, a) / d[i] ** 2
             p = -np.linalg.solve(H, g)
             dec = -g @ p
@@ -174,28 +185,29 @@ class OracleIHMPCLog(OracleIHMPC):
                 break                                          # rounding level reached
             v = v + t * p
         Vt, Vi, d, gi, Hi, rt = evaluate(v)
-        dU, ss = v[:nv], v[nv]
+        z, dU, ss = v[:nz], v[:nv], v[nz]
         # explicit inequalities must be strictly inactive
         u_pred = np.asarray(u0)[None, :] + np.cumsum(dU.reshape(N, nu), axis=0)
-        def margins(dU, ss, d, u_pred):
+        def margins(z, ss, d, u_pred):
+            dU = z[:nv]
             mg = [ss - 1.0, float(np.min(d - 0.01)),
                   float(np.min(u_pred - self.ulb)), float(np.min(self.uub - u_pred)),
                   float(np.min(dU.reshape(N, nu) - self.dulb)), float(np.min(self.duub - dU.reshape(N, nu)))]
             for row, lo_, hi_ in self._extra_lin:
-                mg.append(float(min(row @ dU - lo_, hi_ - row @ dU)))
+                mg.append(float(min(row @ z - lo_, hi_ - row @ z)))
             return mg
-        margin = margins(dU, ss, d, u_pred)
+        margin = margins(z, ss, d, u_pred)
         if min(margin) <= 1e-9:
             # an explicit inequality of the NLP is active: solve the constrained problem with SciPy's trust-constr
             # (its own interior point / SQP machinery -- independent of the product's barrier continuation), from a
             # strictly feasible start, then polish and certify through the KKT conditions below.
-            v, kkt = self._solve_constrained(evaluate, phi, Rt, Wt, gam, u0, nv, N, nu, m)
+            v, kkt = self._solve_constrained(evaluate, phi, Rt, Wt, gam, u0, nv, N, nu, m, nz, v_free=v.copy())
             Vt, Vi, d, gi, Hi, rt = evaluate(v)
-            dU, ss = v[:nv], v[nv]
+            z, dU, ss = v[:nz], v[:nv], v[nz]
             u_pred = np.asarray(u0)[None, :] + np.cumsum(dU.reshape(N, nu), axis=0)
-            margin = margins(dU, ss, d, u_pred)
+            margin = margins(z, ss, d, u_pred)
             self.last_kkt = kkt
-        w = np.concatenate([T @ dU + t0, [ss]])
+        w = np.concatenate([T @ z + t0, [ss]])
         xi = self._xi(w, x0, u0, ySP)
         J = float(Vt + ss ** 2 - np.sum(np.log(d)))
         sol = {
@@ -211,20 +223,21 @@ class OracleIHMPCLog(OracleIHMPC):
             self.ViNant[i] = self.F(V, [0] * self.nx, [0] * self.nu, warm, [0] * self.ny)
         return sol
 
-    def _solve_constrained(self, evaluate, phi, Rt, Wt, gam, u0, nv, N, nu, m):
+    def _solve_constrained(self, evaluate, phi, Rt, Wt, gam, u0, nv, N, nu, m, nz=None, v_free=None):
         """min phi(v) s.t. ss >= 1, ss*gamma_i - V_i >= 0.01, ulb <= u0 + cumsum(dU) <= uub, dulb <= dU <= duub
         (log.py:390-392,420-424,435-440).  Returns (v, kkt) with kkt = dict(stationarity, min multiplier)."""
         from scipy.optimize import minimize, LinearConstraint, NonlinearConstraint, Bounds
-        n = nv + 1
+        nz = nv if nz is None else nz                     # decision variables z = [dU ; rho] (ranged terminal residuals), then ss
+        n = nz + 1
 
         def fgh(v):
             Vt, Vi, d, gi, Hi, rt = evaluate(v)
             g = np.zeros(n); H = np.zeros((n, n))
-            g[:nv] = 2 * Rt.T @ Wt @ rt; H[:nv, :nv] = 2 * Rt.T @ Wt @ Rt
-            g[nv] = 2 * v[nv]; H[nv, nv] = 2.0
+            g[:nz] = 2 * Rt.T @ Wt @ rt; H[:nz, :nz] = 2 * Rt.T @ Wt @ Rt
+            g[nz] = 2 * v[nz]; H[nz, nz] = 2.0
             for i in range(m):
-                a = gi[i].copy(); a[nv] = -gam[i]
-                g += a / d[i]; H[:nv, :nv] += Hi[i] / d[i]; H += np.outer(a, a) / d[i] ** 2
+                a = gi[i].copy(); a[nz] = -gam[i]
+                g += a / d[i]; H[:nz, :nz] += Hi[i] / d[i]; H += np.outer(a, a) / d[i] ** 2
             return g, H
         # linear rows: cumulative input box and move box
         Tc = np.kron(np.tril(np.ones((N, N))), np.eye(nu))
@@ -233,7 +246,7 @@ class OracleIHMPCLog(OracleIHMPC):
         lo = np.concatenate([np.tile(self.ulb - u0, N), np.tile(self.dulb, N), np.zeros(ne)])
         hi = np.concatenate([np.tile(self.uub - u0, N), np.tile(self.duub, N), np.zeros(ne)])
         for k, (row, lo_, hi_) in enumerate(getattr(self, '_extra_lin', [])):       # siN contraction rows
-            A[2 * nv + k, :nv] = row; lo[2 * nv + k] = lo_; hi[2 * nv + k] = hi_
+            A[2 * nv + k, :nz] = row; lo[2 * nv + k] = lo_; hi[2 * nv + k] = hi_
         nrow = A.shape[0]
 
         def dfun(v):
@@ -241,40 +254,61 @@ class OracleIHMPCLog(OracleIHMPC):
 
         def djac(v):
             _, _, _, gi, _, _ = evaluate(v)
-            J = -gi.copy(); J[:, nv] = gam
+            J = -gi.copy(); J[:, nz] = gam
             return J
+        def start_active(v, from_violation):
+            cs = A @ v
+            active = []
+            tol_ = 0.0 if from_violation else 1e-7
+            for k in range(nrow):
+                if np.isfinite(lo[k]) and cs[k] - lo[k] < tol_: active.append(('lin', k, 1.0))
+                elif np.isfinite(hi[k]) and hi[k] - cs[k] < tol_: active.append(('lin', k, -1.0))
+            if v[nz] - 1.0 < tol_: active.append(('ss', 0, 1.0))
+            for i in range(m):
+                if dfun(v)[i] < tol_: active.append(('d', i, 1.0))
+            return active
+
+        # first attempt: primal active-set Newton from the UNCONSTRAINED optimum with the rows it violates held active
+        # (linear rows: one Newton step lands on them); accepted only with its KKT certificate
+        if v_free is not None:
+            try:
+                v1, kkt1 = self._polish(v_free.copy(), start_active(v_free, True), fgh, dfun, djac, phi, A, lo, hi, n, nz, nv, m)
+                c1 = A @ v1
+                feas = min(float(np.min(c1 - lo)), float(np.min(hi - c1)), v1[nz] - 1.0, float(np.min(dfun(v1))))
+                if kkt1['stationarity'] <= 1e-9 and kkt1['lam_min'] >= -1e-10 and feas >= -1e-9:
+                    return v1, kkt1
+            except np.linalg.LinAlgError:
+                pass
         # strictly feasible start: no moves, ss large
         v0 = np.zeros(n)
         Vi0 = evaluate(v0)[1]
-        v0[nv] = max(2.0, 1.1 * float(np.max((Vi0 + 0.02) / gam)) + 0.1)
+        v0[nz] = max(2.0, 1.1 * float(np.max((Vi0 + 0.02) / gam)) + 0.1)
         big = 1e30
 
         def fsafe(v):
             f = phi(v)
             return f if np.isfinite(f) else big
         res = minimize(fsafe, v0, jac=lambda v: fgh(v)[0], hess=lambda v: fgh(v)[1], method='trust-constr',
-                       bounds=Bounds(np.r_[np.full(nv, -np.inf), 1.0], np.full(n, np.inf), keep_feasible=True),
+                       bounds=Bounds(np.r_[np.full(nz, -np.inf), 1.0], np.full(n, np.inf), keep_feasible=True),
                        constraints=[LinearConstraint(A, lo, hi),      # (a state on a bound up to rounding: no keep_feasible)
                                     NonlinearConstraint(dfun, 0.0, np.inf, jac=djac, keep_feasible=True)],
                        options=dict(gtol=1e-8, xtol=1e-12, barrier_tol=1e-9, maxiter=400, initial_barrier_parameter=0.1))
         v = res.x
-        # polish: primal active-set Newton from there.  Rows: ('lin', k, +1/-1) of A v >= lo / <= hi, ('ss',), ('d', i).
-        cs = A @ v
-        active = []
-        for k in range(nrow):
-            if np.isfinite(lo[k]) and cs[k] - lo[k] < 1e-7: active.append(('lin', k, 1.0))
-            elif np.isfinite(hi[k]) and hi[k] - cs[k] < 1e-7: active.append(('lin', k, -1.0))
-        if v[nv] - 1.0 < 1e-7: active.append(('ss', 0, 1.0))
-        for i in range(m):
-            if dfun(v)[i] < 1e-7: active.append(('d', i, 1.0))
+        return self._polish(v, start_active(v, False), fgh, dfun, djac, phi, A, lo, hi, n, nz, nv, m)
+
+    @staticmethod
+    def _polish(v, active, fgh, dfun, djac, phi, A, lo, hi, n, nz, nv, m):
+        """Primal active-set Newton.  Rows: ('lin', k, +1/-1) of A v >= lo / <= hi, ('ss',), ('d', i).  Returns the
+        point and its KKT record (stationarity of the Lagrangian, multipliers in casadi's convention)."""
+        nrow = A.shape[0]
         lam = np.zeros(0); stat = np.inf
-        for _ in range(400):
+        for _ in range(1000):
             g, H = fgh(v)
             dj = djac(v); dv_ = dfun(v); cs = A @ v
             rows, rhs = [], []
             for kind, k, sg in active:
                 if kind == 'lin': rows.append(A[k]); rhs.append((lo[k] if sg > 0 else hi[k]) - cs[k])
-                elif kind == 'ss': e_ = np.zeros(n); e_[nv] = 1.0; rows.append(e_); rhs.append(1.0 - v[nv])
+                elif kind == 'ss': e_ = np.zeros(n); e_[nz] = 1.0; rows.append(e_); rhs.append(1.0 - v[nz])
                 else: rows.append(dj[k]); rhs.append(-dv_[k])
             Aa = np.array(rows).reshape(-1, n); ba = np.array(rhs)
             K = np.block([[H, Aa.T], [Aa, np.zeros((len(ba), len(ba)))]])
@@ -291,14 +325,18 @@ class OracleIHMPCLog(OracleIHMPC):
                 if np.isfinite(hi[k]) and (k, -1.0) not in act_lin and ds[k] > 1e-16:
                     tk = (hi[k] - cs[k]) / ds[k]
                     if tk < t: t, block = max(tk, 0.0), ('lin', k, -1.0)
-            if ('ss', 0, 1.0) not in active and step[nv] < -1e-16:
-                tk = (1.0 - v[nv]) / step[nv]
+            if ('ss', 0, 1.0) not in active and step[nz] < -1e-16:
+                tk = (1.0 - v[nz]) / step[nz]
                 if tk < t: t, block = max(tk, 0.0), ('ss', 0, 1.0)
-            while t > 1e-10:                                   # barrier domain and d_i >= 0.01 (nonlinear): backtrack
-                vn = v + t * step
-                dn = dfun(vn)
+            restoring = len(ba) > 0 and float(np.max(np.abs(ba))) > 1e-9      # step back ONTO violated rows: phi may rise
+            f_here, slope = phi(v), min(float(g @ step), 0.0)
+            while t > 1e-10:                                   # barrier domain and d_i >= 0.01 (nonlinear): backtrack;
+                vn = v + t * step                              # Armijo on phi: a Newton step from far away (trust-constr
+                dn = dfun(vn)                                  # stopped early) must not leave the region where it helps
                 inact = [i for i in range(m) if ('d', i, 1.0) not in active]
-                if np.isfinite(phi(vn)) and all(dn[i] >= -1e-13 for i in inact):
+                f_new = phi(vn)
+                if np.isfinite(f_new) and all(dn[i] >= -1e-13 for i in inact) and \
+                        (restoring or f_new <= f_here + 1e-4 * t * slope + 1e-13 * (1.0 + abs(f_here))):
                     break
                 t *= 0.5; block = None
             v = v + t * step
@@ -337,10 +375,10 @@ class OracleIHMPCLog(OracleIHMPC):
         return np.array([1.0 / (V.gamma - self.F(V, x, u, w0, ysp)) for V in self.VJ])
 
 
-def declare_distillation_log(cls, sys):
+def declare_distillation_log(cls, sys, **bounds):
     """example_distillation_log.py:43-61 (init_Qt is referenced without being called there)."""
     N = 10
-    c = cls(sys, N, ulb=[0, 0])
+    c = cls(sys, N, **{**dict(ulb=[0, 0]), **bounds})
     c.subObjComposed(y=[0], Q=1, sat=N * 0.5 ** 2)
     c.subObjComposed(y=[1], Q=1, sat=N * 2.0 ** 2)
     c.subObj(du=[0], Q=1, sat=N * 0.3 ** 2)

@@ -840,7 +840,6 @@ int sihmpc_stats_reduce(const double *stats, int64_t batch, int32_t nstat, doubl
 
 static int log_launch(sihmpc_plan *plan, const sihmpc_io &io, const double *w0, double *w_warm, int64_t batch,
                       int32_t n_steps, int32_t *iters, void *stream) {
-    if (plan->d.nv != plan->d.nvm) return fail(SIHMPC_E_INVALID, "log variant: ranged terminal residuals are not supported%s");
     const sih::LogLayout lay = sih::make_log_layout(plan->d);
     int wpb = 4;
     while (wpb > 1 && (size_t)lay.total * 8 * wpb > 200 * 1024) --wpb;

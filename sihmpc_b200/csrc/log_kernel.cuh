@@ -146,9 +146,11 @@ ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__
     double *vt = W + lay.vt, *xn = W + lay.xn, *uu = W + lay.uu;
     double *S1 = W + lay.s1, *S2 = W + lay.s2, *b1 = W + lay.b1, *b2 = W + lay.b2;
     double *glo = W + lay.glo, *ghi = W + lay.ghi, *T1 = W + lay.t1, *T2 = W + lay.t2, *vw = W + lay.vw;
+    double *vfree = W + lay.p;                              // minimiser of phi without the explicit inequalities
     const int ncd = P.ncd;
     const int nx = P.nx, nu = P.nu, ny = P.ny, nv = P.nv, m = P.m, R = P.R;
-    const int n = nv + 1, ld = n | 1, nw = nv + 2 * ny + 1;
+    const int nvm = P.nvm;                                  // moves; v[nvm..nv) = ranged terminal residuals rho (log.py:413-427)
+    const int n = nv + 1, ld = n | 1, nw = nvm + 2 * ny + 1;
     const int nstat = ny + SIHMPC_NSTATS_EXTRA;
     const bool advance = (io.flags & SIHMPC_F_ADVANCE) != 0;
     double *const w_opt = io.w_opt;
@@ -158,7 +160,7 @@ ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__
     for (long long s = gw; s < batch; s += nwarps) {
         for (int i = lane; i < nx; i += 32) xs[i] = io.x[s * nx + i];
         for (int i = lane; i < nu; i += 32) uu[i] = io.u[s * nu + i];
-        for (int i = lane; i < nv; i += 32) v[i] = w0 ? w0[s * nw + i] : 0.0;
+        for (int i = lane; i < nv; i += 32) v[i] = (w0 && i < nvm) ? w0[s * nw + i] : 0.0;
         if (lane == 0) v[nv] = w0 ? w0[s * nw + nw - 1] : 1.0;
         double st_ise = 0.0, st_du2 = 0.0, st_J = 0.0;      // lane i < ny holds the ISE of output i
         int st_or = 0, it_total = 0;
@@ -231,7 +233,7 @@ ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__
                 double gc = 2.0 * a;
                 for (int i = 0; i < m; ++i) gc += gi[i * nv + c] * w1f(i);
                 if (mu > 0.0) {
-                    gc += S1[c] + b1[c];
+                    if (c < nvm) gc += S1[c] + b1[c];
                     for (int rr = 0; rr < ncd; ++rr) gc = fma(T1[rr], P.GcT[(size_t)c * ncd + rr], gc);
                 }
                 g[c] = gc;
@@ -256,8 +258,8 @@ ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__
                         if (a == b) h = fma(2.0 * P.Wdu[(size_t)a * m + i], w1f(i), h);
                     }
                     if (mu > 0.0) {
-                        if ((a % nu) == (b % nu)) h += S2[a];          // a >= b: rows k >= k_a cover both moves
-                        if (a == b) h += b2[a];
+                        if (a < nvm && (a % nu) == (b % nu)) h += S2[a];          // a >= b: rows k >= k_a cover both moves
+                        if (a == b && a < nvm) h += b2[a];
                         for (int rr = 0; rr < ncd; ++rr)
                             h = fma(T2[rr] * P.GcT[(size_t)a * ncd + rr], P.GcT[(size_t)b * ncd + rr], h);
                     }
@@ -272,7 +274,17 @@ ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__
                 Hm[a * ld + b] = h;
             }
             __syncwarp();
+#ifdef SIH_LOG_DEBUG
+            double dbg_diag_min = SIH_INF, dbg_diag_max = 0.0;
+            for (int i = 0; i < n; ++i) { dbg_diag_min = fmin(dbg_diag_min, Hm[i * ld + i]); dbg_diag_max = fmax(dbg_diag_max, Hm[i * ld + i]); }
+            const bool dbg_np = warp_cholesky<NVR>(Hm, ld, n, dinv, lane);
+            if (dbg_np) st |= SIHMPC_ST_NOTPD;
+            if (s == SIH_LOG_DEBUG && lane == 0)
+                printf("k=%d mu=%.1e it=%d phi=%.10g ss=%.6g notpd=%d diag[%.3g,%.3g] d=[%.3g %.3g %.3g %.3g] rho=[%.6g %.6g]\n", kabs, mu, itn, phi,
+                       v[nv], (int)dbg_np, dbg_diag_min, dbg_diag_max, d[0], d[1], d[2], d[3], nv > nvm ? v[nvm] : 0.0, nv > nvm + 1 ? v[nvm + 1] : 0.0);
+#else
             if (warp_cholesky<NVR>(Hm, ld, n, dinv, lane)) st |= SIHMPC_ST_NOTPD;
+#endif
             double acc[NVR];
             load_acc<NVR>(acc, g, n, lane, -1.0);
             warp_trsv_lower<NVR>(Hm, ld, dinv, n, acc, lane);
@@ -339,12 +351,32 @@ ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__
                 // (or, when a dense row excludes that, the warm start the caller passed: the shifted plan of the last
                 // step sits ON its contraction row, inside the relaxed one), ss large enough for every barrier
                 __syncwarp();
+                // (a dense row with ONE non-zero, on a ranged residual, is a simple bound on that variable: its anchor is the
+                // centre of the range whatever the moves do, and it takes no part in the choice of the moves' anchor)
+                auto simple_col = [&](const int rr) {
+                    int cnt = 0, col = -1;
+                    for (int c = 0; c < nv; ++c) if (P.GcT[(size_t)c * ncd + rr] != 0.0) { ++cnt; col = c; }
+                    return (cnt == 1 && col >= nvm) ? col : -1;
+                };
                 double feas0 = SIH_INF;
-                for (int rr = lane; rr < ncd; rr += 32) feas0 = fmin(feas0, fmin(0.0 - log_relax(glo[rr], -1.0), log_relax(ghi[rr], 1.0) - 0.0));
+                for (int rr = lane; rr < ncd; rr += 32)
+                    if (simple_col(rr) < 0) feas0 = fmin(feas0, fmin(0.0 - log_relax(glo[rr], -1.0), log_relax(ghi[rr], 1.0) - 0.0));
                 feas0 = -warp_max(-feas0);
                 const bool zero_ok = !(feas0 <= 0.0);
-                for (int i = lane; i < nv; i += 32) v[i] = zero_ok ? 0.0 : vw[i];
+                const double ss_free = v[nv];
+                __syncwarp();
+                for (int i = lane; i < nv; i += 32) { vfree[i] = v[i]; v[i] = (zero_ok && i < nvm) ? 0.0 : vw[i]; }
                 if (lane == 0) v[nv] = 2.0;
+                __syncwarp();
+                for (int rr = lane; rr < ncd; rr += 32) {
+                    const int col = simple_col(rr);
+                    if (col >= 0) {
+                        const double gcv = P.GcT[(size_t)col * ncd + rr], lo = glo[rr], hi = ghi[rr];
+                        const double centre = (lo > -SIH_INF && hi < SIH_INF) ? 0.5 * (lo + hi)
+                                            : (lo > -SIH_INF ? lo + fmax(1.0, fabs(lo)) : hi - fmax(1.0, fabs(hi)));
+                        v[col] = centre / gcv;
+                    }
+                }
                 __syncwarp();
                 if (!zero_ok && lane == 0) {
                     // the shifted plan sits ON its contraction row (slack = the 1e-10 relaxation: a barrier curvature of
@@ -354,7 +386,7 @@ ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__
                     int rows[MB], nb = 0;
                     double G[MB][MB + 1];
                     for (int rr = 0; rr < ncd && nb < MB; ++rr)
-                        if (glo[rr] > -SIH_INF || ghi[rr] < SIH_INF) rows[nb++] = rr;
+                        if ((glo[rr] > -SIH_INF || ghi[rr] < SIH_INF) && simple_col(rr) < 0) rows[nb++] = rr;
                     for (int a = 0; a < nb; ++a) {
                         const int ra = rows[a];
                         const double lo = glo[ra], hi = ghi[ra];
@@ -383,13 +415,110 @@ ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__
                     }
                 }
                 __syncwarp();
-                log_eval(P, v, e, r, Vi, d, lane);
-                {
+                // ---- start of the interior-point rounds: from that strictly feasible anchor TOWARDS a target, 95 % of the way
+                // to the first bound (all rows linear: the segment stays strictly inside).  Two targets, the better start
+                // (lower phi) wins: the minimiser found without the inequalities, and the point this step was entered with
+                // (in a closed loop the shifted plan of the last step: near the optimum, but ON its active bounds).  The
+                // anchor itself (zero moves) can be far off right after a set-point change (V_i ~ 1e2 gamma_i, ss ~ 1e2) and a
+                // barrier method started there creeps along the d_i >= 0.01 wall.
+                // SIMPLE bounds first (a ranged residual's row has one non-zero; the move box): the violated coordinate
+                // of the target is pulled 5 % inside its range, the others keep their values -- the segment then only
+                // shortens for the coupled rows (cumulative inputs, contraction, state boxes)
+                double *va = vt;                                // the anchor
+                for (int i = lane; i < nv; i += 32) va[i] = v[i];
+                __syncwarp();
+                auto towards = [&](double *tg, const bool always_shrink) {
+                    auto inside = [](const double x, const double lo, const double hi) {
+                        const bool fl = lo > -SIH_INF, fh = hi < SIH_INF;
+                        const double wl = (fl && fh) ? 0.05 * (hi - lo) : 0.05 * fmax(1.0, fabs(fl ? lo : hi));
+                        if (fl && x < lo + wl) return lo + wl;
+                        if (fh && x > hi - wl) return hi - wl;
+                        return x;
+                    };
+                    for (int c = lane; c < nvm; c += 32) tg[c] = inside(tg[c], P.dulb[c % nu], P.duub[c % nu]);
+                    for (int rr = lane; rr < ncd; rr += 32) {
+                        const int col = simple_col(rr);
+                        if (col >= 0) {
+                            const double gcv = P.GcT[(size_t)col * ncd + rr];
+                            const double a_ = glo[rr] / gcv, b_ = ghi[rr] / gcv;
+                            tg[col] = inside(tg[col], fmin(a_, b_), fmax(a_, b_));
+                        }
+                    }
+                    __syncwarp();
+                    double th = 1.0;
+                    auto ratio = [&](const double ca, const double cf, const double b) {
+                        const double q = (b - ca) / (cf - ca);
+                        if (q >= 0.0 && q < th) th = q;
+                    };
+                    for (int j = lane; j < nu; j += 32) {
+                        const bool hl = P.ulb[j] > -SIH_INF, hh = P.uub[j] < SIH_INF, dl = P.dulb[j] > -SIH_INF, dh = P.duub[j] < SIH_INF;
+                        const double lo = hl ? log_relax(P.ulb[j], -1.0) : 0.0, hi = hh ? log_relax(P.uub[j], 1.0) : 0.0;
+                        const double dlo = dl ? log_relax(P.dulb[j], -1.0) : 0.0, dhi = dh ? log_relax(P.duub[j], 1.0) : 0.0;
+                        double ca = uu[j], cf = uu[j];
+                        for (int k = 0; k < P.N; ++k) {
+                            const double da = va[k * nu + j], df = tg[k * nu + j];
+                            ca += da; cf += df;
+                            if (hl && cf <= lo) ratio(ca, cf, lo);
+                            if (hh && cf >= hi) ratio(ca, cf, hi);
+                            if (dl && df <= dlo) ratio(da, df, dlo);
+                            if (dh && df >= dhi) ratio(da, df, dhi);
+                        }
+                    }
+                    for (int rr = lane; rr < ncd; rr += 32) {
+                        double ca = 0.0, cf = 0.0;
+                        for (int c = 0; c < nv; ++c) { const double gcv = P.GcT[(size_t)c * ncd + rr]; ca = fma(gcv, va[c], ca); cf = fma(gcv, tg[c], cf); }
+                        if (glo[rr] > -SIH_INF && cf <= log_relax(glo[rr], -1.0)) ratio(ca, cf, log_relax(glo[rr], -1.0));
+                        if (ghi[rr] < SIH_INF && cf >= log_relax(ghi[rr], 1.0)) ratio(ca, cf, log_relax(ghi[rr], 1.0));
+                    }
+                    double nonfin = 0.0;
+                    for (int i = lane; i < nv; i += 32) if (!(fabs(tg[i]) < SIH_INF)) nonfin = 1.0;
+                    th = -warp_max(-th);
+                    if (th < 1.0 || always_shrink) th *= 0.95;
+                    if (warp_max(nonfin) > 0.0 || !(th >= 0.0)) th = 0.0;          // (no usable target: stay at the anchor)
+                    __syncwarp();
+                    for (int i = lane; i < nv; i += 32) v[i] = fma(th, tg[i] - va[i], va[i]);
+                    __syncwarp();
+                    // bound push (cf. IPOPT bound_push / bound_frac): a start whose slack is the 1e-10 relaxation -- u ON its
+                    // bound with no moves, a shifted plan riding a bound -- gives barrier curvatures of 1e18 that no
+                    // factorisation survives; every move and every cumulative input is pushed kappa inside, step by step
+                    for (int j = lane; j < nu; j += 32) {
+                        const bool hl = P.ulb[j] > -SIH_INF, hh = P.uub[j] < SIH_INF, dl = P.dulb[j] > -SIH_INF, dh = P.duub[j] < SIH_INF;
+                        double ku = 1e-3 * fmax(1.0, fmax(hl ? fabs(P.ulb[j]) : 0.0, hh ? fabs(P.uub[j]) : 0.0));
+                        if (hl && hh) ku = fmin(ku, 0.25 * (P.uub[j] - P.ulb[j]));
+                        double kd = 1e-3 * fmax(1.0, fmax(dl ? fabs(P.dulb[j]) : 0.0, dh ? fabs(P.duub[j]) : 0.0));
+                        if (dl && dh) kd = fmin(kd, 0.25 * (P.duub[j] - P.dulb[j]));
+                        double cs = uu[j];
+                        for (int k = 0; k < P.N; ++k) {
+                            double dv = v[k * nu + j];
+                            if (dl && dv < P.dulb[j] + kd) dv = P.dulb[j] + kd;
+                            if (dh && dv > P.duub[j] - kd) dv = P.duub[j] - kd;
+                            const double cn = cs + dv;
+                            if (hl && cn < P.ulb[j] + ku) dv += P.ulb[j] + ku - cn;
+                            else if (hh && cn > P.uub[j] - ku) dv -= cn - (P.uub[j] - ku);
+                            cs += dv;
+                            v[k * nu + j] = dv;
+                        }
+                    }
+                    __syncwarp();
+                    // ss large enough for every barrier; returns phi there
+                    log_eval(P, v, e, r, Vi, d, lane);
                     double smax = 0.0;
                     for (int i = 0; i < m; ++i) smax = fmax(smax, (Vi[i] + 0.02) / P.gamma[i]);
                     __syncwarp();
-                    if (lane == 0) v[nv] = fmax(2.0, 1.1 * smax + 0.1);
+                    if (lane == 0) v[nv] = fmax(fmax(ss_free, 1.01), 1.1 * smax + 0.1);
                     __syncwarp();
+                    return log_eval(P, v, e, r, Vi, d, lane);
+                };
+                {
+                    const double m1 = towards(vfree, false);
+                    for (int i = lane; i < n; i += 32) g[i] = v[i];
+                    __syncwarp();
+                    const double m2 = towards(vw, true);
+                    if (!(m2 < m1)) {
+                        __syncwarp();
+                        for (int i = lane; i < n; i += 32) v[i] = g[i];
+                        __syncwarp();
+                    }
                 }
                 bool fail_ip = false;
                 for (double mu = 1e-1; mu >= 0.99e-14; mu *= 0.1) {
@@ -408,10 +537,10 @@ ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__
         if (last_step) {
             if (io.du) for (int j = lane; j < nu; j += 32) io.du[s * nu + j] = v[j];
             if (w_opt) {
-                for (int i = lane; i < nv; i += 32) w_opt[s * nw + i] = v[i];
+                for (int i = lane; i < nvm; i += 32) w_opt[s * nw + i] = v[i];
                 for (int i = lane; i < ny; i += 32) {
-                    w_opt[s * nw + nv + i] = r[P.o_sy + i];
-                    w_opt[s * nw + nv + ny + i] = r[P.o_si + i];
+                    w_opt[s * nw + nvm + i] = r[P.o_sy + i];
+                    w_opt[s * nw + nvm + ny + i] = r[P.o_si + i];
                 }
                 if (lane == 0) w_opt[s * nw + nw - 1] = v[nv];
             }
@@ -470,10 +599,10 @@ ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__
         {
             double sh[NVR];
 #pragma unroll
-            for (int t = 0; t < NVR; ++t) { const int i = lane + 32 * t; sh[t] = (i + nu < nv) ? v[i + nu] : 0.0; }
+            for (int t = 0; t < NVR; ++t) { const int i = lane + 32 * t; sh[t] = (i + nu < nvm) ? v[i + nu] : 0.0; }
             __syncwarp();
 #pragma unroll
-            for (int t = 0; t < NVR; ++t) { const int i = lane + 32 * t; if (i < nv) v[i] = sh[t]; }
+            for (int t = 0; t < NVR; ++t) { const int i = lane + 32 * t; if (i < nvm) v[i] = sh[t]; }   // (rho keeps its value)
             if (lane == 0) v[nv] = 1.0;
         }
         __syncwarp();
@@ -482,7 +611,7 @@ ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__
             for (int i = lane; i < nx; i += 32) io.x[s * nx + i] = xs[i];
             for (int i = lane; i < nu; i += 32) io.u[s * nu + i] = uu[i];
             if (w_warm) {
-                for (int i = lane; i < nv; i += 32) w_warm[s * nw + i] = v[i];
+                for (int i = lane; i < nvm; i += 32) w_warm[s * nw + i] = v[i];
                 if (lane == 0) w_warm[s * nw + nw - 1] = v[nv];
             }
         }

@@ -91,16 +91,16 @@ class IHMPCController(_Weighted):
     def compile(self):
         if not self._dirty and self._plan is not None:
             return self._plan
-        for lo, hi, nm in ((self.rslb, self.rsub, 'rs'), (self.rilb, self.riub, 'ri')):
-            if not np.array_equal(np.asarray(lo, float), np.asarray(hi, float)):
-                raise NotImplementedError("terminal residual ranges (%slb != %sub) are not supported yet" % (nm, nm))
         if self._ell:
             raise NotImplementedError("siN sub-objective over several outputs (quadratic row) in the log variant")
         if not self.VJ:
             raise ValueError("no log sub-objective declared")
         self._plan = compile_plan(self.sys, self.N, [V.coeff for V in self.VJ], self._bounds(),
                                   Q_bar=self.Q_bar, vin=self._vin,
-                                  rs=np.asarray(self.rslb, float), ri=np.asarray(self.rilb, float))
+                                  rs=np.asarray(self.rslb, float), ri=np.asarray(self.rilb, float),
+                                  rs_hi=np.asarray(self.rsub, float), ri_hi=np.asarray(self.riub, float))
+        # terminal residual RANGES (rs/ri lb != ub, log.py:413-427): the ranged residual rho is a decision variable after
+        # the moves (Plan.n_extra), its range a dense row of the kernel's interior-point phase
         self._eval_plan = None
         self._stepper = None
         self._eval_dp = None
@@ -192,17 +192,24 @@ class IHMPCController(_Weighted):
         N, nu, ny, nx, m = self.N, self.nu, self.ny, self.nx, len(self.VJ)
         nv = N * nu
         dU, ss = w[:nv], w[-1]
+        ne = p.n_extra
+        nz = nv + ne
+        e = p.Px @ x + p.Py @ ysp + p.e0
+        o_sy_, _ = p.row_slices['syN']; o_si_, _ = p.row_slices['siN']
+        r_m = p.E[:, :nv] @ dU + e                             # residuals with rho = 0
+        rho = np.array([r_m[(o_sy_ if kind == 's' else o_si_) + i] - w[nv + (0 if kind == 's' else ny) + i]
+                        for kind, i in p.extra], dtype=float)     # syN = xs(N) - ysp - rho_s, siN = xi(N) - rho_i
+        z = np.concatenate([dU, rho])
         Vi = np.array([vals[self.V.index(V)] for V in self.VJ])
         gam = np.array([V.gamma for V in self.VJ], dtype=float)
         d = ss * gam - Vi
         inv = 1.0 / d
-        e = p.Px @ x + p.Py @ ysp + p.e0
-        r = p.E @ dU + e
+        r = p.E @ z + e
         om = p.Wrow @ inv + p.w0row
-        grad_V = [2.0 * p.E.T @ (p.Wrow[:, i] * r) + 2.0 * p.Wdu[:, i] * dU for i in range(m)]
-        g = np.zeros(nv + 1)
-        g[:nv] = 2.0 * p.E.T @ (om * r) + 2.0 * (p.Wdu @ inv) * dU
-        g[nv] = 2.0 * ss - float(gam @ inv)
+        grad_V = [2.0 * p.E.T @ (p.Wrow[:, i] * r) + 2.0 * p.Wdu[:, i] * z for i in range(m)]
+        g = np.zeros(nz + 1)
+        g[:nz] = 2.0 * p.E.T @ (om * r) + 2.0 * (p.Wdu @ inv) * z
+        g[nz] = 2.0 * ss - float(gam @ inv)
         rows, keys = [], []                                   # (normal over (dU, ss), key) of the rows on a bound
         tol = 1e-7
         Tc = np.kron(np.tril(np.ones((N, N))), np.eye(nu))
@@ -210,21 +217,25 @@ class IHMPCController(_Weighted):
         for k in range(nv):
             j = k % nu
             if abs(dU[k] - np.asarray(self.dulb, float)[j]) <= tol or abs(dU[k] - np.asarray(self.duub, float)[j]) <= tol:
-                n_ = np.zeros(nv + 1); n_[k] = 1.0; rows.append(n_); keys.append(('w', k))
+                n_ = np.zeros(nz + 1); n_[k] = 1.0; rows.append(n_); keys.append(('w', k))
             uk = up[k // nu, j]
             if abs(uk - np.asarray(self.ulb, float)[j]) <= tol or abs(uk - np.asarray(self.uub, float)[j]) <= tol:
-                n_ = np.zeros(nv + 1); n_[:nv] = Tc[k]; rows.append(n_); keys.append(('U', k))
+                n_ = np.zeros(nz + 1); n_[:nv] = Tc[k]; rows.append(n_); keys.append(('U', k))
         if ss - 1.0 <= tol:
-            n_ = np.zeros(nv + 1); n_[nv] = 1.0; rows.append(n_); keys.append(('ss',))
+            n_ = np.zeros(nz + 1); n_[nz] = 1.0; rows.append(n_); keys.append(('ss',))
         for i in range(m):
             if d[i] - 0.01 <= tol:
-                n_ = np.zeros(nv + 1); n_[:nv] = -grad_V[i]; n_[nv] = gam[i]; rows.append(n_); keys.append(('d', i))
+                n_ = np.zeros(nz + 1); n_[:nz] = -grad_V[i]; n_[nz] = gam[i]; rows.append(n_); keys.append(('d', i))
         siN = w[nv + ny:nv + 2 * ny]
         for rr, kind in enumerate(p.row_kind):
             if kind[0] == 'vin' and len(vin) and np.isfinite(vin[kind[1]]):
                 ind, q = self._vin[kind[1]]
                 if abs(abs(siN[ind]) - np.sqrt(max(vin[kind[1]], 0.0) / q)) <= tol:
-                    n_ = np.zeros(nv + 1); n_[:nv] = 2.0 * q * siN[ind] * p.Gc[rr][:nv]; rows.append(n_); keys.append(('vin', kind[1]))
+                    n_ = np.zeros(nz + 1); n_[:nz] = 2.0 * q * siN[ind] * p.Gc[rr][:nz]; rows.append(n_); keys.append(('vin', kind[1]))
+            elif kind[0] == 'rho':                                # a ranged residual on an end of its range: its multiplier is
+                c_ = kind[1]                                      # the one of the res1 / res2 row, set from stationarity below
+                if abs(rho[c_] - p.Lc[rr]) <= tol or abs(rho[c_] - p.Uc[rr]) <= tol:
+                    n_ = np.zeros(nz + 1); n_[nv + c_] = 1.0; rows.append(n_); keys.append(('rho', c_))
         lam = np.zeros(0)
         if rows:
             lam = np.linalg.lstsq(np.array(rows).T, -g, rcond=None)[0]

@@ -980,6 +980,74 @@ def test_log_variant_ss_bound_active():
 
 
 @pytest.mark.parametrize("ranges", [dict(rslb=[-0.1, -0.05], rsub=[0.1, 0.05]),
+                                    dict(rslb=[-0.02, 0.0], rsub=[0.02, 0.0]),
+                                    dict(rslb=[0.01, -0.05], rsub=[0.1, 0.05], ulb=[1.93, 1.60], uub=[2.2, 1.9])])
+def test_log_variant_terminal_residual_ranges_match_oracle(ranges):
+    """Log variant with terminal residual RANGES (rslb != rsub, ihmpccontroller_log.py:413-427): the ranged residual is
+    a decision variable of the Newton / interior-point kernel after the moves, its range a dense row.  Closed loop
+    of example_distillation_log.py:85-135 through the drop-in mpc() against the log oracle (range inactive, range
+    binding, range that excludes 0 together with the input box), then the batched device loop."""
+    from oracle.ihmpc_log_oracle import OracleIHMPCLog, declare_distillation_log
+    from sihmpc.ihmpccontroller_log import IHMPCController as LogController
+    sys_ = sc.distillation_system()
+    c = declare_distillation_log(LogController, sys_, **ranges)
+    orc = declare_distillation_log(OracleIHMPCLog, sys_, **ranges)
+    p = c.compile()
+    assert p.n_extra == sum(1 for a, b in zip(ranges['rslb'], ranges['rsub']) if a != b)
+    u = [1.95, 1.71]; x = np.append([96, 0.5], np.zeros(sys_.nx - 2)); ysp = [96, 0.5]
+    xo, uo = x.copy(), np.array(u)
+    w0 = []; w0o = []
+    scale, n_bound = 0.0, 0
+    lo, hi = np.asarray(ranges['rslb'], float), np.asarray(ranges['rsub'], float)
+    for k in range(14):
+        if k > 1:
+            ysp = [96, 1]
+        sol = c.mpc(x0=x, ySP=ysp, w0=w0, u0=u, lam_w0=[], lam_g0=[], ViN_ant=[])
+        solo = orc.mpc(xo, ysp, w0o, uo, [], [], ViN_ant=[])
+        assert c.status == 0, (k, c.status)
+        scale = max(scale, np.max(np.abs(solo['du_opt'])))
+        assert np.max(np.abs(sol['du_opt'].full() - solo['du_opt'])) <= RTOL * max(scale, 1e-3), k
+        assert abs(float(sol['J']) - solo['J']) <= RTOL * abs(solo['J']), k
+        w = sol['w_opt'].full().reshape(-1)
+        assert w.size == 25 and np.max(np.abs(w - solo['w_opt'])) <= RTOL * max(np.max(np.abs(solo['w_opt'])), 1e-3), k
+        res2 = sol['g'].full().reshape(-1)[10 * sys_.nx + 20 + 2:10 * sys_.nx + 20 + 4]       # g layout, log.py:394-427
+        assert (res2 >= lo - VIOL).all() and (res2 <= hi + VIOL).all(), (k, res2)
+        if min(solo['info']['margins']) <= 1e-8:
+            n_bound += 1
+            assert orc.last_kkt['stationarity'] <= 1e-8 and orc.last_kkt['lam_min'] >= -1e-9
+        du = sol['du_opt'][:, 0].full().reshape(-1)
+        res = c.dynF(x0=x, du0=du, u0=u)
+        x = res['xkp1'].full(); u = res['ukp1'].full()
+        r = orc.dynF(xo, uo, solo['du_opt'][:, 0]); xo, uo = r['xkp1'], r['ukp1']
+        w0 = c.warmStart(sol, ysp); w0o = orc.warmStart(solo, ysp)
+    if lo[1] != hi[1]:
+        assert n_bound >= 3                                    # |rho_s[1]| = 0.05 binds after the set-point change
+    # batched device loop (sihmpc_log_loop) on the same declaration: first moves and costs vs the oracle
+    B, T = 8, 12
+    scen = sc.distillation_scenarios(B)
+    scen["seg_start"][:, 1] = 2; scen["seg_start"][:, 2] = 9
+    eng = c.engine(B)
+    eng.set_state(scen["x0"], scen["u0"])
+    eng.set_schedule(scen["ysp_seq"], scen["seg_start"])
+    tr = eng.run(T, steps_per_launch=5, record=True)
+    du = tr["du"].cpu().numpy(); J = tr["J"].cpu().numpy()
+    assert (eng.stats[:, sys_.ny + 3].cpu().numpy() == 0).all()
+    for idx in (0, 5):
+        orc = declare_distillation_log(OracleIHMPCLog, sys_, **ranges)
+        xo, uo, w0o = scen["x0"][idx].copy(), scen["u0"][idx].copy(), []
+        ysp_of = schedule_fn(scen["ysp_seq"][idx], scen["seg_start"][idx])
+        sc_ = 1e-3
+        for k in range(T):
+            ysp = np.asarray(ysp_of(k), float)
+            solo = orc.mpc(xo, ysp, w0o, uo, [], [], ViN_ant=[])
+            sc_ = max(sc_, np.max(np.abs(solo['du_opt'][:, 0])))
+            assert np.max(np.abs(du[k, idx] - solo['du_opt'][:, 0])) <= RTOL * sc_, (idx, k)
+            assert abs(J[k, idx] - solo['J']) <= RTOL * abs(solo['J']), (idx, k)
+            r = orc.dynF(xo, uo, solo['du_opt'][:, 0]); xo, uo = r['xkp1'], r['ukp1']
+            w0o = orc.warmStart(solo, ysp)
+
+
+@pytest.mark.parametrize("ranges", [dict(rslb=[-0.1, -0.05], rsub=[0.1, 0.05]),
                                     dict(rslb=[-0.02, 0.0], rsub=[0.02, 0.0], ulb=[1.9, 1.6])])
 def test_terminal_residual_ranges_match_oracle(ranges):
     """Terminal residual RANGES (rslb != rsub, ihmpccontroller.py:441-449): single steps through the drop-in mpc()

@@ -194,6 +194,33 @@ def test_log_oracle_constrained_optimum_is_kkt_certified():
         assert sol['J'] >= free['J'] - 1e-12                           # constraining cannot improve the cost
 
 
+def test_log_oracle_terminal_residual_ranges():
+    """Log variant with terminal residual RANGES (rslb != rsub, ihmpccontroller_log.py:413-427): the ranged residual
+    rho = xs(N) - ysp - syN is a decision variable in [lb, ub].  A range that is wide enough changes nothing against
+    a free residual; a tight one binds, carries a KKT certificate, costs more than the wide one and less than the
+    equality rho = 0."""
+    from oracle.ihmpc_log_oracle import OracleIHMPCLog, declare_distillation_log
+    s = sc.distillation_system()
+    x = np.append([96, 0.5], np.zeros(20)); u = np.array([1.95, 1.71]); ysp = [96.0, 1.0]
+    eq = declare_distillation_log(OracleIHMPCLog, s).mpc(x, ysp, [], u, [], [], ViN_ant=[])
+    wide = declare_distillation_log(OracleIHMPCLog, s, rslb=[-5, -5], rsub=[5, 5])
+    sw = wide.mpc(x, ysp, [], u, [], [], ViN_ant=[])
+    assert min(sw['info']['margins']) > 1e-3                            # nothing active: plain Newton optimum
+    tight = declare_distillation_log(OracleIHMPCLog, s, rslb=[-0.1, -0.05], rsub=[0.1, 0.05])
+    st = tight.mpc(x, ysp, [], u, [], [], ViN_ant=[])
+    assert abs(min(st['info']['margins'])) <= 1e-9
+    assert tight.last_kkt['stationarity'] <= 1e-9 and tight.last_kkt['lam_min'] >= -1e-10
+    assert sw['J'] <= st['J'] + 1e-12 and st['J'] <= eq['J'] + 1e-12
+    # the reported residual is inside its range: res2 = xs(N) - ysp - syN
+    XN = tight.X_pred[-1]
+    base = np.zeros(tight.nxi_); base[:20] = st['w_opt'][:20]
+    base[tight.o_x:tight.o_x + 22] = x; base[tight.o_u:tight.o_u + 2] = u; base[tight.o_ysp:tight.o_ysp + 2] = ysp
+    base[tight.o_one] = 1
+    res2 = XN[0:2] @ base - np.asarray(ysp) - st['w_opt'][20:22]
+    assert (res2 >= np.array([-0.1, -0.05]) - 1e-9).all() and (res2 <= np.array([0.1, 0.05]) + 1e-9).all()
+    assert np.max(np.abs(np.abs(res2) - np.array([0.1, 0.05]))[1:]) <= 1e-8      # the second one sits on its end
+
+
 def test_multi_index_siN_ellipsoid_row():
     """siN=[0,1]: ONE quadratic row q0 siN0^2 + q1 siN1^2 <= ViN_ant (ihmpccontroller.py:243-271) on a plant whose
     channels integrate.  The outer multiplier search lands on the boundary when the row is active, the limit
