@@ -182,6 +182,13 @@ __device__ __forceinline__ void back_rows(double (&L)[D::SV][D::NV], double (&fr
 // Storage after block B (columns k = 2B, k+1; slot s = B/2, lanes g0 = 2(B%2), g0+1):
 //   rows below the block:  L[t][k] = w1, L[t][k+1] = w2     (W = [p q] D^-1)
 //   pivot rows:            lane g0: L[s][k] = D^-1_11 ; lane g0+1: L[s][k] = D^-1_21, L[s][k+1] = D^-1_22
+// p ? a : b as a SELECT whatever the compiler's if-conversion heuristics think: ptxas turns a conditional 64-bit move
+// on a per-lane predicate into a divergent branch (BSSY / BRA / BSYNC), which costs ~20 cycles on a dependent chain
+__device__ __forceinline__ double sel_f64(const bool p, const double a, const double b) {
+    double r;
+    asm("{\n .reg .pred q;\n setp.ne.s32 q, %3, 0;\n selp.f64 %0, %1, %2, q;\n}" : "=d"(r) : "d"(a), "d"(b), "r"((int)p));
+    return r;
+}
 __device__ __forceinline__ double fast_rcp(const double d) {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
@@ -202,7 +209,12 @@ __device__ __forceinline__ void ldl_blocks(double (&L)[D::SV][D::NV], double (&f
         const double c = quad_bcast(L[s][k + 1], g0 + 1);
         const double yk = quad_bcast(fr[s], g0), yk1 = quad_bcast(fr[s], g0 + 1);
         double det = fma(a, c, -bb * bb);
-        if (!(a > 0.0) || !(det > 0.0)) { notpd = 1; det = 1e300; a = 1.0; }
+        {   // selects, not a branch: the rounds are one dependent chain and a divergent branch (BSSY/BSYNC) sits on it
+            const bool bad = !(a > 0.0) || !(det > 0.0);
+            notpd |= bad ? 1 : 0;
+            det = sel_f64(bad, 1e300, det);
+            a = sel_f64(bad, 1.0, a);
+        }
         const double idet = fast_rcp(det);
         const double d11 = c * idet, d21 = -bb * idet, d22 = a * idet;
         double pq[SV][2], w[SV][2];
@@ -227,10 +239,12 @@ __device__ __forceinline__ void ldl_blocks(double (&L)[D::SV][D::NV], double (&f
         for (int t = s; t < SV; ++t)
             if (4 * t + 3 > k + 1) {
                 fr[t] = fma(-w[t][1], yk1, fma(-w[t][0], yk, fr[t]));
-                if (4 * t + g > k + 1) { L[t][k] = w[t][0]; L[t][k + 1] = w[t][1]; }
+                const bool below = (4 * t + g > k + 1);
+                L[t][k] = sel_f64(below, w[t][0], L[t][k]);
+                L[t][k + 1] = sel_f64(below, w[t][1], L[t][k + 1]);
             }
-        if (g == g0) L[s][k] = d11;
-        if (g == g0 + 1) { L[s][k] = d21; L[s][k + 1] = d22; }
+        L[s][k] = sel_f64(g == g0, d11, sel_f64(g == g0 + 1, d21, L[s][k]));
+        L[s][k + 1] = sel_f64(g == g0 + 1, d22, L[s][k + 1]);
         ldl_blocks<D, B + 1>(L, fr, g, notpd);
     }
 }
@@ -268,8 +282,7 @@ __device__ __forceinline__ void ldl_back(double (&L)[D::SV][D::NV], double (&fr)
         s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
         s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
         s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
-        if (g == g0) fr[s] -= s1;
-        if (g == g0 + 1) fr[s] -= s2;
+        fr[s] -= sel_f64(g == g0, s1, sel_f64(g == g0 + 1, s2, 0.0));
         ldl_back<D, B - 1>(L, fr, g);
     }
 }

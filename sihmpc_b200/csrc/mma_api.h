@@ -14,6 +14,9 @@ struct MmaConst {            // offsets in doubles into the packed block
     // where the bounds are simple (cspace 1: cumulative moves c = cumsum(dU), input box; 0: dU itself, move box;
     // -1: not available, a violated bound hands the scenario over)
     int bfc, bhc, bdp, bdpt, du_idx, n_du, cspace;
+    // input-box check of the unconstrained optimum as one product: cumulative moves at the live positions (bcum);
+    // cum0: bit j = the first move of input j is presolved, i.e. the cumulative move 0 belongs to the checked set
+    int bcum, cum0;
 };
 
 struct MmaPlan {

@@ -448,6 +448,14 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
 #pragma unroll
     for (int sl = 0; sl < SV; ++sl) vlog[sl] = cint[Q.vlive + D::var_of(sl, g)];
     for (int e = g; e < D::NVL; e += 4) bv[e] = 0.0;      // presolved moves stay exactly zero
+    unsigned jpack = 0u;                      // input index of the live move behind every C-layout element of this lane (2 bits each)
+#pragma unroll
+    for (int T = 0; T < TV; ++T)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int a = (NV % 8 == 4 && T == TV - 1) ? (h == 0 ? NV - 4 + g : -1) : 8 * T + 2 * g + h;
+            if (a >= 0 && a < NV) jpack |= (unsigned)(cint[Q.vlive + a] % NU) << (2 * (2 * T + h));
+        }
     __syncwarp();
     const long long gq = spread ? ((q == 0) ? (long long)blockIdx.x * WARPS + wib : n_work)
                                 : ((long long)blockIdx.x * WARPS + wib) * 8 + q;
@@ -612,7 +620,8 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
             for (int t = 0; t < KH; ++t) {
                 const int e = 4 * t + g;                       // 0 -> 1.0 ; 1+a -> pesos[hj_index[a]]
                 const int a = (e >= 1 && e - 1 < M) ? e - 1 : 0;
-                ahp[t] = (e == 0) ? 1.0 : ((e - 1 < mh) ? sel<M>(pes, cint[Q.hj_idx + a]) : 0.0);
+                const double pa = sel<M>(pes, cint[Q.hj_idx + a]);       // unconditional load + selects: no branch in the step loop
+                ahp[t] = sel_f64(e == 0, 1.0, sel_f64(e - 1 < mh, pa, 0.0));
             }
             // ---------------- K1: e = Px x + Py ysp + e0 ; omega = Wrow pesos + w0row
             double er[TR][2], om[TR][2];
@@ -693,14 +702,37 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
                 }
             }
             if (P.has_cum) {
-                for (int j = g; j < NU; j += 4) {
-                    const double uj = sel<NU>(uu, j);
-                    const double lo = cst[Q.bounds + 2 * NU + j] - uj, hi = cst[Q.bounds + 3 * NU + j] - uj;
-                    double cs = 0.0, cmin = SIH_INF, cmax = -SIH_INF;
+                // cumulative moves at the live positions as ONE product on the tensor pipe (every lane gets 2 TV of
+                // them), an infinite bound drops out by itself (lo - c = -inf); round 1-2: a serial prefix-sum loop over
+                // the horizon on NU of the four lanes (8 % of the step's instructions, divergent)
+                double cm[TV][2];
 #pragma unroll
-                    for (int k = 0; k < D::N; ++k) { cs += bv[k * NU + j]; cmin = fmin(cmin, cs); cmax = fmax(cmax, cs); }
-                    if (lo > -SIH_INF) { const double a = lo - cmin; viol_abs = fmax(viol_abs, a); viol = fmax(viol, fma(-1e-10, 1.0 + fabs(lo), a)); }
-                    if (hi < SIH_INF) { const double a = cmax - hi; viol_abs = fmax(viol_abs, a); viol = fmax(viol, fma(-1e-10, 1.0 + fabs(hi), a)); }
+                for (int T = 0; T < TV; ++T) cm[T][0] = cm[T][1] = 0.0;
+                mma_block<TV, SV>(cst + Q.bcum, fr, cm, lane);
+                double lo_[NU], hi_[NU];
+#pragma unroll
+                for (int j = 0; j < NU; ++j) {
+                    lo_[j] = cst[Q.bounds + 2 * NU + j] - uu[j]; hi_[j] = cst[Q.bounds + 3 * NU + j] - uu[j];
+                }
+#pragma unroll
+                for (int T = 0; T < TV; ++T)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        if (NV % 8 == 4 && T == TV - 1 && h == 1) continue;          // padding row of the half tile
+                        const int j = (jpack >> (2 * (2 * T + h))) & 3;
+                        const double lo = sel<NU>(lo_, j), hi = sel<NU>(hi_, j);
+                        const double a = lo - cm[T][h], b = cm[T][h] - hi;
+                        viol_abs = fmax(viol_abs, fmax(a, b));
+                        viol = fmax(viol, fmax(fma(-1e-10, 1.0 + fabs(lo), a), fma(-1e-10, 1.0 + fabs(hi), b)));
+                    }
+                if (Q.cum0) {                  // uniform, rare: the first move of an input is presolved -> c = 0 is in the set
+#pragma unroll
+                    for (int j = 0; j < NU; ++j)
+                        if ((Q.cum0 >> j) & 1) {
+                            const double a = lo_[j], b = -hi_[j];
+                            viol_abs = fmax(viol_abs, fmax(a, b));
+                            viol = fmax(viol, fmax(fma(-1e-10, 1.0 + fabs(lo_[j]), a), fma(-1e-10, 1.0 + fabs(hi_[j]), b)));
+                        }
                 }
             }
             viol = quad_max(viol);
@@ -767,7 +799,10 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
                 }
             }
             const bool last_step = (step == n_steps - 1);
-            if (alive) {
+            // uniform guard first: a step in the middle of a launch without trajectories writes nothing
+            const bool out_step = last_step || io.traj_du || io.traj_J ||
+                                  ((io.flags & SIHMPC_F_UPDATE_VIN) && io.vinant && !advance);
+            if (out_step && alive) {
                 if (last_step) {
                     if (io.du) for (int j = g; j < NU; j += 4) io.du[s * NU + j] = bv[j];
                     if (io.w_opt) {
@@ -947,6 +982,7 @@ inline void mma_build_constants(const sihmpc_plan_desc *d, const DevPlan &P, Mma
     qc.bhc = take(D::HPAIRS * D::KHC * 32);
     qc.bdp = take(D::TV * SV * 32);
     qc.bdpt = take(D::TV * SV * 32);
+    qc.bcum = take(D::TV * SV * 32);
     qc.total_d = o;
     buf.assign(o, 0.0);
 
@@ -1060,6 +1096,16 @@ inline void mma_build_constants(const sihmpc_plan_desc *d, const DevPlan &P, Mma
         };
         mma_pack(buf, qc.bdp, D::TV, SV, lrow, lcol, [&](int a, int b) { return S[(size_t)a * NV + b]; });
         mma_pack(buf, qc.bdpt, D::TV, SV, lrow, lcol, [&](int a, int b) { return S[(size_t)b * NV + a]; });
+        // cumulative move of input j after the live move a: c_a = sum of the live moves of the same input up to a
+        // (presolved moves are zero) -- the rows of the input box ihmpccontroller.py:420-424 at the unconstrained optimum
+        mma_pack(buf, qc.bcum, D::TV, SV, lrow, lcol,
+                 [&](int a, int b) { return (live[b] % NU == live[a] % NU && live[b] <= live[a]) ? 1.0 : 0.0; });
+        qc.cum0 = 0;
+        for (int j = 0; j < NU; ++j) {
+            bool first_live = false;
+            for (int a = 0; a < NV; ++a) if (live[a] == j) first_live = true;
+            if (!first_live) qc.cum0 |= 1 << j;
+        }
         // gradient map: 2 (E_live S)^T
         std::vector<double> Ec((size_t)R * NV, 0.0);
         for (int r = 0; r < R; ++r)

@@ -1,7 +1,8 @@
 """Aggregate an ncu source page (cuda,sass) by source line / by opcode.  usage: ncu_lines.py rep.ncu-rep [units]"""
 import csv, subprocess, sys, io
 rep = sys.argv[1]; units = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "sass,cuda", "--csv"], capture_output=True, text=True).stdout
+import os
+out = subprocess.run(["ncu", "-i", rep] + os.environ.get("NCU_ARGS", "").split() + ["--page", "source", "--print-source", "sass,cuda", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 cur = None; hdr = None; agg = {}; byop = {}; stall_tot = {}
 for r in rows:
