@@ -29,6 +29,7 @@
 #include <vector>
 #include <functional>
 #include <string.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include "devplan.h"
 #include <math.h>
@@ -914,6 +915,23 @@ cudaError_t tile_configure(const sihmpc_plan_desc *d, const DevPlan &P, TilePlan
     C.kof = tp->ibuf; C.ptr = tp->ibuf + nk; C.hrows = tp->ibuf + nk + np; C.B = tp->dbuf; C.BH = tp->dbuf + nB;
     C.BHc = tp->dbuf + nB + nBH;
     tp->n_tiles = tb.n_stored;
+    if (getenv("SIHMPC_TILE_DEBUG")) {
+        const int *pt = tb.ptr.data();
+        auto grp = [&](int poff, int T) { return (pt[poff + T + 1] - pt[poff + T]) / 4; };
+        struct { const char *name; int off, n, rot; } ms[] = {{"me", C.me, C.n_r, 0}, {"mw", C.mw, C.n_r, 0}, {"mdu", C.mdu, C.n_v, 5},
+            {"mf", C.mf, C.n_f, 0}, {"mr", C.mr, C.n_r, 0}, {"mpl", C.mpl, C.n_x, 2}, {"my", C.my, C.n_y, 0}, {"myp", C.myp, C.n_yp, 3}, {"mvn", C.mvn, C.n_m, 0}};
+        for (auto &mm : ms) {
+            fprintf(stderr, "[tile] %-4s tiles %3d groups/warp:", mm.name, mm.n);
+            int tot = 0, mx = 0;
+            for (int w = 0; w < TL_WARPS; ++w) {
+                int gsum = 0;
+                for (int T = (w + mm.rot) & 7; T < mm.n; T += TL_WARPS) gsum += grp(mm.off, T);
+                fprintf(stderr, " %3d", gsum); tot += gsum; if (gsum > mx) mx = gsum;
+            }
+            fprintf(stderr, "  total %d max %d (balance %.2f)\n", tot, mx, tot / (8.0 * (mx ? mx : 1)));
+        }
+        fprintf(stderr, "[tile] KH %d ntile %d NT %d n_stored %d\n", C.KH, C.ntile, C.NT, tb.n_stored);
+    }
     e = tile_set_smem(C.NT, tp->smem_bytes);
     if (e != cudaSuccess) return e;
     tp->ok = 1;
