@@ -104,13 +104,6 @@ __device__ __forceinline__ void tile_row(const TileCfg &C, const int poff, const
 }
 
 __device__ __forceinline__ double tl_rsqrt(const double d) { return fast_rsqrt(d); }
-// p ? a : b as a SELECT: ptxas turns a conditional 64-bit move on a per-lane predicate into a divergent branch
-// (BSSY / BRA / BSYNC), ~20 cycles each on the dependent chain of the pivot blocks
-__device__ __forceinline__ double tl_sel(const bool p, const double a, const double b) {
-    double r;
-    asm("{\n .reg .pred q;\n setp.ne.s32 q, %3, 0;\n selp.f64 %0, %1, %2, q;\n}" : "=d"(r) : "d"(a), "d"(b), "r"((int)p));
-    return r;
-}
 
 // Right-looking BLOCK elimination (block LDL^T with 4x4 pivot blocks) of the augmented matrix
 // [H ; b^T] of ONE scenario by ONE warp.  A: packed lower 8x8 tiles (row-major 64 doubles each) in
@@ -153,25 +146,19 @@ __device__ __forceinline__ void tfs_panel(double2 (&c)[NT * (NT + 1) / 2], doubl
             double pl[NT];
 #pragma unroll
             for (int I = J; I < NT; ++I) {
-                const double v = A[(I * (I + 1) / 2 + J) * 64 + q * 8 + c0 + g];
-                pl[I] = (I == J) ? tl_sel(q < c0 + nreal, 0.0, v) : v;
+                double v = A[(I * (I + 1) / 2 + J) * 64 + q * 8 + c0 + g];
+                if (I == J && q < c0 + nreal) v = 0.0;
+                pl[I] = v;
             }
             // (b) M = A11^-1, redundantly in every lane
             const double *D = A + (J * (J + 1) / 2 + J) * 64 + c0 * 8 + c0;   // element (r,c) at D[r*8+c]
             double a00 = D[0], a10 = D[8], a11 = D[9], a20 = D[16], a21 = D[17], a22 = D[18];
             double a30 = D[24], a31 = D[25], a32 = D[26], a33 = D[27];
-            {
-                const bool n4 = nreal < 4, n3 = nreal < 3, n2 = nreal < 2;
-                a30 = tl_sel(n4, 0.0, a30); a31 = tl_sel(n4, 0.0, a31); a32 = tl_sel(n4, 0.0, a32); a33 = tl_sel(n4, 1.0, a33);
-                a20 = tl_sel(n3, 0.0, a20); a21 = tl_sel(n3, 0.0, a21); a22 = tl_sel(n3, 1.0, a22);
-                a10 = tl_sel(n2, 0.0, a10); a11 = tl_sel(n2, 1.0, a11);
-            }
+            if (nreal < 4) { a30 = a31 = a32 = 0.0; a33 = 1.0; }
+            if (nreal < 3) { a20 = a21 = 0.0; a22 = 1.0; }
+            if (nreal < 2) { a10 = 0.0; a11 = 1.0; }
             double detp = fma(a00, a11, -a10 * a10);
-            {
-                const bool bad = !(a00 > 0.0) || !(detp > 0.0);
-                notpd |= bad ? 1 : 0;
-                detp = tl_sel(bad, 1.0, detp);
-            }
+            if (!(a00 > 0.0) || !(detp > 0.0)) { notpd = 1; detp = 1.0; }
             const double ip = tl_rcp(detp);
             const double p00 = a11 * ip, p10 = -a10 * ip, p11 = a00 * ip;
             const double t00 = fma(a20, p00, a21 * p10), t01 = fma(a20, p10, a21 * p11);
@@ -180,11 +167,7 @@ __device__ __forceinline__ void tfs_panel(double2 (&c)[NT * (NT + 1) / 2], doubl
             const double s10 = a32 - fma(t10, a20, t11 * a21);
             const double s11 = a33 - fma(t10, a30, t11 * a31);
             double dets = fma(s00, s11, -s10 * s10);
-            {
-                const bool bad = !(s00 > 0.0) || !(dets > 0.0);
-                notpd |= bad ? 1 : 0;
-                dets = tl_sel(bad, 1.0, dets);
-            }
+            if (!(s00 > 0.0) || !(dets > 0.0)) { notpd = 1; dets = 1.0; }
             const double is = tl_rcp(dets);
             const double m22 = s11 * is, m32 = -s10 * is, m33 = s00 * is;
             const double u00 = fma(m22, t00, m32 * t10), u01 = fma(m22, t01, m32 * t11);
@@ -194,12 +177,11 @@ __device__ __forceinline__ void tfs_panel(double2 (&c)[NT * (NT + 1) / 2], doubl
             const double m11 = p11 + fma(t01, u01, t11 * u11);
             double mqg;                                                // M[q][g] (symmetric), zero for q >= 4
             {
-                const bool g0 = g == 0, g1 = g == 1, g2 = g == 2;
-                const double r0 = tl_sel(g0, m00, tl_sel(g1, m10, tl_sel(g2, -u00, -u10)));
-                const double r1 = tl_sel(g0, m10, tl_sel(g1, m11, tl_sel(g2, -u01, -u11)));
-                const double r2 = tl_sel(g0, -u00, tl_sel(g1, -u01, tl_sel(g2, m22, m32)));
-                const double r3 = tl_sel(g0, -u10, tl_sel(g1, -u11, tl_sel(g2, m32, m33)));
-                mqg = tl_sel(q == 0, r0, tl_sel(q == 1, r1, tl_sel(q == 2, r2, tl_sel(q == 3, r3, 0.0))));
+                const double r0 = (g == 0) ? m00 : ((g == 1) ? m10 : ((g == 2) ? -u00 : -u10));
+                const double r1 = (g == 0) ? m10 : ((g == 1) ? m11 : ((g == 2) ? -u01 : -u11));
+                const double r2 = (g == 0) ? -u00 : ((g == 1) ? -u01 : ((g == 2) ? m22 : m32));
+                const double r3 = (g == 0) ? -u10 : ((g == 1) ? -u11 : ((g == 2) ? m32 : m33));
+                mqg = (q == 0) ? r0 : ((q == 1) ? r1 : ((q == 2) ? r2 : ((q == 3) ? r3 : 0.0)));
             }
             // (c) X = A21 M : results (C layout, lanes g<2) back home
             {
@@ -220,8 +202,9 @@ __device__ __forceinline__ void tfs_panel(double2 (&c)[NT * (NT + 1) / 2], doubl
                 double xa[NT];
 #pragma unroll
                 for (int I = J; I < NT; ++I) {
-                    const double v = A[(I * (I + 1) / 2 + J) * 64 + q * 8 + c0 + g];
-                    xa[I] = (I == J) ? tl_sel(q < c0 + 4, 0.0, -v) : -v;
+                    double v = A[(I * (I + 1) / 2 + J) * 64 + q * 8 + c0 + g];
+                    if (I == J && q < c0 + 4) v = 0.0;
+                    xa[I] = -v;
                 }
 #pragma unroll
                 for (int K = J + (c0 ? 1 : 0); K < NT; ++K) {
@@ -915,7 +898,7 @@ cudaError_t tile_configure(const sihmpc_plan_desc *d, const DevPlan &P, TilePlan
     C.kof = tp->ibuf; C.ptr = tp->ibuf + nk; C.hrows = tp->ibuf + nk + np; C.B = tp->dbuf; C.BH = tp->dbuf + nB;
     C.BHc = tp->dbuf + nB + nBH;
     tp->n_tiles = tb.n_stored;
-    if (getenv("SIHMPC_TILE_DEBUG")) {
+    if (getenv("SIHMPC_TILE_DEBUG")) {          // work balance of the product phases: groups of four tiles per warp and matrix
         const int *pt = tb.ptr.data();
         auto grp = [&](int poff, int T) { return (pt[poff + T + 1] - pt[poff + T]) / 4; };
         struct { const char *name; int off, n, rot; } ms[] = {{"me", C.me, C.n_r, 0}, {"mw", C.mw, C.n_r, 0}, {"mdu", C.mdu, C.n_v, 5},
