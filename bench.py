@@ -599,6 +599,7 @@ def main():
     gather_ms = None
     if world > 1:
         full = gather_stats(eng.stats, world * batch)          # warm
+        torch.cuda.synchronize()                               # every rank idle before the timed one (else: the peer's backlog is billed to it)
         cx.barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record(); full = gather_stats(eng.stats, world * batch); g1.record()
