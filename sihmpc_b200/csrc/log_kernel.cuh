@@ -266,9 +266,11 @@ ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__
             }
             __syncwarp();
             // ---- Hessian (lower triangle)
-            for (int idx = lane; idx < n * n; idx += 32) {
-                const int a = idx / n, b = idx % n;
-                if (b > a) continue;
+            for (int idx = lane; idx < (n * (n + 1)) / 2; idx += 32) {        // lanes over the lower triangle itself: a(a+1)/2 + b
+                int a = (int)((sqrtf(8.0f * (float)idx + 1.0f) - 1.0f) * 0.5f);
+                if ((a * (a + 1)) / 2 > idx) --a;
+                if (((a + 1) * (a + 2)) / 2 <= idx) ++a;
+                const int b = idx - (a * (a + 1)) / 2;
                 double h;
                 if (a < nv) {
                     h = P.Ht[a * nv + b];
