@@ -362,7 +362,7 @@ def measure_workload(cx, name, batch, K, W, spl, repeats, fp64_peak, sampler_fac
     return rec, dict(plan=plan, scen=scen, eng=eng, clocks=clocks, snap=snap)
 
 
-def measure_log_variant(cx, K, W, repeats):
+def measure_log_variant(cx, K, W, repeats, fp64_peak=None):
     """configs[1]: the log-barrier controller (example_distillation_log.py) through sihmpc_log_loop --
     throughput at batch 4096 and p50 latency of one step at batch 1 (host call to synchronised result)."""
     torch = cx.torch
@@ -404,8 +404,23 @@ def measure_log_variant(cx, K, W, repeats):
         torch.cuda.synchronize(cx.dev)
         ts.append(time.perf_counter() - a)
     ts = np.asarray(ts[60:]) * 1e6
-    return {"workload": "distillation_log (example_distillation_log.py controller, ihmpc_log_kernel via sihmpc_log_loop)",
-            "value": batch * K / (float(np.median(ms)) * 1e-3), "unit": UNIT,
+    # algorithmic work of one damped-Newton iteration on (dU, ss): gradients of the m sub-objectives
+    # and of Vt through E, lower triangle of the (nv+1)^2 Hessian (mh weighted blocks + rank-m term), Cholesky, two
+    # triangular solves, one line-search evaluation of phi
+    p = c.compile()
+    n = p.nv + 1
+    f_it = (2 * p.R * p.nv * (p.m + 1) + (n * (n + 1) // 2) * (2 * p.mh + 3 * p.m) + n ** 3 / 3 + 4 * n * n
+            + 2 * p.R * p.nv + 2 * (p.R + p.nv) * p.m)
+    value = batch * K / (float(np.median(ms)) * 1e-3)
+    roof = None
+    if fp64_peak:
+        roof = {"bound": "fp64", "flop_per_newton_iteration": float(f_it), "newton_iterations_per_step": iters,
+                "achieved": value * f_it * iters / 1e12, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
+                "frac": value * f_it * iters / fp64_peak,
+                "note": "one warp per scenario, instruction-issue bound (profiles/r02_log_kernel_ncu_summary.md); "
+                        "iterations = mean of the last step of the window"}
+    return {"roofline": roof, "workload": "distillation_log (example_distillation_log.py controller, ihmpc_log_kernel via sihmpc_log_loop)",
+            "value": value, "unit": UNIT,
             "value_min": batch * K / (ms.max() * 1e-3), "value_max": batch * K / (ms.min() * 1e-3),
             "scenarios": batch, "window": [k0, k0 + K], "repeats": repeats, "ms_per_step": float(np.median(ms)) / K,
             "mean_newton_iterations_last_step": iters, "status_or": st_or, "kernel": "sih::ihmpc_log_kernel",
@@ -624,7 +639,7 @@ def main():
             del mm
             torch.cuda.empty_cache()
         if rank == 0:
-            configs["distillation_log"] = measure_log_variant(cx, K, W, max(3, args.repeats // 2))
+            configs["distillation_log"] = measure_log_variant(cx, K, W, max(3, args.repeats // 2), fp64_peak)
         cx.barrier()
 
     if rank != 0:

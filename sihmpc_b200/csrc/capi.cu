@@ -848,12 +848,17 @@ static int log_launch(sihmpc_plan *plan, const sihmpc_io &io, const double *w0, 
     long long blocks = (batch + wpb - 1) / wpb;
     if (blocks > plan->sm_count * 4) blocks = plan->sm_count * 4;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (plan->d.nv + 1 <= 32) {
-        CUDA_TRY(sih_raise_smem_limit(reinterpret_cast<const void *>(sih::ihmpc_log_kernel<1>), smem));
-        sih::ihmpc_log_kernel<1><<<(int)blocks, wpb * 32, smem, st>>>(plan->d, io, w0, w_warm, batch, n_steps, iters, 100);
+    // <rows per lane, compile-time number of sub-objectives (0 = any)>: m = 4 is the reference's example and the
+    // distillation controller (four sub-objectives, example_distillation_log.py:55-66)
+    if (plan->d.nv + 1 <= 32 && plan->d.m == 4) {
+        CUDA_TRY(sih_raise_smem_limit(reinterpret_cast<const void *>(sih::ihmpc_log_kernel<1, 4>), smem));
+        sih::ihmpc_log_kernel<1, 4><<<(int)blocks, wpb * 32, smem, st>>>(plan->d, io, w0, w_warm, batch, n_steps, iters, 100);
+    } else if (plan->d.nv + 1 <= 32) {
+        CUDA_TRY(sih_raise_smem_limit(reinterpret_cast<const void *>(sih::ihmpc_log_kernel<1, 0>), smem));
+        sih::ihmpc_log_kernel<1, 0><<<(int)blocks, wpb * 32, smem, st>>>(plan->d, io, w0, w_warm, batch, n_steps, iters, 100);
     } else {
-        CUDA_TRY(sih_raise_smem_limit(reinterpret_cast<const void *>(sih::ihmpc_log_kernel<2>), smem));
-        sih::ihmpc_log_kernel<2><<<(int)blocks, wpb * 32, smem, st>>>(plan->d, io, w0, w_warm, batch, n_steps, iters, 100);
+        CUDA_TRY(sih_raise_smem_limit(reinterpret_cast<const void *>(sih::ihmpc_log_kernel<2, 0>), smem));
+        sih::ihmpc_log_kernel<2, 0><<<(int)blocks, wpb * 32, smem, st>>>(plan->d, io, w0, w_warm, batch, n_steps, iters, 100);
     }
     CUDA_TRY(cudaGetLastError());
     return 0;

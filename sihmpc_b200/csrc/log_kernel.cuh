@@ -45,10 +45,47 @@ __host__ __device__ inline LogLayout make_log_layout(const DevPlan &P) {
     return w;
 }
 
-// residual r = ET v + e, sub-objective values, d_i; returns phi (inf when some d_i <= 0)
+// residual r = ET v + e, sub-objective values, d_i; returns phi (inf when some d_i <= 0).
+// MM > 0 (= m, compile time): every lane keeps the m partial sums of ITS residual rows / moves in registers (no second
+// pass over r by m lanes out of 32), one warp sum per sub-objective, lane i takes log d_i (the m logarithms were
+// evaluated one after the other by every lane).  The result is bitwise the same on every lane (xor butterfly).
+template <int MM>
 __device__ double log_eval(const DevPlan &P, const double *vv, const double *e, double *r, double *Vi,
                            double *d, int lane) {
     const int R = P.R, nv = P.nv, m = P.m;
+    if constexpr (MM > 0) {
+        double vt = 0.0, acc[MM];
+#pragma unroll
+        for (int i = 0; i < MM; ++i) acc[i] = 0.0;
+        for (int k = lane; k < R; k += 32) {
+            double a = e[k];
+            for (int c = 0; c < nv; ++c) a = fma(P.ET[(size_t)c * R + k], vv[c], a);
+            r[k] = a;
+            const double a2 = a * a;
+            vt = fma(P.w0row[k], a2, vt);
+            const double *wr = P.Wrow + (size_t)k * MM;
+#pragma unroll
+            for (int i = 0; i < MM; ++i) acc[i] = fma(wr[i], a2, acc[i]);
+        }
+        for (int c = lane; c < nv; c += 32) {
+            const double v2 = vv[c] * vv[c];
+            const double *wd = P.Wdu + (size_t)c * MM;
+#pragma unroll
+            for (int i = 0; i < MM; ++i) acc[i] = fma(wd[i], v2, acc[i]);
+        }
+        vt = warp_sum(vt);
+        double mine = 0.0;
+#pragma unroll
+        for (int i = 0; i < MM; ++i) { const double t = warp_sum(acc[i]); if (lane == i) mine = t; }
+        const double ss = vv[nv];
+        const bool own = lane < MM;
+        const double di = ss * P.gamma[own ? lane : 0] - mine;
+        if (own) { Vi[lane] = mine; d[lane] = di; }
+        const bool bad = __any_sync(SIH_FULL, own && !(di > 0.0));
+        const double lg = warp_sum((own && di > 0.0) ? log(di) : 0.0);
+        __syncwarp();
+        return bad ? SIH_INF : (vt + ss * ss) - lg;
+    }
     double vt = 0.0;
     for (int k = lane; k < R; k += 32) {
         double a = e[k];
@@ -133,8 +170,11 @@ __device__ double log_barrier(const DevPlan &P, const double *vv, const double *
 // the log controller (ihmpccontroller_log.py:552-563); with SIHMPC_F_ADVANCE the body of the driver loop
 // (example_distillation_log.py:85-135: mpc, first move to the plant, warmStart with ss = 1, log.py:518-549)
 // runs in place with the state resident in shared memory.
-template <int NVR>
-__global__ void __launch_bounds__(128)
+#ifndef SIH_LOG_MINB
+#define SIH_LOG_MINB 4
+#endif
+template <int NVR, int MM>
+__global__ void __launch_bounds__(128, SIH_LOG_MINB)
 ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__ w0, double *__restrict__ w_warm,
                  const long long batch, const int n_steps, int *iters_out, const int max_iter) {
     extern __shared__ double smem[];
@@ -205,7 +245,7 @@ ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__
         for (int i = lane; i < nv; i += 32) vw[i] = v[i];
         __syncwarp();
         int st = 0, it = 0;
-        double phi = log_eval(P, v, e, r, Vi, d, lane);
+        double phi = log_eval<MM>(P, v, e, r, Vi, d, lane);
         {   // make the start strictly feasible for the barrier: ss >= 1 and ss*gamma_i > V_i
             double smax = 0.0;
             for (int i = 0; i < m; ++i) smax = fmax(smax, Vi[i] / P.gamma[i]);
@@ -213,14 +253,15 @@ ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__
             __syncwarp();
             if (lane == 0) v[nv] = ss0;
             __syncwarp();
-            phi = log_eval(P, v, e, r, Vi, d, lane);
+            phi = log_eval<MM>(P, v, e, r, Vi, d, lane);
         }
         // Newton on phi (mu = 0) or phi_mu = phi - mu sum log c_j (interior-point rounds), at most `lim` iterations
         auto newton = [&](const double mu, const int lim) {
             // weights of the barrier terms, ONCE per iteration (they were two FP64 divisions inside every term of every
             // Hessian element: 17 % of the kernel's samples)
-            auto w1f = [&](const int i) { return w1s[i]; };
-            auto w2f = [&](const int i) { return w2s[i]; };
+            const int m_ = MM > 0 ? MM : m;                  // compile-time trip count of the sub-objective loops when MM > 0
+            constexpr int MR = MM > 0 ? MM : 1;
+            bool near = false;                               // the last step was a full Newton step with a small decrement
         for (int itn = 1; itn <= lim; ++itn) {
             ++it;
             if (mu > 0.0) log_barrier(P, v, uu, d, mu, true, S1, S2, b1, b2, lane, glo, ghi, T1, T2);     // derivative coefficients at v
@@ -230,41 +271,89 @@ ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__
                 w2s[i] = 1.0 / (di * di) + (mu > 0.0 ? mu / (si * si) : 0.0);
             }
             __syncwarp();
+            // (MM > 0: the weights and the weights of the mh Hessian blocks live in registers for the whole iteration)
+            double w1r[MR], w2r[MR], wq[MR];
+            if constexpr (MM > 0) {
+#pragma unroll
+                for (int i = 0; i < MM; ++i) { w1r[i] = w1s[i]; w2r[i] = w2s[i]; wq[i] = (i < P.mh) ? w1s[P.hj_index[i]] : 0.0; }
+            }
+            auto w1f = [&](const int i) { if constexpr (MM > 0) return w1r[i]; else return w1s[i]; };
+            auto w2f = [&](const int i) { if constexpr (MM > 0) return w2r[i]; else return w2s[i]; };
             // ---- gradients a_i = grad_dU V_i (rows of gi), lanes over variables; E and r read once per four sub-objectives
             for (int c = lane; c < nv; c += 32) {
                 double a = 0.0;
-                for (int i0 = 0; i0 < m; i0 += 4) {
-                    const int mi = (m - i0 < 4) ? m - i0 : 4;
-                    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                const double vc = v[c];
+                if constexpr (MM > 0) {
+                    double ai[MM];
+#pragma unroll
+                    for (int i = 0; i < MM; ++i) ai[i] = 0.0;
                     for (int k = 0; k < R; ++k) {
                         const double er = P.E[(size_t)k * nv + c] * r[k];
-                        const double *wr = P.Wrow + (size_t)k * m + i0;
-                        a0 = fma(er, wr[0], a0);
-                        if (mi > 1) a1 = fma(er, wr[1], a1);
-                        if (mi > 2) a2 = fma(er, wr[2], a2);
-                        if (mi > 3) a3 = fma(er, wr[3], a3);
-                        if (i0 == 0) a = fma(er, P.w0row[k], a);
+                        const double *wr = P.Wrow + (size_t)k * MM;
+#pragma unroll
+                        for (int i = 0; i < MM; ++i) ai[i] = fma(er, wr[i], ai[i]);
+                        a = fma(er, P.w0row[k], a);
                     }
-                    gi[i0 * nv + c] = 2.0 * (a0 + P.Wdu[(size_t)c * m + i0] * v[c]);
-                    if (mi > 1) gi[(i0 + 1) * nv + c] = 2.0 * (a1 + P.Wdu[(size_t)c * m + i0 + 1] * v[c]);
-                    if (mi > 2) gi[(i0 + 2) * nv + c] = 2.0 * (a2 + P.Wdu[(size_t)c * m + i0 + 2] * v[c]);
-                    if (mi > 3) gi[(i0 + 3) * nv + c] = 2.0 * (a3 + P.Wdu[(size_t)c * m + i0 + 3] * v[c]);
+                    double gc = 2.0 * a;
+#pragma unroll
+                    for (int i = 0; i < MM; ++i) {
+                        const double gic = 2.0 * fma(P.Wdu[(size_t)c * MM + i], vc, ai[i]);
+                        gi[i * nv + c] = gic;
+                        gc = fma(gic, w1r[i], gc);
+                    }
+                    a = gc;
+                } else {
+                    for (int i0 = 0; i0 < m; i0 += 4) {
+                        const int mi = (m - i0 < 4) ? m - i0 : 4;
+                        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                        for (int k = 0; k < R; ++k) {
+                            const double er = P.E[(size_t)k * nv + c] * r[k];
+                            const double *wr = P.Wrow + (size_t)k * m + i0;
+                            a0 = fma(er, wr[0], a0);
+                            if (mi > 1) a1 = fma(er, wr[1], a1);
+                            if (mi > 2) a2 = fma(er, wr[2], a2);
+                            if (mi > 3) a3 = fma(er, wr[3], a3);
+                            if (i0 == 0) a = fma(er, P.w0row[k], a);
+                        }
+                        gi[i0 * nv + c] = 2.0 * (a0 + P.Wdu[(size_t)c * m + i0] * vc);
+                        if (mi > 1) gi[(i0 + 1) * nv + c] = 2.0 * (a1 + P.Wdu[(size_t)c * m + i0 + 1] * vc);
+                        if (mi > 2) gi[(i0 + 2) * nv + c] = 2.0 * (a2 + P.Wdu[(size_t)c * m + i0 + 2] * vc);
+                        if (mi > 3) gi[(i0 + 3) * nv + c] = 2.0 * (a3 + P.Wdu[(size_t)c * m + i0 + 3] * vc);
+                    }
+                    double gc = 2.0 * a;
+                    for (int i = 0; i < m; ++i) gc += gi[i * nv + c] * w1f(i);
+                    a = gc;
                 }
-                double gc = 2.0 * a;
-                for (int i = 0; i < m; ++i) gc += gi[i * nv + c] * w1f(i);
                 if (mu > 0.0) {
-                    if (c < nvm) gc += S1[c] + b1[c];
-                    for (int rr = 0; rr < ncd; ++rr) gc = fma(T1[rr], P.GcT[(size_t)c * ncd + rr], gc);
+                    if (c < nvm) a += S1[c] + b1[c];
+                    for (int rr = 0; rr < ncd; ++rr) a = fma(T1[rr], P.GcT[(size_t)c * ncd + rr], a);
                 }
-                g[c] = gc;
+                g[c] = a;
             }
             if (lane == 0) {
                 double gs = 2.0 * v[nv];
-                for (int i = 0; i < m; ++i) gs -= P.gamma[i] * w1f(i);
+#pragma unroll
+                for (int i = 0; i < m_; ++i) gs -= P.gamma[i] * w1f(i);
                 if (mu > 0.0) gs -= mu / (v[nv] - log_relax(1.0, -1.0));
                 g[nv] = gs;
             }
             __syncwarp();
+            const double dec_tol = (mu > 0.0) ? fmin(1e-16 * (1.0 + fabs(phi)), 1e-2 * mu) : 1e-18 * (1.0 + fabs(phi));
+            if (near) {
+                // the factor of the LAST iteration is still in Hm: after a full step with a small decrement the Hessian has
+                // moved by a relative ~sqrt(dec), so the decrement through the old factor decides "converged" as well as the
+                // new one would -- the iteration that only confirms convergence skips its Hessian and factorisation
+                double accc[NVR];
+                load_acc<NVR>(accc, g, n, lane, -1.0);
+                warp_trsv_lower<NVR>(Hm, ld, dinv, n, accc, lane);
+                warp_trsv_lower_T<NVR>(Hm, ld, dinv, n, accc, lane);
+                double decc = 0.0;
+#pragma unroll
+                for (int t = 0; t < NVR; ++t) { const int i = lane + 32 * t; if (i < n) decc = fma(-g[i], accc[t], decc); }
+                decc = warp_sum(decc);
+                if (!(decc > 0.5 * dec_tol)) break;
+                __syncwarp();
+            }
             // ---- Hessian (lower triangle)
             for (int idx = lane; idx < (n * (n + 1)) / 2; idx += 32) {        // lanes over the lower triangle itself: a(a+1)/2 + b
                 int a = (int)((sqrtf(8.0f * (float)idx + 1.0f) - 1.0f) * 0.5f);
@@ -273,11 +362,19 @@ ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__
                 const int b = idx - (a * (a + 1)) / 2;
                 double h;
                 if (a < nv) {
-                    h = P.Ht[a * nv + b];
-                    for (int q = 0; q < P.mh; ++q) h = fma(w1f(P.hj_index[q]), P.HJ[((size_t)q * nv + a) * nv + b], h);
-                    for (int i = 0; i < m; ++i) {
-                        h = fma(gi[i * nv + a], gi[i * nv + b] * w2f(i), h);
-                        if (a == b) h = fma(2.0 * P.Wdu[(size_t)a * m + i], w1f(i), h);
+                    const size_t ab = (size_t)a * nv + b;
+                    h = P.Ht[ab];
+                    if constexpr (MM > 0) {
+#pragma unroll
+                        for (int q = 0; q < MM; ++q) if (q < P.mh) h = fma(wq[q], P.HJ[(size_t)q * nv * nv + ab], h);
+                    } else {
+                        for (int q = 0; q < P.mh; ++q) h = fma(w1f(P.hj_index[q]), P.HJ[(size_t)q * nv * nv + ab], h);
+                    }
+#pragma unroll
+                    for (int i = 0; i < m_; ++i) h = fma(gi[i * nv + a] * w2f(i), gi[i * nv + b], h);
+                    if (a == b) {
+#pragma unroll
+                        for (int i = 0; i < m_; ++i) h = fma(2.0 * P.Wdu[(size_t)a * m_ + i], w1f(i), h);
                     }
                     if (mu > 0.0) {
                         if (a < nvm && (a % nu) == (b % nu)) h += S2[a];          // a >= b: rows k >= k_a cover both moves
@@ -287,10 +384,12 @@ ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__
                     }
                 } else if (b < nv) {
                     h = 0.0;
-                    for (int i = 0; i < m; ++i) h -= P.gamma[i] * gi[i * nv + b] * w2f(i);
+#pragma unroll
+                    for (int i = 0; i < m_; ++i) h -= P.gamma[i] * gi[i * nv + b] * w2f(i);
                 } else {
                     h = 2.0;
-                    for (int i = 0; i < m; ++i) h += P.gamma[i] * P.gamma[i] * w2f(i);
+#pragma unroll
+                    for (int i = 0; i < m_; ++i) h += P.gamma[i] * P.gamma[i] * w2f(i);
                     if (mu > 0.0) { const double sl = v[nv] - log_relax(1.0, -1.0); h += mu / (sl * sl); }
                 }
                 Hm[a * ld + b] = h;
@@ -315,7 +414,7 @@ ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__
 #pragma unroll
             for (int t = 0; t < NVR; ++t) { const int i = lane + 32 * t; if (i < n) dec = fma(-g[i], acc[t], dec); }
             dec = warp_sum(dec);
-            if (!(dec > (mu > 0.0 ? fmin(1e-16 * (1.0 + fabs(phi)), 1e-2 * mu) : 1e-18 * (1.0 + fabs(phi))))) break;
+            if (!(dec > dec_tol)) break;
             // ---- backtracking on phi (keeps every d_i > 0)
             double t_ = 1.0, phin = SIH_INF;
             bool ok = false;
@@ -323,7 +422,7 @@ ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__
 #pragma unroll
                 for (int t = 0; t < NVR; ++t) { const int i = lane + 32 * t; if (i < n) vt[i] = fma(t_, acc[t], v[i]); }
                 __syncwarp();
-                phin = log_eval(P, vt, e, r, Vi, d, lane);
+                phin = log_eval<MM>(P, vt, e, r, Vi, d, lane);
                 if (mu > 0.0 && phin < SIH_INF) phin += log_barrier(P, vt, uu, d, mu, false, S1, S2, b1, b2, lane, glo, ghi, T1, T2);
                 if (phin <= phi - 1e-4 * t_ * dec) { ok = true; break; }
                 t_ *= 0.5;
@@ -331,7 +430,7 @@ ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__
             }
             if (!ok) {                     // rounding level: restore the state of v and stop
                 __syncwarp();
-                phi = log_eval(P, v, e, r, Vi, d, lane);
+                phi = log_eval<MM>(P, v, e, r, Vi, d, lane);
                 if (mu > 0.0) phi += log_barrier(P, v, uu, d, mu, false, S1, S2, b1, b2, lane, glo, ghi, T1, T2);
                 break;
             }
@@ -340,6 +439,9 @@ ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__
             const double flat_tol = (mu > 0.0) ? fmin(1e-15 * (1.0 + fabs(phi)), 1e-3 * mu) : 1e-15 * (1.0 + fabs(phi));
             const bool flat = (phi - phin) <= flat_tol;                      // decrease at rounding level: converged
             phi = phin;
+            // (phi is self-concordant: after a full step with decrement dec the Hessian is within (1 - sqrt(dec))^-2 of the old one;
+            // the barrier terms of the interior-point rounds carry the factor mu)
+            near = (t_ == 1.0) && dec <= 1e-4 * (mu > 0.0 ? fmin(mu, 1.0) : 1.0);
             __syncwarp();
             if (flat) break;
         }
@@ -523,13 +625,13 @@ ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__
                     }
                     __syncwarp();
                     // ss large enough for every barrier; returns phi there
-                    log_eval(P, v, e, r, Vi, d, lane);
+                    log_eval<MM>(P, v, e, r, Vi, d, lane);
                     double smax = 0.0;
                     for (int i = 0; i < m; ++i) smax = fmax(smax, (Vi[i] + 0.02) / P.gamma[i]);
                     __syncwarp();
                     if (lane == 0) v[nv] = fmax(fmax(ss_free, 1.01), 1.1 * smax + 0.1);
                     __syncwarp();
-                    return log_eval(P, v, e, r, Vi, d, lane);
+                    return log_eval<MM>(P, v, e, r, Vi, d, lane);
                 };
                 {
                     const double m1 = towards(vfree, false);
@@ -544,13 +646,13 @@ ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__
                 }
                 bool fail_ip = false;
                 for (double mu = 1e-1; mu >= 0.99e-14; mu *= 0.1) {
-                    phi = log_eval(P, v, e, r, Vi, d, lane);
+                    phi = log_eval<MM>(P, v, e, r, Vi, d, lane);
                     const double bar = log_barrier(P, v, uu, d, mu, false, S1, S2, b1, b2, lane, glo, ghi, T1, T2);
                     if (!(phi < SIH_INF) || !(bar < SIH_INF)) { fail_ip = true; break; }
                     phi += bar;
                     newton(mu, 60);
                 }
-                phi = log_eval(P, v, e, r, Vi, d, lane);         // the cost the reference reports: without the barriers
+                phi = log_eval<MM>(P, v, e, r, Vi, d, lane);         // the cost the reference reports: without the barriers
                 if (fail_ip) st |= SIHMPC_ST_ACTIVE_UNSUPPORTED;
             }
         }
