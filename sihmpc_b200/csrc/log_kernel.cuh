@@ -26,6 +26,44 @@
 
 namespace sih {
 
+// Cholesky of the lower triangle of M (n <= NMAX <= 32) with lane i holding ROW i in registers: the Crout dot products
+// s_i = M_ik - sum_{j<k} L_ij L_kj run over compile-time j (both loops fully unrolled), L_kj comes as a broadcast LDS
+// from the finished row k in shared memory, every finished column goes back to shared memory for the substitutions.
+// Same operation order as warp_cholesky (even / odd j on two chains): bitwise the same factor, a third of its instructions
+// (the in-shared-memory loop spent them on addresses, loop control and the second LDS per product).
+template <int NMAX>
+__device__ int warp_cholesky_rows(double *M, const int ld, const int n, double *dinv, const int lane) {
+    double row[NMAX];
+    {
+        const double *Mi = M + (size_t)lane * ld;
+#pragma unroll
+        for (int j = 0; j < NMAX; ++j) row[j] = (lane < n && j <= lane) ? Mi[j] : 0.0;
+    }
+    int bad = 0;
+#pragma unroll
+    for (int k = 0; k < NMAX; ++k) {
+        if (k < n) {                                        // (uniform)
+            const double *Mk = M + (size_t)k * ld;
+            double a0 = row[k], a1 = 0.0;
+#pragma unroll
+            for (int j = 0; j < k; ++j) {
+                if (j & 1) a1 = fma(-row[j], Mk[j], a1);
+                else a0 = fma(-row[j], Mk[j], a0);
+            }
+            const double sv = a0 + a1;
+            double d = __shfl_sync(SIH_FULL, sv, k);
+            if (!(d > 0.0)) { bad = 1; d = 1e-300; }
+            const double inv = rsqrt(d);
+            const double l = sv * inv;                      // lane k: d*inv = sqrt(d)
+            row[k] = l;
+            if (lane >= k && lane < n) M[(size_t)lane * ld + k] = l;
+            if (lane == 0) dinv[k] = inv;
+            __syncwarp();
+        }
+    }
+    return bad;
+}
+
 struct LogLayout { int H, dinv, x, xn, uu, ysp, e, r, v, g, p, gi, d, Vi, vt, s1, s2, b1, b2, glo, ghi, t1, t2, vw, w12, total; };
 
 __host__ __device__ inline LogLayout make_log_layout(const DevPlan &P) {
@@ -404,7 +442,8 @@ ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__
                 printf("k=%d mu=%.1e it=%d phi=%.10g ss=%.6g notpd=%d diag[%.3g,%.3g] d=[%.3g %.3g %.3g %.3g] rho=[%.6g %.6g]\n", kabs, mu, itn, phi,
                        v[nv], (int)dbg_np, dbg_diag_min, dbg_diag_max, d[0], d[1], d[2], d[3], nv > nvm ? v[nvm] : 0.0, nv > nvm + 1 ? v[nvm + 1] : 0.0);
 #else
-            if (warp_cholesky<NVR>(Hm, ld, n, dinv, lane)) st |= SIHMPC_ST_NOTPD;
+            if (NVR == 1 && n <= 24) { if (warp_cholesky_rows<24>(Hm, ld, n, dinv, lane)) st |= SIHMPC_ST_NOTPD; }
+            else if (warp_cholesky<NVR>(Hm, ld, n, dinv, lane)) st |= SIHMPC_ST_NOTPD;
 #endif
             double acc[NVR];
             load_acc<NVR>(acc, g, n, lane, -1.0);
