@@ -816,6 +816,53 @@ def test_log_variant_example_loop_matches_oracle():
     assert len(sol['g'].full()) == 260                                 # SURVEY.md section 8 size table
 
 
+@pytest.mark.parametrize("N,extra", [(16, False), (10, True)])
+def test_log_variant_other_instantiations_match_oracle(N, extra):
+    """The log kernel is compiled as <rows per lane, m>: <1,4> serves the reference's example; this covers <2,0>
+    (N = 16: 33 Newton variables, two rows per lane, in-shared-memory Crout factorisation) and <1,0> (five
+    sub-objectives: the generic loops over m) in closed loop against the log oracle, batched launch."""
+    from oracle.ihmpc_log_oracle import OracleIHMPCLog
+    from sihmpc.ihmpccontroller_log import IHMPCController as LogController
+    sys_ = sc.distillation_system()
+
+    def declare(cls):
+        c = cls(sys_, N, ulb=[0, 0])
+        c.subObjComposed(y=[0], Q=1, sat=N * 0.5 ** 2)
+        c.subObjComposed(y=[1], Q=1, sat=N * 2.0 ** 2)
+        c.subObj(du=[0], Q=1, sat=N * 0.3 ** 2)
+        c.subObj(du=[1], Q=1, sat=N * 0.3 ** 2)
+        if extra:
+            c.subObj(y=[0], Q=1, sat=N * 0.7 ** 2)
+        c.subObj(siN=[0], Q=1, addJ=False)
+        c.subObj(siN=[1], Q=1, addJ=False)
+        return c
+    c = declare(LogController)
+    p = c.compile()
+    assert (p.nv + 1 > 32) == (N == 16) and p.m == (5 if extra else 4)
+    B, T = 8, 14
+    scen = sc.distillation_scenarios(B)
+    scen["seg_start"][:, 1] = 3; scen["seg_start"][:, 2] = 9
+    eng = c.engine(B)
+    eng.set_state(scen["x0"], scen["u0"])
+    eng.set_schedule(scen["ysp_seq"], scen["seg_start"])
+    tr = eng.run(T, steps_per_launch=5, record=True)
+    du = tr["du"].cpu().numpy(); J = tr["J"].cpu().numpy()
+    assert (eng.stats[:, sys_.ny + 3].cpu().numpy() == 0).all()
+    for idx in (0, 7):
+        orc = declare(OracleIHMPCLog)
+        xo, uo, w0o = scen["x0"][idx].copy(), scen["u0"][idx].copy(), []
+        ysp_of = schedule_fn(scen["ysp_seq"][idx], scen["seg_start"][idx])
+        scale = 1e-3
+        for k in range(T):
+            ysp = np.asarray(ysp_of(k), float)
+            solo = orc.mpc(xo, ysp, w0o, uo, [], [], ViN_ant=[])
+            scale = max(scale, np.max(np.abs(solo['du_opt'][:, 0])))
+            assert np.max(np.abs(du[k, idx] - solo['du_opt'][:, 0])) <= RTOL * scale, (idx, k)
+            assert abs(J[k, idx] - solo['J']) <= RTOL * abs(solo['J']), (idx, k)
+            r = orc.dynF(xo, uo, solo['du_opt'][:, 0]); xo, uo = r['xkp1'], r['ukp1']
+            w0o = orc.warmStart(solo, ysp)
+
+
 def test_log_variant_batched_closed_loop_matches_oracle():
     """sihmpc_log_loop: 24 scenarios of the log-variant driver loop (example_distillation_log.py:85-135: mpc,
     first move to the plant, warmStart with ss = 1) in one launch vs the log oracle run scenario by scenario."""
