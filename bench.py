@@ -334,7 +334,8 @@ def measure_workload(cx, name, batch, K, W, spl, repeats, fp64_peak, sampler_fac
     kname = eng.dp.kernel_name()
     has_bounds = bool(np.isfinite(plan.ulb).any() or np.isfinite(plan.uub).any() or np.isfinite(plan.dulb).any()
                       or np.isfinite(plan.duub).any())
-    if kname == "mma_step_kernel" and has_bounds and not os.environ.get("SIHMPC_NO_STREAM_RESUME"):
+    stream_min = int(os.environ.get("SIHMPC_STREAM_MIN_BATCH", "16384"))     # mma_units.cu: workers only for long first passes
+    if kname == "mma_step_kernel" and has_bounds and not os.environ.get("SIHMPC_NO_STREAM_RESUME") and batch >= stream_min:
         kpl, kdesc = 4, "mma_step_kernel resume workers (concurrent) + first pass + sweep pass, ihmpc_step_kernel"
     elif kname in ("mma_step_kernel", "tile_step_kernel") and has_bounds:
         kpl, kdesc = 3, "%s first pass, %s resume pass, ihmpc_step_kernel" % (kname, kname)

@@ -42,6 +42,8 @@ struct MmaPlan {
     cudaStream_t aux;
     cudaEvent_t ev_fork, ev_join;
     int stream_workers;      // CTAs of the worker launch (0: resume pass after the first pass, as in round 1)
+    long long stream_min_batch;   // below this batch the resume pass simply follows the first pass: the workers only pay when the
+                                  // first pass is long, and their launch + fork/join are a third of a batch-1 step
     int sm_count;
 };
 

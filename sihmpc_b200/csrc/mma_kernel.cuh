@@ -1245,7 +1245,8 @@ inline cudaError_t mma_configure_shape(const sihmpc_plan_desc *d, const DevPlan 
 template <typename D>
 inline cudaError_t mma_launch_shape(MmaPlan &qp, const DevPlan &P, const sihmpc_io &io, long long batch,
                                     int n_steps, int grid, cudaStream_t st, bool allow_resume) {
-    const bool stream_resume = allow_resume && !qp.res_active && qp.aux && mma_resumes(qp, batch, n_steps) && qp.stream_workers > 0;
+    const bool stream_resume = allow_resume && !qp.res_active && qp.aux && mma_resumes(qp, batch, n_steps) && qp.stream_workers > 0 &&
+                               batch >= qp.stream_min_batch;
     if (stream_resume) {
         // workers on the auxiliary stream, concurrent with the first pass (which leaves them room when it fills the GPU)
         const int nw = qp.stream_workers;

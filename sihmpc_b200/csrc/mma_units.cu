@@ -69,6 +69,8 @@ cudaError_t mma_configure(const sihmpc_plan_desc *d, const DevPlan &P, MmaPlan *
         qp->sm_count = prop.multiProcessorCount;
         qp->stream_workers = getenv("SIHMPC_NO_STREAM_RESUME") ? 0 : 2;
         if (const char *wv = getenv("SIHMPC_STREAM_WORKERS")) { const int v = atoi(wv); if (v >= 0 && v <= 32) qp->stream_workers = v; }
+        qp->stream_min_batch = 16384;
+        if (const char *bv = getenv("SIHMPC_STREAM_MIN_BATCH")) { const long long v = atoll(bv); if (v >= 0) qp->stream_min_batch = v; }
         e = cudaStreamCreateWithFlags(&qp->aux, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&qp->ev_fork, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&qp->ev_join, cudaEventDisableTiming);
