@@ -263,7 +263,10 @@ int sihmpc_log_step(sihmpc_plan *plan, const double *x, const double *u, const d
  * status, stats, traj_*; io.w_opt is [batch][nv+2ny+1] here; pesos/vinant are not used).  w_warm
  * [batch][nv+2ny+1] is the warm start on entry and the shifted plan on exit (NULL: cold start, not
  * returned).  iters [batch]: Newton iterations of the last step (NULL skips); io.stats[ny+4] accumulates
- * them.                                                                                              */
+ * them.  io.pesos (optional, with SIHMPC_F_ADVANCE): [batch] doubles of solver state carried between launches --
+ * ss of the scenario's last optimum, where the Newton iteration of the next step starts (zero-initialised by the
+ * caller; the warm start itself keeps ss = 1 as the reference writes it, the optimum is the same, the solve is
+ * one iteration shorter).                                                                           */
 int sihmpc_log_loop(sihmpc_plan *plan, const sihmpc_io *io, double *w_warm, int64_t batch, int32_t n_steps,
                     int32_t *iters, void *stream);
 

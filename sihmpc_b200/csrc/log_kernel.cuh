@@ -26,6 +26,7 @@
 
 namespace sih {
 
+
 // Cholesky of the lower triangle of M (n <= NMAX <= 32) with lane i holding ROW i in registers: the Crout dot products
 // s_i = M_ik - sum_{j<k} L_ij L_kj run over compile-time j (both loops fully unrolled), L_kj comes as a broadcast LDS
 // from the finished row k in shared memory, every finished column goes back to shared memory for the substitutions.
@@ -242,6 +243,11 @@ ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__
         for (int i = lane; i < nu; i += 32) uu[i] = io.u[s * nu + i];
         for (int i = lane; i < nv; i += 32) v[i] = (w0 && i < nvm) ? w0[s * nw + i] : 0.0;
         if (lane == 0) v[nv] = w0 ? w0[s * nw + nw - 1] : 1.0;
+        // ss of the last optimum of this scenario (0: none).  The warm start of the reference resets ss to 1 (log.py:548); the
+        // Newton iteration of the NEXT step may start wherever it likes -- the minimiser of the strictly convex phi is the
+        // same -- and started at the last ss* (sqrt(m/2) near steady state) it needs one iteration less (5 -> 4; 1 at rest).
+        // Carried between launches in io.pesos [batch] (unused otherwise by the log variant; NULL: within the launch only).
+        double ss_hint = ((io.flags & SIHMPC_F_ADVANCE) && io.pesos) ? io.pesos[s] : 0.0;
         double st_ise = 0.0, st_du2 = 0.0, st_J = 0.0;      // lane i < ny holds the ISE of output i
         int st_or = 0, it_total = 0;
         if (io.stats) {
@@ -287,7 +293,7 @@ ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__
         {   // make the start strictly feasible for the barrier: ss >= 1 and ss*gamma_i > V_i
             double smax = 0.0;
             for (int i = 0; i < m; ++i) smax = fmax(smax, Vi[i] / P.gamma[i]);
-            const double ss0 = fmax(fmax(v[nv], 1.0), 1.1 * smax + 0.1);
+            const double ss0 = fmax(fmax(fmax(v[nv], 1.0), 1.1 * smax + 0.1), (ss_hint < 1e6) ? ss_hint : 0.0);
             __syncwarp();
             if (lane == 0) v[nv] = ss0;
             __syncwarp();
@@ -696,6 +702,7 @@ ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__
             }
         }
         st_or |= st; it_total += it; st_J = phi;
+        ss_hint = (st == 0) ? v[nv] : 0.0;
         const bool last_step = (step == n_steps - 1);
         if (last_step) {
             if (io.du) for (int j = lane; j < nu; j += 32) io.du[s * nu + j] = v[j];
@@ -777,6 +784,7 @@ ihmpc_log_kernel(const DevPlan P, const sihmpc_io io, const double *__restrict__
                 for (int i = lane; i < nvm; i += 32) w_warm[s * nw + i] = v[i];
                 if (lane == 0) w_warm[s * nw + nw - 1] = v[nv];
             }
+            if (io.pesos && lane == 0) io.pesos[s] = ss_hint;
         }
         if (io.stats) {
             if (lane < ny) io.stats[s * nstat + lane] = st_ise;

@@ -241,6 +241,7 @@ class LogBatchedEngine:
         self.w_opt = torch.zeros(B, self.nw, dtype=f64, device=dev)
         self.w_warm = torch.zeros(B, self.nw, dtype=f64, device=dev)
         self.w_warm[:, -1] = 1.0
+        self.ss_last = torch.zeros(B, dtype=f64, device=dev)      # ss of the last optimum: start of the next Newton solve (io.pesos)
         self.vinant = torch.full((B, max(p.n_vin, 1)), float("inf"), dtype=f64, device=dev)   # contracting ViN_ant
         self.status = torch.zeros(B, dtype=torch.int32, device=dev)
         self.iters = torch.zeros(B, dtype=torch.int32, device=dev)
@@ -252,6 +253,7 @@ class LogBatchedEngine:
         self.x.copy_(torch.as_tensor(np.asarray(x, dtype=np.float64)).reshape(self.batch, -1))
         self.u.copy_(torch.as_tensor(np.asarray(u, dtype=np.float64)).reshape(self.batch, -1))
         self.w_warm.zero_(); self.w_warm[:, -1] = 1.0
+        self.ss_last.zero_()
         self.vinant.fill_(float("inf"))
         self.k = 0
         self.stats.zero_()
@@ -262,11 +264,11 @@ class LogBatchedEngine:
 
     def snapshot(self):
         return dict(x=self.x.clone(), u=self.u.clone(), w_warm=self.w_warm.clone(), stats=self.stats.clone(),
-                    vinant=self.vinant.clone(), k=self.k)
+                    vinant=self.vinant.clone(), ss_last=self.ss_last.clone(), k=self.k)
 
     def restore(self, snap):
         self.x.copy_(snap["x"]); self.u.copy_(snap["u"]); self.w_warm.copy_(snap["w_warm"])
-        self.stats.copy_(snap["stats"]); self.vinant.copy_(snap["vinant"])
+        self.stats.copy_(snap["stats"]); self.vinant.copy_(snap["vinant"]); self.ss_last.copy_(snap["ss_last"])
         self.k = int(snap["k"])
 
     def run(self, n_steps: int, steps_per_launch: Optional[int] = None, record: bool = False):
@@ -296,6 +298,7 @@ class LogBatchedEngine:
                     io.plant_val = self.plant_val.data_ptr()
                 io.du, io.J, io.w_opt = self.du.data_ptr(), self.J.data_ptr(), self.w_opt.data_ptr()
                 io.status, io.stats = self.status.data_ptr(), self.stats.data_ptr()
+                io.pesos = self.ss_last.data_ptr()
                 if record:
                     io.traj_du = traj_all["du"][done:done + n].data_ptr()
                     io.traj_J = traj_all["J"][done:done + n].data_ptr()

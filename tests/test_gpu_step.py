@@ -447,7 +447,7 @@ def test_no_kernel_writes_outside_its_buffers(which, monkeypatch):
     eng.set_disturbance(np.minimum(scen["dist_step"], 15), scen["dist"])
     stores = {}
     names = ["x", "u", "du", "J", "w_opt", "status", "stats", "ysp_seq", "seg_start", "dist", "dist_step"]
-    names += ["w_warm", "iters"] if which == "log" else ["pesos", "vinant", "n_active"]
+    names += ["w_warm", "iters", "ss_last"] if which == "log" else ["pesos", "vinant", "n_active"]
     for name in names:
         view, store = _guarded(getattr(eng, name))
         setattr(eng, name, view); stores[name] = (store, view.numel())
@@ -861,6 +861,34 @@ def test_log_variant_other_instantiations_match_oracle(N, extra):
             assert abs(J[k, idx] - solo['J']) <= RTOL * abs(solo['J']), (idx, k)
             r = orc.dynF(xo, uo, solo['du_opt'][:, 0]); xo, uo = r['xkp1'], r['ukp1']
             w0o = orc.warmStart(solo, ysp)
+
+
+def test_log_variant_carried_ss_start_saves_iterations_not_accuracy():
+    """The Newton iteration of a step starts at ss of the scenario's last optimum (carried in io.pesos between launches)
+    instead of the ss = 1 the reference's warm start writes (log.py:548): same minimiser (moves within 1e-9 of a run
+    without the carried value), fewer iterations; one step per launch and many per launch agree bit for bit."""
+    from sihmpc.ihmpccontroller_log import IHMPCController as LogController
+    sys_ = sc.distillation_system()
+    c = sc.declare_distillation_log(LogController, sys_)
+    B, T = 16, 24
+    scen = sc.distillation_scenarios(B)
+    scen["seg_start"][:, 1] = 4; scen["seg_start"][:, 2] = 15
+    runs = {}
+    for tag, spl, carry in (("one", 1, True), ("many", 8, True), ("reset", 1, False)):
+        eng = c.engine(B)
+        eng.set_state(scen["x0"], scen["u0"]); eng.set_schedule(scen["ysp_seq"], scen["seg_start"])
+        du = []
+        for k in range(0, T, spl):
+            if not carry:
+                eng.ss_last.zero_()
+            tr = eng.run(spl, record=True)
+            du.append(tr["du"].cpu().numpy())
+        runs[tag] = (np.concatenate(du), eng.stats[:, sys_.ny + 4].cpu().numpy().copy())
+        assert (eng.stats[:, sys_.ny + 3].cpu().numpy() == 0).all()
+    assert np.array_equal(runs["one"][0], runs["many"][0])
+    scale = np.max(np.abs(runs["reset"][0]))
+    assert np.max(np.abs(runs["one"][0] - runs["reset"][0])) <= 1e-8 * scale          # both stop at rounding level of phi
+    assert runs["one"][1].sum() <= 0.9 * runs["reset"][1].sum()          # Newton iterations of the whole loop
 
 
 def test_log_variant_batched_closed_loop_matches_oracle():
