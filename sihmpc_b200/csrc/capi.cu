@@ -768,7 +768,7 @@ int sihmpc_resident_step(sihmpc_plan *plan, void *state, size_t state_bytes, con
         plan->mma.res_active = 0;
         if (rc) return rc;
         {
-            long long blocks = (n + 127) / 128;
+            long long blocks = (n + 3) / 4;                      // one warp per scenario, four per CTA
             if (blocks > plan->sm_count * 16) blocks = plan->sm_count * 16;
             sih::resident_advance_kernel<<<(int)blocks, 128, 0, st>>>(
                 P, D(L.x) + lo * P.nx, D(L.w_opt) + lo * plan->nw, D(L.ysp) + lo * P.ny, D(L.u) + lo * P.nu,

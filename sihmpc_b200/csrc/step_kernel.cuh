@@ -908,24 +908,28 @@ __global__ void resident_weights_kernel(const DevPlan P_in, const double *__rest
 }
 
 // resident_advance_kernel: u += du (ihmpccontroller.py:108), warmStart (:534-564: shifted moves, syN kept,
-// siN_next = xi(N+1) with a zero move appended), the set-point the plan was made for; one thread per scenario.
+// siN_next = xi(N+1) with a zero move appended), the set-point the plan was made for.  One WARP per scenario, lanes over
+// the elements (coalesced rows of x / w_opt / w_start; one thread per scenario walked 2 (nx + nv) dependent strided loads:
+// 10-20 us per launch in the tail of every sihmpc_resident_step).
 __global__ void resident_advance_kernel(const DevPlan P, const double *__restrict__ x, const double *__restrict__ w_opt,
                                         const double *__restrict__ ysp, double *__restrict__ u,
                                         double *__restrict__ w_start, double *__restrict__ ysp_prev, const long long batch) {
     const int nx = P.nx, nu = P.nu, ny = P.ny, nvm = P.nvm, nw = nvm + 2 * ny;
-    for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < batch; s += (long long)gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (long long s = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); s < batch; s += (long long)gridDim.x * wpb) {
         const double *w = w_opt + s * nw;
+        const double *xs = x + s * nx;
         double *ws = w_start + s * nw;
         for (int i = 0; i < ny; ++i) {
             double a = 0.0;
-            for (int j = 0; j < nx; ++j) a = fma(P.Mi1xT[(size_t)j * ny + i], x[s * nx + j], a);
-            for (int c = 0; c < nvm; ++c) a = fma(P.Mi1uT[(size_t)c * ny + i], w[c], a);
-            ws[nvm + ny + i] = a;
-            ws[nvm + i] = w[nvm + i];
-            ysp_prev[s * ny + i] = ysp[s * ny + i];
+            for (int j = lane; j < nx; j += 32) a = fma(P.Mi1xT[(size_t)j * ny + i], xs[j], a);
+            for (int c = lane; c < nvm; c += 32) a = fma(P.Mi1uT[(size_t)c * ny + i], w[c], a);
+            a = warp_sum(a);
+            if (lane == 0) ws[nvm + ny + i] = a;
         }
-        for (int j = 0; j < nu; ++j) u[s * nu + j] += w[j];
-        for (int i = 0; i < nvm; ++i) ws[i] = (i + nu < nvm) ? w[i + nu] : 0.0;
+        for (int i = lane; i < ny; i += 32) { ws[nvm + i] = w[nvm + i]; ysp_prev[s * ny + i] = ysp[s * ny + i]; }
+        for (int j = lane; j < nu; j += 32) u[s * nu + j] += w[j];
+        for (int i = lane; i < nvm; i += 32) ws[i] = (i + nu < nvm) ? w[i + nu] : 0.0;
     }
 }
 
