@@ -437,7 +437,21 @@ mma_step_kernel(const DevPlan P, const MmaConst Q, const double *__restrict__ qb
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int g = lane & 3, q = lane >> 2;
     double *cst = smem;
-    for (int i = threadIdx.x; i < Q.total_d; i += blockDim.x) cst[i] = qbuf[i];
+    {   // constant block -> shared memory, 16 bytes per load and eight loads in flight per thread: with one 8-byte load per
+        // iteration this staging was ~25 us per CTA -- two thirds of a ONE-step launch (batch-1 latency, the chunks of
+        // sihmpc_resident_step); it is amortised over the steps of a longer launch
+        const double2 *src2 = reinterpret_cast<const double2 *>(qbuf);
+        double2 *dst2 = reinterpret_cast<double2 *>(cst);
+        const int n2 = Q.total_d >> 1;
+        for (int i0 = threadIdx.x; i0 < n2; i0 += 8 * blockDim.x) {
+            double2 v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { const int i = i0 + k * blockDim.x; if (i < n2) v[k] = src2[i]; }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { const int i = i0 + k * blockDim.x; if (i < n2) dst2[i] = v[k]; }
+        }
+        if ((Q.total_d & 1) && threadIdx.x == 0) cst[Q.total_d - 1] = qbuf[Q.total_d - 1];
+    }
     int *cint = reinterpret_cast<int *>(cst + Q.total_d);
     {
         const int *src = reinterpret_cast<const int *>(qbuf + Q.total_d);
